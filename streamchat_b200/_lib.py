@@ -1,0 +1,100 @@
+"""ctypes binding of libstreamchat_b200.so (the C-ABI declared in include/streamchat_b200.h).
+
+The library is built in-tree by `make -C streamchat_b200/csrc` (see __graft_entry__.build).
+There is no CPU fallback: every op raises if the library is missing or a call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstreamchat_b200.so")
+
+SCB_F32, SCB_F16 = 0, 1
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
+
+
+class ScbError(RuntimeError):
+    pass
+
+
+class CosineTopkArgs(C.Structure):
+    _fields_ = [
+        ("index", C.c_void_p), ("queries", C.c_void_p),
+        ("n_rows", C.c_int64), ("dim", C.c_int32), ("n_queries", C.c_int32),
+        ("ld_index", C.c_int64), ("ld_query", C.c_int64),
+        ("index_dtype", C.c_int32), ("query_dtype", C.c_int32),
+        ("k", C.c_int32), ("_pad", C.c_int32),
+        ("out_indices", C.c_void_p), ("out_scores", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class KmeansStepArgs(C.Structure):
+    _fields_ = [
+        ("points", C.c_void_p), ("weights", C.c_void_p), ("centroids", C.c_void_p),
+        ("n_points", C.c_int32), ("n_clusters", C.c_int32), ("n_batch", C.c_int32),
+        ("points_dtype", C.c_int32), ("dim", C.c_int64),
+        ("dist_eps", C.c_float), ("do_update", C.c_int32),
+        ("out_labels", C.c_void_p), ("out_dist", C.c_void_p), ("out_centroids", C.c_void_p),
+        ("out_wsum", C.c_void_p), ("out_shift", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("out", C.c_void_p),
+        ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo", C.c_int64),
+        ("act", C.c_int32), ("out_dtype", C.c_int32), ("batch", C.c_int32), ("_pad", C.c_int32),
+        ("stride_a", C.c_int64), ("stride_w", C.c_int64), ("stride_r", C.c_int64),
+        ("stride_o", C.c_int64),
+        ("alpha", C.c_float), ("_pad2", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/streamchat_b200.h declares
+SYMBOLS = {
+    "scb_version": (C.c_int, []),
+    "scb_last_error": (C.c_char_p, []),
+    "scb_launch_count": (C.c_uint64, []),
+    "scb_cosine_topk_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "scb_cosine_topk": (C.c_int, [C.POINTER(CosineTopkArgs), C.c_void_p]),
+    "scb_kmeans_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "scb_kmeans_step": (C.c_int, [C.POINTER(KmeansStepArgs), C.c_void_p]),
+    "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and type every exported symbol. Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ScbError(
+            f"{LIB_PATH} not found: build it with `make -C streamchat_b200/csrc` "
+            "(or python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().scb_last_error().decode("utf-8", "replace")
+        raise ScbError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().scb_launch_count())

@@ -1,0 +1,326 @@
+// cosine_topk.cu — cosine-similarity top-k over a row-major embedding index (HBM-bound).
+//
+// Replaces sentence_transformers.util.cos_sim + running arg-max of the memory-tree search
+// (reference utiles.py:732-742,764-772) and the FAISS IndexFlatL2 search behind
+// memory_bank/memory_retrieval/local_doc_qa.py:140,270.
+//
+// One launch per call.  grid = (gx, n_queries); every warp streams whole rows with 128-bit
+// L1-bypassing loads (8 x 16 B in flight per lane for a 1024-d fp32 row), reduces <x,q> and
+// <x,x> with shuffles in one pass (rows are not pre-normalised) and keeps a lane-distributed
+// sorted top-k list in registers.  Warps merge through shared memory, blocks through a
+// candidate buffer in the workspace; the last block to finish (atomic ticket) produces the
+// final (score desc, row asc) ordered answer, so no second launch is needed.
+//
+// Algorithmic bytes per launch: n_rows*dim*sizeof(T) + n_queries*dim*sizeof(Tq) + n_queries*k*12.
+#include "scb_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxK = 32;
+constexpr int kMaxGx = 1024;
+
+struct TopkList {
+  float s;       // this lane's entry (lane i = i-th best)
+  long long i;
+};
+
+// true if candidate (s, i) ranks strictly before entry (es, ei): score desc, row asc.
+SCB_DEVICE bool ranks_before(float s, long long i, float es, long long ei) {
+  return (s > es) || (s == es && i < ei);
+}
+
+// Warp-collective insert of (s, idx) into the lane-distributed sorted list of length k.
+SCB_DEVICE void topk_insert(TopkList& l, float s, long long idx, int k, int lane) {
+  // entries that stay ahead of the candidate
+  bool ahead = (lane < k) && !ranks_before(s, idx, l.s, l.i);
+  unsigned m = __ballot_sync(0xffffffffu, ahead);
+  int pos = __popc(m);
+  if (pos >= k) return;  // warp-uniform
+  float ps = __shfl_up_sync(0xffffffffu, l.s, 1);
+  long long pi = __shfl_up_sync(0xffffffffu, l.i, 1);
+  if (lane == pos) {
+    l.s = s;
+    l.i = idx;
+  } else if (lane > pos) {
+    l.s = ps;
+    l.i = pi;
+  }
+}
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int kElems = 4;
+  SCB_DEVICE static void fma(const uint4& v, const float* q, float& dot, float& xx) {
+    float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z),
+          x3 = __uint_as_float(v.w);
+    dot = fmaf(x0, q[0], dot); xx = fmaf(x0, x0, xx);
+    dot = fmaf(x1, q[1], dot); xx = fmaf(x1, x1, xx);
+    dot = fmaf(x2, q[2], dot); xx = fmaf(x2, x2, xx);
+    dot = fmaf(x3, q[3], dot); xx = fmaf(x3, x3, xx);
+  }
+  SCB_DEVICE static float load1(const float* p) { return *p; }
+};
+template <>
+struct Vec<__half> {
+  static constexpr int kElems = 8;
+  SCB_DEVICE static void fma(const uint4& v, const float* q, float& dot, float& xx) {
+    float2 a = h2_to_f2(v.x), b = h2_to_f2(v.y), c = h2_to_f2(v.z), d = h2_to_f2(v.w);
+    dot = fmaf(a.x, q[0], dot); xx = fmaf(a.x, a.x, xx);
+    dot = fmaf(a.y, q[1], dot); xx = fmaf(a.y, a.y, xx);
+    dot = fmaf(b.x, q[2], dot); xx = fmaf(b.x, b.x, xx);
+    dot = fmaf(b.y, q[3], dot); xx = fmaf(b.y, b.y, xx);
+    dot = fmaf(c.x, q[4], dot); xx = fmaf(c.x, c.x, xx);
+    dot = fmaf(c.y, q[5], dot); xx = fmaf(c.y, c.y, xx);
+    dot = fmaf(d.x, q[6], dot); xx = fmaf(d.x, d.x, xx);
+    dot = fmaf(d.y, q[7], dot); xx = fmaf(d.y, d.y, xx);
+  }
+  SCB_DEVICE static float load1(const __half* p) { return __half2float(*p); }
+};
+
+// kVec: rows are 16-byte aligned and are read with 128-bit loads; otherwise scalar loads.
+// kChunks > 0: dim == kChunks * 32 * Vec<T>::kElems exactly, all loads of a row issued up front.
+template <typename T, bool kVec, int kChunks>
+__global__ void __launch_bounds__(kThreads)
+cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries, int query_is_f16,
+                   long long n_rows, int dim, long long ld_index, long long ld_query, int k,
+                   float* __restrict__ cand_s, long long* __restrict__ cand_i,
+                   unsigned* __restrict__ tickets, long long* __restrict__ out_i,
+                   float* __restrict__ out_s) {
+  extern __shared__ __align__(16) float smem[];
+  float* q_s = smem;  // [dim_padded]
+  __shared__ float red_s[kWarps];
+  __shared__ float m_s[kWarps * kMaxK];
+  __shared__ long long m_i[kWarps * kMaxK];
+  __shared__ unsigned is_last_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = blockIdx.y;
+  const int gx = gridDim.x;
+
+  // ---- stage the query in shared memory as fp32 and compute |q|
+  float qq = 0.f;
+  for (int d = tid; d < dim; d += kThreads) {
+    float v = query_is_f16
+                  ? __half2float(reinterpret_cast<const __half*>(queries)[qi * ld_query + d])
+                  : reinterpret_cast<const float*>(queries)[qi * ld_query + d];
+    q_s[d] = v;
+    qq = fmaf(v, v, qq);
+  }
+  qq = warp_sum(qq);
+  if (lane == 0) red_s[warp] = qq;
+  __syncthreads();
+  float qtot = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) qtot += red_s[w];
+  const float qn = fmaxf(sqrtf(qtot), 1e-12f);
+
+  TopkList list;
+  list.s = -INFINITY;
+  list.i = -1;
+
+  constexpr int E = Vec<T>::kElems;
+  const long long warp_stride = (long long)gx * kWarps;
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < n_rows; row += warp_stride) {
+    const T* x = index + row * ld_index;
+    float dot = 0.f, xx = 0.f;
+    if constexpr (kVec && kChunks > 0) {
+      uint4 v[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) v[c] = ld_stream_u4(x + (c * 32 + lane) * E);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) Vec<T>::fma(v[c], q_s + (c * 32 + lane) * E, dot, xx);
+    } else if constexpr (kVec) {
+      const int nvec = dim / E;
+      for (int c = lane; c < nvec; c += 32) {
+        uint4 v = ld_stream_u4(x + c * E);
+        Vec<T>::fma(v, q_s + c * E, dot, xx);
+      }
+      for (int d = nvec * E + lane; d < dim; d += 32) {
+        float xv = Vec<T>::load1(x + d);
+        dot = fmaf(xv, q_s[d], dot);
+        xx = fmaf(xv, xv, xx);
+      }
+    } else {
+      for (int d = lane; d < dim; d += 32) {
+        float xv = Vec<T>::load1(x + d);
+        dot = fmaf(xv, q_s[d], dot);
+        xx = fmaf(xv, xv, xx);
+      }
+    }
+    dot = warp_sum(dot);
+    xx = warp_sum(xx);
+    const float sim = dot / (fmaxf(sqrtf(xx), 1e-12f) * qn);
+    topk_insert(list, sim, row, k, lane);
+  }
+
+  // ---- block merge: every warp publishes its list, warp 0 merges
+  if (lane < k) {
+    m_s[warp * kMaxK + lane] = list.s;
+    m_i[warp * kMaxK + lane] = list.i;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kWarps; ++w) {
+      for (int j = 0; j < k; ++j) {
+        float s = m_s[w * kMaxK + j];
+        long long i = m_i[w * kMaxK + j];
+        if (i < 0) break;  // lists are sorted, the rest is empty
+        topk_insert(list, s, i, k, lane);
+      }
+    }
+    if (lane < k) {
+      cand_s[((long long)qi * gx + blockIdx.x) * k + lane] = list.s;
+      cand_i[((long long)qi * gx + blockIdx.x) * k + lane] = list.i;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      unsigned t = atomicAdd(&tickets[qi], 1u);
+      is_last_s = (t == (unsigned)gx - 1u) ? 1u : 0u;
+    }
+  }
+  __syncthreads();
+  if (!is_last_s) return;
+  __threadfence();
+
+  // ---- final merge by the last block of this query: 8 warps split the block lists
+  list.s = -INFINITY;
+  list.i = -1;
+  for (int b = warp; b < gx; b += kWarps) {
+    const float* cs = cand_s + ((long long)qi * gx + b) * k;
+    const long long* ci = cand_i + ((long long)qi * gx + b) * k;
+    for (int j = 0; j < k; ++j) {
+      float s = __ldcg(cs + j);
+      long long i = __ldcg(ci + j);
+      if (i < 0) break;
+      topk_insert(list, s, i, k, lane);
+    }
+  }
+  __syncthreads();  // m_s/m_i reuse
+  if (lane < k) {
+    m_s[warp * kMaxK + lane] = list.s;
+    m_i[warp * kMaxK + lane] = list.i;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < kWarps; ++w) {
+      for (int j = 0; j < k; ++j) {
+        float s = m_s[w * kMaxK + j];
+        long long i = m_i[w * kMaxK + j];
+        if (i < 0) break;
+        topk_insert(list, s, i, k, lane);
+      }
+    }
+    if (lane < k) {
+      out_s[(long long)qi * k + lane] = list.s;
+      out_i[(long long)qi * k + lane] = list.i;
+    }
+    if (lane == 0) tickets[qi] = 0;  // leave the workspace reusable
+  }
+}
+
+struct Layout {
+  size_t tickets_off, cand_s_off, cand_i_off, total;
+};
+Layout make_layout(int n_queries, int k) {
+  Layout l;
+  size_t off = 0;
+  l.tickets_off = off;
+  off = scb_align_up(off + sizeof(unsigned) * (size_t)n_queries, 256);
+  l.cand_i_off = off;
+  off = scb_align_up(off + sizeof(long long) * (size_t)n_queries * kMaxGx * k, 256);
+  l.cand_s_off = off;
+  off = scb_align_up(off + sizeof(float) * (size_t)n_queries * kMaxGx * k, 256);
+  l.total = off;
+  return l;
+}
+
+template <typename T>
+int launch(const scb_cosine_topk_args* a, cudaStream_t st) {
+  Layout lay = make_layout(a->n_queries, a->k);
+  char* ws = reinterpret_cast<char*>(a->workspace);
+  unsigned* tickets = reinterpret_cast<unsigned*>(ws + lay.tickets_off);
+  float* cand_s = reinterpret_cast<float*>(ws + lay.cand_s_off);
+  long long* cand_i = reinterpret_cast<long long*>(ws + lay.cand_i_off);
+  SCB_CUDA_OK(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * a->n_queries, st));
+
+  const int sms = scb_num_sms();
+  long long want = (a->n_rows + kWarps - 1) / kWarps;  // one row per warp at least
+  int gx = (int)(want < 1 ? 1 : (want > (long long)sms * 4 ? (long long)sms * 4 : want));
+  if (gx > kMaxGx) gx = kMaxGx;
+  dim3 grid(gx, a->n_queries);
+  size_t smem = sizeof(float) * (size_t)a->dim;
+  constexpr int E = Vec<T>::kElems;
+  const bool vec = ((uintptr_t)a->index % 16 == 0) && ((a->ld_index * sizeof(T)) % 16 == 0);
+  const T* idx = reinterpret_cast<const T*>(a->index);
+  const int qf16 = a->query_dtype == SCB_F16;
+
+#define SCB_TOPK_LAUNCH(VEC, CH)                                                               \
+  do {                                                                                         \
+    auto kern = cosine_topk_kernel<T, VEC, CH>;                                                \
+    if (smem > 48 * 1024)                                                                      \
+      SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                       (int)smem));                                            \
+    kern<<<grid, kThreads, smem, st>>>(idx, a->queries, qf16, a->n_rows, a->dim, a->ld_index,  \
+                                       a->ld_query, a->k, cand_s, cand_i, tickets,             \
+                                       reinterpret_cast<long long*>(a->out_indices),           \
+                                       a->out_scores);                                         \
+  } while (0)
+
+  if (vec && a->dim == 8 * 32 * E) {
+    SCB_TOPK_LAUNCH(true, 8);
+  } else if (vec && a->dim == 4 * 32 * E) {
+    SCB_TOPK_LAUNCH(true, 4);
+  } else if (vec && a->dim == 3 * 32 * E) {
+    SCB_TOPK_LAUNCH(true, 3);
+  } else if (vec) {
+    SCB_TOPK_LAUNCH(true, 0);
+  } else {
+    SCB_TOPK_LAUNCH(false, 0);
+  }
+#undef SCB_TOPK_LAUNCH
+  SCB_LAUNCH_OK("cosine_topk_kernel");
+  return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t scb_cosine_topk_workspace_bytes(int64_t n_rows, int32_t n_queries, int32_t k) {
+  (void)n_rows;
+  if (n_queries < 1 || k < 1 || k > kMaxK) return 0;
+  return make_layout(n_queries, k).total;
+}
+
+int scb_cosine_topk(const scb_cosine_topk_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_cosine_topk: args is NULL");
+  SCB_REQUIRE(a->k >= 1 && a->k <= kMaxK, SCB_ERR_INVALID_ARG, "scb_cosine_topk: k=%d not in 1..%d",
+              a->k, kMaxK);
+  SCB_REQUIRE(a->n_queries >= 1 && a->n_queries <= 65535, SCB_ERR_INVALID_ARG,
+              "scb_cosine_topk: n_queries=%d not in 1..65535", a->n_queries);
+  SCB_REQUIRE(a->n_rows >= 0, SCB_ERR_INVALID_ARG, "scb_cosine_topk: n_rows < 0");
+  SCB_REQUIRE(a->dim >= 1 && a->dim <= 32768, SCB_ERR_INVALID_ARG,
+              "scb_cosine_topk: dim=%d not in 1..32768", a->dim);
+  SCB_REQUIRE(a->ld_index >= a->dim && a->ld_query >= a->dim, SCB_ERR_INVALID_ARG,
+              "scb_cosine_topk: leading dimension smaller than dim");
+  SCB_REQUIRE(a->queries && a->out_indices && a->out_scores && (a->index || a->n_rows == 0),
+              SCB_ERR_INVALID_ARG, "scb_cosine_topk: NULL buffer");
+  SCB_REQUIRE(a->index_dtype == SCB_F32 || a->index_dtype == SCB_F16, SCB_ERR_UNSUPPORTED,
+              "scb_cosine_topk: index dtype %d unsupported", a->index_dtype);
+  SCB_REQUIRE(a->query_dtype == SCB_F32 || a->query_dtype == SCB_F16, SCB_ERR_UNSUPPORTED,
+              "scb_cosine_topk: query dtype %d unsupported", a->query_dtype);
+  size_t need = scb_cosine_topk_workspace_bytes(a->n_rows, a->n_queries, a->k);
+  SCB_REQUIRE(a->workspace && a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
+              "scb_cosine_topk: workspace %zu B < required %zu B", a->workspace_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->index_dtype == SCB_F32) return launch<float>(a, st);
+  return launch<__half>(a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// kmeans.cu — one Lloyd iteration (assign + weighted update + centre shift), HBM-bound.
+//
+// Replaces the ATen broadcast formulation of weighted_kmeans_feature (reference
+// utiles.py:297-317: an [N,K,D] temporary per iteration plus a Python loop over clusters)
+// and torch_kmeans' _assign / group_by_label_mean (torch_kmeans/clustering/kmeans.py:572-597,
+// torch_kmeans/utils/utils.py:33-66: (BS*num_init*N*K) x D expanded rows).
+//
+// Data layout: points [N, D] row-major fp16/fp32 (read exactly twice per iteration — once by
+// assign, once by update), centroids [B, K, D] fp32 (L2-resident: K*D*4 bytes).
+// Algorithmic bytes per iteration: 2 * N*D*sizeof(T)  (+ 3 * B*K*D*4 for the centroids).
+//
+//   assign_partial : grid (column tiles, point splits, B).  The block stages its centroid
+//                    tile in shared memory; a thread owns 16-byte vector columns, keeps
+//                    4 points x K accumulators in registers and does the (x-c)^2 sums with
+//                    packed fp32x2 FADD2/FFMA2.  Partials are reduced in a fixed order
+//                    (deterministic labels; no float atomics).
+//   assign_final   : per (b): sum slices in order, sqrt, first-min argmin, weighted counts,
+//                    counting sort of the points by label.
+//   update_partial : grid (column chunks, B).  Thread owns a vector column, walks the sorted
+//                    member list cluster by cluster (single accumulator set), writes the new
+//                    centroid and a partial of |c_old - c_new|^2.
+//   update_final   : shift[b,k] = sqrt(sum of partials).
+#include "scb_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPG = 4;        // points per group (accumulator rows per thread)
+constexpr int kKT = 8;        // clusters per register tile
+constexpr int kTileBytes = 96 * 1024;  // centroid tile in shared memory (2 blocks / SM)
+constexpr int kMaxClusters = 64;
+
+typedef unsigned long long u64;
+
+SCB_DEVICE u64 pack2(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+SCB_DEVICE float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+SCB_DEVICE u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+SCB_DEVICE u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+SCB_DEVICE void sqacc2(u64& acc, u64 d) {
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(d));
+}
+
+template <typename T>
+struct PVec;  // one 16-byte vector of points -> fp32 pairs
+template <>
+struct PVec<float> {
+  static constexpr int kElems = 4, kPairs = 2;
+  SCB_DEVICE static void unpack(const uint4& v, u64* p) {
+    p[0] = ((u64)v.y << 32) | v.x;
+    p[1] = ((u64)v.w << 32) | v.z;
+  }
+  SCB_DEVICE static void to_float(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  SCB_DEVICE static float load1(const float* p) { return *p; }
+};
+template <>
+struct PVec<__half> {
+  static constexpr int kElems = 8, kPairs = 4;
+  SCB_DEVICE static void unpack(const uint4& v, u64* p) {
+    float2 a = h2_to_f2(v.x), b = h2_to_f2(v.y), c = h2_to_f2(v.z), d = h2_to_f2(v.w);
+    p[0] = pack2(a.x, a.y); p[1] = pack2(b.x, b.y);
+    p[2] = pack2(c.x, c.y); p[3] = pack2(d.x, d.y);
+  }
+  SCB_DEVICE static void to_float(const uint4& v, float* f) {
+    float2 a = h2_to_f2(v.x), b = h2_to_f2(v.y), c = h2_to_f2(v.z), d = h2_to_f2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  SCB_DEVICE static float load1(const __half* p) { return __half2float(*p); }
+};
+
+// ------------------------------------------------------------------------------------------
+// assign_partial
+//   partial[b][tile][n][k] = sum over the tile's columns of (x[n][d] - c[b][k][d] + eps)^2
+// The block stages its [kt, tile_cols] centroid tile in shared memory once and re-uses it for
+// every point it owns, so L2 sees the centroids only (point splits) times.
+// kVec: D % E == 0 and 16-byte aligned rows -> 128-bit loads; else one column per thread.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool kVec, bool kEps>
+__global__ void __launch_bounds__(kThreads, 2)
+kmeans_assign_partial(const T* __restrict__ x, const float* __restrict__ cent, int n_points,
+                      int n_clusters, long long dim, int tile_cols, int points_per_split, float eps,
+                      float* __restrict__ partial) {
+  constexpr int E = kVec ? PVec<T>::kElems : 1;
+  constexpr int NP = kVec ? PVec<T>::kPairs : 1;
+  extern __shared__ __align__(16) float cs[];  // [kKT][tile_cols]
+  __shared__ float red[kThreads / 32][kPG][kKT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.z;
+  const int n_tiles = gridDim.x;
+  const long long col0 = (long long)tile * tile_cols;
+  const int ncols = (int)min((long long)tile_cols, dim - col0);
+  const int n_begin = blockIdx.y * points_per_split;
+  const int n_end = min(n_points, n_begin + points_per_split);
+  const float* cb = cent + (long long)b * n_clusters * dim + col0;
+  const u64 eps2 = pack2(eps, eps);
+
+  for (int k0 = 0; k0 < n_clusters; k0 += kKT) {
+    const int kt = min(kKT, n_clusters - k0);
+    // ---- stage the centroid tile
+    if constexpr (kVec) {
+      const int n4 = ncols >> 2;
+      for (int i = tid; i < kt * n4; i += kThreads) {
+        const int k = i / n4, c = (i - k * n4) << 2;
+        *reinterpret_cast<float4*>(cs + k * tile_cols + c) =
+            *reinterpret_cast<const float4*>(cb + (long long)(k0 + k) * dim + c);
+      }
+    } else {
+      for (int i = tid; i < kt * ncols; i += kThreads) {
+        const int k = i / ncols, c = i - k * ncols;
+        cs[k * tile_cols + c] = cb[(long long)(k0 + k) * dim + c];
+      }
+    }
+    __syncthreads();
+
+    for (int p0 = n_begin; p0 < n_end; p0 += kPG) {
+      u64 acc[kPG][kKT];  // packed (even, odd) partial sums
+#pragma unroll
+      for (int p = 0; p < kPG; ++p)
+#pragma unroll
+        for (int k = 0; k < kKT; ++k) acc[p][k] = 0ull;
+
+      for (int c = tid * E; c < ncols; c += kThreads * E) {
+        u64 xv[kPG][NP];
+        if constexpr (kVec) {
+          uint4 raw[kPG];
+#pragma unroll
+          for (int p = 0; p < kPG; ++p) {
+            int n = p0 + p;
+            if (n >= n_end) n = n_end - 1;  // clamped duplicate, discarded below
+            raw[p] = ld_stream_u4(x + (long long)n * dim + col0 + c);
+          }
+#pragma unroll
+          for (int p = 0; p < kPG; ++p) PVec<T>::unpack(raw[p], xv[p]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < kPG; ++p) {
+            int n = p0 + p;
+            if (n >= n_end) n = n_end - 1;
+            xv[p][0] = pack2(PVec<T>::load1(x + (long long)n * dim + col0 + c), 0.f);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kKT; ++k) {
+          if (k < kt) {
+            u64 cv[NP];
+            const float* cp = cs + k * tile_cols + c;
+            if constexpr (kVec) {
+#pragma unroll
+              for (int j = 0; j < NP; j += 2) {
+                ulonglong2 t = *reinterpret_cast<const ulonglong2*>(cp + j * 2);
+                cv[j] = t.x;
+                cv[j + 1] = t.y;
+              }
+            } else {
+              // unused upper half: (0 - eps) + eps == 0 exactly, so it never contributes
+              cv[0] = pack2(*cp, kEps ? eps : 0.f);
+            }
+#pragma unroll
+            for (int p = 0; p < kPG; ++p)
+#pragma unroll
+              for (int j = 0; j < NP; ++j) {
+                u64 d = sub2(xv[p][j], cv[j]);
+                if constexpr (kEps) d = add2(d, eps2);
+                sqacc2(acc[p][k], d);
+              }
+          }
+        }
+      }
+
+      // block reduction in a fixed order: lanes (xor tree), then warps 0..7
+#pragma unroll
+      for (int p = 0; p < kPG; ++p)
+#pragma unroll
+        for (int k = 0; k < kKT; ++k) {
+          if (k < kt) {
+            float2 a = unpack2(acc[p][k]);
+            float v = warp_sum(a.x + a.y);
+            if (lane == 0) red[warp][p][k] = v;
+          }
+        }
+      __syncthreads();
+      if (tid < kPG * kKT) {
+        const int p = tid / kKT, k = tid % kKT;
+        const int n = p0 + p;
+        if (n < n_end && k < kt) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) v += red[w][p][k];
+          partial[(((long long)b * n_tiles + tile) * n_points + n) * n_clusters + k0 + k] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// assign_final: one block per batch entry.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+kmeans_assign_final(const float* __restrict__ partial, const float* __restrict__ weights,
+                    int n_points, int n_clusters, int n_slices, int* __restrict__ labels,
+                    float* __restrict__ out_dist, float* __restrict__ wsum,
+                    int* __restrict__ order, int* __restrict__ starts) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ int cnt[kMaxClusters + 1];
+  for (int n = tid; n < n_points; n += kThreads) {
+    float best = INFINITY;
+    int bi = 0;
+    for (int k = 0; k < n_clusters; ++k) {
+      float s = 0.f;
+      for (int sl = 0; sl < n_slices; ++sl)
+        s += partial[(((long long)b * n_slices + sl) * n_points + n) * n_clusters + k];
+      float d = sqrtf(s);
+      if (k == 0 || d < best) {  // first minimum wins (torch.argmin; NaN-free inputs assumed)
+        best = d;
+        bi = k;
+      }
+    }
+    labels[(long long)b * n_points + n] = bi;
+    if (out_dist) out_dist[(long long)b * n_points + n] = best;
+  }
+  if (order == nullptr) return;
+  __syncthreads();
+  // Stable counting sort by label (serial over points per cluster owner: N is small) and
+  // weight sums in ascending point order (deterministic).
+  if (tid <= n_clusters) cnt[tid] = 0;
+  __syncthreads();
+  if (tid < n_clusters) {
+    int c = 0;
+    float ws = 0.f;
+    for (int n = 0; n < n_points; ++n)
+      if (labels[(long long)b * n_points + n] == tid) {
+        ++c;
+        ws += weights ? weights[n] : 1.f;
+      }
+    cnt[tid + 1] = c;
+    wsum[(long long)b * n_clusters + tid] = ws;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 0; k < n_clusters; ++k) cnt[k + 1] += cnt[k];
+    for (int k = 0; k <= n_clusters; ++k) starts[(long long)b * (n_clusters + 1) + k] = cnt[k];
+  }
+  __syncthreads();
+  if (tid < n_clusters) {
+    int pos = cnt[tid];
+    for (int n = 0; n < n_points; ++n)
+      if (labels[(long long)b * n_points + n] == tid) order[(long long)b * n_points + pos++] = n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// update_partial
+// ------------------------------------------------------------------------------------------
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kThreads)
+kmeans_update_partial(const T* __restrict__ x, const float* __restrict__ weights,
+                      const float* __restrict__ cent, const int* __restrict__ order,
+                      const int* __restrict__ starts, const float* __restrict__ wsum, int n_points,
+                      int n_clusters, long long dim, float* __restrict__ new_cent,
+                      float* __restrict__ shift_partial) {
+  constexpr int E = kVec ? PVec<T>::kElems : 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int n_chunks = gridDim.x;
+  extern __shared__ int sm_order[];  // [n_points] member list of this batch entry
+  __shared__ int sm_starts[kMaxClusters + 1];
+  __shared__ float red[kThreads / 32];
+  for (int i = tid; i < n_points; i += kThreads) sm_order[i] = order[(long long)b * n_points + i];
+  if (tid <= n_clusters) sm_starts[tid] = starts[(long long)b * (n_clusters + 1) + tid];
+  __syncthreads();
+
+  const long long col = ((long long)blockIdx.x * kThreads + tid) * E;
+  const bool active = col < dim;
+  for (int k = 0; k < n_clusters; ++k) {
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    const int beg = sm_starts[k], end = sm_starts[k + 1];
+    float sq = 0.f;
+    if (active) {
+      int i = beg;
+      if constexpr (kVec) {
+        for (; i + 4 <= end; i += 4) {  // four independent 16-byte loads in flight
+          uint4 r[4];
+          float w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int n = sm_order[i + u];
+            r[u] = ld_stream_u4(x + (long long)n * dim + col);
+            w[u] = weights ? weights[n] : 1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[E];
+            PVec<T>::to_float(r[u], f);
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = fmaf(w[u], f[e], acc[e]);
+          }
+        }
+      }
+      for (; i < end; ++i) {
+        const int n = sm_order[i];
+        const float w = weights ? weights[n] : 1.f;
+        if constexpr (kVec) {
+          uint4 r = ld_stream_u4(x + (long long)n * dim + col);
+          float f[E];
+          PVec<T>::to_float(r, f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[e] = fmaf(w, f[e], acc[e]);
+        } else {
+          acc[0] = fmaf(w, PVec<T>::load1(x + (long long)n * dim + col), acc[0]);
+        }
+      }
+      const float ws = wsum[(long long)b * n_clusters + k];
+      const long long off = ((long long)b * n_clusters + k) * dim + col;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float nc = ws > 0.f ? acc[e] / ws : 0.f;
+        const float d = cent[off + e] - nc;
+        sq = fmaf(d, d, sq);
+        new_cent[off + e] = nc;
+      }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) v += red[w];
+      shift_partial[((long long)b * n_clusters + k) * n_chunks + blockIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void kmeans_update_final(const float* __restrict__ shift_partial, int n_chunks,
+                                    float* __restrict__ shift) {
+  // one warp per (b, k); fixed-order strided sum then xor tree
+  const int bk = blockIdx.x, lane = threadIdx.x;
+  float v = 0.f;
+  for (int c = lane; c < n_chunks; c += 32) v += shift_partial[(long long)bk * n_chunks + c];
+  v = warp_sum(v);
+  if (lane == 0) shift[bk] = sqrtf(v);
+}
+
+struct Plan {
+  bool vec;
+  int tile_cols, n_tiles;         // assign: centroid tile (columns) and tile count
+  int points_per_split, n_splits; // assign: points per block
+  size_t assign_smem;
+  int n_chunks;                   // update: column chunks
+  size_t partial_off, order_off, starts_off, shiftp_off, total;
+};
+
+Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esize, bool aligned) {
+  Plan p;
+  const int E = 16 / esize;
+  p.vec = aligned && (dim % E == 0);
+  const int ce = p.vec ? E : 1;
+  const long long cols_per_pass = (long long)kThreads * ce;
+  const long long passes = (dim + cols_per_pass - 1) / cols_per_pass;
+  const int kt = n_clusters < kKT ? n_clusters : kKT;
+  long long tile_passes = kTileBytes / ((long long)kt * 4 * cols_per_pass);
+  if (tile_passes < 1) tile_passes = 1;
+  if (tile_passes > passes) tile_passes = passes;
+  p.tile_cols = (int)(tile_passes * cols_per_pass);
+  p.n_tiles = (int)((dim + p.tile_cols - 1) / p.tile_cols);
+  p.assign_smem = (size_t)kt * p.tile_cols * sizeof(float);
+  // split the points so that ~4 blocks per SM exist (each split re-reads the centroid tile from L2)
+  const int n_groups = (n_points + kPG - 1) / kPG;
+  long long splits = (148LL * 4 + (long long)p.n_tiles * n_batch - 1) / ((long long)p.n_tiles * n_batch);
+  if (splits < 1) splits = 1;
+  if (splits > n_groups) splits = n_groups;
+  const int groups_per_split = (int)((n_groups + splits - 1) / splits);
+  p.points_per_split = groups_per_split * kPG;
+  p.n_splits = (n_points + p.points_per_split - 1) / p.points_per_split;
+  p.n_chunks = (int)passes;
+  size_t off = 0;
+  p.partial_off = off;
+  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * p.n_tiles * n_points * n_clusters, 256);
+  p.order_off = off;
+  off = scb_align_up(off + sizeof(int) * (size_t)n_batch * n_points, 256);
+  p.starts_off = off;
+  off = scb_align_up(off + sizeof(int) * (size_t)n_batch * (n_clusters + 1), 256);
+  p.shiftp_off = off;
+  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * n_clusters * p.n_chunks, 256);
+  p.total = off;
+  return p;
+}
+
+template <typename T>
+int run(const scb_kmeans_step_args* a, cudaStream_t st) {
+  const bool aligned = ((uintptr_t)a->points % 16 == 0) && ((uintptr_t)a->centroids % 16 == 0) &&
+                       ((a->dim * sizeof(T)) % 16 == 0) && ((a->dim * sizeof(float)) % 16 == 0) &&
+                       (!a->out_centroids || (uintptr_t)a->out_centroids % 16 == 0);
+  Plan p = make_plan(a->n_points, a->n_clusters, a->n_batch, a->dim, (int)sizeof(T), aligned);
+  SCB_REQUIRE(a->workspace_bytes >= p.total, SCB_ERR_WORKSPACE,
+              "scb_kmeans_step: workspace %zu B < required %zu B", a->workspace_bytes, p.total);
+  SCB_REQUIRE(p.n_splits <= 65535 && a->n_batch <= 65535, SCB_ERR_INVALID_ARG,
+              "scb_kmeans_step: grid too large");
+  char* ws = reinterpret_cast<char*>(a->workspace);
+  float* partial = reinterpret_cast<float*>(ws + p.partial_off);
+  int* order = reinterpret_cast<int*>(ws + p.order_off);
+  int* starts = reinterpret_cast<int*>(ws + p.starts_off);
+  float* shiftp = reinterpret_cast<float*>(ws + p.shiftp_off);
+  const T* x = reinterpret_cast<const T*>(a->points);
+
+  dim3 g1(p.n_tiles, p.n_splits, a->n_batch);
+  const bool eps = a->dist_eps != 0.f;
+#define SCB_KM_ASSIGN(VEC, EPS)                                                                    \
+  do {                                                                                             \
+    auto kern = kmeans_assign_partial<T, VEC, EPS>;                                                \
+    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                     (int)p.assign_smem));                                         \
+    kern<<<g1, kThreads, p.assign_smem, st>>>(x, a->centroids, a->n_points, a->n_clusters, a->dim, \
+                                              p.tile_cols, p.points_per_split, a->dist_eps,        \
+                                              partial);                                            \
+  } while (0)
+  if (p.vec) {
+    if (eps) SCB_KM_ASSIGN(true, true); else SCB_KM_ASSIGN(true, false);
+  } else {
+    if (eps) SCB_KM_ASSIGN(false, true); else SCB_KM_ASSIGN(false, false);
+  }
+#undef SCB_KM_ASSIGN
+  SCB_LAUNCH_OK("kmeans_assign_partial");
+
+  kmeans_assign_final<<<a->n_batch, kThreads, 0, st>>>(
+      partial, a->weights, a->n_points, a->n_clusters, p.n_tiles, a->out_labels, a->out_dist,
+      a->do_update ? a->out_wsum : nullptr, a->do_update ? order : nullptr, starts);
+  SCB_LAUNCH_OK("kmeans_assign_final");
+  if (!a->do_update) return SCB_OK;
+
+  dim3 g2(p.n_chunks, a->n_batch);
+  size_t smem = sizeof(int) * (size_t)a->n_points;
+  if (p.vec)
+    kmeans_update_partial<T, true><<<g2, kThreads, smem, st>>>(
+        x, a->weights, a->centroids, order, starts, a->out_wsum, a->n_points, a->n_clusters, a->dim,
+        a->out_centroids, shiftp);
+  else
+    kmeans_update_partial<T, false><<<g2, kThreads, smem, st>>>(
+        x, a->weights, a->centroids, order, starts, a->out_wsum, a->n_points, a->n_clusters, a->dim,
+        a->out_centroids, shiftp);
+  SCB_LAUNCH_OK("kmeans_update_partial");
+  kmeans_update_final<<<a->n_batch * a->n_clusters, 32, 0, st>>>(shiftp, p.n_chunks, a->out_shift);
+  SCB_LAUNCH_OK("kmeans_update_final");
+  return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t scb_kmeans_step_workspace_bytes(int32_t n_points, int32_t n_clusters, int32_t n_batch,
+                                       int64_t dim) {
+  if (n_points < 1 || n_clusters < 1 || n_batch < 1 || dim < 1) return 0;
+  // upper bound over both element sizes and both load paths
+  size_t m = 0;
+  for (int esize = 2; esize <= 4; esize += 2)
+    for (int al = 0; al < 2; ++al) {
+      size_t t = make_plan(n_points, n_clusters, n_batch, dim, esize, al != 0).total;
+      if (t > m) m = t;
+    }
+  return m;
+}
+
+int scb_kmeans_step(const scb_kmeans_step_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_kmeans_step: args is NULL");
+  SCB_REQUIRE(a->n_points >= 1 && a->n_points <= 12000, SCB_ERR_INVALID_ARG,
+              "scb_kmeans_step: n_points=%d not in 1..12000", a->n_points);
+  SCB_REQUIRE(a->n_clusters >= 1 && a->n_clusters <= kMaxClusters, SCB_ERR_INVALID_ARG,
+              "scb_kmeans_step: n_clusters=%d not in 1..%d", a->n_clusters, kMaxClusters);
+  SCB_REQUIRE(a->n_batch >= 1 && a->n_batch <= 65535, SCB_ERR_INVALID_ARG,
+              "scb_kmeans_step: n_batch=%d not in 1..65535", a->n_batch);
+  SCB_REQUIRE(a->dim >= 1, SCB_ERR_INVALID_ARG, "scb_kmeans_step: dim < 1");
+  SCB_REQUIRE(a->points && a->centroids && a->out_labels && a->workspace, SCB_ERR_INVALID_ARG,
+              "scb_kmeans_step: NULL buffer");
+  SCB_REQUIRE(!a->do_update || (a->out_centroids && a->out_wsum && a->out_shift),
+              SCB_ERR_INVALID_ARG, "scb_kmeans_step: do_update needs out_centroids/out_wsum/out_shift");
+  SCB_REQUIRE(a->points_dtype == SCB_F32 || a->points_dtype == SCB_F16, SCB_ERR_UNSUPPORTED,
+              "scb_kmeans_step: points dtype %d unsupported", a->points_dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->points_dtype == SCB_F32) return run<float>(a, st);
+  return run<__half>(a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,433 @@
+// linear_tcgen05.cu — out = act(alpha * A·Wᵀ + bias) + residual on the 5th-gen tensor cores.
+//
+// Replaces every nn.Linear the reference reaches through HF transformers on the hot path
+// (CLIP q/k/v/out/fc1/fc2 via longva/model/multimodal_encoder/clip_encoder.py:76, the
+// mm_projector longva/model/multimodal_projector/builder.py:41-48, Qwen2 q/k/v/o/gate/up/down
+// and lm_head via longva/model/language_model/llava_qwen.py:155).
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0   : TMA producer — cp.async.bulk.tensor 3-D tiles (k, rows, batch) of A [128 x 64]
+//              and W [BN x 64] fp16 into a kStages-deep shared-memory ring (128-byte swizzle).
+//   warp 1   : MMA issuer — one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+//              K=16) x4 per stage; accumulators live in TMEM (2 stages x BN fp32 columns), smem
+//              slots are released with tcgen05.commit -> mbarrier.
+//   warps 2-5: epilogue — tcgen05.ld 32 lanes x 32 columns, alpha/bias/activation/residual in
+//              fp32 registers, 16-byte stores; overlaps the next tile's main loop through the
+//              double-buffered TMEM accumulator.
+// FLOPs per launch: 2*m*n*k*batch.  Bytes are secondary (operands stream through L2).
+#include "scb_common.cuh"
+#include <math.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  const __half* bias;
+  const __half* residual;
+  void* out;
+  long long m, n, k;
+  long long ldr, ldo;
+  long long stride_r, stride_o;
+  int act;
+  int out_f32;
+  int batch;
+  int res_vec, out_vec;  // 16-byte vector access is legal for residual / out rows
+  float alpha;
+};
+
+SCB_DEVICE float apply_act(float v, int act) {
+  switch (act) {
+    case SCB_ACT_QUICK_GELU:
+      return v / (1.f + __expf(-1.702f * v));
+    case SCB_ACT_GELU_ERF:
+      return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case SCB_ACT_SILU:
+      return v / (1.f + __expf(-v));
+    default:
+      return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
+                      const __grid_constant__ CUtensorMap map_w, const EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms need 1024-byte aligned tile bases
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + C::kStages;         // [kStages]
+  uint64_t* tfull = bars + 2 * C::kStages;     // [2]
+  uint64_t* tempty = bars + 2 * C::kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (int)((ep.m + BM - 1) / BM);
+  const int tiles_n = (int)((ep.n + BN - 1) / BN);
+  const long long tiles_per_batch = (long long)tiles_m * tiles_n;
+  const long long n_tiles = tiles_per_batch * ep.batch;
+  const int k_blocks = (int)((ep.k + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int b = (int)(t / tiles_per_batch);
+        const int r = (int)(t - (long long)b * tiles_per_batch);
+        const int tm = r % tiles_m, tn = r / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+          tma_load_3d(smem_a + stage * C::kABytes, &map_a, &full[stage], kb * BK, tm * BM, b);
+          tma_load_3d(smem_b + stage * C::kBBytes, &map_w, &full[stage], kb * BK, tn * BN, b);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);  // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * C::kABytes));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the >>4 address field
+            umma_f16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                        (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int b = (int)(t / tiles_per_batch);
+      const int r = (int)(t - (long long)b * tiles_per_batch);
+      const int tm = r % tiles_m, tn = r / tiles_m;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const long long row = (long long)tm * BM + quad * 32 + lane;
+      const bool row_ok = row < ep.m;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const long long col0 = (long long)tn * BN + c0;
+        if (col0 >= ep.n) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const bool full_chunk = col0 + 32 <= ep.n;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+          if (ep.bias) {
+            if (full_chunk) {
+              const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 bv = __ldg(bp + q);
+                float2 b0 = h2_to_f2(bv.x), b1 = h2_to_f2(bv.y), b2 = h2_to_f2(bv.z),
+                       b3 = h2_to_f2(bv.w);
+                f[q * 8 + 0] += b0.x; f[q * 8 + 1] += b0.y; f[q * 8 + 2] += b1.x;
+                f[q * 8 + 3] += b1.y; f[q * 8 + 4] += b2.x; f[q * 8 + 5] += b2.y;
+                f[q * 8 + 6] += b3.x; f[q * 8 + 7] += b3.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n) f[j] += __half2float(ep.bias[col0 + j]);
+            }
+          }
+          if (ep.act != SCB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+          }
+          if (ep.residual) {
+            const __half* rp = ep.residual + (long long)b * ep.stride_r + row * ep.ldr + col0;
+            if (full_chunk && ep.res_vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
+                float2 r0 = h2_to_f2(rv.x), r1 = h2_to_f2(rv.y), r2 = h2_to_f2(rv.z),
+                       r3 = h2_to_f2(rv.w);
+                f[q * 8 + 0] += r0.x; f[q * 8 + 1] += r0.y; f[q * 8 + 2] += r1.x;
+                f[q * 8 + 3] += r1.y; f[q * 8 + 4] += r2.x; f[q * 8 + 5] += r2.y;
+                f[q * 8 + 6] += r3.x; f[q * 8 + 7] += r3.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n) f[j] += __half2float(rp[j]);
+            }
+          }
+          if (ep.out_f32) {
+            float* op = reinterpret_cast<float*>(ep.out) + (long long)b * ep.stride_o +
+                        row * ep.ldo + col0;
+            if (full_chunk && ep.out_vec) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(op + q * 4) =
+                    make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n) op[j] = f[j];
+            }
+          } else {
+            __half* op = reinterpret_cast<__half*>(ep.out) + (long long)b * ep.stride_o +
+                         row * ep.ldo + col0;
+            if (full_chunk && ep.out_vec) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                o.x = f2_to_h2(f[q * 8 + 0], f[q * 8 + 1]);
+                o.y = f2_to_h2(f[q * 8 + 2], f[q * 8 + 3]);
+                o.z = f2_to_h2(f[q * 8 + 4], f[q * 8 + 5]);
+                o.w = f2_to_h2(f[q * 8 + 6], f[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + q * 8) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.n) op[j] = __float2half_rn(f[j]);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): release the stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point fetched through the runtime, so the
+// library does not link libcuda) with a small cache keyed on the full descriptor contents.
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long rows, k, ld, stride;
+  int batch, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && k == o.k && ld == o.ld && stride == o.stride &&
+           batch == o.batch && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](long long v) { h ^= (size_t)v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.rows); mix(k.k); mix(k.ld); mix(k.stride); mix(k.batch); mix(k.box_rows);
+    return h;
+  }
+};
+
+// [batch, rows, k] fp16 tensor, k contiguous; box = (64, box_rows, 1); 128-byte swizzle;
+// out-of-bounds elements read as zero (so ragged m / n / k tails need no special casing).
+int make_map(CUtensorMap* out, const void* ptr, long long rows, long long k, long long ld,
+             long long stride, int batch, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, rows, k, ld, stride, batch, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return SCB_OK;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  SCB_REQUIRE(fn != nullptr, SCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? stride : rows * ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCB_REQUIRE(r == CUDA_SUCCESS, SCB_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed (%d) rows=%lld k=%lld ld=%lld stride=%lld batch=%d",
+              (int)r, rows, k, ld, stride, batch);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return SCB_OK;
+}
+
+template <int BN>
+int launch(const scb_linear_args* a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap ma, mw;
+  int rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->stride_a, a->batch, BM);
+  if (rc != SCB_OK) return rc;
+  rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, BN);
+  if (rc != SCB_OK) return rc;
+  EpiParams ep;
+  ep.bias = reinterpret_cast<const __half*>(a->bias);
+  ep.residual = reinterpret_cast<const __half*>(a->residual);
+  ep.out = a->out;
+  ep.m = a->m; ep.n = a->n; ep.k = a->k;
+  ep.ldr = a->ldr; ep.ldo = a->ldo;
+  ep.stride_r = a->stride_r; ep.stride_o = a->stride_o;
+  ep.act = a->act;
+  ep.out_f32 = a->out_dtype == SCB_F32;
+  ep.batch = a->batch;
+  ep.alpha = a->alpha;
+  const int ov = ep.out_f32 ? 4 : 8;
+  ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
+  ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
+  static bool attr_set = false;  // per template instantiation
+  auto kern = linear_tcgen05_kernel<BN>;
+  if (!attr_set) {
+    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::kSmemBytes));
+    attr_set = true;
+  }
+  const long long tiles = ((a->m + BM - 1) / BM) * ((a->n + BN - 1) / BN) * a->batch;
+  const int sms = scb_num_sms();
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  kern<<<grid, kGemmThreads, C::kSmemBytes, st>>>(ma, mw, ep);
+  SCB_LAUNCH_OK("linear_tcgen05_kernel");
+  return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_linear: args is NULL");
+  SCB_REQUIRE(a->m >= 1 && a->n >= 1 && a->k >= 1 && a->batch >= 1, SCB_ERR_INVALID_ARG,
+              "scb_linear: m=%lld n=%lld k=%lld batch=%d must be >= 1", (long long)a->m,
+              (long long)a->n, (long long)a->k, a->batch);
+  SCB_REQUIRE(a->a && a->w && a->out, SCB_ERR_INVALID_ARG, "scb_linear: NULL buffer");
+  SCB_REQUIRE(a->lda >= a->k && a->ldw >= a->k && a->ldo >= a->n, SCB_ERR_INVALID_ARG,
+              "scb_linear: leading dimension too small");
+  SCB_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0, SCB_ERR_INVALID_ARG,
+              "scb_linear: lda/ldw must be multiples of 8 elements (TMA 16-byte strides)");
+  SCB_REQUIRE((uintptr_t)a->a % 16 == 0 && (uintptr_t)a->w % 16 == 0 && (uintptr_t)a->out % 16 == 0,
+              SCB_ERR_INVALID_ARG, "scb_linear: a/w/out must be 16-byte aligned");
+  SCB_REQUIRE(a->batch == 1 || (a->stride_a % 8 == 0 && a->stride_w % 8 == 0), SCB_ERR_INVALID_ARG,
+              "scb_linear: batch strides must be multiples of 8 elements");
+  SCB_REQUIRE(!a->residual || a->ldr >= a->n, SCB_ERR_INVALID_ARG, "scb_linear: ldr too small");
+  SCB_REQUIRE(!a->bias || (uintptr_t)a->bias % 16 == 0, SCB_ERR_INVALID_ARG,
+              "scb_linear: bias must be 16-byte aligned");
+  SCB_REQUIRE(!a->residual || (uintptr_t)a->residual % 16 == 0, SCB_ERR_INVALID_ARG,
+              "scb_linear: residual must be 16-byte aligned");
+  SCB_REQUIRE(a->out_dtype == SCB_F16 || a->out_dtype == SCB_F32, SCB_ERR_UNSUPPORTED,
+              "scb_linear: out dtype %d unsupported", a->out_dtype);
+  SCB_REQUIRE(a->act >= SCB_ACT_NONE && a->act <= SCB_ACT_SILU, SCB_ERR_UNSUPPORTED,
+              "scb_linear: activation %d unsupported", a->act);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Narrow problems keep more CTAs busy with 128-wide tiles; wide ones amortise A with 256.
+  const long long tiles256 = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256) * a->batch;
+  if (a->n <= 128 || tiles256 < scb_num_sms()) return launch<128>(a, st);
+  return launch<256>(a, st);
+}

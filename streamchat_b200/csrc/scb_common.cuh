@@ -1,0 +1,235 @@
+// scb_common.cuh — shared host/device helpers for libstreamchat_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/streamchat_b200.h"
+
+// ----------------------------------------------------------------------------------------
+// host: error reporting + launch accounting
+// ----------------------------------------------------------------------------------------
+void scb_set_error(const char* fmt, ...);
+void scb_count_launch(int n = 1);
+
+#define SCB_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      scb_set_error(__VA_ARGS__);               \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define SCB_CUDA_OK(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      scb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                    __LINE__);                                                         \
+      return SCB_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+// Checks the launch itself (configuration errors); never synchronises.
+#define SCB_LAUNCH_OK(name)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      scb_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
+      return SCB_ERR_CUDA;                                                             \
+    }                                                                                  \
+    scb_count_launch();                                                                \
+  } while (0)
+
+int scb_num_sms();  // SM count of the current device (cached)
+
+static inline size_t scb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ----------------------------------------------------------------------------------------
+// device: small utilities
+// ----------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define SCB_DEVICE __device__ __forceinline__
+
+SCB_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+SCB_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 128-bit streaming load that does not allocate in L1 (data touched once).
+SCB_DEVICE uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+SCB_DEVICE float2 h2_to_f2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+SCB_DEVICE uint32_t f2_to_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+SCB_DEVICE uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---------------------------------------------------------------- mbarrier
+SCB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+SCB_DEVICE void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SCB_DEVICE void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+SCB_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+SCB_DEVICE void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+SCB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+SCB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// ---------------------------------------------------------------- TMA
+SCB_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tile load global -> shared, completion counted in bytes on an mbarrier.
+SCB_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                            int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1)
+      : "memory");
+}
+SCB_DEVICE void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                            int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+SCB_DEVICE void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+SCB_DEVICE void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+SCB_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+SCB_DEVICE void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+SCB_DEVICE void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc];  kind::f16 (fp16/bf16 in, fp32 accumulate)
+SCB_DEVICE void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread retired.
+SCB_DEVICE void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
+SCB_DEVICE void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+SCB_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major operand tile stored as rows of 64 fp16
+// (128 bytes) with the 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B):
+//   start address >>4 in bits [0,14); LBO (ignored for swizzled K-major) = 1 in [16,30);
+//   SBO = 1024 B (8 rows x 128 B) >>4 in [32,46); version = 1 in [46,48); layout type
+//   SWIZZLE_128B = 2 in [61,64).  Tile base must be 1024-byte aligned.
+SCB_DEVICE uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate (c_format 1),
+// both operands K-major, dense.  n>>3 in bits [17,23), m>>4 in bits [24,29).
+SCB_DEVICE constexpr uint32_t umma_idesc_f16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+SCB_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,220 @@
+"""Host-side mirrors of the reference's memory functions (utiles.py), same names and argument
+order, with the arithmetic on the sm_100a kernels.
+
+  calculate_forgetting_probabilities      <- utiles.py:251-255  (a-S1)
+  select_data_without_replacement         <- utiles.py:257-262  (a-S2)
+  MultimodalTreeNode                      <- utiles.py:48-56    (a-T1)
+  count_nodes_by_depth                    <- utiles.py:1002-1011
+  fast_building_memory_tree_summarize_token <- utiles.py:489-620 (a-T2)
+  fast_search_tree_multi_modal_with_embedding <- utiles.py:685-788 (a-R1)
+
+Differences from the reference, all deliberate and listed in DESIGN.md:
+  * node text embeddings are computed once per node and cached on the node (`text_embedding`)
+    instead of one batch-1 BERT forward + D2H sync per visited child per question; the per-level
+    similarity + arg-max is one `cosine_topk` launch over the stacked child embeddings;
+  * captions can be generated greedily (`caption_do_sample=False`) for parity runs (hazard H2).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .kmeans import weighted_kmeans_feature
+
+RED = "\033[31m"
+BLUE = "\033[34m"
+RESET = "\033[0m"
+
+VERBOSE = False  # the reference prints the whole tree on every update (utiles.py:491-504)
+
+
+class MultimodalTreeNode:
+    def __init__(self, centroids, text, text_distance=None, image_distance=None, labels=None, depth=0):
+        self.centroids = centroids
+        self.text = text
+        self.text_distance = text_distance
+        self.image_distance = image_distance
+        self.labels = labels
+        self.children = []
+        self.depth = depth
+        self.text_embedding = None  # cached [D] embedding of `text` (not in the reference)
+
+
+def calculate_forgetting_probabilities(length, tau=10):
+    t = np.arange(length)
+    R_t = np.exp(-t / tau)
+    return R_t / R_t.sum()
+
+
+def select_data_without_replacement(queue, probabilities, selection_length=10):
+    indices = np.arange(len(queue))
+    selected_indices = np.random.choice(indices, size=selection_length, replace=False, p=probabilities)
+    return [queue[idx] for idx in selected_indices]
+
+
+def count_nodes_by_depth(nodes):
+    depth_count = defaultdict(int)
+    for node in nodes:
+        depth_count[node.depth] += 1
+        stack = node.children.copy()
+        while stack:
+            current_node = stack.pop()
+            depth_count[current_node.depth] += 1
+            stack.extend(current_node.children)
+    return depth_count
+
+
+def _print_tree(node, indent=0):
+    if isinstance(node, list):
+        for n in node:
+            _print_tree(n, indent)
+        return
+    print(" " * indent + f"{RED}Depth{RESET}: {node.depth}, {RED}Centroids{RESET}: "
+          f"{tuple(node.centroids.shape)}, {RED}Text{RESET} :{node.text}")
+    for child in node.children:
+        _print_tree(child, indent + 4)
+
+
+def get_summarize_depth(nodes, interval):
+    """utiles.py:525-536: highest depth whose node count is a positive multiple of `interval`."""
+    depth_count = defaultdict(int)
+    for node in nodes:
+        depth_count[node.depth] += 1
+    max_depth = max(depth_count.keys())
+    for depth in range(max_depth, -1, -1):
+        if depth_count[depth] % interval == 0 and depth_count[depth] > 0:
+            return depth, depth_count
+    return 0, depth_count
+
+
+def make_summary_prompt(caption_list, tokenizer, conv_templates):
+    """utiles.py:506-523."""
+    order = ["first", "second", "third", "fourth", "fifth", "sixth", "seventh", "eighth", "ninth", "tenth"]
+    new_caption = ["The caption of the {} video clip is:{} \n".format(order[i], c) for i, c in enumerate(caption_list)]
+    qs = " ".join(new_caption)
+    qs = ("You need to write a summary of the following, including as many key details as possible "
+          "into one sentence." + qs)
+    conv = conv_templates["qwen_1_5_summarize"].copy()
+    conv.append_message(conv.roles[0], qs)
+    conv.append_message(conv.roles[1], None)
+    summarize_prompt = conv.get_prompt()
+    return torch.tensor(tokenizer(summarize_prompt).input_ids, dtype=torch.long).unsqueeze(0)
+
+
+def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_clusters, interval, summarizer,
+                                              input_ids, tokenizer, chunked_feature_list, existing_tree=None,
+                                              *, caption_do_sample=True, kmeans_init_indices=None,
+                                              conv_templates=None):
+    """One memory-tree update: caption every new chunk, append depth-0 nodes, perform at most one
+    merge (k-means over the merged nodes' frames + text summary).  Same positional signature as
+    utiles.py:489; keyword-only extras inject determinism."""
+    output_list = []
+    for chunk_feature in chunked_feature_list:
+        dimension = chunk_feature[0].shape[-1]
+        chunk_feature = torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device)
+        with torch.no_grad():
+            output_ids = summarizer.generate_with_image_embedding(
+                input_ids.to(summarizer.device), image_embeddings=[chunk_feature], modalities=["video"],
+                do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
+                max_new_tokens=128, use_cache=False)
+        output_list.append(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip())
+
+    nodes = [MultimodalTreeNode(t, text, depth=0) for (t, text) in zip(k_means_chunk_feature_list, output_list)]
+    if existing_tree:
+        nodes = existing_tree + nodes
+
+    summarize_depth, _ = get_summarize_depth(nodes, interval)
+    start_index = next((i for i, n in enumerate(nodes) if n.depth == summarize_depth), None)
+    chunk_length = len([x for x in nodes if x.depth == summarize_depth])
+    if VERBOSE:
+        print("summarize_depth:{}/ start_index:{}/ chunk_length:{} / len(nodes):{}".format(
+            summarize_depth, start_index, chunk_length, len(nodes)))
+
+    if chunk_length % interval >= 0 and len(nodes) > 0 and chunk_length >= interval:   # utiles.py:575
+        chunk = nodes[start_index: start_index + interval]
+        combined_centroids = torch.cat([n.centroids for n in chunk], dim=0)
+        caption_list = [n.text for n in chunk]
+        if combined_centroids.shape[0] > num_clusters:
+            new_centroids, _ = weighted_kmeans_feature(combined_centroids, num_clusters,
+                                                       init_indices=kmeans_init_indices)
+        else:
+            new_centroids = combined_centroids
+        if conv_templates is None:
+            from .longva.conversation import conv_templates as _ct
+            conv_templates = _ct
+        summarize_ids = make_summary_prompt(caption_list, tokenizer, conv_templates)
+        with torch.no_grad():
+            output_ids = summarizer.generate_with_image_embedding(
+                summarize_ids.to(summarizer.device), image_embeddings=None, modalities=["video"],
+                do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
+                max_new_tokens=256, use_cache=False)
+        summarize_text = tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip()
+        new_node = MultimodalTreeNode(new_centroids, summarize_text, depth=chunk[0].depth + 1)
+        for node in chunk:
+            new_node.children.append(node)
+        nodes[start_index: start_index + interval] = [new_node]
+    if VERBOSE:
+        _print_tree(nodes)
+    return nodes
+
+
+# ------------------------------------------------------------------------------------------
+def embed_text(model, tokenizer, text: str) -> torch.Tensor:
+    """CLS embedding of `text` (utiles.py:704-708: `model(**ids).last_hidden_state[:, 0]`).
+    `model` may also be any callable `(tokenizer, text) -> Tensor[D]` (used by tests / synthetic
+    streams where no BERT weights exist)."""
+    if not hasattr(model, "forward") and callable(model):
+        return model(tokenizer, text)
+    ids = tokenizer(text, padding=True, return_tensors="pt")
+    dev = next(model.parameters()).device
+    ids = {k: v.to(dev) for k, v in ids.items()}
+    with torch.no_grad():
+        return model(**ids).last_hidden_state[:, 0][0]
+
+
+def _node_embedding(node, model, tokenizer) -> torch.Tensor:
+    if node.text_embedding is None:
+        node.text_embedding = embed_text(model, tokenizer, node.text).detach()
+    return node.text_embedding
+
+
+def _best_by_cosine(nodes: Sequence[MultimodalTreeNode], query_embedding: torch.Tensor, model, tokenizer,
+                    default):
+    """Reference rule (utiles.py:719-742): best_sim starts at 0, strict '>' — first maximum wins,
+    non-positive similarities never win.  One cosine_topk launch replaces the Python loop."""
+    index = torch.stack([_node_embedding(n, model, tokenizer) for n in nodes]).to(query_embedding.device)
+    scores, idx = ops.cosine_topk(index, query_embedding, k=1)
+    s, i = float(scores[0, 0]), int(idx[0, 0])
+    if VERBOSE:
+        print(f"{RED}sim{RESET}:{s} best child {i}")
+    return i if s > 0 else default
+
+
+def fast_search_tree_multi_modal_with_embedding(all_nodes, query, image_embedding, model, tokenizer, top_k=1):
+    """Walk every non-leaf root down its most similar child chain, then pick the most similar
+    depth-0 root.  `image_embedding` and `top_k` are accepted and ignored, as in the reference."""
+    path_features: List[torch.Tensor] = []
+    path_text: List[str] = []
+    redundant_nodes = []
+    query_embedding = embed_text(model, tokenizer, query)
+    for node in all_nodes:
+        current_node = node
+        if current_node.depth == 0:
+            redundant_nodes.append(node)
+        else:
+            while current_node.children:
+                best_child_index = _best_by_cosine(current_node.children, query_embedding, model, tokenizer, None)
+                # the reference indexes children[None] here and raises TypeError when no child has a
+                # positive similarity (utiles.py:746); list indexing with None reproduces that.
+                path_features.append(current_node.children[best_child_index].centroids)
+                path_text.append(current_node.children[best_child_index].text)
+                current_node = current_node.children[best_child_index]
+    if len(redundant_nodes) >= 1:
+        best_index = _best_by_cosine(redundant_nodes, query_embedding, model, tokenizer, 0)   # utiles.py:751
+        path_features.append(redundant_nodes[best_index].centroids)
+        path_text.append(redundant_nodes[best_index].text)
+    return path_features, path_text

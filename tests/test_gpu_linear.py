@@ -1,0 +1,108 @@
+"""GPU parity: tcgen05 linear kernel (through the C-ABI) vs a plain PyTorch fp32 reference of
+the same op.  Tolerance: fp16 operands, fp32 accumulation -> |err| <= 2e-3 * (|ref| + 1)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias=None, residual=None, act=0, alpha=1.0):
+    y = alpha * (a.double() @ w.double().transpose(-1, -2))
+    if bias is not None:
+        y = y + bias.double()
+    if act == 1:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    elif act == 3:
+        y = torch.nn.functional.silu(y)
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+def _check(out, ref, tol=2e-3):
+    out = out.double().cpu()
+    ref = ref.cpu()
+    err = (out - ref).abs()
+    bound = tol * (ref.abs() + 1.0)
+    bad = (err > bound).sum().item()
+    assert bad == 0, f"{bad} elements out of tolerance, max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("m,n,k", [
+    (128, 128, 64), (128, 256, 64), (256, 256, 128), (128, 128, 1024),
+    (577, 1024, 1024),          # one ViT frame, out_proj
+    (1154, 4096, 1024),         # ViT fc1 (two frames)
+    (1154, 1024, 4096),         # ViT fc2
+    (300, 3584, 592),           # ragged m, k tail (592 = 9.25 x 64)
+    (130, 200, 72),             # ragged everything
+    (4672, 4608, 3584),         # Qwen2 fused QKV at config #4 prefill length
+])
+def test_linear_plain(cuda, m, n, k):
+    from streamchat_b200 import ops
+    torch.manual_seed(m * 7 + n * 3 + k)
+    a = (torch.randn(m, k) * 0.5).half().to(cuda)
+    w = (torch.randn(n, k) * 0.05).half().to(cuda)
+    out = ops.linear(a, w)
+    torch.cuda.synchronize()
+    _check(out, _ref(a.cpu(), w.cpu()))
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_linear_epilogues(cuda, act):
+    from streamchat_b200 import ops
+    torch.manual_seed(act)
+    m, n, k = 600, 1000, 320
+    a = torch.randn(m, k).half().to(cuda)
+    w = (torch.randn(n, k) * 0.1).half().to(cuda)
+    bias = torch.randn(n).half().to(cuda)
+    res = torch.randn(m, n).half().to(cuda)
+    out = ops.linear(a, w, bias=bias, residual=res, act=act, alpha=0.5)
+    _check(out, _ref(a.cpu(), w.cpu(), bias.cpu(), res.cpu(), act, 0.5), tol=3e-3)
+    out32 = ops.linear(a, w, bias=bias, act=act, out_dtype=torch.float32)
+    assert out32.dtype == torch.float32
+    _check(out32, _ref(a.cpu(), w.cpu(), bias.cpu(), None, act), tol=1e-3)
+
+
+def test_linear_batched_and_strided(cuda):
+    from streamchat_b200 import ops
+    torch.manual_seed(9)
+    b, m, n, k = 5, 577, 577, 64          # attention-score shape: Q K^T per (frame, head)
+    q = torch.randn(b, m, k).half().to(cuda)
+    kk = torch.randn(b, n, k).half().to(cuda)
+    out = ops.linear(q, kk, alpha=0.125, out_dtype=torch.float32)
+    _check(out, _ref(q.cpu(), kk.cpu(), alpha=0.125), tol=1e-3)
+    # strided views (head slices of a fused QKV buffer): lda != k
+    qkv = torch.randn(700, 3 * 256).half().to(cuda)
+    a = qkv[:, 0:64]
+    w = qkv[:, 256:320]
+    out = ops.linear(a, w, out_dtype=torch.float32)
+    _check(out, _ref(a.cpu(), w.cpu()), tol=1e-3)
+    # 3-D activations with a shared 2-D weight
+    x = torch.randn(3, 50, 128).half().to(cuda)
+    w2 = torch.randn(96, 128).half().to(cuda)
+    out = ops.linear(x, w2)
+    assert out.shape == (3, 50, 96)
+    _check(out, _ref(x.cpu(), w2.cpu()))
+
+
+def test_linear_linearity_full_size(cuda):
+    """Full-size property (Qwen2 MLP width, no CPU oracle needed): f(a1 + a2) == f(a1) + f(a2)
+    up to fp16 rounding, and a one-hot activation row selects a weight column exactly."""
+    from streamchat_b200 import ops
+    torch.manual_seed(2)
+    m, n, k = 1024, 18944, 3584
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()
+    a = torch.zeros(m, k, device=cuda, dtype=torch.float16)
+    cols = torch.randint(0, k, (m,), device=cuda)
+    a[torch.arange(m, device=cuda), cols] = 1.0
+    out = ops.linear(a, w, out_dtype=torch.float32)
+    assert torch.equal(out, w[:, cols].t().float())
+    a1 = (torch.randn(m, k, device=cuda) * 0.5).half()
+    a2 = (torch.randn(m, k, device=cuda) * 0.5).half()
+    y1 = ops.linear(a1, w, out_dtype=torch.float32)
+    y2 = ops.linear(a2, w, out_dtype=torch.float32)
+    y12 = ops.linear((a1.float() + a2.float()).half(), w, out_dtype=torch.float32)
+    assert (y12 - (y1 + y2)).abs().max().item() < 2e-2

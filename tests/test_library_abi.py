@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/streamchat_b200.h declares
+(no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from streamchat_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib
+
+
+def test_header_symbols_exported():
+    _lib = _ensure_built()
+    header = open(os.path.join(ROOT, "include", "streamchat_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, f"symbols declared in the header but not exported: {missing}"
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+
+
+def test_version_and_error_string():
+    _lib = _ensure_built()
+    lib = _lib.load()
+    assert lib.scb_version() >= 100
+    assert isinstance(lib.scb_last_error(), bytes)
+    # argument validation happens before any CUDA call: NULL args -> INVALID_ARG + message
+    assert lib.scb_cosine_topk(None, None) == -1
+    assert b"NULL" in lib.scb_last_error()
+    assert lib.scb_cosine_topk_workspace_bytes(10000, 1, 8) > 0
+    assert lib.scb_cosine_topk_workspace_bytes(10000, 1, 64) == 0
+    assert lib.scb_kmeans_step_workspace_bytes(400, 5, 1, 516096) > 0
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from streamchat_b200 import ops, _lib
+    with pytest.raises(_lib.ScbError):
+        ops.cosine_topk(torch.randn(4, 8), torch.randn(8), k=1)
+    with pytest.raises(_lib.ScbError):
+        ops.kmeans_step(torch.randn(4, 8), torch.randn(1, 2, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "streamchat_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, f"product modules import the oracle: {bad}"

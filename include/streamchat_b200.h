@@ -157,6 +157,135 @@ typedef struct scb_linear_args {
 
 int scb_linear(const scb_linear_args* a, void* stream);
 
+
+/* ------------------------------------------------------------------------- *
+ * Row-wise glue kernels (fp16 I/O, fp32 statistics).  Operator order follows the
+ * third-party math the reference executes (HF transformers).
+ * ------------------------------------------------------------------------- */
+
+/* CLIP patch-embedding im2col (Conv2d k=s=patch, no bias; modeling_clip.py:148-154 reached
+ * from longva/model/multimodal_encoder/clip_encoder.py:76).  pixels [n,c,h,w] fp16 ->
+ * out [n*(h/p)*(w/p), ld_out] fp16, columns c*p*p.. zero-padded. */
+int scb_im2col_patch(const void* pixels, void* out, int32_t n_img, int32_t channels, int32_t height,
+                     int32_t width, int32_t patch, int64_t ld_out, void* stream);
+
+/* nn.LayerNorm over the last dim (CLIP layer_norm1/2, modeling_clip.py:354-386). */
+int scb_layernorm(const void* x, int64_t ld_x, const void* gamma, const void* beta, float eps,
+                  int64_t rows, int32_t dim, void* out, int64_t ld_out, void* stream);
+
+/* Qwen2RMSNorm (modeling_qwen2.py:249-263): fp32 normalise, round to fp16, then * weight. */
+int scb_rmsnorm(const void* x, int64_t ld_x, const void* weight, float eps, int64_t rows,
+                int32_t dim, void* out, int64_t ld_out, void* stream);
+
+/* CLIP token assembly + pre_layrnorm (modeling_clip.py:209-217,677): row (n,t) =
+ * LN((t==0 ? cls : patch[n*(T-1)+t-1]) + pos[t]). */
+int scb_vit_embed_layernorm(const void* patch_embeds, int64_t ld_patch, const void* cls_embedding,
+                            const void* pos_embedding, const void* gamma, const void* beta, float eps,
+                            int32_t n_img, int32_t tokens_per_img, int32_t dim, void* out,
+                            int64_t ld_out, void* stream);
+
+/* SpatialPool average, stride 2 (longva/model/multimodal_resampler/spatial_pool.py:23-32):
+ * in rows [n*img_stride_rows + tok_offset + y*grid + x] -> out rows [n*(grid/2)^2 + ...]. */
+int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows, int32_t tok_offset,
+                          int32_t grid, int32_t n_img, int32_t dim, void* out, int64_t ld_out,
+                          void* stream);
+
+/* Qwen2 MLP gate (modeling_qwen2.py:41-48): out[m,i] = silu(gu[m,i]) * gu[m,inter+i]. */
+int scb_silu_mul(const void* gate_up, int64_t ld_gu, int64_t rows, int32_t inter, void* out,
+                 int64_t ld_out, void* stream);
+
+/* Qwen2 rotary embedding, NeoX half-split (modeling_qwen2.py:116-146), applied in place to the
+ * q and k slices of fused qkv rows [n_q*hd | n_kv*hd | n_kv*hd]; k (rotated) and v are appended
+ * to the layer's KV cache [n_kv][max_pos][hd] when the cache pointers are non-NULL.
+ * positions == NULL -> pos_base + row.  inv_freq == NULL -> theta^(-2i/hd). */
+int scb_rope_append(void* qkv, int64_t ld_qkv, int64_t rows, int32_t n_q_heads, int32_t n_kv_heads,
+                    int32_t head_dim, const int32_t* positions, int32_t pos_base, float theta,
+                    const float* inv_freq, void* k_cache, void* v_cache, int64_t max_pos,
+                    void* stream);
+
+/* embed_tokens lookup (inference_streaming_longva_v2.py:177, llava_arch.py:264). ids<0 -> zeros. */
+int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_t dim, void* out,
+                    int64_t ld_out, void* stream);
+
+/* Greedy token choice: arg-max per row of logits (fp16 or fp32), lowest index wins ties —
+ * torch.argmax over the fp16 lm_head output as HF generate does.  If counter != NULL the
+ * device int32 it points to is incremented by one (position bookkeeping of a replayed graph). */
+int scb_argmax_rows(const void* logits, int32_t dtype, int64_t ld, int64_t rows, int32_t n,
+                    int64_t* out, int32_t* counter, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused attention softmax(scale * Q K^T [+ causal mask]) V on tcgen05 tensor cores.
+ * Replaces the SDPA reached through HF transformers: CLIP self-attention
+ * (modeling_clip.py:282-337 via clip_encoder.py:76) and Qwen2 prefill attention with
+ * GQA (modeling_qwen2.py:161-184 via llava_qwen.py:155).
+ * Element (b, head, token, :) of q/k/v/out lives at base + b*stride_b + token*stride_t
+ * + head*stride_h with head_dim contiguous fp16 values; strides in elements, multiples
+ * of 8.  causal: query t sees keys s <= t + (kv_len - q_len).
+ * ------------------------------------------------------------------------- */
+typedef struct scb_attention_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  int32_t batch, n_q_heads, n_kv_heads, head_dim;   /* head_dim: 64 or 128 */
+  int64_t q_len, kv_len;
+  int64_t q_stride_b, q_stride_t, q_stride_h;
+  int64_t k_stride_b, k_stride_t, k_stride_h;
+  int64_t v_stride_b, v_stride_t, v_stride_h;
+  int64_t o_stride_b, o_stride_t, o_stride_h;
+  float scale;
+  int32_t causal;
+} scb_attention_args;
+
+int scb_attention(const scb_attention_args* a, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Decode-step kernels (cached generation, HBM-bound).  Replace the batch-1 Linear and
+ * SDPA-over-DynamicCache calls of Qwen2ForCausalLM.generate reached from
+ * longva/model/language_model/llava_qwen.py:155 (use_cache forced on:
+ * generation/utils.py:2425-2428).
+ * ------------------------------------------------------------------------- */
+typedef enum scb_gemv_prologue {
+  SCB_PRO_NONE = 0,
+  SCB_PRO_RMSNORM = 1,   /* a' = fp16(a * rsqrt(mean(a^2)+eps)) * gamma   (modeling_qwen2.py:249-263) */
+  SCB_PRO_SILU_MUL = 2   /* a' = fp16(silu(a[:k])) * a[k:2k]              (modeling_qwen2.py:41-48)   */
+} scb_gemv_prologue;
+
+typedef struct scb_gemv_args {
+  const void* a;          /* [rows, lda] fp16 activations (2k wide for SCB_PRO_SILU_MUL) */
+  const void* w;          /* [n, ldw] fp16 weights, k contiguous */
+  const void* bias;       /* [n] fp16 or NULL */
+  const void* residual;   /* [rows, ldr] fp16 or NULL */
+  const void* gamma;      /* [k] fp16 RMSNorm weight (SCB_PRO_RMSNORM) */
+  void* out;              /* [rows, ldo] */
+  int64_t n, k;
+  int64_t lda, ldw, ldr, ldo;
+  int32_t rows;           /* 1, 2 or 4 */
+  int32_t prologue;       /* scb_gemv_prologue */
+  int32_t out_dtype;      /* scb_dtype */
+  float eps;
+} scb_gemv_args;
+
+int scb_gemv(const scb_gemv_args* a, void* stream);
+
+typedef struct scb_decode_attention_args {
+  const void* q;            /* [n_q_heads, head_dim] fp16 (already rotated) */
+  const void* k_cache;      /* [n_kv_heads, max_pos, head_dim] fp16 */
+  const void* v_cache;      /* [n_kv_heads, max_pos, head_dim] fp16 */
+  void* out;                /* [n_q_heads, head_dim] fp16 */
+  const int32_t* kv_len_dev;/* device scalar with the context length, or NULL -> kv_len */
+  int64_t max_pos;
+  int32_t kv_len;
+  int32_t n_q_heads, n_kv_heads, head_dim;
+  int32_t n_splits;
+  float scale;
+  void* workspace;
+  size_t workspace_bytes;
+} scb_decode_attention_args;
+
+size_t scb_decode_attention_workspace_bytes(int32_t n_q_heads, int32_t head_dim, int32_t n_splits);
+int scb_decode_attention(const scb_decode_attention_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

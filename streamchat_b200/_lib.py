@@ -56,6 +56,43 @@ class LinearArgs(C.Structure):
     ]
 
 
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+        ("batch", C.c_int32), ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("q_len", C.c_int64), ("kv_len", C.c_int64),
+        ("q_stride_b", C.c_int64), ("q_stride_t", C.c_int64), ("q_stride_h", C.c_int64),
+        ("k_stride_b", C.c_int64), ("k_stride_t", C.c_int64), ("k_stride_h", C.c_int64),
+        ("v_stride_b", C.c_int64), ("v_stride_t", C.c_int64), ("v_stride_h", C.c_int64),
+        ("o_stride_b", C.c_int64), ("o_stride_t", C.c_int64), ("o_stride_h", C.c_int64),
+        ("scale", C.c_float), ("causal", C.c_int32),
+    ]
+
+
+class GemvArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("gamma", C.c_void_p), ("out", C.c_void_p),
+        ("n", C.c_int64), ("k", C.c_int64),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo", C.c_int64),
+        ("rows", C.c_int32), ("prologue", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+class DecodeAttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("out", C.c_void_p),
+        ("kv_len_dev", C.c_void_p), ("max_pos", C.c_int64), ("kv_len", C.c_int32),
+        ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
+        ("n_splits", C.c_int32), ("scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
+
+_vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
 # name -> (restype, argtypes); every symbol include/streamchat_b200.h declares
 SYMBOLS = {
     "scb_version": (C.c_int, []),
@@ -66,6 +103,19 @@ SYMBOLS = {
     "scb_kmeans_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "scb_kmeans_step": (C.c_int, [C.POINTER(KmeansStepArgs), C.c_void_p]),
     "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "scb_attention": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
+    "scb_gemv": (C.c_int, [C.POINTER(GemvArgs), C.c_void_p]),
+    "scb_decode_attention_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
+    "scb_decode_attention": (C.c_int, [C.POINTER(DecodeAttentionArgs), C.c_void_p]),
+    "scb_im2col_patch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp]),
+    "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
+    "scb_rmsnorm": (C.c_int, [_vp, _i64, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
+    "scb_vit_embed_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "scb_avgpool2x2_tokens": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "scb_silu_mul": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _vp]),
+    "scb_rope_append": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _f, _vp, _vp, _vp, _i64, _vp]),
+    "scb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "scb_argmax_rows": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,415 @@
+// attention_tcgen05.cu — fused softmax(scale·Q·Kᵀ [+causal])·V on tcgen05 tensor cores.
+//
+// Replaces the SDPA calls the reference reaches through HF transformers: CLIP self-attention
+// (non-causal, 16 heads x 64, 577 tokens; modeling_clip.py:282-337 via clip_encoder.py:76) and
+// Qwen2 prefill attention (causal, GQA 28q/4kv x 128; modeling_qwen2.py:161-184,227-228 via
+// llava_qwen.py:155).  Scores never touch HBM.
+//
+// One CTA per (128-query tile, q head, batch); 192 threads:
+//   warp 0   : TMA producer — Q once, then K and V tiles of kBKV keys (4-D tensor maps
+//              (d, token, head, batch), 128-byte swizzle, 64-column sub-tiles) into 2-stage rings.
+//   warp 1   : MMA issuer — S = Q·Kᵀ (M=128, N=kBKV, both operands K-major) into TMEM cols
+//              [0,kBKV); O_j = P·V (A = P from shared memory, B = V MN-major, N = head_dim) into
+//              TMEM cols [128,128+D).  S_{j+1} is issued before P·V_j so it overlaps the softmax.
+//   warps 2-5: softmax — thread r owns query row r (TMEM lane r): two passes of tcgen05.ld over
+//              the S row (max, then exp2/sum), P written as fp16 into the swizzled A-operand
+//              layout, running (m, l) and the fp32 output row kept in registers
+//              (O = O*alpha + O_j), final 1/l scaling and 16-byte stores.
+// FLOPs per launch: 4 * batch * heads * q_len * kv_len * head_dim (x 1/2 when causal, q_len==kv_len).
+#include "scb_common.cuh"
+#include <math.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+constexpr int kBQ = 128;
+constexpr int kAttnThreads = 192;
+constexpr int kKVStages = 2;
+
+SCB_DEVICE void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// MN-major (N contiguous) B operand made of 64-column sub-tiles [rows=K][64] with the 128-byte
+// swizzle: LBO = byte distance between sub-tiles (next 64 of N), SBO = 1024 (next 8 K rows).
+SCB_DEVICE uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct AttnParams {
+  __half* out;
+  long long o_stride_b, o_stride_t, o_stride_h;
+  int q_len, kv_len;
+  int n_q_heads, n_kv_heads;
+  int causal;
+  float scale_log2;  // scale * log2(e)
+};
+
+template <int D, int kBKV>
+struct ACfg {
+  static constexpr int kSub = D / 64;                  // 64-column sub-tiles per row
+  static constexpr int kQBytes = kBQ * D * 2;
+  static constexpr int kKBytes = kBKV * D * 2;
+  static constexpr int kPBytes = kBQ * kBKV * 2;
+  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 128;
+  static constexpr int kTmemCols = 256;                // S: [0,kBKV)  O_j: [128,128+D)
+};
+
+template <int D, int kBKV>
+__global__ void __launch_bounds__(kAttnThreads, (D == 64) ? 2 : 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
+                         const __grid_constant__ CUtensorMap map_k,
+                         const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
+  using C = ACfg<D, kBKV>;
+  // 128-byte swizzle atoms need 1024-byte aligned tiles; there is no static shared memory in this
+  // kernel, so the dynamic window starts aligned (checked below — two CTAs per SM leave no slack).
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sq = smem;
+  uint8_t* sk = sq + C::kQBytes;
+  uint8_t* sv = sk + kKVStages * C::kKBytes;
+  uint8_t* sp = sv + kKVStages * C::kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp + C::kPBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [2]
+  uint64_t* k_empty = bars + 3;            // [2]
+  uint64_t* v_full = bars + 5;             // [2]
+  uint64_t* v_empty = bars + 7;            // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;
+  uint64_t* o_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.n_q_heads / p.n_kv_heads);
+  const int causal_off = p.kv_len - p.q_len;
+  int n_blocks = (p.kv_len + kBKV - 1) / kBKV;
+  if (p.causal) {
+    const int last_key = min(p.kv_len - 1, q0 + kBQ - 1 + causal_off);
+    n_blocks = last_key < 0 ? 0 : min(n_blocks, last_key / kBKV + 1);
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && n_blocks > 0) {
+      mbar_arrive_expect_tx(q_full, C::kQBytes);
+      for (int s = 0; s < C::kSub; ++s)
+        tma_load_4d(sq + s * (kBQ * 128), &map_q, q_full, s * 64, q0, h, b);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (uint32_t)(j / kKVStages) & 1u;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], C::kKBytes);
+        for (int s = 0; s < C::kSub; ++s)
+          tma_load_4d(sk + st * C::kKBytes + s * (kBKV * 128), &map_k, &k_full[st], s * 64,
+                      j * kBKV, hk, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], C::kKBytes);
+        for (int s = 0; s < C::kSub; ++s)
+          tma_load_4d(sv + st * C::kKBytes + s * (kBKV * 128), &map_v, &v_full[st], s * 64,
+                      j * kBKV, hk, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && n_blocks > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, D, 0, 1);  // B = V is MN-major
+      auto issue_s = [&](int j) {
+        const int st = j % kKVStages;
+        mbar_wait(&k_full[st], (uint32_t)(j / kKVStages) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint64_t da =
+              umma_desc_k_sw128(smem_u32(sq + (kk / 4) * (kBQ * 128))) + (uint64_t)((kk % 4) * 2);
+          const uint64_t db =
+              umma_desc_k_sw128(smem_u32(sk + st * C::kKBytes + (kk / 4) * (kBKV * 128))) +
+              (uint64_t)((kk % 4) * 2);
+          umma_f16_ss(tmem_s, da, db, idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j % kKVStages;
+        if (j + 1 < n_blocks) {
+          mbar_wait(s_empty, (uint32_t)j & 1u);  // softmax finished reading S_j
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(&v_full[st], (uint32_t)(j / kKVStages) & 1u);
+        mbar_wait(p_full, (uint32_t)j & 1u);
+        if (j > 0) mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBKV / 16; ++kk) {
+          const uint64_t da =
+              umma_desc_k_sw128(smem_u32(sp + (kk / 4) * (kBQ * 128))) + (uint64_t)((kk % 4) * 2);
+          const uint64_t db = umma_desc_mn_sw128(smem_u32(sv + st * C::kKBytes + kk * 2048),
+                                                 (uint32_t)(kBKV * 128));
+          umma_f16_ss(tmem_o, da, db, idesc_o, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax + output (warps 2..5) =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;        // row inside the query tile == TMEM lane
+    const int qpos = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    const int key_limit = p.causal ? min(p.kv_len - 1, qpos + causal_off) : p.kv_len - 1;
+
+    for (int j = 0; j < n_blocks; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      const int key0 = j * kBKV;
+      // ---- pass 1: row maximum of this block
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + c0 + i <= key_limit) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, m_blk);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f((m_run - m_use) * p.scale_log2);  // m_run == -inf -> 0
+      const float mb = m_use * p.scale_log2;
+      // ---- pass 2: P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (key0 + c0 + i <= key_limit) p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+          if (key0 + c0 + i + 1 <= key_limit)
+            p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          // the row sum uses the rounded probabilities the tensor core will see
+          const float2 back = __half22float2(hp);
+          l_blk += back.x + back.y;
+          packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        uint8_t* tile = sp + (c0 / 64) * (kBQ * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c0 % 64) / 8 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(tile + chunk * 16) =
+              make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+        }
+      }
+      // S fully consumed -> the issuer may overwrite it with S_{j+1}
+      tc_fence_before();
+      fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      // ---- O = O*alpha + P·V
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+
+    if (qpos < p.q_len) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __half* op = p.out + (long long)b * p.o_stride_b + (long long)qpos * p.o_stride_t +
+                   (long long)h * p.o_stride_h;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 o;
+        o.x = f2_to_h2(o_acc[c] * inv, o_acc[c + 1] * inv);
+        o.y = f2_to_h2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        o.z = f2_to_h2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+        o.w = f2_to_h2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(op + c) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn attn_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// (d, token, head, batch) fp16 view; box (64, box_rows, 1, 1); OOB rows read as zero.
+int make_map4(CUtensorMap* out, const void* ptr, int d, long long len, int heads, int batch,
+              long long stride_t, long long stride_h, long long stride_b, int box_rows) {
+  EncodeTiledFn fn = attn_encode_fn();
+  SCB_REQUIRE(fn != nullptr, SCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)len, (cuuint64_t)heads, (cuuint64_t)batch};
+  // a size-1 dimension may carry any legal stride; keep them 16-byte multiples
+  cuuint64_t strides[3] = {(cuuint64_t)stride_t * 2, (cuuint64_t)(heads > 1 ? stride_h : d) * 2,
+                           (cuuint64_t)(batch > 1 ? stride_b : d) * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCB_REQUIRE(r == CUDA_SUCCESS, SCB_ERR_CUDA,
+              "cuTensorMapEncodeTiled(4d) failed (%d): d=%d len=%lld heads=%d batch=%d strides=%lld/%lld/%lld",
+              (int)r, d, len, heads, batch, stride_t, stride_h, stride_b);
+  return SCB_OK;
+}
+
+template <int D, int kBKV>
+int launch_attn(const scb_attention_args* a, cudaStream_t st) {
+  using C = ACfg<D, kBKV>;
+  CUtensorMap mq, mk, mv;
+  int rc = make_map4(&mq, a->q, D, a->q_len, a->n_q_heads, a->batch, a->q_stride_t, a->q_stride_h,
+                     a->q_stride_b, kBQ);
+  if (rc != SCB_OK) return rc;
+  rc = make_map4(&mk, a->k, D, a->kv_len, a->n_kv_heads, a->batch, a->k_stride_t, a->k_stride_h,
+                 a->k_stride_b, kBKV);
+  if (rc != SCB_OK) return rc;
+  rc = make_map4(&mv, a->v, D, a->kv_len, a->n_kv_heads, a->batch, a->v_stride_t, a->v_stride_h,
+                 a->v_stride_b, kBKV);
+  if (rc != SCB_OK) return rc;
+  AttnParams p;
+  p.out = reinterpret_cast<__half*>(a->out);
+  p.o_stride_b = a->o_stride_b; p.o_stride_t = a->o_stride_t; p.o_stride_h = a->o_stride_h;
+  p.q_len = (int)a->q_len; p.kv_len = (int)a->kv_len;
+  p.n_q_heads = a->n_q_heads; p.n_kv_heads = a->n_kv_heads;
+  p.causal = a->causal;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  auto kern = attention_tcgen05_kernel<D, kBKV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a->q_len + kBQ - 1) / kBQ), (unsigned)a->n_q_heads, (unsigned)a->batch);
+  kern<<<grid, kAttnThreads, C::kSmemBytes, st>>>(mq, mk, mv, p);
+  SCB_LAUNCH_OK("attention_tcgen05_kernel");
+  return SCB_OK;
+}
+
+}  // namespace
+
+extern "C" int scb_attention(const scb_attention_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_attention: args is NULL");
+  SCB_REQUIRE(a->q && a->k && a->v && a->out, SCB_ERR_INVALID_ARG, "scb_attention: NULL buffer");
+  SCB_REQUIRE(a->head_dim == 64 || a->head_dim == 128, SCB_ERR_UNSUPPORTED,
+              "scb_attention: head_dim=%d (64 or 128 only)", a->head_dim);
+  SCB_REQUIRE(a->batch >= 1 && a->batch <= 65535 && a->n_q_heads >= 1 && a->n_q_heads <= 65535 &&
+                  a->n_kv_heads >= 1 && a->n_q_heads % a->n_kv_heads == 0,
+              SCB_ERR_INVALID_ARG, "scb_attention: bad batch/head counts");
+  SCB_REQUIRE(a->q_len >= 1 && a->kv_len >= 1 && a->q_len < (1ll << 30) && a->kv_len < (1ll << 30),
+              SCB_ERR_INVALID_ARG, "scb_attention: bad sequence lengths");
+  SCB_REQUIRE(!a->causal || a->kv_len >= a->q_len, SCB_ERR_INVALID_ARG,
+              "scb_attention: causal needs kv_len >= q_len");
+  const long long strides[] = {a->q_stride_t, a->q_stride_h, a->q_stride_b, a->k_stride_t,
+                               a->k_stride_h, a->k_stride_b, a->v_stride_t, a->v_stride_h,
+                               a->v_stride_b, a->o_stride_t, a->o_stride_h, a->o_stride_b};
+  for (long long s : strides)
+    SCB_REQUIRE(s % 8 == 0, SCB_ERR_INVALID_ARG,
+                "scb_attention: strides must be multiples of 8 elements (got %lld)", s);
+  SCB_REQUIRE(((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v | (uintptr_t)a->out) % 16 == 0,
+              SCB_ERR_INVALID_ARG, "scb_attention: buffers must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->head_dim == 64) return launch_attn<64, 128>(a, st);
+  return launch_attn<128, 128>(a, st);
+}

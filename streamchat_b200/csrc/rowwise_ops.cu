@@ -1,0 +1,468 @@
+// rowwise_ops.cu — the HBM-bound glue between the tensor-core layers: patch im2col, token
+// assembly + LayerNorm, LayerNorm, RMSNorm, 2x2 token average pool, SiLU-gate, RoPE + KV-cache
+// append, embedding gather, arg-max.  All fp16 I/O with fp32 statistics, 128-bit accesses.
+//
+// Operator order follows HF transformers 5.5.0 as executed by the reference:
+//   CLIP embeddings/pre-LN  models/clip/modeling_clip.py:148-217,659-677  (via clip_encoder.py:76)
+//   SpatialPool             longva/model/multimodal_resampler/spatial_pool.py:23-32
+//   Qwen2 RMSNorm / RoPE    models/qwen2/modeling_qwen2.py:249-263,51-146 (via llava_qwen.py:155)
+#include "scb_common.cuh"
+#include <math.h>
+
+namespace {
+
+SCB_DEVICE float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect red from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nw; ++w) t += red[w];
+  return t;
+}
+
+SCB_DEVICE void unpack8(const uint4& v, float* f) {
+  float2 a = h2_to_f2(v.x), b = h2_to_f2(v.y), c = h2_to_f2(v.z), d = h2_to_f2(v.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+SCB_DEVICE uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = f2_to_h2(f[0], f[1]); o.y = f2_to_h2(f[2], f[3]);
+  o.z = f2_to_h2(f[4], f[5]); o.w = f2_to_h2(f[6], f[7]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col for a stride==kernel patch convolution (CLIP patch embed, Conv2d k=14 s=14 no bias):
+// out[(n*gh + py)*gw + px][c*P*P + ky*P + kx] = pix[n][c][py*P+ky][px*P+kx]; columns >= C*P*P
+// (padding up to ld_out so that the row stride is TMA-legal) are zero.
+// ------------------------------------------------------------------------------------------
+__global__ void im2col_patch_kernel(const __half* __restrict__ pix, __half* __restrict__ out,
+                                    int n_img, int C, int H, int W, int P, int ld_out) {
+  const int gh = H / P, gw = W / P;
+  const long long row = blockIdx.x;  // one block per output row (patch)
+  const int n = (int)(row / (gh * gw));
+  const int pr = (int)(row % (gh * gw));
+  const int py = pr / gw, px = pr % gw;
+  const int kdim = C * P * P;
+  for (int col = threadIdx.x; col < ld_out; col += blockDim.x) {
+    __half v = __float2half(0.f);
+    if (col < kdim) {
+      const int c = col / (P * P), r = col % (P * P), ky = r / P, kx = r % P;
+      v = pix[(((long long)n * C + c) * H + py * P + ky) * W + px * P + kx];
+    }
+    out[row * ld_out + col] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm family.  One block of 128 threads per row; the row lives in registers (D <= 8192).
+//   kind 0: LayerNorm(x)                       (gamma, beta, eps)   two-pass mean / variance
+//   kind 1: RMSNorm(x)                         HF order: fp32 normalise -> round to fp16 -> * weight
+//   kind 2: LayerNorm(token assembly)          x = (t==0 ? cls : patch[n*(T-1)+t-1]) + pos[t]
+// ------------------------------------------------------------------------------------------
+constexpr int kNormThreads = 128;
+constexpr int kNormMaxChunks = 8;  // 128 threads * 8 halfs * 8 chunks = 8192
+
+template <int KIND>
+__global__ void __launch_bounds__(kNormThreads)
+norm_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ gamma,
+            const __half* __restrict__ beta, float eps, int D, __half* __restrict__ out,
+            long long ld_out, const __half* __restrict__ cls, const __half* __restrict__ pos,
+            int tokens_per_img) {
+  __shared__ float red[kNormThreads / 32];
+  const long long row = blockIdx.x;
+  const int nvec = D >> 3;
+  float v[kNormMaxChunks][8];
+  const __half* src;
+  const __half* posrow = nullptr;
+  if constexpr (KIND == 2) {
+    const int n = (int)(row / tokens_per_img), t = (int)(row % tokens_per_img);
+    src = (t == 0) ? cls : x + ((long long)n * (tokens_per_img - 1) + (t - 1)) * ld_x;
+    posrow = pos + (long long)t * D;
+  } else {
+    src = x + row * ld_x;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(src + i * 8), v[c]);
+      if constexpr (KIND == 2) {
+        float p[8];
+        unpack8(*reinterpret_cast<const uint4*>(posrow + i * 8), p);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] = __half2float(__float2half_rn(v[c][e] + p[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += (KIND == 1) ? v[c][e] * v[c][e] : v[c][e];
+    }
+  }
+  s = block_sum(s, red);
+  float mean = 0.f, rstd;
+  if constexpr (KIND == 1) {
+    rstd = rsqrtf(s / (float)D + eps);
+  } else {
+    mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int i = c * kNormThreads + threadIdx.x;
+      if (i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[c][e] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    q = block_sum(q, red);
+    rstd = rsqrtf(q / (float)D + eps);
+  }
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      float g[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + i * 8), g);
+      if constexpr (KIND == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float nrm = __half2float(__float2half_rn(v[c][e] * rstd));
+          o[e] = nrm * g[e];
+        }
+      } else {
+        float b[8];
+        unpack8(*reinterpret_cast<const uint4*>(beta + i * 8), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * g[e] + b[e];
+      }
+      *reinterpret_cast<uint4*>(out + row * ld_out + i * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 average pool over a g x g token grid (SpatialPool avg, stride 2): in rows are
+// [n][tok_offset + y*g + x], out rows [n][(y/2)*(g/2) + x/2].
+// ------------------------------------------------------------------------------------------
+__global__ void pool2x2_kernel(const __half* __restrict__ in, long long ld_in,
+                               long long img_stride_rows, int tok_offset, int g, int D,
+                               __half* __restrict__ out, long long ld_out) {
+  const int og = g / 2;
+  const long long orow = blockIdx.x;
+  const int n = (int)(orow / (og * og)), r = (int)(orow % (og * og));
+  const int oy = r / og, ox = r % og;
+  const __half* base = in + ((long long)n * img_stride_rows + tok_offset) * ld_in;
+  for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(
+                    base + (long long)((oy * 2 + dy) * g + ox * 2 + dx) * ld_in + i * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= 0.25f;
+    *reinterpret_cast<uint4*>(out + orow * ld_out + i * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SiLU gate: out[m][i] = silu(gu[m][i]) * gu[m][I + i]   (Qwen2 MLP, modeling_qwen2.py:41-48;
+// fp16 rounding after silu and after the product, as the eager fp16 graph does)
+// ------------------------------------------------------------------------------------------
+__global__ void silu_mul_kernel(const __half* __restrict__ gu, long long ld_gu, int I,
+                                __half* __restrict__ out, long long ld_out, long long rows) {
+  const long long nvec = (long long)(I >> 3);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * nvec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / nvec;
+    const int i = (int)(idx % nvec) * 8;
+    float g[8], u[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(gu + m * ld_gu + i), g);
+    unpack8(*reinterpret_cast<const uint4*>(gu + m * ld_gu + I + i), u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s = __half2float(__float2half_rn(g[e] / (1.f + __expf(-g[e]))));
+      o[e] = s * u[e];
+    }
+    *reinterpret_cast<uint4*>(out + m * ld_out + i) = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RoPE (NeoX half-split) on the q and k slices of a fused qkv row + append of k, v to the
+// per-layer KV cache.  qkv row layout: [n_q*hd | n_kv*hd | n_kv*hd].  Angles in fp32, cos/sin
+// rounded to fp16, products and sum rounded to fp16 like the eager fp16 graph
+// (modeling_qwen2.py:116-146).  Cache layout: [n_kv][max_pos][hd] for K and for V.
+// ------------------------------------------------------------------------------------------
+__global__ void rope_append_kernel(__half* __restrict__ qkv, long long ld_qkv, int n_q, int n_kv,
+                                   int hd, const int* __restrict__ positions, int pos_base,
+                                   float theta, const float* __restrict__ inv_freq_tab,
+                                   __half* __restrict__ k_cache,
+                                   __half* __restrict__ v_cache, long long max_pos,
+                                   long long rows) {
+  const long long row = blockIdx.x;
+  if (row >= rows) return;
+  const int pos = positions ? positions[row] : pos_base + (int)row;
+  __half* r = qkv + row * ld_qkv;
+  const int half = hd >> 1;
+  const int n_rot = n_q + n_kv;
+  for (int idx = threadIdx.x; idx < n_rot * half; idx += blockDim.x) {
+    const int h = idx / half, i = idx % half;
+    const float inv_freq = inv_freq_tab ? inv_freq_tab[i] : powf(theta, -(float)(2 * i) / (float)hd);
+    const float ang = (float)pos * inv_freq;
+    const float c = __half2float(__float2half_rn(cosf(ang)));
+    const float s = __half2float(__float2half_rn(sinf(ang)));
+    __half* p = r + (long long)h * hd;
+    const float x1 = __half2float(p[i]), x2 = __half2float(p[i + half]);
+    // out1 = x1*cos + (-x2)*sin ; out2 = x2*cos + x1*sin, each product rounded to fp16
+    const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * s));
+    const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * s));
+    const __half o1 = __float2half_rn(a1 + b1), o2 = __float2half_rn(a2 + b2);
+    p[i] = o1;
+    p[i + half] = o2;
+    if (h >= n_q && k_cache) {
+      __half* kc = k_cache + ((long long)(h - n_q) * max_pos + pos) * hd;
+      kc[i] = o1;
+      kc[i + half] = o2;
+    }
+  }
+  if (v_cache) {
+    const __half* v = r + (long long)(n_q + n_kv) * hd;
+    for (int idx = threadIdx.x; idx < n_kv * hd; idx += blockDim.x) {
+      const int h = idx / hd, i = idx % hd;
+      v_cache[((long long)h * max_pos + pos) * hd + i] = v[idx];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Embedding gather: out[r] = table[ids[r]]  (ids < 0 -> zeros)
+// ------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const __half* __restrict__ table, const long long* __restrict__ ids,
+                                   int D, __half* __restrict__ out, long long ld_out) {
+  const long long row = blockIdx.x;
+  const long long id = ids[row];
+  for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (id >= 0) v = *reinterpret_cast<const uint4*>(table + id * D + i * 8);
+    *reinterpret_cast<uint4*>(out + row * ld_out + i * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Arg-max over rows of fp32 logits, lowest index wins ties (greedy decoding,
+// generation/utils.py greedy branch == torch.argmax).  One block per row.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024)
+argmax_kernel(const T* __restrict__ logits, long long ld, int n, long long* __restrict__ out,
+              int* __restrict__ counter) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const T* p = logits + (long long)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = (float)p[i];
+    if (v > best || bi == 0x7fffffff) {  // indices ascend within a thread: first maximum stays
+      best = v;
+      bi = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sv[warp] = best;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      out[blockIdx.x] = bi;
+      if (counter && blockIdx.x == 0) *counter += 1;
+    }
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int scb_im2col_patch(const void* pixels, void* out, int32_t n_img, int32_t channels, int32_t height,
+                     int32_t width, int32_t patch, int64_t ld_out, void* stream) {
+  SCB_REQUIRE(pixels && out, SCB_ERR_INVALID_ARG, "scb_im2col_patch: NULL buffer");
+  SCB_REQUIRE(n_img >= 1 && channels >= 1 && patch >= 1 && height % patch == 0 && width % patch == 0,
+              SCB_ERR_INVALID_ARG, "scb_im2col_patch: bad geometry");
+  SCB_REQUIRE(ld_out >= (int64_t)channels * patch * patch, SCB_ERR_INVALID_ARG,
+              "scb_im2col_patch: ld_out too small");
+  const long long rows = (long long)n_img * (height / patch) * (width / patch);
+  im2col_patch_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(pixels), reinterpret_cast<__half*>(out), n_img, channels,
+      height, width, patch, (int)ld_out);
+  SCB_LAUNCH_OK("im2col_patch_kernel");
+  return SCB_OK;
+}
+
+static int norm_common(int kind, const void* x, int64_t ld_x, const void* gamma, const void* beta,
+                       float eps, int64_t rows, int32_t dim, void* out, int64_t ld_out,
+                       const void* cls, const void* pos, int32_t tokens_per_img, void* stream) {
+  SCB_REQUIRE(x && gamma && out && rows >= 1, SCB_ERR_INVALID_ARG, "scb norm: NULL buffer / rows < 1");
+  SCB_REQUIRE(dim % 8 == 0 && dim >= 8 && dim <= kNormThreads * 8 * kNormMaxChunks,
+              SCB_ERR_INVALID_ARG, "scb norm: dim=%d must be a multiple of 8 in 8..%d", dim,
+              kNormThreads * 8 * kNormMaxChunks);
+  SCB_REQUIRE(ld_x % 8 == 0 && ld_out % 8 == 0 && aligned16(x) && aligned16(out) && aligned16(gamma) &&
+                  (!beta || aligned16(beta)),
+              SCB_ERR_INVALID_ARG, "scb norm: rows must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  const __half* g = reinterpret_cast<const __half*>(gamma);
+  const __half* b = reinterpret_cast<const __half*>(beta);
+  __half* o = reinterpret_cast<__half*>(out);
+  if (kind == 0)
+    norm_kernel<0><<<(unsigned)rows, kNormThreads, 0, st>>>(xh, ld_x, g, b, eps, dim, o, ld_out,
+                                                            nullptr, nullptr, 0);
+  else if (kind == 1)
+    norm_kernel<1><<<(unsigned)rows, kNormThreads, 0, st>>>(xh, ld_x, g, b, eps, dim, o, ld_out,
+                                                            nullptr, nullptr, 0);
+  else
+    norm_kernel<2><<<(unsigned)rows, kNormThreads, 0, st>>>(
+        xh, ld_x, g, b, eps, dim, o, ld_out, reinterpret_cast<const __half*>(cls),
+        reinterpret_cast<const __half*>(pos), tokens_per_img);
+  SCB_LAUNCH_OK("norm_kernel");
+  return SCB_OK;
+}
+
+int scb_layernorm(const void* x, int64_t ld_x, const void* gamma, const void* beta, float eps,
+                  int64_t rows, int32_t dim, void* out, int64_t ld_out, void* stream) {
+  SCB_REQUIRE(beta != nullptr, SCB_ERR_INVALID_ARG, "scb_layernorm: beta is NULL");
+  return norm_common(0, x, ld_x, gamma, beta, eps, rows, dim, out, ld_out, nullptr, nullptr, 0, stream);
+}
+
+int scb_rmsnorm(const void* x, int64_t ld_x, const void* weight, float eps, int64_t rows,
+                int32_t dim, void* out, int64_t ld_out, void* stream) {
+  return norm_common(1, x, ld_x, weight, nullptr, eps, rows, dim, out, ld_out, nullptr, nullptr, 0,
+                     stream);
+}
+
+int scb_vit_embed_layernorm(const void* patch_embeds, int64_t ld_patch, const void* cls_embedding,
+                            const void* pos_embedding, const void* gamma, const void* beta, float eps,
+                            int32_t n_img, int32_t tokens_per_img, int32_t dim, void* out,
+                            int64_t ld_out, void* stream) {
+  SCB_REQUIRE(cls_embedding && pos_embedding && beta && aligned16(cls_embedding) &&
+                  aligned16(pos_embedding),
+              SCB_ERR_INVALID_ARG, "scb_vit_embed_layernorm: NULL / unaligned embedding tables");
+  SCB_REQUIRE(n_img >= 1 && tokens_per_img >= 2, SCB_ERR_INVALID_ARG,
+              "scb_vit_embed_layernorm: bad token geometry");
+  return norm_common(2, patch_embeds, ld_patch, gamma, beta, eps, (int64_t)n_img * tokens_per_img, dim,
+                     out, ld_out, cls_embedding, pos_embedding, tokens_per_img, stream);
+}
+
+int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows, int32_t tok_offset,
+                          int32_t grid, int32_t n_img, int32_t dim, void* out, int64_t ld_out,
+                          void* stream) {
+  SCB_REQUIRE(in && out && n_img >= 1 && grid >= 2 && grid % 2 == 0 && dim % 8 == 0,
+              SCB_ERR_INVALID_ARG, "scb_avgpool2x2_tokens: bad arguments");
+  SCB_REQUIRE(ld_in % 8 == 0 && ld_out % 8 == 0 && aligned16(in) && aligned16(out), SCB_ERR_INVALID_ARG,
+              "scb_avgpool2x2_tokens: rows must be 16-byte aligned");
+  const long long rows = (long long)n_img * (grid / 2) * (grid / 2);
+  pool2x2_kernel<<<(unsigned)rows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(in), ld_in, img_stride_rows, tok_offset, grid, dim,
+      reinterpret_cast<__half*>(out), ld_out);
+  SCB_LAUNCH_OK("pool2x2_kernel");
+  return SCB_OK;
+}
+
+int scb_silu_mul(const void* gate_up, int64_t ld_gu, int64_t rows, int32_t inter, void* out,
+                 int64_t ld_out, void* stream) {
+  SCB_REQUIRE(gate_up && out && rows >= 1 && inter % 8 == 0 && ld_gu % 8 == 0 && ld_out % 8 == 0 &&
+                  aligned16(gate_up) && aligned16(out),
+              SCB_ERR_INVALID_ARG, "scb_silu_mul: bad arguments");
+  const long long work = rows * (inter / 8);
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)scb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  silu_mul_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(gate_up), ld_gu, inter, reinterpret_cast<__half*>(out), ld_out,
+      rows);
+  SCB_LAUNCH_OK("silu_mul_kernel");
+  return SCB_OK;
+}
+
+int scb_rope_append(void* qkv, int64_t ld_qkv, int64_t rows, int32_t n_q_heads, int32_t n_kv_heads,
+                    int32_t head_dim, const int32_t* positions, int32_t pos_base, float theta,
+                    const float* inv_freq, void* k_cache, void* v_cache, int64_t max_pos,
+                    void* stream) {
+  SCB_REQUIRE(qkv && rows >= 1 && n_q_heads >= 1 && n_kv_heads >= 0 && head_dim % 2 == 0,
+              SCB_ERR_INVALID_ARG, "scb_rope_append: bad arguments");
+  SCB_REQUIRE((k_cache == nullptr) == (v_cache == nullptr), SCB_ERR_INVALID_ARG,
+              "scb_rope_append: k_cache and v_cache must both be given or both be NULL");
+  SCB_REQUIRE(!k_cache || positions || pos_base + rows <= max_pos, SCB_ERR_INVALID_ARG,
+              "scb_rope_append: positions exceed the cache (%lld + %lld > %lld)", (long long)pos_base,
+              (long long)rows, (long long)max_pos);
+  rope_append_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__half*>(qkv), ld_qkv, n_q_heads, n_kv_heads, head_dim, positions, pos_base,
+      theta, inv_freq, reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), max_pos,
+      rows);
+  SCB_LAUNCH_OK("rope_append_kernel");
+  return SCB_OK;
+}
+
+int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_t dim, void* out,
+                    int64_t ld_out, void* stream) {
+  SCB_REQUIRE(table && ids && out && n_ids >= 1 && dim % 8 == 0 && ld_out % 8 == 0 &&
+                  aligned16(table) && aligned16(out),
+              SCB_ERR_INVALID_ARG, "scb_gather_rows: bad arguments");
+  gather_rows_kernel<<<(unsigned)n_ids, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(table), reinterpret_cast<const long long*>(ids), dim,
+      reinterpret_cast<__half*>(out), ld_out);
+  SCB_LAUNCH_OK("gather_rows_kernel");
+  return SCB_OK;
+}
+
+int scb_argmax_rows(const void* logits, int32_t dtype, int64_t ld, int64_t rows, int32_t n,
+                    int64_t* out, int32_t* counter, void* stream) {
+  SCB_REQUIRE(logits && out && rows >= 1 && n >= 1, SCB_ERR_INVALID_ARG, "scb_argmax_rows: bad arguments");
+  SCB_REQUIRE(dtype == SCB_F32 || dtype == SCB_F16, SCB_ERR_UNSUPPORTED, "scb_argmax_rows: dtype %d", dtype);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SCB_F32)
+    argmax_kernel<float><<<(unsigned)rows, 1024, 0, st>>>(reinterpret_cast<const float*>(logits), ld, n,
+                                                          reinterpret_cast<long long*>(out), counter);
+  else
+    argmax_kernel<__half><<<(unsigned)rows, 1024, 0, st>>>(reinterpret_cast<const __half*>(logits), ld,
+                                                           n, reinterpret_cast<long long*>(out), counter);
+  SCB_LAUNCH_OK("argmax_kernel");
+  return SCB_OK;
+}
+
+}  // extern "C"

@@ -205,3 +205,174 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if lead_shape is not None:
         out = out.view(*lead_shape, n)
     return out
+
+
+# ------------------------------------------------------------------------------------------
+def _call(name: str, dev: torch.device, *args) -> None:
+    with torch.cuda.device(dev):
+        L.check(getattr(L.load(), name)(*args, _stream(dev)), name)
+
+
+def _f16(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float16:
+        raise TypeError(f"{what} must be float16")
+    return t
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, causal: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused attention.  q [B, Tq, Hq, D], k/v [B, Tk, Hkv, D] — any strided views whose last dim
+    is contiguous (e.g. slices of a fused qkv buffer, or a [Hkv, T, D] cache permuted to this
+    order).  Returns out [B, Tq, Hq, D] fp16 (contiguous unless `out` is given)."""
+    dev = _require_cuda(q, k, v, out)
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _f16(t, n)
+        if t.dim() != 4 or t.stride(3) != 1:
+            raise ValueError(f"{n} must be [B, T, H, D] with a contiguous last dim")
+    B, Tq, Hq, D = q.shape
+    _, Tk, Hkv, _ = k.shape
+    if out is None:
+        out = torch.empty((B, Tq, Hq, D), dtype=torch.float16, device=dev)
+    a = L.AttentionArgs(
+        q=_ptr(q), k=_ptr(k), v=_ptr(v), out=_ptr(out), batch=B, n_q_heads=Hq, n_kv_heads=Hkv, head_dim=D,
+        q_len=Tq, kv_len=Tk,
+        q_stride_b=q.stride(0), q_stride_t=q.stride(1), q_stride_h=q.stride(2),
+        k_stride_b=k.stride(0), k_stride_t=k.stride(1), k_stride_h=k.stride(2),
+        v_stride_b=v.stride(0), v_stride_t=v.stride(1), v_stride_h=v.stride(2),
+        o_stride_b=out.stride(0), o_stride_t=out.stride(1), o_stride_h=out.stride(2),
+        scale=scale, causal=int(causal))
+    _call("scb_attention", dev, C.byref(a))
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(x, gamma, beta, out)
+    x2 = _f16(x, "x").reshape(-1, x.shape[-1])
+    if out is None:
+        out = torch.empty_like(x2)
+    o2 = out.view(-1, x.shape[-1])
+    _call("scb_layernorm", dev, _ptr(x2), x2.stride(0), _ptr(gamma), _ptr(beta), eps, x2.shape[0],
+          x2.shape[1], _ptr(o2), o2.stride(0))
+    return out.view(x.shape)
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(x, weight, out)
+    x2 = _f16(x, "x").reshape(-1, x.shape[-1])
+    if out is None:
+        out = torch.empty_like(x2)
+    o2 = out.view(-1, x.shape[-1])
+    _call("scb_rmsnorm", dev, _ptr(x2), x2.stride(0), _ptr(weight), eps, x2.shape[0], x2.shape[1],
+          _ptr(o2), o2.stride(0))
+    return out.view(x.shape)
+
+
+def im2col_patch(pixels: torch.Tensor, patch: int, ld_out: int) -> torch.Tensor:
+    dev = _require_cuda(pixels)
+    pixels = _f16(pixels, "pixels").contiguous()
+    n, c, h, w = pixels.shape
+    out = torch.empty((n * (h // patch) * (w // patch), ld_out), dtype=torch.float16, device=dev)
+    _call("scb_im2col_patch", dev, _ptr(pixels), _ptr(out), n, c, h, w, patch, ld_out)
+    return out
+
+
+def vit_embed_layernorm(patch_embeds: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor,
+                        gamma: torch.Tensor, beta: torch.Tensor, eps: float, n_img: int) -> torch.Tensor:
+    dev = _require_cuda(patch_embeds, cls, pos, gamma, beta)
+    tokens, dim = pos.shape
+    out = torch.empty((n_img * tokens, dim), dtype=torch.float16, device=dev)
+    _call("scb_vit_embed_layernorm", dev, _ptr(patch_embeds), patch_embeds.stride(0), _ptr(cls), _ptr(pos),
+          _ptr(gamma), _ptr(beta), eps, n_img, tokens, dim, _ptr(out), out.stride(0))
+    return out
+
+
+def avgpool2x2_tokens(x: torch.Tensor, n_img: int, tokens_per_img: int, tok_offset: int, grid: int) -> torch.Tensor:
+    """x [n_img*tokens_per_img, D] -> [n_img*(grid/2)^2, D]."""
+    dev = _require_cuda(x)
+    dim = x.shape[-1]
+    out = torch.empty((n_img * (grid // 2) ** 2, dim), dtype=torch.float16, device=dev)
+    _call("scb_avgpool2x2_tokens", dev, _ptr(x), x.stride(0), tokens_per_img, tok_offset, grid, n_img, dim,
+          _ptr(out), out.stride(0))
+    return out
+
+
+def silu_mul(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(gate_up, out)
+    rows, two_i = gate_up.shape
+    inter = two_i // 2
+    if out is None:
+        out = torch.empty((rows, inter), dtype=torch.float16, device=dev)
+    _call("scb_silu_mul", dev, _ptr(gate_up), gate_up.stride(0), rows, inter, _ptr(out), out.stride(0))
+    return out
+
+
+def rope_append(qkv: torch.Tensor, n_q: int, n_kv: int, head_dim: int, inv_freq: Optional[torch.Tensor],
+                theta: float, pos_base: int = 0, positions: Optional[torch.Tensor] = None,
+                k_cache: Optional[torch.Tensor] = None, v_cache: Optional[torch.Tensor] = None) -> None:
+    """In-place RoPE on the q,k slices of qkv [rows, (n_q+2*n_kv)*head_dim]; appends k,v to the
+    caches [n_kv, max_pos, head_dim] when given."""
+    dev = _require_cuda(qkv, inv_freq, positions, k_cache, v_cache)
+    max_pos = k_cache.shape[1] if k_cache is not None else 0
+    _call("scb_rope_append", dev, _ptr(qkv), qkv.stride(0), qkv.shape[0], n_q, n_kv, head_dim,
+          _ptr(positions), pos_base, theta, _ptr(inv_freq), _ptr(k_cache), _ptr(v_cache), max_pos)
+
+
+def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(table, ids, out)
+    ids = ids.reshape(-1)
+    if ids.dtype != torch.int64:
+        raise TypeError("ids must be int64")
+    if out is None:
+        out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float16, device=dev)
+    _call("scb_gather_rows", dev, _ptr(table), _ptr(ids), ids.numel(), table.shape[1], _ptr(out), out.stride(0))
+    return out
+
+
+def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
+                counter: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(logits, out, counter)
+    rows, n = logits.shape
+    if out is None:
+        out = torch.empty((rows,), dtype=torch.int64, device=dev)
+    _call("scb_argmax_rows", dev, _ptr(logits), _dtype_code(logits), logits.stride(0), rows, n, _ptr(out),
+          _ptr(counter))
+    return out
+
+
+def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, prologue: int = L.PRO_NONE,
+         gamma: Optional[torch.Tensor] = None, eps: float = 0.0, out: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
+    """Decode-step linear layer for 1, 2 or 4 activation rows (see scb_gemv)."""
+    dev = _require_cuda(a, w, bias, residual, gamma, out)
+    rows = a.shape[0]
+    n, k = w.shape
+    if out is None:
+        out = torch.empty((rows, n), dtype=out_dtype, device=dev)
+    args = L.GemvArgs(a=_ptr(a), w=_ptr(w), bias=_ptr(bias), residual=_ptr(residual), gamma=_ptr(gamma),
+                      out=_ptr(out), n=n, k=k, lda=a.stride(0), ldw=w.stride(0),
+                      ldr=residual.stride(0) if residual is not None else 0, ldo=out.stride(0),
+                      rows=rows, prologue=prologue, out_dtype=_dtype_code(out), eps=eps)
+    _call("scb_gemv", dev, C.byref(args))
+    return out
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, scale: float,
+                     kv_len: int = 0, kv_len_dev: Optional[torch.Tensor] = None, n_splits: int = 32,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [Hq, D] against caches [Hkv, max_pos, D]; context length from `kv_len_dev` (int32 device
+    scalar, graph-replayable) or `kv_len`."""
+    dev = _require_cuda(q, k_cache, v_cache, kv_len_dev, out)
+    hq, d = q.shape
+    hkv, max_pos, _ = k_cache.shape
+    if out is None:
+        out = torch.empty((hq, d), dtype=torch.float16, device=dev)
+    lib = L.load()
+    ws = _workspace(dev, "decode_attn", lib.scb_decode_attention_workspace_bytes(hq, d, n_splits))
+    args = L.DecodeAttentionArgs(q=_ptr(q), k_cache=_ptr(k_cache), v_cache=_ptr(v_cache), out=_ptr(out),
+                                 kv_len_dev=_ptr(kv_len_dev), max_pos=max_pos, kv_len=kv_len,
+                                 n_q_heads=hq, n_kv_heads=hkv, head_dim=d, n_splits=n_splits, scale=scale,
+                                 workspace=_ptr(ws), workspace_bytes=ws.numel())
+    _call("scb_decode_attention", dev, C.byref(args))
+    return out

@@ -1,0 +1,232 @@
+"""GPU parity of the fused attention, row-wise glue and decode kernels (through the C-ABI)
+against plain PyTorch fp32 references of the same ops."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sdpa_ref(q, k, v, scale, causal):
+    # q [B,Tq,Hq,D], k/v [B,Tk,Hkv,D] -> [B,Tq,Hq,D] in fp64
+    B, Tq, Hq, D = q.shape
+    Hkv = k.shape[2]
+    g = Hq // Hkv
+    qd = q.double().permute(0, 2, 1, 3)
+    kd = k.double().permute(0, 2, 1, 3).repeat_interleave(g, dim=1)
+    vd = v.double().permute(0, 2, 1, 3).repeat_interleave(g, dim=1)
+    s = qd @ kd.transpose(-1, -2) * scale
+    if causal:
+        Tk = k.shape[1]
+        mask = torch.arange(Tk)[None, :] > (torch.arange(Tq)[:, None] + (Tk - Tq))
+        s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ vd).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,Tq,Tk,Hq,Hkv,D,causal", [
+    (2, 577, 577, 16, 16, 64, False),     # CLIP ViT-L/14-336 self-attention
+    (1, 128, 128, 1, 1, 64, False),
+    (1, 100, 300, 2, 2, 64, False),       # ragged, several kv blocks
+    (1, 512, 512, 4, 2, 128, True),       # GQA causal
+    (1, 700, 700, 7, 1, 128, True),       # Qwen2 group size 7, ragged
+    (1, 130, 500, 7, 1, 128, True),       # chunked prefill: causal with offset
+    (1, 1, 257, 2, 1, 128, True),
+])
+def test_attention_matches_reference(cuda, B, Tq, Tk, Hq, Hkv, D, causal):
+    from streamchat_b200 import ops
+    torch.manual_seed(B * 1000 + Tq + Tk)
+    q = torch.randn(B, Tq, Hq, D).half()
+    k = torch.randn(B, Tk, Hkv, D).half()
+    v = torch.randn(B, Tk, Hkv, D).half()
+    scale = 1.0 / math.sqrt(D)
+    ref = _sdpa_ref(q, k, v, scale, causal)
+    out = ops.attention(q.to(cuda), k.to(cuda), v.to(cuda), scale, causal)
+    torch.cuda.synchronize()
+    err = (out.double().cpu() - ref).abs().max().item()
+    assert err < 4e-3, err
+
+
+def test_attention_fused_qkv_views_and_cache_layout(cuda):
+    """q/k/v as strided slices of a fused [T, 3*H*D] buffer (ViT) and k/v in the [Hkv, T, D] cache
+    layout permuted to [1, T, Hkv, D] (Qwen2)."""
+    from streamchat_b200 import ops
+    torch.manual_seed(4)
+    T, H, D = 300, 4, 64
+    qkv = torch.randn(2, T, 3 * H * D).half().to(cuda)
+    q = qkv[:, :, :H * D].view(2, T, H, D)
+    k = qkv[:, :, H * D:2 * H * D].view(2, T, H, D)
+    v = qkv[:, :, 2 * H * D:].view(2, T, H, D)
+    out = ops.attention(q, k, v, 0.125, False)
+    ref = _sdpa_ref(q.cpu(), k.cpu(), v.cpu(), 0.125, False)
+    assert (out.double().cpu() - ref).abs().max().item() < 4e-3
+    # cache layout with a max_pos larger than the live context and garbage (NaN) beyond it
+    Hkv, maxp, Dk, ctx = 2, 640, 128, 333
+    kc = torch.full((Hkv, maxp, Dk), float("nan")).half()
+    vc = torch.full((Hkv, maxp, Dk), float("nan")).half()
+    kc[:, :ctx] = torch.randn(Hkv, ctx, Dk).half()
+    vc[:, :ctx] = torch.randn(Hkv, ctx, Dk).half()
+    qq = torch.randn(1, ctx, 4, Dk).half()
+    kcd, vcd = kc.to(cuda), vc.to(cuda)
+    kview = kcd[:, :ctx].permute(1, 0, 2).unsqueeze(0)
+    vview = vcd[:, :ctx].permute(1, 0, 2).unsqueeze(0)
+    out = ops.attention(qq.to(cuda), kview, vview, 0.0884, True)
+    ref = _sdpa_ref(qq, kc[:, :ctx].permute(1, 0, 2).unsqueeze(0), vc[:, :ctx].permute(1, 0, 2).unsqueeze(0),
+                    0.0884, True)
+    assert torch.isfinite(out).all()
+    assert (out.double().cpu() - ref).abs().max().item() < 4e-3
+
+
+def test_layernorm_rmsnorm_embed(cuda):
+    from streamchat_b200 import ops
+    torch.manual_seed(0)
+    x = (torch.randn(300, 1024) * 2 + 0.5).half()
+    g, b = torch.randn(1024).half(), torch.randn(1024).half()
+    ref = torch.nn.functional.layer_norm(x.float(), (1024,), g.float(), b.float(), 1e-5)
+    out = ops.layernorm(x.to(cuda), g.to(cuda), b.to(cuda), 1e-5).cpu().float()
+    assert (out - ref).abs().max().item() < 1e-2 and (out - ref).abs().mean().item() < 1e-3
+    # RMSNorm in HF order (modeling_qwen2.py:249-263)
+    x2 = torch.randn(17, 3584).half()
+    w = (1 + 0.1 * torch.randn(3584)).half()
+    xf = x2.float()
+    nrm = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).half()
+    ref2 = (w * nrm).float()
+    out2 = ops.rmsnorm(x2.to(cuda), w.to(cuda), 1e-6).cpu().float()
+    assert (out2 - ref2).abs().max().item() < 4e-3
+    # token assembly + pre-LN
+    n, T, D = 3, 10, 64
+    patch = torch.randn(n * (T - 1), D).half()
+    cls, pos = torch.randn(D).half(), torch.randn(T, D).half()
+    gg, bb = torch.randn(D).half(), torch.randn(D).half()
+    emb = torch.cat([cls.expand(n, 1, D), patch.view(n, T - 1, D)], 1) + pos
+    ref3 = torch.nn.functional.layer_norm(emb.float(), (D,), gg.float(), bb.float(), 1e-5).view(-1, D)
+    out3 = ops.vit_embed_layernorm(patch.to(cuda), cls.to(cuda), pos.to(cuda), gg.to(cuda), bb.to(cuda),
+                                   1e-5, n).cpu().float()
+    assert (out3 - ref3).abs().max().item() < 1e-2
+
+
+def test_im2col_pool_silu_gather_argmax(cuda):
+    from streamchat_b200 import ops
+    torch.manual_seed(1)
+    pix = torch.randn(2, 3, 28, 42).half()
+    cols = ops.im2col_patch(pix.to(cuda), 14, 592).cpu()
+    ref = torch.nn.functional.unfold(pix.float(), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(cols[:, :588].float(), ref) and (cols[:, 588:] == 0).all()
+    # pool: [n, 1+g*g, D] with CLS skipped
+    n, g, D = 2, 6, 64
+    x = torch.randn(n, 1 + g * g, D).half()
+    ref = torch.nn.functional.avg_pool2d(x[:, 1:].float().view(n, g, g, D).permute(0, 3, 1, 2), 2)
+    ref = ref.flatten(2).transpose(1, 2).reshape(-1, D)
+    out = ops.avgpool2x2_tokens(x.view(-1, D).to(cuda), n, 1 + g * g, 1, g).cpu().float()
+    assert (out - ref).abs().max().item() < 2e-3
+    # silu * up
+    gu = torch.randn(5, 2 * 256).half()
+    ref = (torch.nn.functional.silu(gu[:, :256].float()).half().float() * gu[:, 256:].float())
+    out = ops.silu_mul(gu.to(cuda)).cpu().float()
+    assert (out - ref).abs().max().item() < 4e-3
+    # gather
+    table = torch.randn(50, 128).half()
+    ids = torch.tensor([3, 49, 0, 3], dtype=torch.int64)
+    assert torch.equal(ops.gather_rows(table.to(cuda), ids.to(cuda)).cpu(), table[ids])
+    # argmax: fp16 logits with ties -> lowest index; counter increments
+    lg = torch.randn(3, 152064).half()
+    lg[0, 777] = 9.0
+    lg[0, 90000] = 9.0
+    lg[1, 152063] = 10.0
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    out = ops.argmax_rows(lg.to(cuda), counter=cnt).cpu()
+    assert out.tolist() == torch.argmax(lg.float(), dim=1).tolist() and out[0] == 777
+    assert int(cnt) == 1
+    out32 = ops.argmax_rows(lg.float().to(cuda)).cpu()
+    assert out32.tolist() == out.tolist()
+
+
+def _rope_ref(x, pos, inv_freq):
+    # HF apply_rotary_pos_emb in fp16 (modeling_qwen2.py:116-146)
+    ang = pos[:, None].float() * inv_freq[None, :]
+    emb = torch.cat([ang, ang], -1)
+    cos, sin = emb.cos().half(), emb.sin().half()
+    half = x.shape[-1] // 2
+    rot = torch.cat([-x[..., half:], x[..., :half]], -1)
+    return (x * cos[:, None, :]) + (rot * sin[:, None, :])
+
+
+def test_rope_append(cuda):
+    from streamchat_b200 import ops
+    torch.manual_seed(2)
+    rows, nq, nkv, hd, maxp = 9, 4, 2, 128, 64
+    qkv = torch.randn(rows, (nq + 2 * nkv) * hd).half()
+    inv_freq = 1.0 / (1000000.0 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    pos = torch.arange(rows) + 5
+    q_ref = _rope_ref(qkv[:, :nq * hd].view(rows, nq, hd), pos, inv_freq)
+    k_ref = _rope_ref(qkv[:, nq * hd:(nq + nkv) * hd].view(rows, nkv, hd), pos, inv_freq)
+    v_ref = qkv[:, (nq + nkv) * hd:].view(rows, nkv, hd)
+    d = qkv.to(cuda)
+    kc = torch.zeros(nkv, maxp, hd, dtype=torch.float16, device=cuda)
+    vc = torch.zeros_like(kc)
+    ops.rope_append(d, nq, nkv, hd, inv_freq.to(cuda), 1e6, pos_base=5, k_cache=kc, v_cache=vc)
+    got_q = d[:, :nq * hd].view(rows, nq, hd).cpu().float()
+    got_k = d[:, nq * hd:(nq + nkv) * hd].view(rows, nkv, hd).cpu().float()
+    assert (got_q - q_ref.float()).abs().max().item() < 4e-3
+    assert (got_k - k_ref.float()).abs().max().item() < 4e-3
+    assert torch.equal(kc[:, 5:5 + rows].permute(1, 0, 2).cpu().float(), got_k)
+    assert torch.equal(vc[:, 5:5 + rows].permute(1, 0, 2).cpu(), v_ref)
+    assert (kc[:, :5] == 0).all() and (kc[:, 5 + rows:] == 0).all()
+    # device-side positions (graph-replayable decode step)
+    d2 = qkv[:1].clone().to(cuda)
+    p = torch.tensor([20], dtype=torch.int32, device=cuda)
+    ops.rope_append(d2, nq, nkv, hd, inv_freq.to(cuda), 1e6, positions=p, k_cache=kc, v_cache=vc)
+    k20 = _rope_ref(qkv[:1, nq * hd:(nq + nkv) * hd].view(1, nkv, hd), torch.tensor([20]), inv_freq)
+    assert (kc[:, 20].cpu().float() - k20[0].float()).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("rows,n,k,pro", [(1, 4608, 3584, 1), (1, 3584, 3584, 0), (1, 3584, 18944, 2),
+                                          (2, 1000, 512, 0), (4, 300, 1024, 1), (1, 152064, 3584, 1)])
+def test_gemv(cuda, rows, n, k, pro):
+    from streamchat_b200 import ops
+    torch.manual_seed(rows + n + k)
+    w = (torch.randn(n, k) * 0.02).half()
+    bias = torch.randn(n).half() if n < 10000 else None
+    res = torch.randn(rows, n).half() if pro != 1 else None
+    if pro == 2:
+        a = torch.randn(rows, 2 * k).half()
+        eff = (torch.nn.functional.silu(a[:, :k].float()).half().float() * a[:, k:].float()).half()
+        gamma = None
+    elif pro == 1:
+        a = torch.randn(rows, k).half()
+        gamma = (1 + 0.1 * torch.randn(k)).half()
+        af = a.float()
+        eff = (gamma * (af * torch.rsqrt(af.pow(2).mean(-1, keepdim=True) + 1e-6)).half())
+    else:
+        a = torch.randn(rows, k).half()
+        eff, gamma = a, None
+    ref = eff.double() @ w.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if res is not None:
+        ref = ref + res.double()
+    out = ops.gemv(a.to(cuda), w.to(cuda), bias=None if bias is None else bias.to(cuda),
+                   residual=None if res is None else res.to(cuda), prologue=pro,
+                   gamma=None if gamma is None else gamma.to(cuda), eps=1e-6, out_dtype=torch.float32)
+    err = (out.double().cpu() - ref).abs()
+    assert (err <= 2e-3 * (ref.abs() + 1)).all(), err.max().item()
+
+
+@pytest.mark.parametrize("hq,hkv,d,ctx,splits", [(28, 4, 128, 4700, 37), (28, 4, 128, 5, 37), (4, 4, 64, 300, 8)])
+def test_decode_attention(cuda, hq, hkv, d, ctx, splits):
+    from streamchat_b200 import ops
+    torch.manual_seed(ctx)
+    maxp = ctx + 100
+    q = torch.randn(hq, d).half()
+    kc = torch.randn(hkv, maxp, d).half()
+    vc = torch.randn(hkv, maxp, d).half()
+    scale = 1 / math.sqrt(d)
+    ref = _sdpa_ref(q.view(1, 1, hq, d), kc[:, :ctx].permute(1, 0, 2).unsqueeze(0),
+                    vc[:, :ctx].permute(1, 0, 2).unsqueeze(0), scale, False)[0, 0]
+    out = ops.decode_attention(q.to(cuda), kc.to(cuda), vc.to(cuda), scale, kv_len=ctx, n_splits=splits)
+    assert (out.double().cpu() - ref).abs().max().item() < 3e-3
+    lens = torch.tensor([ctx], dtype=torch.int32, device=cuda)
+    out2 = ops.decode_attention(q.to(cuda), kc.to(cuda), vc.to(cuda), scale, kv_len_dev=lens, n_splits=splits)
+    assert torch.equal(out, out2)

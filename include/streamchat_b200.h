@@ -208,10 +208,11 @@ int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_
                     int64_t ld_out, void* stream);
 
 /* Greedy token choice: arg-max per row of logits (fp16 or fp32), lowest index wins ties —
- * torch.argmax over the fp16 lm_head output as HF generate does.  If counter != NULL the
- * device int32 it points to is incremented by one (position bookkeeping of a replayed graph). */
+ * torch.argmax over the fp16 lm_head output as HF generate does.  If counters != NULL the
+ * n_counters device int32 values it points to are each incremented by one (position / length
+ * bookkeeping of a replayed CUDA graph). */
 int scb_argmax_rows(const void* logits, int32_t dtype, int64_t ld, int64_t rows, int32_t n,
-                    int64_t* out, int32_t* counter, void* stream);
+                    int64_t* out, int32_t* counters, int32_t n_counters, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused attention softmax(scale * Q K^T [+ causal mask]) V on tcgen05 tensor cores.

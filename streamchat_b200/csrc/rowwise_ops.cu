@@ -265,7 +265,7 @@ __global__ void gather_rows_kernel(const __half* __restrict__ table, const long 
 template <typename T>
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const T* __restrict__ logits, long long ld, int n, long long* __restrict__ out,
-              int* __restrict__ counter) {
+              int* __restrict__ counter, int n_counters) {
   __shared__ float sv[32];
   __shared__ int si[32];
   const T* p = logits + (long long)blockIdx.x * ld;
@@ -308,7 +308,8 @@ argmax_kernel(const T* __restrict__ logits, long long ld, int n, long long* __re
     }
     if (lane == 0) {
       out[blockIdx.x] = bi;
-      if (counter && blockIdx.x == 0) *counter += 1;
+      if (counter && blockIdx.x == 0)
+        for (int c = 0; c < n_counters; ++c) counter[c] += 1;
     }
   }
 }
@@ -451,16 +452,18 @@ int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_
 }
 
 int scb_argmax_rows(const void* logits, int32_t dtype, int64_t ld, int64_t rows, int32_t n,
-                    int64_t* out, int32_t* counter, void* stream) {
+                    int64_t* out, int32_t* counters, int32_t n_counters, void* stream) {
   SCB_REQUIRE(logits && out && rows >= 1 && n >= 1, SCB_ERR_INVALID_ARG, "scb_argmax_rows: bad arguments");
   SCB_REQUIRE(dtype == SCB_F32 || dtype == SCB_F16, SCB_ERR_UNSUPPORTED, "scb_argmax_rows: dtype %d", dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == SCB_F32)
     argmax_kernel<float><<<(unsigned)rows, 1024, 0, st>>>(reinterpret_cast<const float*>(logits), ld, n,
-                                                          reinterpret_cast<long long*>(out), counter);
+                                                          reinterpret_cast<long long*>(out), counters,
+                                                          n_counters);
   else
     argmax_kernel<__half><<<(unsigned)rows, 1024, 0, st>>>(reinterpret_cast<const __half*>(logits), ld,
-                                                           n, reinterpret_cast<long long*>(out), counter);
+                                                           n, reinterpret_cast<long long*>(out), counters,
+                                                          n_counters);
   SCB_LAUNCH_OK("argmax_kernel");
   return SCB_OK;
 }

@@ -336,7 +336,7 @@ def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty((rows,), dtype=torch.int64, device=dev)
     _call("scb_argmax_rows", dev, _ptr(logits), _dtype_code(logits), logits.stride(0), rows, n, _ptr(out),
-          _ptr(counter))
+          _ptr(counter), 0 if counter is None else counter.numel())
     return out
 
 

@@ -1,0 +1,257 @@
+"""Qwen2 decoder (LongVA's language model) on the sm_100a kernels: long-context prefill on
+tcgen05 GEMM + fused attention, cached greedy decode as a CUDA-graph of weight-streaming GEMVs.
+
+Replaces the third-party math under `generate_with_image_embedding`
+(longva/model/language_model/llava_qwen.py:137-155 -> Qwen2ForCausalLM.generate with
+inputs_embeds; prefill + DynamicCache decode because HF forces use_cache when inputs_embeds are
+given, generation/utils.py:2425-2428).  Operator order: SURVEY.md Appendix B.3.
+
+Data layout in HBM (per engine): fused QKV weight [(Hq+2Hkv)*hd, H] (+bias), o_proj [H, H], fused
+gate|up [2I, H], down [H, I], all fp16 row-major (K contiguous); KV cache per layer
+[Hkv, max_ctx, hd] fp16 for K (post-RoPE) and V.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+@dataclass
+class Qwen2Config:
+    hidden_size: int = 3584
+    intermediate_size: int = 18944
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 28
+    num_key_value_heads: int = 4
+    vocab_size: int = 152064
+    rope_theta: float = 1000000.0
+    rms_norm_eps: float = 1e-6
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_attention_heads
+
+
+class Qwen2Engine:
+    def __init__(self, weights: Dict[str, torch.Tensor], cfg: Qwen2Config, device: torch.device,
+                 max_ctx: int = 16384, decode_splits: int = 37):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.max_ctx = max_ctx
+        self.decode_splits = decode_splits
+        c = cfg
+        if c.head_dim not in (64, 128):
+            raise ValueError(f"head_dim {c.head_dim} unsupported (64 or 128)")
+
+        def w(name):
+            return weights[name].to(device=self.device, dtype=torch.float16).contiguous()
+
+        self.embed = w("model.embed_tokens.weight")
+        self.lm_head = w("lm_head.weight")
+        self.final_norm = w("model.norm.weight")
+        self.layers = []
+        for i in range(c.num_hidden_layers):
+            p = f"model.layers.{i}."
+            self.layers.append(dict(
+                ln1=w(p + "input_layernorm.weight"),
+                qkv_w=torch.cat([w(p + "self_attn.q_proj.weight"), w(p + "self_attn.k_proj.weight"),
+                                 w(p + "self_attn.v_proj.weight")], 0).contiguous(),
+                qkv_b=torch.cat([w(p + "self_attn.q_proj.bias"), w(p + "self_attn.k_proj.bias"),
+                                 w(p + "self_attn.v_proj.bias")], 0).contiguous(),
+                o_w=w(p + "self_attn.o_proj.weight"),
+                ln2=w(p + "post_attention_layernorm.weight"),
+                gu_w=torch.cat([w(p + "mlp.gate_proj.weight"), w(p + "mlp.up_proj.weight")], 0).contiguous(),
+                down_w=w(p + "mlp.down_proj.weight")))
+        hd = c.head_dim
+        # inv_freq exactly as HF computes it (modeling_qwen2.py:51-114): fp32 table
+        self.inv_freq = (1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(self.device)
+        self.k_cache = [torch.zeros((c.num_key_value_heads, max_ctx, hd), dtype=torch.float16, device=self.device)
+                        for _ in range(c.num_hidden_layers)]
+        self.v_cache = [torch.zeros_like(k) for k in self.k_cache]
+        self.ctx_len = 0
+        # decode state (device-resident so the step graph is replayable)
+        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)     # [position, kv_len]
+        self.next_id = torch.zeros(1, dtype=torch.int64, device=self.device)
+        qkv_dim = (c.num_attention_heads + 2 * c.num_key_value_heads) * hd
+        self._x = torch.zeros((1, c.hidden_size), dtype=torch.float16, device=self.device)
+        self._x2 = torch.zeros_like(self._x)
+        self._qkv = torch.zeros((1, qkv_dim), dtype=torch.float16, device=self.device)
+        self._attn = torch.zeros((c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
+        self._gu = torch.zeros((1, 2 * c.intermediate_size), dtype=torch.float16, device=self.device)
+        self._logits = torch.zeros((1, c.vocab_size), dtype=torch.float16, device=self.device)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+
+    # ---------------------------------------------------------------- weights / work accounting
+    def weight_bytes(self) -> int:
+        n = self.lm_head.numel() + self.final_norm.numel()
+        for ly in self.layers:
+            n += sum(t.numel() for t in ly.values())
+        return 2 * n
+
+    def decode_bytes_per_token(self, ctx: int) -> int:
+        c = self.cfg
+        return self.weight_bytes() + 2 * c.num_hidden_layers * c.num_key_value_heads * ctx * c.head_dim * 2
+
+    def prefill_flops(self, T: int) -> float:
+        c = self.cfg
+        hd = c.head_dim
+        per_tok = 2 * c.hidden_size * ((c.num_attention_heads + 2 * c.num_key_value_heads) * hd
+                                       + c.hidden_size + 3 * c.intermediate_size)
+        attn = 2.0 * T * T * c.num_attention_heads * hd   # causal: half of 4*T*T*H*hd
+        return c.num_hidden_layers * (per_tok * T + attn)
+
+    # ---------------------------------------------------------------- prefill
+    def reset(self) -> None:
+        self.ctx_len = 0
+
+    @torch.no_grad()
+    def prefill(self, inputs_embeds: torch.Tensor) -> torch.Tensor:
+        """Append T tokens ([T, H] fp16) to the context; returns fp16 logits [1, V] of the last one."""
+        c = self.cfg
+        hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
+        x = inputs_embeds.to(device=self.device, dtype=torch.float16).contiguous()
+        T = x.shape[0]
+        pos0 = self.ctx_len
+        if pos0 + T > self.max_ctx:
+            raise ValueError(f"context {pos0 + T} exceeds max_ctx {self.max_ctx}")
+        scale = hd ** -0.5
+        for i, ly in enumerate(self.layers):
+            y = ops.rmsnorm(x, ly["ln1"], c.rms_norm_eps)
+            qkv = ops.linear(y, ly["qkv_w"], bias=ly["qkv_b"])
+            ops.rope_append(qkv, Hq, Hkv, hd, self.inv_freq, c.rope_theta, pos_base=pos0,
+                            k_cache=self.k_cache[i], v_cache=self.v_cache[i])
+            q = qkv[:, :Hq * hd].view(1, T, Hq, hd)
+            kv_len = pos0 + T
+            k = self.k_cache[i][:, :kv_len].permute(1, 0, 2).unsqueeze(0)
+            v = self.v_cache[i][:, :kv_len].permute(1, 0, 2).unsqueeze(0)
+            ctx = ops.attention(q, k, v, scale, causal=True)
+            x = ops.linear(ctx.view(T, Hq * hd), ly["o_w"], residual=x)
+            y = ops.rmsnorm(x, ly["ln2"], c.rms_norm_eps)
+            gu = ops.linear(y, ly["gu_w"])
+            y = ops.silu_mul(gu)
+            x = ops.linear(y, ly["down_w"], residual=x)
+        self.ctx_len = pos0 + T
+        # final norm + lm_head on the last position only (logits_to_keep, modeling_qwen2.py:474-475)
+        return ops.gemv(x[T - 1:T], self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm,
+                        eps=c.rms_norm_eps, out=self._logits)
+
+    # ---------------------------------------------------------------- decode
+    def _decode_step_launches(self) -> None:
+        """One cached decode step: embeds next_id at device position state[0]; leaves the new
+        logits in self._logits, the new arg-max in next_id and advances state."""
+        c = self.cfg
+        hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
+        scale = hd ** -0.5
+        ops.gather_rows(self.embed, self.next_id, out=self._x)
+        x, x2 = self._x, self._x2
+        for i, ly in enumerate(self.layers):
+            ops.gemv(x, ly["qkv_w"], bias=ly["qkv_b"], prologue=L.PRO_RMSNORM, gamma=ly["ln1"],
+                     eps=c.rms_norm_eps, out=self._qkv)
+            ops.rope_append(self._qkv, Hq, Hkv, hd, self.inv_freq, c.rope_theta, positions=self.state[0:1],
+                            k_cache=self.k_cache[i], v_cache=self.v_cache[i])
+            ops.decode_attention(self._qkv[0, :Hq * hd].view(Hq, hd), self.k_cache[i], self.v_cache[i], scale,
+                                 kv_len_dev=self.state[1:2], n_splits=self.decode_splits, out=self._attn)
+            ops.gemv(self._attn.view(1, Hq * hd), ly["o_w"], residual=x, out=x2)
+            ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps, out=self._gu)
+            ops.gemv(self._gu, ly["down_w"], residual=x2, prologue=L.PRO_SILU_MUL, out=x)
+        ops.gemv(x, self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm, eps=c.rms_norm_eps,
+                 out=self._logits)
+        ops.argmax_rows(self._logits, out=self.next_id, counter=self.state)
+
+    def launches_per_decode_step(self) -> int:
+        return 1 + self.cfg.num_hidden_layers * 7 + 2
+
+    def _ensure_graph(self) -> None:
+        if self._graph is not None:
+            return
+        # warm-up on a side stream (loads modules, sets func attributes), then capture
+        saved_state, saved_id = self.state.clone(), self.next_id.clone()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.state.copy_(torch.tensor([0, 1], dtype=torch.int32))
+            self._decode_step_launches()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._decode_step_launches()
+        self._graph = g
+        self.state.copy_(saved_state)
+        self.next_id.copy_(saved_id)
+        # the warm-up / capture wrote K,V at positions 0..; the caller's context is rebuilt by prefill
+        torch.cuda.synchronize(self.device)
+
+    @torch.no_grad()
+    def generate(self, inputs_embeds: torch.Tensor, max_new_tokens: int, do_sample: bool = False,
+                 temperature: float = 1.0, top_k: Optional[int] = 50, top_p: Optional[float] = None,
+                 eos_token_id=None, use_graph: bool = True) -> torch.Tensor:
+        """Prefill + decode; returns the NEW token ids only, [1, T_new] int64 (HF generate with
+        inputs_embeds).  Greedy (do_sample False or temperature 0) is the parity path."""
+        with torch.cuda.device(self.device):
+            if use_graph:
+                self._ensure_graph()          # before prefill: capture scribbles on cache rows 0..1
+            self.reset()
+            logits = self.prefill(inputs_embeds)
+            greedy = (not do_sample) or temperature == 0
+            eos = set()
+            if eos_token_id is not None:
+                eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else {int(eos_token_id)}
+            out = torch.zeros(max_new_tokens, dtype=torch.int64, device=self.device)
+            T = self.ctx_len
+            self.state.copy_(torch.tensor([T, T + 1], dtype=torch.int32), non_blocking=True)
+            if greedy:
+                ops.argmax_rows(logits, out=self.next_id)
+            else:
+                self.next_id.copy_(self._sample(logits, temperature, top_k, top_p))
+            n_done = 0
+            for step in range(max_new_tokens):
+                out[step:step + 1].copy_(self.next_id, non_blocking=True)
+                n_done = step + 1
+                if eos and (step % 16 == 15 or step == max_new_tokens - 1):
+                    hit = [j for j, t in enumerate(out[:n_done].tolist()) if t in eos]
+                    if hit:
+                        n_done = hit[0] + 1
+                        break
+                if step == max_new_tokens - 1:
+                    break
+                if greedy:
+                    if use_graph:
+                        self._graph.replay()
+                    else:
+                        self._decode_step_launches()
+                else:
+                    # sampling path: same kernels, token drawn by torch.multinomial as HF does
+                    saved = self.state.clone()
+                    self._decode_step_launches()
+                    self.next_id.copy_(self._sample(self._logits, temperature, top_k, top_p))
+                    self.state.copy_(saved + 1)
+            if eos:
+                toks = out[:n_done].tolist()
+                for j, t in enumerate(toks):
+                    if t in eos:
+                        n_done = j + 1
+                        break
+            self.ctx_len = T + n_done - 1
+            return out[:n_done].unsqueeze(0).clone()
+
+    @staticmethod
+    def _sample(logits: torch.Tensor, temperature: float, top_k: Optional[int], top_p: Optional[float]) -> torch.Tensor:
+        """HF sampling warpers (temperature, top-k 50 default, optional top-p) on the [1,V] logits.
+        Not a parity path (hazard H2): the reference's draws depend on the global torch RNG."""
+        lg = logits.float() / max(temperature, 1e-6)
+        if top_k:
+            kth = torch.topk(lg, min(top_k, lg.shape[-1])).values[..., -1, None]
+            lg = lg.masked_fill(lg < kth, float("-inf"))
+        if top_p is not None and top_p < 1.0:
+            sl, si = torch.sort(lg, descending=False)
+            cp = sl.softmax(-1).cumsum(-1)
+            rm = cp <= (1 - top_p)
+            rm[..., -1:] = False
+            lg = lg.masked_fill(rm.scatter(-1, si, rm), float("-inf"))
+        return torch.multinomial(lg.softmax(-1), 1).view(1)

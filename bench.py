@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — streamed frames/sec of the StreamChat hot path (ViT -> k-means -> retrieve -> LongVA
+decode) on N B200s, plus the reference's CPU path timed beside it.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                 # our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0 # CPU oracle port on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One step = one pass of the hot path over one synthetic stream per rank (BASELINE.json configs[4]
+shape): `--frames` 336x336 frames in segments of `--segment`; per segment [A] CLIP-ViT encode,
+[B] memory update (forgetting-curve short memory, 40-frame chunks each captioned with a 128-token
+greedy LongVA generation, tree merge = k-means over 400 frames + 256-token text summary); then
+(N>1) one NCCL all-gather of the per-rank memory embeddings, [C] cosine top-k tree search and a
+256-token answer.  Random-init LongVA-7B-shaped weights, synthetic frames (no datasets/checkpoints
+exist here).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "streamed frames/sec (ViT->kmeans->retrieve->LongVA decode)"
+QUESTION = "What objects did I see on the table before I left the room, and where did I put the keys?"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="synthetic:longva7b")
+    ap.add_argument("--frames", type=int, default=None, help="frames per rank per step (default 1000; tiny: 160)")
+    ap.add_argument("--segment", type=int, default=200, help="frames per ingest/update segment")
+    ap.add_argument("--caption-tokens", type=int, default=128)
+    ap.add_argument("--answer-tokens", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, device, e2e: bool):
+    """One step.  Returns (answer ids tensor, h2d bytes, d2h bytes)."""
+    import torch.distributed as dist
+    from streamchat_b200 import ops
+    sess = session_factory()
+    n = frames_dev.shape[0] if frames_dev is not None else host_frames.shape[0]
+    h2d = d2h = 0
+    for s0 in range(0, n, segment):
+        if e2e:
+            seg = host_frames[s0:s0 + segment].to(device, non_blocking=True)   # pinned -> HBM inside the timed region
+            h2d += seg.numel() * seg.element_size()
+        else:
+            seg = frames_dev[s0:s0 + segment]
+        feats = sess.ingest(seg)
+        sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
+    if world > 1:
+        # the one exchange step: all-gather the per-rank memory embeddings (root-node text embeddings
+        # [max_roots, 1024] fp32 + validity) so every rank searches the global index
+        roots = sess.long_memory_tree
+        max_roots = 16
+        emb = torch.zeros((max_roots, 1025), dtype=torch.float32, device=device)
+        for i, node in enumerate(roots[:max_roots]):
+            emb[i, :1024] = M_embed(sess, node)
+            emb[i, 1024] = 1.0
+        gathered = torch.empty((world * max_roots, 1025), dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(gathered, emb)
+        q = sess.embedding_model(sess.embedding_tokenizer, QUESTION)
+        valid = gathered[:, 1024] > 0
+        scores, idx = ops.cosine_topk(gathered[valid][:, :1024].contiguous(), q, k=1)
+        sess.global_best = (scores, idx)
+    text, ids = sess.answer(QUESTION)
+    if e2e:
+        ids_host = ids.cpu()                                                  # device -> host read of the result
+        d2h += ids_host.numel() * ids_host.element_size()
+    return ids, h2d, d2h
+
+
+def M_embed(sess, node):
+    from streamchat_b200 import memory as M
+    return M._node_embedding(node, sess.embedding_model, sess.embedding_tokenizer)
+
+
+def ours(args):
+    import torch.distributed as dist
+    from streamchat_b200 import _lib
+    from streamchat_b200.longva.model.builder import load_pretrained_model
+    from streamchat_b200.stream import HashTextEmbedder, StreamConfig, StreamingSession
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    _lib.load()
+
+    tiny = args.model.endswith("tiny")
+    n_frames = args.frames or (160 if tiny else 1000)
+    tokenizer, model, _, _ = load_pretrained_model(args.model, None, "llava_qwen", device_map=str(device),
+                                                   overwrite_config=None if tiny else {"max_context": 32768})
+    S = model.config.vision.image_size
+    embedder = HashTextEmbedder(1024, device)
+    cfg = StreamConfig(answer_tokens=args.answer_tokens)
+    import streamchat_b200.memory as M
+    M.CAPTION_TOKENS = args.caption_tokens
+
+    def factory():
+        np.random.seed(1234)                 # forgetting-curve sampling uses the global numpy RNG (H1)
+        return StreamingSession(model, tokenizer, embedder, None, None, cfg)
+
+    g = torch.Generator(device=device).manual_seed(1000 + rank)
+    frames_dev = torch.randn((n_frames, 3, S, S), generator=g, device=device, dtype=torch.float16)
+    host_frames = torch.empty(frames_dev.shape, dtype=torch.float16, pin_memory=True)
+    host_frames.copy_(frames_dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e: bool, steps: int):
+        model.llm.profile = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        r0 = model.llm.graph_replays
+        e0.record()
+        h2d = d2h = 0
+        for _ in range(steps):
+            _, a, b = run_stream(factory, None if e2e else frames_dev, host_frames, args.segment, world, rank,
+                                 device, e2e)
+            h2d, d2h = a, b
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        launches = (_lib.launch_count() - l0) + (model.llm.graph_replays - r0) * model.llm.launches_per_decode_step()
+        return ms, h2d, d2h, launches, list(model.llm.profile)
+
+    for _ in range(max(args.warmup, 0)):
+        run_stream(factory, frames_dev, host_frames, args.segment, world, rank, device, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, _, _, launches, prof = timed(False, args.steps)
+    clocks = sampler.stop()
+    ms_e2e, h2d, d2h, _, _ = timed(True, args.steps)
+
+    total_frames = n_frames * world * args.steps
+    value = total_frames / (ms * 1e-3)
+    e2e_value = total_frames / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel family: the weight-streaming GEMVs of the decode step,
+    # timed live (CUDA events on the launching stream around every decode loop of the timed region)
+    peak, peak_src = load_peaks()
+    for p in prof:
+        p["ms"] = p["events"][0].elapsed_time(p["events"][1])
+    dec_ms = sum(p["ms"] for p in prof)
+    dec_steps = sum(p["steps"] for p in prof)
+    dec_bytes = sum(p["bytes"] for p in prof)
+    roofline = None
+    if dec_steps:
+        achieved = dec_bytes / (dec_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "gemv_kernel (decode step: 169 of 199 launches)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "traffic": None,
+                    "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,
+                    "share_of_step_time": dec_ms / (ms if ms else 1)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": f"stream: {n_frames} frames/rank 336x336 in segments of {args.segment}, chunk 40, "
+                               f"{args.caption_tokens}-token greedy caption per chunk, tree merge every 10 chunks "
+                               f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)"
+                               if not tiny else f"tiny smoke stream: {n_frames} frames/rank",
+                   "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_per_rank": n_frames,
+                   "sharding": "frames sharded by rank; one NCCL all-gather of memory embeddings" if world > 1 else "single rank",
+                   "l2": "inputs larger than L2 (677 MB frames + 15 GB weights per step); no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "impl": "ours",
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(n_frames, args, tiny)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(n_frames: int, args, tiny: bool, budget_s: float = 25.0):
+    """The oracle port (oracle/longva_model.py) timed on the host cores on a bounded sample of the
+    same workload, extrapolated linearly in frames / layers / tokens."""
+    from oracle import longva_model as om
+    from streamchat_b200.longva.model.builder import SYNTHETIC
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = SYNTHETIC["tiny" if tiny else "longva7b"]
+    v, l = cfg.vision, cfg.llm
+    g = torch.Generator().manual_seed(0)
+
+    def rnd(*shape):
+        return torch.randn(shape, generator=g) * 0.02
+
+    # ---- ViT: one frame through 2 of the needed layers at true width, extrapolated to all layers
+    D, I = v.hidden_size, v.intermediate_size
+    VT = om.VT
+    W = {VT + "embeddings.class_embedding": rnd(D), VT + "embeddings.patch_embedding.weight": rnd(D, 3, v.patch_size, v.patch_size),
+         VT + "embeddings.position_embedding.weight": rnd(v.tokens, D),
+         VT + "pre_layrnorm.weight": torch.ones(D), VT + "pre_layrnorm.bias": torch.zeros(D)}
+    vit_layers = 2
+    for i in range(vit_layers):
+        p = f"{VT}encoder.layers.{i}."
+        for nme in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            W[p + f"self_attn.{nme}.weight"], W[p + f"self_attn.{nme}.bias"] = rnd(D, D), rnd(D)
+        for nme in ("layer_norm1", "layer_norm2"):
+            W[p + nme + ".weight"], W[p + nme + ".bias"] = torch.ones(D), torch.zeros(D)
+        W[p + "mlp.fc1.weight"], W[p + "mlp.fc1.bias"] = rnd(I, D), rnd(I)
+        W[p + "mlp.fc2.weight"], W[p + "mlp.fc2.bias"] = rnd(D, I), rnd(D)
+    H = l.hidden_size
+    W["model.mm_projector.0.weight"], W["model.mm_projector.0.bias"] = rnd(H, D), rnd(H)
+    W["model.mm_projector.2.weight"], W["model.mm_projector.2.bias"] = rnd(H, H), rnd(H)
+    px = torch.randn(1, 3, v.image_size, v.image_size, generator=g)
+    with torch.no_grad():
+        om.clip_tower(W, px, v.num_attention_heads, select_layer=vit_layers)          # warm-up
+        t0 = time.perf_counter(); om.clip_tower(W, px, v.num_attention_heads, select_layer=vit_layers)
+        t_vit2 = time.perf_counter() - t0
+        feats = torch.randn(1, v.tokens - 1, D, generator=g)
+        t0 = time.perf_counter()
+        y = torch.nn.functional.gelu(om._lin(feats, W, "model.mm_projector.0")); om._lin(y, W, "model.mm_projector.2")
+        t_proj = time.perf_counter() - t0
+    t_frame = t_vit2 / vit_layers * v.layers_needed + t_proj
+
+    # ---- Qwen2: 1 layer at true width; prefill sample of 256 tokens, 2 cached decode tokens, lm_head once
+    LW = {}
+    hd = l.head_dim
+    p = "model.layers.0."
+    LW[p + "self_attn.q_proj.weight"], LW[p + "self_attn.q_proj.bias"] = rnd(l.num_attention_heads * hd, H), rnd(l.num_attention_heads * hd)
+    LW[p + "self_attn.k_proj.weight"], LW[p + "self_attn.k_proj.bias"] = rnd(l.num_key_value_heads * hd, H), rnd(l.num_key_value_heads * hd)
+    LW[p + "self_attn.v_proj.weight"], LW[p + "self_attn.v_proj.bias"] = rnd(l.num_key_value_heads * hd, H), rnd(l.num_key_value_heads * hd)
+    LW[p + "self_attn.o_proj.weight"] = rnd(H, H)
+    LW[p + "mlp.gate_proj.weight"], LW[p + "mlp.up_proj.weight"] = rnd(l.intermediate_size, H), rnd(l.intermediate_size, H)
+    LW[p + "mlp.down_proj.weight"] = rnd(H, l.intermediate_size)
+    LW[p + "input_layernorm.weight"] = LW[p + "post_attention_layernorm.weight"] = LW["model.norm.weight"] = torch.ones(H)
+    lm = rnd(l.vocab_size, H)
+    Tp = 64 if tiny else 256
+    x = torch.randn(Tp, H, generator=g)
+    with torch.no_grad():
+        cache = []
+        t0 = time.perf_counter(); om.qwen2_forward(LW, x, l.num_attention_heads, l.num_key_value_heads, l.rope_theta, l.rms_norm_eps, cache, 0)
+        t_prefill_layer_per_tok = (time.perf_counter() - t0) / Tp
+        t0 = time.perf_counter()
+        for s in range(2):
+            om.qwen2_forward(LW, x[:1], l.num_attention_heads, l.num_key_value_heads, l.rope_theta, l.rms_norm_eps, cache, Tp + s)
+        t_decode_layer = (time.perf_counter() - t0) / 2
+        t0 = time.perf_counter(); (x[:1] @ lm.t()).argmax(); t_lm = time.perf_counter() - t0
+    L = l.num_hidden_layers
+    chunk_tokens = 40 * ((v.grid // 2) ** 2) + 60
+    n_chunks = math.ceil(n_frames / 40)
+    t_caption = chunk_tokens * t_prefill_layer_per_tok * L + args.caption_tokens * (t_decode_layer * L + t_lm)
+    t_answer = 3 * chunk_tokens * t_prefill_layer_per_tok * L + args.answer_tokens * (t_decode_layer * L + t_lm)
+    total = n_frames * t_frame + n_chunks * t_caption + t_answer
+    return {"value": n_frames / total, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": (f"oracle/longva_model.py fp32 on {cores} threads: 1 frame x {vit_layers} ViT layers + projector "
+                       f"({t_vit2:.2f}s+{t_proj:.2f}s), 1 Qwen2 layer x {Tp}-token prefill ({t_prefill_layer_per_tok * Tp:.2f}s), "
+                       f"2 cached decode tokens ({t_decode_layer:.3f}s/tok/layer), lm_head ({t_lm:.3f}s); extrapolated "
+                       f"linearly to {v.layers_needed} ViT layers, {L} Qwen2 layers, {n_chunks} captions x ({chunk_tokens} prefill + "
+                       f"{args.caption_tokens} decode tokens), 1 answer; attention's quadratic term ignored (favours the CPU)"),
+            "extrapolated_seconds_per_stream": total}
+
+
+def reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure
+    Python over HF transformers and /root/reference does not exist on the GPU box, so the timed
+    code is the oracle port (kind "port"), which tests/ pin against the reference's own outputs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tiny = args.model.endswith("tiny")
+    n_frames = args.frames or (160 if tiny else 1000)
+    vals = []
+    for _ in range(max(args.warmup, 0) + max(args.steps, 1)):
+        vals.append(cpu_baseline(n_frames, args, tiny))
+    best = vals[-1]
+    v = float(np.median([x["value"] for x in vals[max(args.warmup, 0):]]))
+    best["value"] = v
+    print(json.dumps({
+        "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n_frames / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"stream: {n_frames} frames (bounded CPU sample, extrapolated)", "model": args.model},
+        "cpu_baseline": best,
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        reference(a)
+    else:
+        ours(a)

@@ -31,7 +31,10 @@ SYNTHETIC = {
 
 
 class ByteTokenizer:
-    """Stand-in tokenizer for synthetic checkpoints: UTF-8 bytes (+ offset) as ids."""
+    """Stand-in tokenizer for synthetic (random-init) checkpoints.  Whitespace-separated words are
+    one token each: a word of the form t<id> maps back to that id (so decode -> encode is the
+    identity on generated text, like a real tokenizer's ~1 token per sub-word), any other word is
+    hashed into the vocabulary."""
     bos_token_id = None
     eos_token_id = None
     pad_token_id = 0
@@ -39,20 +42,26 @@ class ByteTokenizer:
     def __init__(self, vocab_size: int):
         self.vocab_size = vocab_size
 
+    def _word_id(self, word: str) -> int:
+        if len(word) > 1 and word[0] == "t" and word[1:].isdigit() and int(word[1:]) < self.vocab_size:
+            return int(word[1:])
+        h = 2166136261
+        for b in word.encode("utf-8"):
+            h = ((h ^ b) * 16777619) & 0xFFFFFFFF
+        return 3 + h % (self.vocab_size - 3)
+
     def __call__(self, text, **kw):
         class _Enc(dict):
             __getattr__ = dict.get
-        ids = [3 + (b % (self.vocab_size - 3)) for b in text.encode("utf-8")]
+        ids = [self._word_id(w) for w in text.split()]
         if kw.get("return_tensors") == "pt":
             return _Enc(input_ids=torch.tensor([ids], dtype=torch.long),
                         attention_mask=torch.ones((1, len(ids)), dtype=torch.long))
         return _Enc(input_ids=ids, attention_mask=[1] * len(ids))
 
     def batch_decode(self, ids, skip_special_tokens=True):
-        out = []
-        for row in (ids.tolist() if hasattr(ids, "tolist") else ids):
-            out.append(" ".join(str(int(t)) for t in row))
-        return out
+        rows = ids.tolist() if hasattr(ids, "tolist") else ids
+        return [" ".join(f"t{int(t)}" for t in row) for row in rows]
 
     def add_tokens(self, *a, **k):
         return 0

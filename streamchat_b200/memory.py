@@ -30,6 +30,8 @@ BLUE = "\033[34m"
 RESET = "\033[0m"
 
 VERBOSE = False  # the reference prints the whole tree on every update (utiles.py:491-504)
+CAPTION_TOKENS = 128   # max_new_tokens of the per-chunk caption (utiles.py:555)
+SUMMARY_TOKENS = 256   # max_new_tokens of the merge summary (utiles.py:604)
 
 
 class MultimodalTreeNode:
@@ -120,7 +122,7 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
             output_ids = summarizer.generate_with_image_embedding(
                 input_ids.to(summarizer.device), image_embeddings=[chunk_feature], modalities=["video"],
                 do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
-                max_new_tokens=128, use_cache=False)
+                max_new_tokens=CAPTION_TOKENS, use_cache=False)
         output_list.append(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip())
 
     nodes = [MultimodalTreeNode(t, text, depth=0) for (t, text) in zip(k_means_chunk_feature_list, output_list)]
@@ -151,7 +153,7 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
             output_ids = summarizer.generate_with_image_embedding(
                 summarize_ids.to(summarizer.device), image_embeddings=None, modalities=["video"],
                 do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
-                max_new_tokens=256, use_cache=False)
+                max_new_tokens=SUMMARY_TOKENS, use_cache=False)
         summarize_text = tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip()
         new_node = MultimodalTreeNode(new_centroids, summarize_text, depth=chunk[0].depth + 1)
         for node in chunk:

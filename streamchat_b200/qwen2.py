@@ -85,6 +85,8 @@ class Qwen2Engine:
         self._gu = torch.zeros((1, 2 * c.intermediate_size), dtype=torch.float16, device=self.device)
         self._logits = torch.zeros((1, c.vocab_size), dtype=torch.float16, device=self.device)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_replays = 0
+        self.profile: Optional[list] = None   # bench.py: (start event, end event, steps, bytes) per decode loop
 
     # ---------------------------------------------------------------- weights / work accounting
     def weight_bytes(self) -> int:
@@ -210,6 +212,11 @@ class Qwen2Engine:
             else:
                 self.next_id.copy_(self._sample(logits, temperature, top_k, top_p))
             n_done = 0
+            ev0 = ev1 = None
+            replays0 = self.graph_replays
+            if self.profile is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             for step in range(max_new_tokens):
                 out[step:step + 1].copy_(self.next_id, non_blocking=True)
                 n_done = step + 1
@@ -223,6 +230,7 @@ class Qwen2Engine:
                 if greedy:
                     if use_graph:
                         self._graph.replay()
+                        self.graph_replays += 1
                     else:
                         self._decode_step_launches()
                 else:
@@ -231,6 +239,11 @@ class Qwen2Engine:
                     self._decode_step_launches()
                     self.next_id.copy_(self._sample(self._logits, temperature, top_k, top_p))
                     self.state.copy_(saved + 1)
+            if ev0 is not None:
+                ev1.record()
+                n_rep = self.graph_replays - replays0
+                self.profile.append({"events": (ev0, ev1), "steps": n_rep,
+                                     "bytes": n_rep * self.decode_bytes_per_token(T + n_rep // 2)})
             if eos:
                 toks = out[:n_done].tolist()
                 for j, t in enumerate(toks):

@@ -44,7 +44,9 @@ class StreamConfig:
 
 class HashTextEmbedder:
     """Synthetic stand-in for the BERT-large CLS embedder (mxbai-colbert-large-v1, 1024-d;
-    utiles.py:704-708) when no weights exist: a deterministic unit-variance vector per text.
+    utiles.py:704-708) when no weights exist: a deterministic vector per text with a common positive
+    component (sentence embeddings of related captions correlate positively; the reference's search
+    raises when no child has a positive similarity, utiles.py:746).
     Callable as `model(tokenizer, text)` — see memory.embed_text."""
 
     def __init__(self, dim: int = 1024, device="cuda:0"):
@@ -54,7 +56,7 @@ class HashTextEmbedder:
     def __call__(self, tokenizer, text: str) -> torch.Tensor:
         seed = int.from_bytes(hashlib.sha256(text.encode("utf-8")).digest()[:7], "little")
         g = torch.Generator(device=self.device).manual_seed(seed)
-        return torch.randn(self.dim, generator=g, device=self.device, dtype=torch.float32)
+        return torch.randn(self.dim, generator=g, device=self.device, dtype=torch.float32) + 1.0
 
 
 class StreamingSession:

@@ -261,12 +261,21 @@ typedef struct scb_gemv_args {
   void* out;              /* [rows, ldo] */
   int64_t n, k;
   int64_t lda, ldw, ldr, ldo;
-  int32_t rows;           /* 1, 2 or 4 */
+  int32_t rows;           /* 1..8 (k % 32 == 0), else 1, 2 or 4 */
   int32_t prologue;       /* scb_gemv_prologue */
   int32_t out_dtype;      /* scb_dtype */
   float eps;
+  /* optional fused greedy choice (lm_head): argmax_out[r] = arg-max over n of the STORED output
+   * row r (lowest index wins ties), then counters[0..n_counters) += 1.  Needs the workspace. */
+  int64_t* argmax_out;
+  int32_t* counters;
+  int32_t n_counters;
+  int32_t _pad;
+  void* workspace;
+  size_t workspace_bytes;
 } scb_gemv_args;
 
+size_t scb_gemv_workspace_bytes(int32_t rows);
 int scb_gemv(const scb_gemv_args* a, void* stream);
 
 typedef struct scb_decode_attention_args {
@@ -286,6 +295,30 @@ typedef struct scb_decode_attention_args {
 
 size_t scb_decode_attention_workspace_bytes(int32_t n_q_heads, int32_t head_dim, int32_t n_splits);
 int scb_decode_attention(const scb_decode_attention_args* a, void* stream);
+
+/* One launch for the attention block of a decode step: RoPE of the new q/k (same rounding as
+ * scb_rope_append), append of k/v at position kv_len-1, split-KV attention for every q head and
+ * the cross-split combine.  qkv is ONE fused row [n_q*hd | n_kv*hd | n_kv*hd] (un-rotated);
+ * *kv_len_dev is the context length INCLUDING the token being decoded.  The first 256 bytes of
+ * the workspace hold the tickets and must be zero before the first call (they are left zero). */
+typedef struct scb_decode_attention_fused_args {
+  const void* qkv;
+  const float* inv_freq;     /* [head_dim/2] fp32 or NULL -> theta^(-2i/hd) */
+  void* k_cache;             /* [n_kv_heads, max_pos, head_dim] fp16 */
+  void* v_cache;
+  void* out;                 /* [n_q_heads, head_dim] fp16 */
+  const int32_t* kv_len_dev;
+  int64_t max_pos;
+  int32_t n_q_heads, n_kv_heads, head_dim, n_splits;
+  float scale;
+  float theta;
+  void* workspace;
+  size_t workspace_bytes;
+} scb_decode_attention_fused_args;
+
+size_t scb_decode_attention_fused_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads,
+                                                  int32_t head_dim, int32_t n_splits);
+int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream);
 
 #ifdef __cplusplus
 }

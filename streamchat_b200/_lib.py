@@ -76,6 +76,8 @@ class GemvArgs(C.Structure):
         ("n", C.c_int64), ("k", C.c_int64),
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo", C.c_int64),
         ("rows", C.c_int32), ("prologue", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float),
+        ("argmax_out", C.c_void_p), ("counters", C.c_void_p), ("n_counters", C.c_int32), ("_pad", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -85,6 +87,16 @@ class DecodeAttentionArgs(C.Structure):
         ("kv_len_dev", C.c_void_p), ("max_pos", C.c_int64), ("kv_len", C.c_int32),
         ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32),
         ("n_splits", C.c_int32), ("scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class DecodeAttentionFusedArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("inv_freq", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
+        ("out", C.c_void_p), ("kv_len_dev", C.c_void_p), ("max_pos", C.c_int64),
+        ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("n_splits", C.c_int32),
+        ("scale", C.c_float), ("theta", C.c_float),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -105,8 +117,11 @@ SYMBOLS = {
     "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "scb_attention": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "scb_gemv": (C.c_int, [C.POINTER(GemvArgs), C.c_void_p]),
+    "scb_gemv_workspace_bytes": (C.c_size_t, [_i32]),
     "scb_decode_attention_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "scb_decode_attention": (C.c_int, [C.POINTER(DecodeAttentionArgs), C.c_void_p]),
+    "scb_decode_attention_fused_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32]),
+    "scb_decode_attention_fused": (C.c_int, [C.POINTER(DecodeAttentionFusedArgs), C.c_void_p]),
     "scb_im2col_patch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp]),
     "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
     "scb_rmsnorm": (C.c_int, [_vp, _i64, _vp, _f, _i64, _i32, _vp, _i64, _vp]),

@@ -159,6 +159,258 @@ gemv_kernel(const GemvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// gemv_mma_kernel — the decode linear layer for 1..8 activation rows as a streaming kernel that
+// uses the warp-level tensor-core MMA (m16n8k16, fp16 in / fp32 accumulate) purely as a
+// dot-product engine: the kernel is HBM-bound, the point of the MMA is that the k-reduction
+// happens inside the instruction (no shuffle tree) and that 1..8 activation rows cost the same.
+//
+//   block  = W warps working on one group of 8 weight rows at a time (grid-stride over groups);
+//            the K range is split evenly over the W warps, partial sums meet in shared memory in
+//            a fixed order (deterministic).
+//   lane   (g = lane/4, t = lane%4) loads 16 B of weight row n0+g at k = tile*32 + t*8: a warp
+//            load covers 8 rows x 64 contiguous bytes (full 32-byte sectors).  The 8 halfs feed two
+//            MMAs as the B fragment; the matching A fragment is ONE 16-byte shared-memory read of
+//            activation row g at the same k offset (rows g >= R read as zero; MMA rows 8..15 are
+//            zero registers), i.e. the logical k order inside an MMA is a fixed permutation of the
+//            physical one, identical for A and B.
+//   loads  U = 8 tiles (4 KB per warp) are issued before the previous group is consumed; the
+//            first group is requested BEFORE the activation prologue, so the RMSNorm / SiLU-gate
+//            staging overlaps the weight stream.
+//   lm_head: optional fused arg-max (block-local best, last block reduces; lowest index wins).
+// ------------------------------------------------------------------------------------------
+constexpr int kMU = 8;             // k-tiles (32 halfs each) in flight per warp
+constexpr int kMaxMmaWarps = 16;
+
+SCB_DEVICE void mma16816(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of A are zero (a1 = a3 = 0)
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+
+struct ArgmaxFuse {
+  float* blk_val;          // [gridDim.x * R]
+  int* blk_idx;            // [gridDim.x * R]
+  unsigned* ticket;        // [1], zero on entry, reset on exit
+  long long* out_ids;      // [R]
+  int* counters;           // optional device ints to increment (graph bookkeeping)
+  int n_counters;
+};
+
+template <int PRO>
+__global__ void __launch_bounds__(kMaxMmaWarps * 32)
+gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int K = p.K;
+  const int lds = K + 32;                                   // row stride (halfs): +64 B breaks bank aliasing
+  __half* a_s = reinterpret_cast<__half*>(gsm);             // [R][lds]
+  float* red = reinterpret_cast<float*>(gsm + (size_t)R * lds * sizeof(__half));   // [W][8][8]
+  __shared__ float sred[kMaxMmaWarps];
+  __shared__ unsigned last_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_groups = (p.N + 7) >> 3;
+  const int ktiles = K >> 5;
+  const int tiles_per_warp = (ktiles + W - 1) / W;
+  const int kt_begin = warp * tiles_per_warp;
+  const int kt_end = min(ktiles, kt_begin + tiles_per_warp);
+  const int steps_per_group = (tiles_per_warp + kMU - 1) / kMU;
+
+  // flattened iteration space of this warp: (group, step) with step covering kMU k-tiles
+  int grp = blockIdx.x;
+  int step = 0;
+  auto issue = [&](uint4 (&w)[kMU], int gq, int sq) {
+    const int row = gq * 8 + g;
+    const bool row_ok = gq < n_groups && row < p.N;
+    const __half* wr = p.w + (long long)row * p.ldw + t * 8;
+#pragma unroll
+    for (int u = 0; u < kMU; ++u) {
+      const int kt = kt_begin + sq * kMU + u;
+      w[u] = (row_ok && kt < kt_end) ? ld_stream_u4(wr + kt * 32) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 cur[kMU], nxt[kMU];
+  issue(cur, grp, 0);   // weights do not depend on the previous kernel: request them first
+
+  // ---- prologue: stage (and transform) the activation rows as fp16 values
+  for (int r = 0; r < R; ++r) {
+    const __half* ar = p.a + (long long)r * p.lda;
+    __half* dst = a_s + r * lds;
+    if constexpr (PRO == PRO_RMSNORM) {
+      float ss = 0.f;
+      for (int i = tid; i < (K >> 3); i += blockDim.x) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+      }
+      ss = warp_sum(ss);
+      __syncthreads();
+      if (lane == 0) sred[warp] = ss;
+      __syncthreads();
+      float tot = 0.f;
+      for (int w = 0; w < W; ++w) tot += sred[w];
+      const float rstd = rsqrtf(tot / (float)K + p.eps);
+      for (int i = tid; i < (K >> 3); i += blockDim.x) {
+        float f[8], gm[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
+        unpack8(*reinterpret_cast<const uint4*>(p.gamma + i * 8), gm);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(f[e] * rstd)) * gm[e];
+        uint4 q;
+        q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
+        q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dst + i * 8) = q;
+      }
+    } else if constexpr (PRO == PRO_SILU_MUL) {
+      for (int i = tid; i < (K >> 3); i += blockDim.x) {
+        float gg[8], uu[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), gg);
+        unpack8(*reinterpret_cast<const uint4*>(ar + K + i * 8), uu);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          o[e] = __half2float(__float2half_rn(gg[e] / (1.f + __expf(-gg[e])))) * uu[e];
+        uint4 q;
+        q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
+        q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dst + i * 8) = q;
+      }
+    } else {
+      for (int i = tid; i < (K >> 3); i += blockDim.x)
+        *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(ar + i * 8);
+    }
+  }
+  __syncthreads();
+
+  const bool a_ok = g < R;
+  const __half* a_row = a_s + (a_ok ? g : 0) * lds + t * 8;
+  float best_v[8];
+  int best_i[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    best_v[r] = -INFINITY;
+    best_i[r] = 0x7fffffff;
+  }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  while (grp < n_groups) {
+    // next (group, step) of this warp
+    int ngrp = grp, nstep = step + 1;
+    if (nstep == steps_per_group) {
+      nstep = 0;
+      ngrp = grp + gridDim.x;
+    }
+    issue(nxt, ngrp, nstep);
+#pragma unroll
+    for (int u = 0; u < kMU; ++u) {
+      const int kt = kt_begin + step * kMU + u;
+      uint4 av = make_uint4(0, 0, 0, 0);
+      if (a_ok && kt < kt_end) av = *reinterpret_cast<const uint4*>(a_row + kt * 32);
+      mma16816(acc, av.x, av.y, cur[u].x, cur[u].y);
+      mma16816(acc, av.z, av.w, cur[u].z, cur[u].w);
+    }
+    if (nstep == 0) {
+      // ---- group finished for this warp: combine the K splits in warp order, epilogue
+      // acc[0], acc[1] = out[row r = g][n = grp*8 + t*2 + {0,1}]
+      red[(warp * 8 + g) * 8 + t * 2] = acc[0];
+      red[(warp * 8 + g) * 8 + t * 2 + 1] = acc[1];
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      __syncthreads();
+      if (tid < R * 8) {
+        const int r = tid >> 3, j = tid & 7;
+        const int n = grp * 8 + j;
+        if (n < p.N) {
+          float v = 0.f;
+          for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
+          if (p.bias) v += __half2float(p.bias[n]);
+          if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
+          if (p.out_f32) {
+            reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + n] = v;
+          } else {
+            const __half hv = __float2half_rn(v);
+            reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + n] = hv;
+            v = __half2float(hv);          // arg-max sees the stored (rounded) logits
+          }
+          if (am.out_ids) {
+            // threads r*8 .. r*8+7 hold 8 consecutive n of row r: keep the first maximum
+            if (v > best_v[0] || (v == best_v[0] && n < best_i[0])) {
+              best_v[0] = v;
+              best_i[0] = n;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < kMU; ++u) cur[u] = nxt[u];
+    grp = ngrp;
+    step = nstep;
+  }
+
+  if (am.out_ids) {
+    // ---- fused arg-max: thread (r, j) holds the best over its column residue; reduce the 8
+    // threads of each row, publish per block, the last block reduces the blocks
+    float bv = best_v[0];
+    int bi = best_i[0];
+    if (tid < 64) {   // R <= 8 rows x 8 threads, aligned groups of 8 lanes
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (tid < R * 8 && (tid & 7) == 0) {
+        am.blk_val[(long long)blockIdx.x * R + (tid >> 3)] = bv;
+        am.blk_idx[(long long)blockIdx.x * R + (tid >> 3)] = bi;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned tk = atomicAdd(am.ticket, 1u);
+      last_flag = (tk == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last_flag) {
+      __threadfence();
+      // warp r (strided) reduces row r over all blocks
+      for (int row = warp; row < R; row += W) {
+        float v = -INFINITY;
+        int ix = 0x7fffffff;
+        for (int b = lane; b < (int)gridDim.x; b += 32) {
+          const float ov = __ldcg(am.blk_val + (long long)b * R + row);
+          const int oi = __ldcg(am.blk_idx + (long long)b * R + row);
+          if (ov > v || (ov == v && oi < ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
+          if (ov > v || (ov == v && oi < ix)) {
+            v = ov;
+            ix = oi;
+          }
+        }
+        if (lane == 0) am.out_ids[row] = ix;
+      }
+      if (tid == 0) {
+        *am.ticket = 0;
+        for (int c = 0; c < am.n_counters; ++c) am.counters[c] += 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // decode attention
 // ------------------------------------------------------------------------------------------
 constexpr int kDAThreads = 256;
@@ -278,6 +530,187 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ part_m,
   out[(long long)h * HD + d] = __float2half_rn(ll > 0.f ? oo / ll : 0.f);
 }
 
+// ------------------------------------------------------------------------------------------
+// decode_attn_fused_kernel — one launch per layer for the whole attention block of a decode step:
+// RoPE of the new q and k (same fp16 rounding as rope_append_kernel), append of k/v to the cache,
+// split-KV attention for all q heads of a kv group, and the cross-split combine by the last
+// block of each kv head (atomic ticket).  Context length comes from device memory.
+//   phase 1  thread = cached position: dot of the 256-byte K row with the G rotated q rows
+//            (shared-memory broadcast reads), scores to shared memory        -> reads K once
+//   phase 2  warp = q head: max / exp2 / sum over the block's positions
+//   phase 3  thread = (dim, position half): P·V with coalesced V reads        -> reads V once
+// ------------------------------------------------------------------------------------------
+template <int HD, int G>
+__global__ void __launch_bounds__(256)
+decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict__ inv_freq,
+                         float theta, __half* __restrict__ k_cache, __half* __restrict__ v_cache,
+                         long long max_pos, const int* __restrict__ len_dev, float scale_log2,
+                         int n_q, int n_kv, int per_max, float* __restrict__ part_m,
+                         float* __restrict__ part_l, float* __restrict__ part_o,
+                         unsigned* __restrict__ tickets, __half* __restrict__ out) {
+  constexpr int HALF = HD / 2;
+  extern __shared__ __align__(16) float dsm[];
+  float* q_s = dsm;                 // [G][HD] rotated q, pre-scaled by scale*log2(e)
+  float* s_s = dsm + G * HD;        // [G][per_max] scores -> probabilities
+  __shared__ float m_s[G], l_s[G];
+  __shared__ float o_s[2][G][HD];
+  __shared__ unsigned last_flag;
+  const int hk = blockIdx.x, split = blockIdx.y, n_splits = gridDim.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kv_len = *len_dev;
+  const int pos = kv_len - 1;       // position of the token being decoded
+  const int per = (kv_len + n_splits - 1) / n_splits;
+  const int begin = split * per, end = min(kv_len, begin + per);
+  const int n_local = max(0, end - begin);
+
+  // ---- RoPE of this group's q rows (every block recomputes: G*HD/2 pairs)
+  for (int idx = tid; idx < G * HALF; idx += 256) {
+    const int h = idx / HALF, i = idx % HALF;
+    const float f = inv_freq ? inv_freq[i] : powf(theta, -(float)(2 * i) / (float)HD);
+    const float ang = (float)pos * f;
+    const float c = __half2float(__float2half_rn(cosf(ang))), sn = __half2float(__float2half_rn(sinf(ang)));
+    const __half* qp = qkv + (long long)(hk * G + h) * HD;
+    const float x1 = __half2float(qp[i]), x2 = __half2float(qp[i + HALF]);
+    const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
+    const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
+    q_s[h * HD + i] = __half2float(__float2half_rn(a1 + b1)) * scale_log2;
+    q_s[h * HD + i + HALF] = __half2float(__float2half_rn(a2 + b2)) * scale_log2;
+  }
+  // ---- the block that owns `pos` rotates and appends the new k, copies the new v
+  if (pos >= begin && pos < end) {
+    const __half* kp = qkv + (long long)(n_q + hk) * HD;
+    const __half* vp = qkv + (long long)(n_q + n_kv + hk) * HD;
+    __half* kc = k_cache + ((long long)hk * max_pos + pos) * HD;
+    __half* vc = v_cache + ((long long)hk * max_pos + pos) * HD;
+    for (int i = tid; i < HALF; i += 256) {
+      const float f = inv_freq ? inv_freq[i] : powf(theta, -(float)(2 * i) / (float)HD);
+      const float ang = (float)pos * f;
+      const float c = __half2float(__float2half_rn(cosf(ang))), sn = __half2float(__float2half_rn(sinf(ang)));
+      const float x1 = __half2float(kp[i]), x2 = __half2float(kp[i + HALF]);
+      const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
+      const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
+      kc[i] = __float2half_rn(a1 + b1);
+      kc[i + HALF] = __float2half_rn(a2 + b2);
+    }
+    for (int i = tid; i < HD; i += 256) vc[i] = vp[i];
+  }
+  __syncthreads();   // q_s ready; the appended row is visible to this block
+
+  // ---- phase 1: scores
+  const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD;
+  for (int pl = tid; pl < n_local; pl += 256) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)pl * HD);
+    float sc[G];
+#pragma unroll
+    for (int h = 0; h < G; ++h) sc[h] = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < HD / 32; ++c4) {
+      uint4 kv4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) kv4[u] = kr[c4 * 4 + u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float kf[8];
+        unpack8(kv4[u], kf);
+        const int d0 = (c4 * 4 + u) * 8;
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+          const float4 qa = *reinterpret_cast<const float4*>(q_s + h * HD + d0);
+          const float4 qb = *reinterpret_cast<const float4*>(q_s + h * HD + d0 + 4);
+          sc[h] = fmaf(kf[0], qa.x, sc[h]); sc[h] = fmaf(kf[1], qa.y, sc[h]);
+          sc[h] = fmaf(kf[2], qa.z, sc[h]); sc[h] = fmaf(kf[3], qa.w, sc[h]);
+          sc[h] = fmaf(kf[4], qb.x, sc[h]); sc[h] = fmaf(kf[5], qb.y, sc[h]);
+          sc[h] = fmaf(kf[6], qb.z, sc[h]); sc[h] = fmaf(kf[7], qb.w, sc[h]);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < G; ++h) s_s[h * per_max + pl] = sc[h];
+  }
+  __syncthreads();
+
+  // ---- phase 2: per-head softmax statistics (warp h)
+  if (warp < G) {
+    float mx = -INFINITY;
+    for (int pl = lane; pl < n_local; pl += 32) mx = fmaxf(mx, s_s[warp * per_max + pl]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int pl = lane; pl < n_local; pl += 32) {
+      const float e = exp2f(s_s[warp * per_max + pl] - mx);
+      s_s[warp * per_max + pl] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      m_s[warp] = mx;
+      l_s[warp] = sum;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: P·V, thread = (dim, position parity group)
+  {
+    constexpr int NG = 256 / HD;          // position groups (2 for HD=128, 4 for HD=64)
+    const int d = tid % HD, pg = tid / HD;
+    const __half* vb = v_cache + ((long long)hk * max_pos + begin) * HD + d;
+    float acc[G];
+#pragma unroll
+    for (int h = 0; h < G; ++h) acc[h] = 0.f;
+    for (int pl = pg; pl < n_local; pl += NG) {
+      const float v = __half2float(vb[(long long)pl * HD]);
+#pragma unroll
+      for (int h = 0; h < G; ++h) acc[h] = fmaf(s_s[h * per_max + pl], v, acc[h]);
+    }
+    // merge the position groups through o_s (fixed order)
+    static_assert(HD == 128 || HD == 64, "head_dim");
+    float* o_flat = &o_s[0][0][0];        // reuse as [NG][G][HD] (NG*G*HD <= 2*G*128)
+#pragma unroll
+    for (int h = 0; h < G; ++h) o_flat[(pg * G + h) * HD + d] = acc[h];
+  }
+  __syncthreads();
+  {
+    constexpr int NG = 256 / HD;
+    const float* o_flat = &o_s[0][0][0];
+    for (int idx = tid; idx < G * HD; idx += 256) {
+      const int h = idx / HD, d = idx % HD;
+      float v = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < NG; ++g2) v += o_flat[(g2 * G + h) * HD + d];
+      const long long pi = (long long)(hk * G + h) * n_splits + split;
+      part_o[pi * HD + d] = v;
+      if (d == 0) {
+        part_m[pi] = m_s[h];
+        part_l[pi] = l_s[h];
+      }
+    }
+  }
+  // ---- last block of this kv head combines the splits
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned tk = atomicAdd(&tickets[hk], 1u);
+    last_flag = (tk == (unsigned)n_splits - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!last_flag) return;
+  __threadfence();
+  for (int idx = tid; idx < G * HD; idx += 256) {
+    const int h = idx / HD, d = idx % HD;
+    const long long base = (long long)(hk * G + h) * n_splits;
+    float mm = -INFINITY;
+    for (int sp = 0; sp < n_splits; ++sp) mm = fmaxf(mm, __ldcg(part_m + base + sp));
+    float ll = 0.f, oo = 0.f;
+    for (int sp = 0; sp < n_splits; ++sp) {
+      const float pm = __ldcg(part_m + base + sp);
+      const float scl = (pm == -INFINITY) ? 0.f : exp2f(pm - mm);
+      ll = fmaf(__ldcg(part_l + base + sp), scl, ll);
+      oo = fmaf(__ldcg(part_o + (base + sp) * HD + d), scl, oo);
+    }
+    out[(long long)(hk * G + h) * HD + d] = __float2half_rn(ll > 0.f ? oo / ll : 0.f);
+  }
+  if (tid == 0) tickets[hk] = 0;
+}
+
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int R>
@@ -302,11 +735,17 @@ int launch_gemv(const GemvParams& p, int prologue, int grid, size_t smem, cudaSt
 
 extern "C" {
 
+size_t scb_gemv_workspace_bytes(int32_t rows) {
+  if (rows < 1 || rows > 8) return 0;
+  // fused arg-max scratch: ticket + per-block (value, index) for up to 2048 blocks
+  return 256 + (size_t)2048 * rows * (sizeof(float) + sizeof(int));
+}
+
 int scb_gemv(const scb_gemv_args* a, void* stream) {
   SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_gemv: args is NULL");
   SCB_REQUIRE(a->a && a->w && a->out, SCB_ERR_INVALID_ARG, "scb_gemv: NULL buffer");
-  SCB_REQUIRE(a->rows == 1 || a->rows == 2 || a->rows == 4, SCB_ERR_UNSUPPORTED,
-              "scb_gemv: rows=%d (1, 2 or 4; larger batches use scb_linear)", a->rows);
+  SCB_REQUIRE(a->rows >= 1 && a->rows <= 8, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: rows=%d (1..8; larger batches use scb_linear)", a->rows);
   SCB_REQUIRE(a->n >= 1 && a->k >= 8 && a->k % 8 == 0, SCB_ERR_INVALID_ARG,
               "scb_gemv: n=%lld k=%lld (k must be a multiple of 8)", (long long)a->n, (long long)a->k);
   SCB_REQUIRE(a->prologue >= PRO_NONE && a->prologue <= PRO_SILU_MUL, SCB_ERR_UNSUPPORTED,
@@ -320,9 +759,6 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   SCB_REQUIRE(al16(a->a) && al16(a->w) && (!a->gamma || al16(a->gamma)), SCB_ERR_INVALID_ARG,
               "scb_gemv: a / w / gamma must be 16-byte aligned");
   SCB_REQUIRE(!a->residual || a->ldr >= a->n, SCB_ERR_INVALID_ARG, "scb_gemv: ldr too small");
-  const size_t smem = (size_t)a->rows * a->k * sizeof(__half);
-  SCB_REQUIRE(smem <= 200 * 1024, SCB_ERR_UNSUPPORTED,
-              "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
   GemvParams p;
   p.a = reinterpret_cast<const __half*>(a->a);
   p.w = reinterpret_cast<const __half*>(a->w);
@@ -334,15 +770,68 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   p.N = (int)a->n; p.K = (int)a->k;
   p.out_f32 = a->out_dtype == SCB_F32;
   p.eps = a->eps;
-  // resident blocks per SM are bounded by the staged activations; aim for >= 32 warps per SM
   const int sms = scb_num_sms();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  if (a->k % 32 == 0) {
+    // ---- tensor-core streaming path
+    ArgmaxFuse am{};
+    if (a->argmax_out) {
+      const size_t need = scb_gemv_workspace_bytes(a->rows);
+      SCB_REQUIRE(a->workspace && a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
+                  "scb_gemv: fused arg-max needs a %zu B workspace", need);
+      SCB_REQUIRE(!p.out_f32 || true, SCB_ERR_INVALID_ARG, "unreachable");
+      char* ws = reinterpret_cast<char*>(a->workspace);
+      am.ticket = reinterpret_cast<unsigned*>(ws);
+      am.blk_val = reinterpret_cast<float*>(ws + 256);
+      am.blk_idx = reinterpret_cast<int*>(ws + 256 + (size_t)2048 * a->rows * sizeof(float));
+      am.out_ids = reinterpret_cast<long long*>(a->argmax_out);
+      am.counters = a->counters;
+      am.n_counters = a->counters ? a->n_counters : 0;
+    }
+    const size_t act = (size_t)a->rows * (a->k + 32) * sizeof(__half);
+    SCB_REQUIRE(act + kMaxMmaWarps * 256 <= 220 * 1024, SCB_ERR_UNSUPPORTED,
+                "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
+    int per_sm = (int)((220 * 1024) / (act + 4096 + 1024));
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int W = (16 + per_sm - 1) / per_sm;       // >= 16 warps (64 KB of loads in flight) per SM
+    W = W <= 4 ? 4 : (W <= 8 ? 8 : 16);
+    const size_t smem = act + (size_t)W * 256;
+    const long long n_groups = (a->n + 7) / 8;
+    long long cap = (long long)sms * per_sm;
+    if (cap > 2048) cap = 2048;
+    const int grid = (int)(n_groups < cap ? n_groups : cap);
+    if (a->argmax_out) SCB_CUDA_OK(cudaMemsetAsync(am.ticket, 0, sizeof(unsigned), st));
+#define SCB_GEMV_MMA(PRO)                                                                        \
+  do {                                                                                           \
+    auto kern = gemv_mma_kernel<PRO>;                                                            \
+    if (smem > 48 * 1024)                                                                        \
+      SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                       (int)smem));                                              \
+    kern<<<grid, W * 32, smem, st>>>(p, a->rows, am);                                            \
+  } while (0)
+    if (a->prologue == PRO_RMSNORM) SCB_GEMV_MMA(PRO_RMSNORM);
+    else if (a->prologue == PRO_SILU_MUL) SCB_GEMV_MMA(PRO_SILU_MUL);
+    else SCB_GEMV_MMA(PRO_NONE);
+#undef SCB_GEMV_MMA
+    SCB_LAUNCH_OK("gemv_mma_kernel");
+    return SCB_OK;
+  }
+
+  // ---- SIMT path for k not a multiple of 32
+  SCB_REQUIRE(a->rows == 1 || a->rows == 2 || a->rows == 4, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: k %% 32 != 0 supports rows 1, 2 or 4 only");
+  SCB_REQUIRE(!a->argmax_out, SCB_ERR_UNSUPPORTED, "scb_gemv: fused arg-max needs k %% 32 == 0");
+  const size_t smem = (size_t)a->rows * a->k * sizeof(__half);
+  SCB_REQUIRE(smem <= 200 * 1024, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   long long want = ((long long)a->n + kGemvWarps - 1) / kGemvWarps;
   long long cap = (long long)sms * per_sm;
   int grid = (int)(want < cap ? want : cap);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->rows == 1) return launch_gemv<1>(p, a->prologue, grid, smem, st);
   if (a->rows == 2) return launch_gemv<2>(p, a->prologue, grid, smem, st);
   return launch_gemv<4>(p, a->prologue, grid, smem, st);
@@ -409,6 +898,77 @@ int scb_decode_attention(const scb_decode_attention_args* a, void* stream) {
     decode_attn_combine_kernel<64><<<a->n_q_heads, 64, 0, st>>>(
         part_m, part_l, part_o, a->n_splits, reinterpret_cast<__half*>(a->out));
   SCB_LAUNCH_OK("decode_attn_combine_kernel");
+  return SCB_OK;
+}
+
+
+size_t scb_decode_attention_fused_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads,
+                                                  int32_t head_dim, int32_t n_splits) {
+  if (n_q_heads < 1 || n_kv_heads < 1 || head_dim < 1 || n_splits < 1) return 0;
+  return 256 + sizeof(float) * (size_t)n_q_heads * n_splits * (head_dim + 2);
+}
+
+int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_decode_attention_fused: args is NULL");
+  SCB_REQUIRE(a->qkv && a->k_cache && a->v_cache && a->out && a->workspace && a->kv_len_dev,
+              SCB_ERR_INVALID_ARG, "scb_decode_attention_fused: NULL buffer");
+  SCB_REQUIRE(a->head_dim == 128 || a->head_dim == 64, SCB_ERR_UNSUPPORTED,
+              "scb_decode_attention_fused: head_dim=%d (64 or 128)", a->head_dim);
+  SCB_REQUIRE(a->n_kv_heads >= 1 && a->n_kv_heads <= 64 && a->n_q_heads % a->n_kv_heads == 0,
+              SCB_ERR_INVALID_ARG, "scb_decode_attention_fused: bad head counts");
+  const int G = a->n_q_heads / a->n_kv_heads;
+  SCB_REQUIRE(G == 1 || G == 2 || G == 4 || G == 7 || G == 8, SCB_ERR_UNSUPPORTED,
+              "scb_decode_attention_fused: group size %d unsupported (1,2,4,7,8)", G);
+  SCB_REQUIRE(a->n_splits >= 1 && a->n_splits <= 1024, SCB_ERR_INVALID_ARG,
+              "scb_decode_attention_fused: n_splits out of range");
+  const size_t need = scb_decode_attention_fused_workspace_bytes(a->n_q_heads, a->n_kv_heads,
+                                                                 a->head_dim, a->n_splits);
+  SCB_REQUIRE(a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
+              "scb_decode_attention_fused: workspace %zu B < %zu B", a->workspace_bytes, need);
+  char* ws = reinterpret_cast<char*>(a->workspace);
+  unsigned* tickets = reinterpret_cast<unsigned*>(ws);   // zeroed by scb_decode_attention_fused_init
+  float* part_m = reinterpret_cast<float*>(ws + 256);
+  float* part_l = part_m + (size_t)a->n_q_heads * a->n_splits;
+  float* part_o = part_l + (size_t)a->n_q_heads * a->n_splits;
+  const int per_max = (int)((a->max_pos + a->n_splits - 1) / a->n_splits);
+  const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_max);
+  SCB_REQUIRE(smem <= 160 * 1024, SCB_ERR_UNSUPPORTED,
+              "scb_decode_attention_fused: max_pos/n_splits too large for shared memory");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(a->n_kv_heads, a->n_splits);
+  const float sl2 = a->scale * 1.4426950408889634f;
+#define SCB_DAF(HD, GG)                                                                           \
+  do {                                                                                            \
+    auto kern = decode_attn_fused_kernel<HD, GG>;                                                 \
+    if (smem > 48 * 1024)                                                                         \
+      SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       (int)smem));                                               \
+    kern<<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(a->qkv), a->inv_freq, a->theta, \
+                                  reinterpret_cast<__half*>(a->k_cache),                          \
+                                  reinterpret_cast<__half*>(a->v_cache), a->max_pos,              \
+                                  a->kv_len_dev, sl2, a->n_q_heads, a->n_kv_heads, per_max,       \
+                                  part_m, part_l, part_o, tickets,                                \
+                                  reinterpret_cast<__half*>(a->out));                             \
+  } while (0)
+  if (a->head_dim == 128) {
+    switch (G) {
+      case 1: SCB_DAF(128, 1); break;
+      case 2: SCB_DAF(128, 2); break;
+      case 4: SCB_DAF(128, 4); break;
+      case 7: SCB_DAF(128, 7); break;
+      default: SCB_DAF(128, 8); break;
+    }
+  } else {
+    switch (G) {
+      case 1: SCB_DAF(64, 1); break;
+      case 2: SCB_DAF(64, 2); break;
+      case 4: SCB_DAF(64, 4); break;
+      case 7: SCB_DAF(64, 7); break;
+      default: SCB_DAF(64, 8); break;
+    }
+  }
+#undef SCB_DAF
+  SCB_LAUNCH_OK("decode_attn_fused_kernel");
   return SCB_OK;
 }
 

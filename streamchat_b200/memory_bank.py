@@ -1,0 +1,259 @@
+"""Dialogue-history retrieval (row a-R2) on the sm_100a cosine_topk kernel.
+
+Mirrors the surface the streaming driver uses from the reference's memory_bank package:
+  LocalMemoryRetrieval        memory_bank/memory_retrieval/local_doc_qa.py:180-288
+    .init_cfg / .init_memory_vector_store / .load_memory_index / .search_memory
+  neighbour expansion         local_doc_qa.py:135-178 (patched similarity_search_with_score_by_vector)
+  JsonMemoryLoader.load       local_doc_qa.py:17-61
+  enter_name / save_local_memory   memory_bank/memory_utils.py:61-109
+  only_related_prompt_dict_ego     memory_bank/prompt_utils.py:37-44
+  build_prompt_with_search_memory_only_related   utiles.py:1057-1078
+
+The reference stacks langchain 0.0.142 FAISS (IndexFlatL2) over HuggingFaceEmbeddings (MiniLM-L6,
+mean-pool + L2-normalise).  On unit vectors the L2 ranking equals the cosine ranking, so one
+cosine_topk launch over the device-resident [n_turns, d] embedding matrix replaces the FAISS
+search; the reported score is converted back to FAISS's squared L2 (2 - 2 cos).  The index is a
+tensor in HBM plus the Python doc list — no on-disk FAISS files; `vs_path` keeps its role as the
+cache key so the driver's rmtree/rebuild dance (memory_utils.py:76-83) still works.
+"""
+from __future__ import annotations
+
+import datetime
+import json
+import os
+import shutil
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+VECTOR_SEARCH_TOP_K = 3     # local_doc_qa.py:15
+CHUNK_SIZE = 200            # configs/model_config.py:51
+
+embedding_model_dict = {"minilm-l6": "sentence-transformers/all-MiniLM-L6-v2"}   # configs/model_config.py:5-18
+
+
+@dataclass
+class Document:
+    page_content: str
+    metadata: Dict[str, object] = field(default_factory=dict)
+
+
+def load_memory_file(filepath: str, user_name: str, language: str = "cn") -> List[Document]:
+    """One Document per dialogue turn (+ one per daily summary), local_doc_qa.py:24-61."""
+    with open(filepath, "r", encoding="utf-8") as f:
+        memories = json.loads(f.read())
+    docs: List[Document] = []
+    for name, user_memory in memories.items():
+        if name != user_name:
+            continue
+        docs = []
+        if "history" not in user_memory:
+            continue
+        for date, content in user_memory["history"].items():
+            head = f"时间{date}的对话内容：" if language == "cn" else f"Conversation content on {date}:"
+            user_kw = "[|用户|]：" if language == "cn" else "[|User|]:"
+            ai_kw = "[|AI恋人|]：" if language == "cn" else "[|AI|]:"
+            for dialog in content:
+                text = head + f"{user_kw} {dialog['query'].strip()}; " + f"{ai_kw} {dialog['response'].strip()}"
+                docs.append(Document(text, {"source": date}))
+            if "summary" in user_memory and date in user_memory["summary"]:
+                s = user_memory["summary"][date]
+                text = f"时间{date}的对话总结为：{s}" if language == "cn" else f"The summary of the conversation on {date} is: {s}"
+                docs.append(Document(text, {"source": date}))
+    return docs
+
+
+class MemoryIndex:
+    """Device-resident flat index: embeddings [n, d] fp32 (unit rows) + the documents."""
+
+    def __init__(self, docs: List[Document], embeddings: torch.Tensor, embed_fn, chunk_size: int = CHUNK_SIZE):
+        self.docs = docs
+        self.embeddings = embeddings
+        self.embed_fn = embed_fn
+        self.chunk_size = chunk_size
+
+    def similarity_search_with_score(self, query: str, k: int = 4) -> List[Tuple[Document, float]]:
+        q = self.embed_fn([query])[0]
+        scores, indices = ops.cosine_topk(self.embeddings, q.to(self.embeddings.device), k=k)
+        scores, indices = scores[0].tolist(), indices[0].tolist()          # one D2H read per question
+        n = len(self.docs)
+        out: List[Tuple[Document, float]] = []
+        id_set = set()
+        last_j = 0
+        for j, i in enumerate(indices):
+            if i == -1:
+                continue
+            last_j = j
+            doc = self.docs[i]
+            id_set.add(i)
+            docs_len = len(doc.page_content)
+            # neighbour expansion, local_doc_qa.py:149-163 (`len(docs)` there is the still-empty
+            # OUTPUT list, so the range is 1..i-1; `break` leaves only the inner two-element loop)
+            for kk in range(1, max(i, len(out) - i)):
+                for l in (i + kk, i - kk):
+                    if 0 <= l < n:
+                        doc0 = self.docs[l]
+                        if docs_len + len(doc0.page_content) > self.chunk_size:
+                            break
+                        elif doc0.metadata["source"] == doc.metadata["source"]:
+                            docs_len += len(doc0.page_content)
+                            id_set.add(l)
+        if not id_set:
+            return out
+        runs, run = [], []
+        for idx in sorted(id_set):
+            if run and idx != run[-1] + 1:
+                runs.append(run)
+                run = []
+            run.append(idx)
+        runs.append(run)
+        l2 = 2.0 - 2.0 * scores[last_j]                                    # FAISS IndexFlatL2 reports squared L2
+        for seq in runs:
+            # the reference concatenates into the stored document in place (:170); a copy is returned
+            # here so repeated searches on one index do not accumulate text
+            merged = Document("".join(self.docs[i].page_content for i in seq), dict(self.docs[seq[0]].metadata))
+            out.append((merged, l2))
+        return out
+
+
+class LocalMemoryRetrieval:
+    embeddings = None
+    top_k: int = VECTOR_SEARCH_TOP_K
+    chunk_size: int = CHUNK_SIZE
+    _stores: Dict[str, MemoryIndex] = {}
+
+    def init_cfg(self, embedding_model: str = "minilm-l6", embedding_device="cuda", top_k=VECTOR_SEARCH_TOP_K,
+                 language="cn", embed_fn: Optional[Callable[[Sequence[str]], torch.Tensor]] = None):
+        """`embed_fn(list[str]) -> [n, d]` unit-norm embeddings on the device.  Without it the HF
+        sentence encoder named by `embedding_model` is loaded (mean-pool + normalise, what
+        langchain's HuggingFaceEmbeddings does) — the text encoder itself is the 'next' row §8f-1."""
+        self.language = language
+        self.top_k = top_k
+        self.device = torch.device(embedding_device if str(embedding_device).startswith("cuda") else "cuda:0")
+        if embed_fn is None:
+            embed_fn = _hf_sentence_embedder(embedding_model_dict[embedding_model], self.device)
+        self.embeddings = embed_fn
+
+    def init_memory_vector_store(self, filepath, vs_path=None, user_name=None, cur_date=None):
+        files = [filepath] if isinstance(filepath, str) else list(filepath)
+        if isinstance(filepath, str) and not os.path.exists(filepath):
+            return None, None
+        if isinstance(filepath, str) and os.path.isdir(filepath):
+            files = [os.path.join(filepath, f) for f in os.listdir(filepath)]
+        docs, loaded = [], []
+        for f in files:
+            try:
+                docs += load_memory_file(f, user_name, self.language)
+                loaded.append(f)
+            except Exception as e:  # noqa: BLE001  (the reference swallows per-file errors too, :226-229)
+                print(e)
+        if not docs:
+            return None, loaded
+        if not vs_path:
+            vs_path = f"memory_index_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}"
+        emb = self.embeddings([d.page_content for d in docs]).to(self.device, torch.float32).contiguous()
+        prev = self._stores.get(vs_path) if os.path.isdir(vs_path) else None
+        if prev is not None:                                                # FAISS.load_local + add_documents (:238-241)
+            docs = prev.docs + docs
+            emb = torch.cat([prev.embeddings, emb], 0)
+        self._stores[vs_path] = MemoryIndex(docs, emb, self.embeddings, self.chunk_size)
+        os.makedirs(vs_path, exist_ok=True)                                 # keeps the driver's exists()/rmtree logic valid
+        return vs_path, loaded
+
+    def load_memory_index(self, vs_path):
+        store = self._stores[vs_path]
+        store.chunk_size = self.chunk_size
+        return store
+
+    def search_memory(self, query, vector_store):
+        related = vector_store.similarity_search_with_score(query, k=self.top_k)
+        docs = []
+        for doc, score in related:
+            doc.metadata["score"] = score
+            docs.append(doc)
+        docs = sorted(docs, key=lambda d: d.metadata["source"])
+        pre_date, date_docs, dates = "", [], []
+        for doc in docs:
+            doc.page_content = doc.page_content.replace(f'时间{doc.metadata["source"]}的对话内容：', "").strip()
+            if doc.metadata["source"] != pre_date:
+                date_docs.append(doc.page_content)
+                pre_date = doc.metadata["source"]
+                dates.append(pre_date)
+            else:
+                date_docs[-1] += f"\n{doc.page_content}"
+        return date_docs, ", ".join(dates)
+
+
+def _hf_sentence_embedder(model_name: str, device: torch.device):
+    from transformers import AutoModel, AutoTokenizer
+    tok = AutoTokenizer.from_pretrained(model_name)
+    model = AutoModel.from_pretrained(model_name).to(device).eval()
+
+    @torch.no_grad()
+    def embed(texts: Sequence[str]) -> torch.Tensor:
+        enc = tok(list(texts), padding=True, truncation=True, return_tensors="pt").to(device)
+        h = model(**enc).last_hidden_state
+        m = enc["attention_mask"].unsqueeze(-1).float()
+        pooled = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)
+        return torch.nn.functional.normalize(pooled, p=2, dim=1)
+    return embed
+
+
+# ---- memory_bank/memory_utils.py ----------------------------------------------------------------
+def enter_name(name, memory, local_memory_qa, data_args, update_memory_index=True):
+    """memory_utils.py:61-90 (gradio State unwrapping dropped: the driver passes plain objects)."""
+    cur_date = datetime.date.today().strftime("%Y-%m-%d")
+    user_memory_index = None
+    memory_dir = os.path.join(data_args.memory_basic_dir, data_args.memory_file)
+    if name in memory.keys():
+        user_memory = memory[name]
+        memory_index_path = os.path.join(data_args.memory_basic_dir, f"memory_index/{name}_index")
+        os.makedirs(os.path.dirname(memory_index_path), exist_ok=True)
+        if (not os.path.exists(memory_index_path)) or update_memory_index:
+            if os.path.exists(memory_index_path):
+                shutil.rmtree(memory_index_path)
+            memory_index_path, _ = local_memory_qa.init_memory_vector_store(
+                filepath=memory_dir, vs_path=memory_index_path, user_name=name, cur_date=cur_date)
+        user_memory_index = local_memory_qa.load_memory_index(memory_index_path) if memory_index_path else None
+        msg = f"欢迎回来，{name}！" if data_args.language == "cn" else f"Wellcome Back, {name}！"
+        return msg, user_memory, memory, name, user_memory_index
+    memory[name] = {}
+    memory[name].update({"name": name})
+    msg = (f"欢迎新用户{name}！我会记住你的名字，下次见面就能叫你的名字啦！" if data_args.language == "cn"
+           else f"Welcome, new user {name}! I will remember your name, so next time we meet, I'll be able to call you by your name!")
+    return msg, memory[name], memory, name, user_memory_index
+
+
+def save_local_memory(memory, b, user_name, data_args):
+    """memory_utils.py:95-109."""
+    memory_dir = os.path.join(data_args.memory_basic_dir, data_args.memory_file)
+    date = time.strftime("%Y-%m-%d", time.localtime())
+    if memory[user_name].get("history") is None:
+        memory[user_name].update({"history": {}})
+    if memory[user_name]["history"].get(date) is None:
+        memory[user_name]["history"][date] = []
+    memory[user_name]["history"][date].append({"query": b[-1][0], "response": b[-1][1]})
+    json.dump(memory, open(memory_dir, "w", encoding="utf-8"), ensure_ascii=False, indent=4)
+    return memory
+
+
+def only_related_prompt_dict_ego():
+    """memory_bank/prompt_utils.py:37-44."""
+    return {"en": """
+    Based on the current user's question, the most relevant historical contextual conversation records are: "{related_memory_content}".
+    """}
+
+
+def build_prompt_with_search_memory_only_related(text, user_name, user_memory_index, local_memory_qa, meta_prompt,
+                                                 user_keyword, ai_keyword, boot_actual_name):
+    """utiles.py:1057-1078."""
+    query = text.replace(user_keyword, user_name).replace(ai_keyword, "AI")
+    if user_memory_index:
+        related_memos, _ = local_memory_qa.search_memory(query, user_memory_index)
+        related_memory_content = f"\n{str(chr(10).join(related_memos)).strip()}\n"
+        return meta_prompt.format(related_memory_content=related_memory_content)
+    return None

@@ -343,9 +343,12 @@ def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
 def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, prologue: int = L.PRO_NONE,
          gamma: Optional[torch.Tensor] = None, eps: float = 0.0, out: Optional[torch.Tensor] = None,
-         out_dtype: torch.dtype = torch.float16) -> torch.Tensor:
-    """Decode-step linear layer for 1, 2 or 4 activation rows (see scb_gemv)."""
-    dev = _require_cuda(a, w, bias, residual, gamma, out)
+         out_dtype: torch.dtype = torch.float16, argmax_out: Optional[torch.Tensor] = None,
+         counters: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode-step linear layer for 1..8 activation rows (see scb_gemv).  `argmax_out` (int64
+    [rows]) fuses the greedy token choice over the stored output; `counters` (int32) are then
+    incremented by one."""
+    dev = _require_cuda(a, w, bias, residual, gamma, out, argmax_out, counters)
     rows = a.shape[0]
     n, k = w.shape
     if out is None:
@@ -354,6 +357,13 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                       out=_ptr(out), n=n, k=k, lda=a.stride(0), ldw=w.stride(0),
                       ldr=residual.stride(0) if residual is not None else 0, ldo=out.stride(0),
                       rows=rows, prologue=prologue, out_dtype=_dtype_code(out), eps=eps)
+    if argmax_out is not None:
+        ws = _workspace(dev, "gemv_argmax", L.load().scb_gemv_workspace_bytes(rows))
+        args.argmax_out = _ptr(argmax_out)
+        args.counters = _ptr(counters)
+        args.n_counters = 0 if counters is None else counters.numel()
+        args.workspace = _ptr(ws)
+        args.workspace_bytes = ws.numel()
     _call("scb_gemv", dev, C.byref(args))
     return out
 
@@ -376,3 +386,27 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
                                  workspace=_ptr(ws), workspace_bytes=ws.numel())
     _call("scb_decode_attention", dev, C.byref(args))
     return out
+
+
+def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], theta: float,
+                           k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len_dev: torch.Tensor,
+                           n_q: int, scale: float, workspace: torch.Tensor, n_splits: int = 37,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """RoPE + KV append + split attention + combine for ONE new token (see
+    scb_decode_attention_fused).  `workspace` is a caller-held uint8 tensor whose first 256 bytes
+    are zero (use `decode_attention_fused_workspace`)."""
+    dev = _require_cuda(qkv, inv_freq, k_cache, v_cache, kv_len_dev, workspace, out)
+    hkv, max_pos, d = k_cache.shape
+    if out is None:
+        out = torch.empty((n_q, d), dtype=torch.float16, device=dev)
+    args = L.DecodeAttentionFusedArgs(
+        qkv=_ptr(qkv), inv_freq=_ptr(inv_freq), k_cache=_ptr(k_cache), v_cache=_ptr(v_cache), out=_ptr(out),
+        kv_len_dev=_ptr(kv_len_dev), max_pos=max_pos, n_q_heads=n_q, n_kv_heads=hkv, head_dim=d,
+        n_splits=n_splits, scale=scale, theta=theta, workspace=_ptr(workspace), workspace_bytes=workspace.numel())
+    _call("scb_decode_attention_fused", dev, C.byref(args))
+    return out
+
+
+def decode_attention_fused_workspace(dev, n_q: int, n_kv: int, head_dim: int, n_splits: int) -> torch.Tensor:
+    n = L.load().scb_decode_attention_fused_workspace_bytes(n_q, n_kv, head_dim, n_splits)
+    return torch.zeros(n, dtype=torch.uint8, device=dev)

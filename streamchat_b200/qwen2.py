@@ -84,6 +84,8 @@ class Qwen2Engine:
         self._attn = torch.zeros((c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
         self._gu = torch.zeros((1, 2 * c.intermediate_size), dtype=torch.float16, device=self.device)
         self._logits = torch.zeros((1, c.vocab_size), dtype=torch.float16, device=self.device)
+        self._attn_ws = ops.decode_attention_fused_workspace(self.device, c.num_attention_heads,
+                                                             c.num_key_value_heads, hd, decode_splits)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_replays = 0
         self.profile: Optional[list] = None   # bench.py: (start event, end event, steps, bytes) per decode loop
@@ -144,8 +146,11 @@ class Qwen2Engine:
 
     # ---------------------------------------------------------------- decode
     def _decode_step_launches(self) -> None:
-        """One cached decode step: embeds next_id at device position state[0]; leaves the new
-        logits in self._logits, the new arg-max in next_id and advances state."""
+        """One cached decode step (142 launches for 28 layers): embeds next_id, runs every layer as
+        qkv GEMV (RMSNorm fused) -> fused RoPE/append/attention/combine -> o_proj GEMV (+residual)
+        -> gate|up GEMV (RMSNorm fused) -> down GEMV (SiLU-gate fused, +residual), then the lm_head
+        GEMV with the final norm and the greedy arg-max fused; leaves logits in self._logits, the new
+        token in next_id and advances the device-side [position, kv_len] state."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         scale = hd ** -0.5
@@ -154,19 +159,17 @@ class Qwen2Engine:
         for i, ly in enumerate(self.layers):
             ops.gemv(x, ly["qkv_w"], bias=ly["qkv_b"], prologue=L.PRO_RMSNORM, gamma=ly["ln1"],
                      eps=c.rms_norm_eps, out=self._qkv)
-            ops.rope_append(self._qkv, Hq, Hkv, hd, self.inv_freq, c.rope_theta, positions=self.state[0:1],
-                            k_cache=self.k_cache[i], v_cache=self.v_cache[i])
-            ops.decode_attention(self._qkv[0, :Hq * hd].view(Hq, hd), self.k_cache[i], self.v_cache[i], scale,
-                                 kv_len_dev=self.state[1:2], n_splits=self.decode_splits, out=self._attn)
+            ops.decode_attention_fused(self._qkv, self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
+                                       self.state[1:2], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
+                                       out=self._attn)
             ops.gemv(self._attn.view(1, Hq * hd), ly["o_w"], residual=x, out=x2)
             ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps, out=self._gu)
             ops.gemv(self._gu, ly["down_w"], residual=x2, prologue=L.PRO_SILU_MUL, out=x)
         ops.gemv(x, self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm, eps=c.rms_norm_eps,
-                 out=self._logits)
-        ops.argmax_rows(self._logits, out=self.next_id, counter=self.state)
+                 out=self._logits, argmax_out=self.next_id, counters=self.state)
 
     def launches_per_decode_step(self) -> int:
-        return 1 + self.cfg.num_hidden_layers * 7 + 2
+        return 1 + self.cfg.num_hidden_layers * 5 + 1
 
     def _ensure_graph(self) -> None:
         if self._graph is not None:

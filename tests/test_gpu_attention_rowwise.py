@@ -183,7 +183,9 @@ def test_rope_append(cuda):
 
 
 @pytest.mark.parametrize("rows,n,k,pro", [(1, 4608, 3584, 1), (1, 3584, 3584, 0), (1, 3584, 18944, 2),
-                                          (2, 1000, 512, 0), (4, 300, 1024, 1), (1, 152064, 3584, 1)])
+                                          (2, 1000, 512, 0), (4, 300, 1024, 1), (1, 152064, 3584, 1),
+                                          (5, 3584, 18944, 2), (8, 4608, 3584, 1), (3, 37888, 3584, 1),
+                                          (7, 1003, 96, 0), (1, 77, 32, 0), (2, 50, 40, 0)])
 def test_gemv(cuda, rows, n, k, pro):
     from streamchat_b200 import ops
     torch.manual_seed(rows + n + k)
@@ -229,4 +231,64 @@ def test_decode_attention(cuda, hq, hkv, d, ctx, splits):
     assert (out.double().cpu() - ref).abs().max().item() < 3e-3
     lens = torch.tensor([ctx], dtype=torch.int32, device=cuda)
     out2 = ops.decode_attention(q.to(cuda), kc.to(cuda), vc.to(cuda), scale, kv_len_dev=lens, n_splits=splits)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("rows", [1, 5])
+def test_gemv_fused_argmax(cuda, rows):
+    from streamchat_b200 import ops, _lib
+    torch.manual_seed(rows)
+    n, k = 152064, 3584
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()
+    a = torch.randn(rows, k, device=cuda).half()
+    gamma = (1 + 0.1 * torch.randn(k, device=cuda)).half()
+    ids = torch.full((rows,), -1, dtype=torch.int64, device=cuda)
+    cnt = torch.tensor([10, 11], dtype=torch.int32, device=cuda)
+    out = ops.gemv(a, w, prologue=_lib.PRO_RMSNORM, gamma=gamma, eps=1e-6, argmax_out=ids, counters=cnt)
+    assert out.dtype == torch.float16
+    assert ids.tolist() == torch.argmax(out.float(), dim=1).tolist()      # over the stored fp16 logits
+    assert cnt.tolist() == [11, 12]
+    # ties -> lowest index: duplicate the winning weight row at a lower and a higher index
+    best = int(ids[0])
+    w2 = w.clone()
+    lo, hi = 5, n - 3
+    w2[lo] = w[best]
+    w2[hi] = w[best]
+    out2 = ops.gemv(a, w2, prologue=_lib.PRO_RMSNORM, gamma=gamma, eps=1e-6, argmax_out=ids, counters=cnt)
+    assert int(ids[0]) == min(lo, best) and ids.tolist() == torch.argmax(out2.float(), dim=1).tolist()
+    assert cnt.tolist() == [12, 13]
+
+
+@pytest.mark.parametrize("hq,hkv,d,ctx,splits,maxp", [(28, 4, 128, 4701, 37, 8192), (28, 4, 128, 1, 37, 8192),
+                                                      (28, 4, 128, 38, 37, 32768), (4, 2, 64, 300, 8, 512),
+                                                      (2, 1, 128, 77, 37, 2048)])
+def test_decode_attention_fused(cuda, hq, hkv, d, ctx, splits, maxp):
+    """ctx counts the token being decoded: its k/v come from the fused qkv row, not from the cache."""
+    from streamchat_b200 import ops
+    torch.manual_seed(ctx + hq)
+    pos = ctx - 1
+    qkv = torch.randn(1, (hq + 2 * hkv) * d).half()
+    inv_freq = 1.0 / (1000000.0 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+    kc = torch.zeros(hkv, maxp, d).half()
+    vc = torch.zeros(hkv, maxp, d).half()
+    kc[:, :pos] = torch.randn(hkv, pos, d).half()
+    vc[:, :pos] = torch.randn(hkv, pos, d).half()
+    scale = 1 / math.sqrt(d)
+    p = torch.tensor([pos])
+    q_rot = _rope_ref(qkv[:, :hq * d].view(1, hq, d), p, inv_freq)
+    k_new = _rope_ref(qkv[:, hq * d:(hq + hkv) * d].view(1, hkv, d), p, inv_freq)
+    v_new = qkv[:, (hq + hkv) * d:].view(1, hkv, d)
+    k_all = torch.cat([kc[:, :pos], k_new.permute(1, 0, 2)], 1)
+    v_all = torch.cat([vc[:, :pos], v_new.permute(1, 0, 2)], 1)
+    ref = _sdpa_ref(q_rot.view(1, 1, hq, d), k_all.permute(1, 0, 2).unsqueeze(0), v_all.permute(1, 0, 2).unsqueeze(0),
+                    scale, False)[0, 0]
+    kcd, vcd = kc.to(cuda), vc.to(cuda)
+    ws = ops.decode_attention_fused_workspace(cuda, hq, hkv, d, splits)
+    lens = torch.tensor([ctx], dtype=torch.int32, device=cuda)
+    out = ops.decode_attention_fused(qkv.to(cuda), inv_freq.to(cuda), 1e6, kcd, vcd, lens, hq, scale, ws, splits)
+    assert (out.double().cpu() - ref).abs().max().item() < 4e-3
+    assert (kcd[:, pos].cpu().float() - k_new[0].float()).abs().max().item() < 4e-3
+    assert torch.equal(vcd[:, pos].cpu(), v_new[0])
+    assert (ws[:256] == 0).all()                                        # tickets left clean
+    out2 = ops.decode_attention_fused(qkv.to(cuda), inv_freq.to(cuda), 1e6, kcd, vcd, lens, hq, scale, ws, splits)
     assert torch.equal(out, out2)

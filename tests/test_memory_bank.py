@@ -1,0 +1,112 @@
+"""Dialogue-history retrieval (a-R2): CPU checks of the oracle restatement, GPU parity of the
+LocalMemoryRetrieval mirror against it on the same injected embeddings."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fakes  # noqa: E402
+from oracle import memory_bank as omb
+
+
+def _memory_json(tmp_path):
+    mem = {"User": {"name": "User", "history": {
+        "2024-05-01": [{"query": "where did I leave my keys", "response": "on the kitchen table"},
+                       {"query": "what colour is the car", "response": "red"},
+                       {"query": "who was at the door", "response": "the postman"}],
+        "2024-05-02": [{"query": "what did I cook", "response": "pasta with tomato sauce"},
+                       {"query": "is the window open", "response": "yes, the left one"}]},
+        "summary": {"2024-05-01": "keys, car and a visitor"}},
+        "Other": {"name": "Other", "history": {"2024-05-01": [{"query": "x", "response": "y"}]}}}
+    p = tmp_path / "memory.json"
+    p.write_text(json.dumps(mem, ensure_ascii=False), encoding="utf-8")
+    return str(p), mem
+
+
+def _embed_np(texts, dim=384):
+    v = np.stack([fakes.text_vector(t, dim) for t in texts])
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+def test_oracle_flat_l2_and_expansion(tmp_path):
+    from streamchat_b200.memory_bank import load_memory_file
+    path, _ = _memory_json(tmp_path)
+    docs = load_memory_file(path, "User", "en")
+    assert len(docs) == 6                                    # 3 turns + summary, 2 turns; other users skipped
+    assert docs[0].page_content.startswith("Conversation content on 2024-05-01:[|User|]: where did I leave my keys; [|AI|]: on")
+    assert docs[3].page_content.startswith("The summary of the conversation on 2024-05-01 is:")
+    xb = _embed_np([d.page_content for d in docs])
+    s, i = omb.index_flat_l2_search(xb, xb[2:3], 3)
+    assert i[0, 0] == 2 and abs(s[0, 0]) < 1e-6 and (np.diff(s[0]) >= 0).all()
+    s, i = omb.index_flat_l2_search(xb[:2], xb[2:3], 3)
+    assert i[0, 2] == -1
+    out, dates = omb.search_memory(docs, xb, xb[4], top_k=1, chunk_size=200)
+    assert dates == "2024-05-02" and len(out) == 1 and "pasta" in out[0]
+
+
+@pytest.mark.gpu
+def test_local_memory_retrieval_matches_oracle(cuda, tmp_path):
+    from streamchat_b200.memory_bank import (LocalMemoryRetrieval, build_prompt_with_search_memory_only_related,
+                                             enter_name, load_memory_file, only_related_prompt_dict_ego,
+                                             save_local_memory)
+    path, mem = _memory_json(tmp_path)
+
+    def embed_fn(texts):
+        return torch.from_numpy(_embed_np(list(texts))).to(cuda)
+    qa = LocalMemoryRetrieval()
+    qa.init_cfg("minilm-l6", "cuda:0", 1, "en", embed_fn=embed_fn)
+    args = types.SimpleNamespace(memory_basic_dir=str(tmp_path), memory_file="memory.json", language="en")
+    msg, user_memory, memory, name, index = enter_name("User", mem, qa, args)
+    assert index is not None and msg.startswith("Wellcome Back")
+    docs = load_memory_file(path, "User", "en")
+    xb = _embed_np([d.page_content for d in docs])
+    for top_k in (1, 3):
+        qa.top_k = top_k
+        for chunk_size in (200, 120, 1000):
+            index.chunk_size = chunk_size
+            for q in ["what did I cook yesterday", "where are the keys", docs[1].page_content]:
+                got = qa.search_memory(q, index)
+                want = omb.search_memory(docs, xb, _embed_np([q])[0], top_k, chunk_size)
+                assert got == want, (top_k, chunk_size, q, got, want)
+    # prompt assembly + a new turn + index rebuild (the per-question cycle of the driver, :918-920)
+    qa.top_k, index.chunk_size = 1, 200
+    prompt = build_prompt_with_search_memory_only_related("where are the keys", "User", index, qa,
+                                                          only_related_prompt_dict_ego()["en"], "[|User|]", "[|AI|]", "AI")
+    assert "most relevant historical contextual conversation records" in prompt
+    memory = save_local_memory(memory, [["new question", "new answer"]], "User", args)
+    _, _, _, _, index2 = enter_name("User", memory, qa, args)
+    assert len(index2.docs) == len(index.docs) + 1
+    # unknown user -> fresh entry, no index
+    _, um, _, _, idx = enter_name("Nobody", memory, qa, args)
+    assert idx is None and um == {"name": "Nobody"}
+    assert build_prompt_with_search_memory_only_related("q", "Nobody", None, qa, "x", "a", "b", "c") is None
+
+
+def test_dropin_import_paths():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        for m in [k for k in sys.modules if k.split(".")[0] in ("longva", "utiles", "torch_kmeans", "memory_bank")]:
+            del sys.modules[m]
+        from longva.model.builder import load_pretrained_model  # noqa: F401
+        from longva.conversation import conv_templates, SeparatorStyle  # noqa: F401
+        from longva.mm_utils import tokenizer_image_token  # noqa: F401
+        from longva.constants import IMAGE_TOKEN_INDEX
+        from torch_kmeans import KMeans  # noqa: F401
+        from utiles import (weighted_kmeans_feature, fast_building_memory_tree_summarize_token,  # noqa: F401
+                            fast_search_tree_multi_modal_with_embedding, calculate_forgetting_probabilities,
+                            select_data_without_replacement, count_nodes_by_depth, MultimodalTreeNode,
+                            build_prompt_with_search_memory_only_related, process_images)
+        from memory_bank.memory_retrieval.local_doc_qa import LocalMemoryRetrieval  # noqa: F401
+        from memory_bank.memory_utils import enter_name, save_local_memory  # noqa: F401
+        from memory_bank.prompt_utils import only_related_prompt_dict_ego  # noqa: F401
+        assert IMAGE_TOKEN_INDEX == -200 and "qwen_1_5_ego" in conv_templates
+    finally:
+        sys.path.remove(os.path.join(root, "dropin"))
+        for m in [k for k in sys.modules if k.split(".")[0] in ("longva", "utiles", "torch_kmeans", "memory_bank")]:
+            del sys.modules[m]

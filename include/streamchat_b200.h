@@ -135,7 +135,9 @@ typedef enum scb_act {
   SCB_ACT_NONE = 0,
   SCB_ACT_QUICK_GELU = 1,  /* x * sigmoid(1.702 x)   — CLIP MLP           */
   SCB_ACT_GELU_ERF = 2,    /* exact GELU             — mm_projector        */
-  SCB_ACT_SILU = 3
+  SCB_ACT_SILU = 3,
+  SCB_ACT_SILU_PAIR = 4    /* columns (2i, 2i+1) are (gate_i, up_i): out[m, i] = fp16(silu(fp16 gate)) * fp16 up,
+                            * out is [m, n/2]; no bias / residual */
 } scb_act;
 
 typedef struct scb_linear_args {
@@ -266,11 +268,14 @@ typedef struct scb_gemv_args {
   int32_t out_dtype;      /* scb_dtype */
   float eps;
   /* optional fused greedy choice (lm_head): argmax_out[r] = arg-max over n of the STORED output
-   * row r (lowest index wins ties), then counters[0..n_counters) += 1.  Needs the workspace. */
+   * row r (lowest index wins ties), then counters[0..n_counters) += 1.  Needs the workspace, whose
+   * first 256 bytes (the ticket) must be zero before the first call and are left zero. */
   int64_t* argmax_out;
   int32_t* counters;
   int32_t n_counters;
-  int32_t _pad;
+  int32_t epilogue;       /* 0: none.  1: SiLU-pair — rows (2i, 2i+1) of w are (gate_i, up_i) and
+                           * out[r, i] = fp16(silu(fp16 gate)) * fp16 up, out is [rows, n/2] fp16
+                           * (Qwen2 MLP gate, modeling_qwen2.py:41-48, fused into the gate|up layer) */
   void* workspace;
   size_t workspace_bytes;
 } scb_gemv_args;
@@ -298,26 +303,33 @@ int scb_decode_attention(const scb_decode_attention_args* a, void* stream);
 
 /* One launch for the attention block of a decode step: RoPE of the new q/k (same rounding as
  * scb_rope_append), append of k/v at position kv_len-1, split-KV attention for every q head and
- * the cross-split combine.  qkv is ONE fused row [n_q*hd | n_kv*hd | n_kv*hd] (un-rotated);
- * *kv_len_dev is the context length INCLUDING the token being decoded.  The first 256 bytes of
- * the workspace hold the tickets and must be zero before the first call (they are left zero). */
+ * the cross-split combine — for n_seqs independent sequences (batched chunk captions): sequence
+ * s uses fused row qkv + s*ld_qkv ([n_q*hd | n_kv*hd | n_kv*hd], un-rotated), caches
+ * k_cache + s*cache_seq_stride, length kv_len_dev[s] (INCLUDING the token being decoded) and
+ * writes out[s].  The first 256 bytes of the workspace hold the tickets and must be zero before
+ * the first call (they are left zero). */
 typedef struct scb_decode_attention_fused_args {
   const void* qkv;
   const float* inv_freq;     /* [head_dim/2] fp32 or NULL -> theta^(-2i/hd) */
   void* k_cache;             /* [n_kv_heads, max_pos, head_dim] fp16 */
   void* v_cache;
-  void* out;                 /* [n_q_heads, head_dim] fp16 */
-  const int32_t* kv_len_dev;
+  void* out;                 /* [n_seqs, n_q_heads, head_dim] fp16 */
+  const int32_t* kv_len_dev; /* [n_seqs] */
   int64_t max_pos;
   int32_t n_q_heads, n_kv_heads, head_dim, n_splits;
   float scale;
   float theta;
+  int32_t n_seqs;            /* >= 1, n_seqs * n_kv_heads <= 64 */
+  int32_t _pad;
+  int64_t ld_qkv;            /* elements between the sequences' qkv rows */
+  int64_t cache_seq_stride;  /* elements between the sequences' caches */
   void* workspace;
   size_t workspace_bytes;
 } scb_decode_attention_fused_args;
 
-size_t scb_decode_attention_fused_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads,
-                                                  int32_t head_dim, int32_t n_splits);
+size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_heads,
+                                                  int32_t n_kv_heads, int32_t head_dim,
+                                                  int32_t n_splits);
 int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream);
 
 #ifdef __cplusplus

@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstreamchat_b200.so")
 
 SCB_F32, SCB_F16 = 0, 1
-ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF, ACT_SILU, ACT_SILU_PAIR = 0, 1, 2, 3, 4
+EPI_NONE, EPI_SILU_PAIR = 0, 1
 
 
 class ScbError(RuntimeError):
@@ -76,7 +77,7 @@ class GemvArgs(C.Structure):
         ("n", C.c_int64), ("k", C.c_int64),
         ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo", C.c_int64),
         ("rows", C.c_int32), ("prologue", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float),
-        ("argmax_out", C.c_void_p), ("counters", C.c_void_p), ("n_counters", C.c_int32), ("_pad", C.c_int32),
+        ("argmax_out", C.c_void_p), ("counters", C.c_void_p), ("n_counters", C.c_int32), ("epilogue", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -96,7 +97,8 @@ class DecodeAttentionFusedArgs(C.Structure):
         ("qkv", C.c_void_p), ("inv_freq", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p),
         ("out", C.c_void_p), ("kv_len_dev", C.c_void_p), ("max_pos", C.c_int64),
         ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32), ("head_dim", C.c_int32), ("n_splits", C.c_int32),
-        ("scale", C.c_float), ("theta", C.c_float),
+        ("scale", C.c_float), ("theta", C.c_float), ("n_seqs", C.c_int32), ("_pad", C.c_int32),
+        ("ld_qkv", C.c_int64), ("cache_seq_stride", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -120,7 +122,7 @@ SYMBOLS = {
     "scb_gemv_workspace_bytes": (C.c_size_t, [_i32]),
     "scb_decode_attention_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "scb_decode_attention": (C.c_int, [C.POINTER(DecodeAttentionArgs), C.c_void_p]),
-    "scb_decode_attention_fused_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32]),
+    "scb_decode_attention_fused_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
     "scb_decode_attention_fused": (C.c_int, [C.POINTER(DecodeAttentionFusedArgs), C.c_void_p]),
     "scb_im2col_patch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp]),
     "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),

@@ -41,6 +41,7 @@ struct GemvParams {
   long long lda, ldw, ldr, ldo;
   int N, K;
   int out_f32;
+  int silu_pair;  // rows (2i, 2i+1) of w are (gate_i, up_i): out[r][i] = fp16(silu(gate)) * up
   float eps;
 };
 
@@ -234,6 +235,8 @@ gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
   };
   uint4 cur[kMU], nxt[kMU];
   issue(cur, grp, 0);   // weights do not depend on the previous kernel: request them first
+  pdl_launch_dependents();
+  pdl_wait();           // activations (and everything we write) belong to the dependency chain
 
   // ---- prologue: stage (and transform) the activation rows as fp16 values
   for (int r = 0; r < R; ++r) {
@@ -318,7 +321,22 @@ gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
       red[(warp * 8 + g) * 8 + t * 2 + 1] = acc[1];
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
       __syncthreads();
-      if (tid < R * 8) {
+      if (p.silu_pair) {
+        // gate|up interleaved: threads (r, j even) and (r, j+1) hold gate_i and up_i
+        if (tid < 64) {
+          const int r = tid >> 3, j = tid & 7;
+          const int n = grp * 8 + j;
+          float v = 0.f;
+          if (r < R && n < p.N)
+            for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
+          v = __half2float(__float2half_rn(v));                     // Linear output is fp16 in HF
+          const float up = __shfl_xor_sync(0xffffffffu, v, 1);
+          if (r < R && n < p.N && (j & 1) == 0) {
+            const float sg = __half2float(__float2half_rn(v / (1.f + __expf(-v))));
+            reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + (n >> 1)] = __float2half_rn(sg * up);
+          }
+        }
+      } else if (tid < R * 8) {
         const int r = tid >> 3, j = tid & 7;
         const int n = grp * 8 + j;
         if (n < p.N) {
@@ -547,17 +565,29 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
                          long long max_pos, const int* __restrict__ len_dev, float scale_log2,
                          int n_q, int n_kv, int per_max, float* __restrict__ part_m,
                          float* __restrict__ part_l, float* __restrict__ part_o,
-                         unsigned* __restrict__ tickets, __half* __restrict__ out) {
+                         unsigned* __restrict__ tickets, __half* __restrict__ out, long long ld_qkv,
+                         long long cache_seq_stride) {
   constexpr int HALF = HD / 2;
   extern __shared__ __align__(16) float dsm[];
   float* q_s = dsm;                 // [G][HD] rotated q, pre-scaled by scale*log2(e)
   float* s_s = dsm + G * HD;        // [G][per_max] scores -> probabilities
   __shared__ float m_s[G], l_s[G];
-  __shared__ float o_s[2][G][HD];
+  __shared__ float o_s[8][G][HD];   // per-warp partial outputs
   __shared__ unsigned last_flag;
   const int hk = blockIdx.x, split = blockIdx.y, n_splits = gridDim.y;
+  const int seq = blockIdx.z;       // independent sequences (batched captions): own row, cache, length
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int kv_len = *len_dev;
+  qkv += (long long)seq * ld_qkv;
+  k_cache += (long long)seq * cache_seq_stride;
+  v_cache += (long long)seq * cache_seq_stride;
+  out += (long long)seq * n_q * HD;
+  part_m += (long long)seq * n_q * n_splits;
+  part_l += (long long)seq * n_q * n_splits;
+  part_o += (long long)seq * n_q * n_splits * HD;
+  tickets += seq * n_kv;
+  const int kv_len = len_dev[seq];
   const int pos = kv_len - 1;       // position of the token being decoded
   const int per = (kv_len + n_splits - 1) / n_splits;
   const int begin = split * per, end = min(kv_len, begin + per);
@@ -596,23 +626,29 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   __syncthreads();   // q_s ready; the appended row is visible to this block
 
-  // ---- phase 1: scores
-  const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD;
-  for (int pl = tid; pl < n_local; pl += 256) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (long long)pl * HD);
-    float sc[G];
+  // ---- phase 1: scores.  A quad of threads owns a position: thread j reads the 16-byte chunks
+  // j, j+4, j+8, ... of the K row (the quad covers 64 contiguous bytes per load), all loads of
+  // the row are in flight at once, partial dots meet with two shuffles.
+  {
+    constexpr int CH = HD / 32;           // 16-byte chunks per thread
+    const int quad = tid >> 2, j = tid & 3;
+    const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD;
+    for (int p0 = 0; p0 < n_local; p0 += 64) {
+      const int pl = p0 + quad;
+      const bool ok = pl < n_local;
+      uint4 kv4[CH];
 #pragma unroll
-    for (int h = 0; h < G; ++h) sc[h] = 0.f;
+      for (int c = 0; c < CH; ++c)
+        kv4[c] = ok ? *reinterpret_cast<const uint4*>(kb + (long long)pl * HD + (c * 4 + j) * 8)
+                    : make_uint4(0, 0, 0, 0);
+      float sc[G];
 #pragma unroll
-    for (int c4 = 0; c4 < HD / 32; ++c4) {
-      uint4 kv4[4];
+      for (int h = 0; h < G; ++h) sc[h] = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) kv4[u] = kr[c4 * 4 + u];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int c = 0; c < CH; ++c) {
         float kf[8];
-        unpack8(kv4[u], kf);
-        const int d0 = (c4 * 4 + u) * 8;
+        unpack8(kv4[c], kf);
+        const int d0 = (c * 4 + j) * 8;
 #pragma unroll
         for (int h = 0; h < G; ++h) {
           const float4 qa = *reinterpret_cast<const float4*>(q_s + h * HD + d0);
@@ -623,9 +659,16 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
           sc[h] = fmaf(kf[6], qb.z, sc[h]); sc[h] = fmaf(kf[7], qb.w, sc[h]);
         }
       }
-    }
 #pragma unroll
-    for (int h = 0; h < G; ++h) s_s[h * per_max + pl] = sc[h];
+      for (int h = 0; h < G; ++h) {
+        sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 1);
+        sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 2);
+      }
+      if (ok && j == 0) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) s_s[h * per_max + pl] = sc[h];
+      }
+    }
   }
   __syncthreads();
 
@@ -648,40 +691,67 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   __syncthreads();
 
-  // ---- phase 3: P·V, thread = (dim, position parity group)
+  // ---- phase 3: P·V.  thread = (dim group of 8, position group): 16-byte V loads, 4 in flight;
+  // position groups meet by one shuffle (lanes l, l^16) and a fixed-order sum over the warps.
   {
-    constexpr int NG = 256 / HD;          // position groups (2 for HD=128, 4 for HD=64)
-    const int d = tid % HD, pg = tid / HD;
-    const __half* vb = v_cache + ((long long)hk * max_pos + begin) * HD + d;
-    float acc[G];
+    constexpr int DG = HD / 8;            // 16 (HD=128) or 8 (HD=64) dim groups
+    constexpr int LPG = 32 / DG;          // position groups inside a warp: 2 or 4
+    constexpr int NPG = 8 * LPG;          // position groups per block
+    const int dg = lane % DG, pg = warp * LPG + lane / DG;
+    const __half* vb = v_cache + ((long long)hk * max_pos + begin) * HD + dg * 8;
+    float acc[G][8];
 #pragma unroll
-    for (int h = 0; h < G; ++h) acc[h] = 0.f;
-    for (int pl = pg; pl < n_local; pl += NG) {
-      const float v = __half2float(vb[(long long)pl * HD]);
+    for (int h = 0; h < G; ++h)
 #pragma unroll
-      for (int h = 0; h < G; ++h) acc[h] = fmaf(s_s[h * per_max + pl], v, acc[h]);
+      for (int e = 0; e < 8; ++e) acc[h][e] = 0.f;
+    for (int p0 = pg; p0 < n_local; p0 += 4 * NPG) {
+      uint4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pl = p0 + u * NPG;
+        vv[u] = pl < n_local ? *reinterpret_cast<const uint4*>(vb + (long long)pl * HD)
+                             : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pl = p0 + u * NPG;
+        if (pl < n_local) {
+          float vf[8];
+          unpack8(vv[u], vf);
+#pragma unroll
+          for (int h = 0; h < G; ++h) {
+            const float pr = s_s[h * per_max + pl];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[h][e] = fmaf(pr, vf[e], acc[h][e]);
+          }
+        }
+      }
     }
-    // merge the position groups through o_s (fixed order)
-    static_assert(HD == 128 || HD == 64, "head_dim");
-    float* o_flat = &o_s[0][0][0];        // reuse as [NG][G][HD] (NG*G*HD <= 2*G*128)
 #pragma unroll
-    for (int h = 0; h < G; ++h) o_flat[(pg * G + h) * HD + d] = acc[h];
+    for (int h = 0; h < G; ++h)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if constexpr (LPG == 4) acc[h][e] += __shfl_xor_sync(0xffffffffu, acc[h][e], 8);
+        acc[h][e] += __shfl_xor_sync(0xffffffffu, acc[h][e], 16);
+      }
+    if (lane < DG) {
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o_s[warp][h][dg * 8 + e] = acc[h][e];
+    }
   }
   __syncthreads();
-  {
-    constexpr int NG = 256 / HD;
-    const float* o_flat = &o_s[0][0][0];
-    for (int idx = tid; idx < G * HD; idx += 256) {
-      const int h = idx / HD, d = idx % HD;
-      float v = 0.f;
+  for (int idx = tid; idx < G * HD; idx += 256) {
+    const int h = idx / HD, d = idx % HD;
+    float v = 0.f;
 #pragma unroll
-      for (int g2 = 0; g2 < NG; ++g2) v += o_flat[(g2 * G + h) * HD + d];
-      const long long pi = (long long)(hk * G + h) * n_splits + split;
-      part_o[pi * HD + d] = v;
-      if (d == 0) {
-        part_m[pi] = m_s[h];
-        part_l[pi] = l_s[h];
-      }
+    for (int w = 0; w < 8; ++w) v += o_s[w][h][d];
+    const long long pi = (long long)(hk * G + h) * n_splits + split;
+    part_o[pi * HD + d] = v;
+    if (d == 0) {
+      part_m[pi] = m_s[h];
+      part_l[pi] = l_s[h];
     }
   }
   // ---- last block of this kv head combines the splits
@@ -753,12 +823,17 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   SCB_REQUIRE(a->prologue != PRO_RMSNORM || a->gamma, SCB_ERR_INVALID_ARG,
               "scb_gemv: RMSNorm prologue needs gamma");
   const long long min_lda = a->prologue == PRO_SILU_MUL ? 2 * a->k : a->k;
-  SCB_REQUIRE(a->lda >= min_lda && a->ldw >= a->k && a->ldo >= a->n && a->lda % 8 == 0 &&
+  SCB_REQUIRE(a->lda >= min_lda && a->ldw >= a->k && (a->ldo >= a->n || a->epilogue == 1) && a->lda % 8 == 0 &&
                   a->ldw % 8 == 0,
               SCB_ERR_INVALID_ARG, "scb_gemv: bad leading dimensions");
   SCB_REQUIRE(al16(a->a) && al16(a->w) && (!a->gamma || al16(a->gamma)), SCB_ERR_INVALID_ARG,
               "scb_gemv: a / w / gamma must be 16-byte aligned");
   SCB_REQUIRE(!a->residual || a->ldr >= a->n, SCB_ERR_INVALID_ARG, "scb_gemv: ldr too small");
+  SCB_REQUIRE(a->epilogue == 0 || a->epilogue == 1, SCB_ERR_UNSUPPORTED, "scb_gemv: epilogue %d", a->epilogue);
+  SCB_REQUIRE(a->epilogue == 0 || (a->k % 32 == 0 && a->n % 2 == 0 && !a->bias && !a->residual &&
+                                   a->out_dtype == SCB_F16 && !a->argmax_out && a->ldo >= a->n / 2),
+              SCB_ERR_INVALID_ARG,
+              "scb_gemv: the SiLU-pair epilogue needs k%%32==0, even n, fp16 out, no bias/residual/arg-max");
   GemvParams p;
   p.a = reinterpret_cast<const __half*>(a->a);
   p.w = reinterpret_cast<const __half*>(a->w);
@@ -769,6 +844,7 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   p.lda = a->lda; p.ldw = a->ldw; p.ldr = a->ldr; p.ldo = a->ldo;
   p.N = (int)a->n; p.K = (int)a->k;
   p.out_f32 = a->out_dtype == SCB_F32;
+  p.silu_pair = a->epilogue == 1;
   p.eps = a->eps;
   const int sms = scb_num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -802,14 +878,13 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
     long long cap = (long long)sms * per_sm;
     if (cap > 2048) cap = 2048;
     const int grid = (int)(n_groups < cap ? n_groups : cap);
-    if (a->argmax_out) SCB_CUDA_OK(cudaMemsetAsync(am.ticket, 0, sizeof(unsigned), st));
 #define SCB_GEMV_MMA(PRO)                                                                        \
   do {                                                                                           \
     auto kern = gemv_mma_kernel<PRO>;                                                            \
     if (smem > 48 * 1024)                                                                        \
       SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                        (int)smem));                                              \
-    kern<<<grid, W * 32, smem, st>>>(p, a->rows, am);                                            \
+    SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(W * 32), smem, st, p, (int)a->rows, am));  \
   } while (0)
     if (a->prologue == PRO_RMSNORM) SCB_GEMV_MMA(PRO_RMSNORM);
     else if (a->prologue == PRO_SILU_MUL) SCB_GEMV_MMA(PRO_SILU_MUL);
@@ -902,10 +977,12 @@ int scb_decode_attention(const scb_decode_attention_args* a, void* stream) {
 }
 
 
-size_t scb_decode_attention_fused_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads,
-                                                  int32_t head_dim, int32_t n_splits) {
-  if (n_q_heads < 1 || n_kv_heads < 1 || head_dim < 1 || n_splits < 1) return 0;
-  return 256 + sizeof(float) * (size_t)n_q_heads * n_splits * (head_dim + 2);
+size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_heads,
+                                                  int32_t n_kv_heads, int32_t head_dim,
+                                                  int32_t n_splits) {
+  if (n_seqs < 1 || n_q_heads < 1 || n_kv_heads < 1 || head_dim < 1 || n_splits < 1) return 0;
+  if (n_seqs * n_kv_heads > 64) return 0;  // tickets live in the first 256 bytes
+  return 256 + sizeof(float) * (size_t)n_seqs * n_q_heads * n_splits * (head_dim + 2);
 }
 
 int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream) {
@@ -921,21 +998,23 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
               "scb_decode_attention_fused: group size %d unsupported (1,2,4,7,8)", G);
   SCB_REQUIRE(a->n_splits >= 1 && a->n_splits <= 1024, SCB_ERR_INVALID_ARG,
               "scb_decode_attention_fused: n_splits out of range");
-  const size_t need = scb_decode_attention_fused_workspace_bytes(a->n_q_heads, a->n_kv_heads,
+  SCB_REQUIRE(a->n_seqs >= 1 && a->n_seqs * a->n_kv_heads <= 64, SCB_ERR_INVALID_ARG,
+              "scb_decode_attention_fused: n_seqs=%d out of range (n_seqs * n_kv_heads <= 64)", a->n_seqs);
+  const size_t need = scb_decode_attention_fused_workspace_bytes(a->n_seqs, a->n_q_heads, a->n_kv_heads,
                                                                  a->head_dim, a->n_splits);
   SCB_REQUIRE(a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
               "scb_decode_attention_fused: workspace %zu B < %zu B", a->workspace_bytes, need);
   char* ws = reinterpret_cast<char*>(a->workspace);
   unsigned* tickets = reinterpret_cast<unsigned*>(ws);   // zeroed by scb_decode_attention_fused_init
   float* part_m = reinterpret_cast<float*>(ws + 256);
-  float* part_l = part_m + (size_t)a->n_q_heads * a->n_splits;
-  float* part_o = part_l + (size_t)a->n_q_heads * a->n_splits;
+  float* part_l = part_m + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
+  float* part_o = part_l + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   const int per_max = (int)((a->max_pos + a->n_splits - 1) / a->n_splits);
   const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_max);
   SCB_REQUIRE(smem <= 160 * 1024, SCB_ERR_UNSUPPORTED,
               "scb_decode_attention_fused: max_pos/n_splits too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid(a->n_kv_heads, a->n_splits);
+  dim3 grid(a->n_kv_heads, a->n_splits, a->n_seqs);
   const float sl2 = a->scale * 1.4426950408889634f;
 #define SCB_DAF(HD, GG)                                                                           \
   do {                                                                                            \
@@ -943,12 +1022,14 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
     if (smem > 48 * 1024)                                                                         \
       SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                        (int)smem));                                               \
-    kern<<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(a->qkv), a->inv_freq, a->theta, \
-                                  reinterpret_cast<__half*>(a->k_cache),                          \
-                                  reinterpret_cast<__half*>(a->v_cache), a->max_pos,              \
-                                  a->kv_len_dev, sl2, a->n_q_heads, a->n_kv_heads, per_max,       \
-                                  part_m, part_l, part_o, tickets,                                \
-                                  reinterpret_cast<__half*>(a->out));                             \
+    SCB_CUDA_OK(scb_launch_pdl(kern, grid, dim3(256), smem, st,                                   \
+                               reinterpret_cast<const __half*>(a->qkv), a->inv_freq, a->theta,    \
+                               reinterpret_cast<__half*>(a->k_cache),                             \
+                               reinterpret_cast<__half*>(a->v_cache), (long long)a->max_pos,      \
+                               a->kv_len_dev, sl2, (int)a->n_q_heads, (int)a->n_kv_heads, per_max,\
+                               part_m, part_l, part_o, tickets,                                   \
+                               reinterpret_cast<__half*>(a->out), (long long)a->ld_qkv,           \
+                               (long long)a->cache_seq_stride));                                  \
   } while (0)
   if (a->head_dim == 128) {
     switch (G) {

@@ -211,7 +211,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (col0 + j < ep.n) f[j] += __half2float(ep.bias[col0 + j]);
             }
           }
-          if (ep.act != SCB_ACT_NONE) {
+          if (ep.act != SCB_ACT_NONE && ep.act != SCB_ACT_SILU_PAIR) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
           }
@@ -233,7 +233,34 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (col0 + j < ep.n) f[j] += __half2float(rp[j]);
             }
           }
-          if (ep.out_f32) {
+          if (ep.act == SCB_ACT_SILU_PAIR) {
+            // (gate, up) in adjacent columns -> 16 gated outputs per 32-column chunk
+            __half* op = reinterpret_cast<__half*>(ep.out) + (long long)b * ep.stride_o +
+                         row * ep.ldo + (col0 >> 1);
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float gt = __half2float(__float2half_rn(f[2 * j]));
+              const float up = __half2float(__float2half_rn(f[2 * j + 1]));
+              const float sg = __half2float(__float2half_rn(gt / (1.f + __expf(-gt))));
+              o[j] = sg * up;
+            }
+            if (full_chunk && ep.out_vec) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint4 ov;
+                ov.x = f2_to_h2(o[q * 8 + 0], o[q * 8 + 1]);
+                ov.y = f2_to_h2(o[q * 8 + 2], o[q * 8 + 3]);
+                ov.z = f2_to_h2(o[q * 8 + 4], o[q * 8 + 5]);
+                ov.w = f2_to_h2(o[q * 8 + 6], o[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + q * 8) = ov;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + 2 * j + 1 < ep.n) op[j] = __float2half_rn(o[j]);
+            }
+          } else if (ep.out_f32) {
             float* op = reinterpret_cast<float*>(ep.out) + (long long)b * ep.stride_o +
                         row * ep.ldo + col0;
             if (full_chunk && ep.out_vec) {
@@ -408,8 +435,13 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
               "scb_linear: m=%lld n=%lld k=%lld batch=%d must be >= 1", (long long)a->m,
               (long long)a->n, (long long)a->k, a->batch);
   SCB_REQUIRE(a->a && a->w && a->out, SCB_ERR_INVALID_ARG, "scb_linear: NULL buffer");
-  SCB_REQUIRE(a->lda >= a->k && a->ldw >= a->k && a->ldo >= a->n, SCB_ERR_INVALID_ARG,
-              "scb_linear: leading dimension too small");
+  SCB_REQUIRE(a->lda >= a->k && a->ldw >= a->k &&
+                  a->ldo >= (a->act == SCB_ACT_SILU_PAIR ? a->n / 2 : a->n),
+              SCB_ERR_INVALID_ARG, "scb_linear: leading dimension too small");
+  SCB_REQUIRE(a->act != SCB_ACT_SILU_PAIR ||
+                  (a->n % 2 == 0 && !a->bias && !a->residual && a->out_dtype == SCB_F16),
+              SCB_ERR_INVALID_ARG,
+              "scb_linear: SILU_PAIR needs even n, fp16 out and no bias / residual");
   SCB_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0, SCB_ERR_INVALID_ARG,
               "scb_linear: lda/ldw must be multiples of 8 elements (TMA 16-byte strides)");
   SCB_REQUIRE((uintptr_t)a->a % 16 == 0 && (uintptr_t)a->w % 16 == 0 && (uintptr_t)a->out % 16 == 0,
@@ -423,7 +455,7 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
               "scb_linear: residual must be 16-byte aligned");
   SCB_REQUIRE(a->out_dtype == SCB_F16 || a->out_dtype == SCB_F32, SCB_ERR_UNSUPPORTED,
               "scb_linear: out dtype %d unsupported", a->out_dtype);
-  SCB_REQUIRE(a->act >= SCB_ACT_NONE && a->act <= SCB_ACT_SILU, SCB_ERR_UNSUPPORTED,
+  SCB_REQUIRE(a->act >= SCB_ACT_NONE && a->act <= SCB_ACT_SILU_PAIR, SCB_ERR_UNSUPPORTED,
               "scb_linear: activation %d unsupported", a->act);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Narrow problems keep more CTAs busy with 128-wide tiles; wide ones amortise A with 256.

@@ -249,6 +249,8 @@ __global__ void rope_append_kernel(__half* __restrict__ qkv, long long ld_qkv, i
 // ------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const __half* __restrict__ table, const long long* __restrict__ ids,
                                    int D, __half* __restrict__ out, long long ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();   // ids may come from the previous decode step's fused arg-max
   const long long row = blockIdx.x;
   const long long id = ids[row];
   for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) {
@@ -444,9 +446,11 @@ int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_
   SCB_REQUIRE(table && ids && out && n_ids >= 1 && dim % 8 == 0 && ld_out % 8 == 0 &&
                   aligned16(table) && aligned16(out),
               SCB_ERR_INVALID_ARG, "scb_gather_rows: bad arguments");
-  gather_rows_kernel<<<(unsigned)n_ids, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(table), reinterpret_cast<const long long*>(ids), dim,
-      reinterpret_cast<__half*>(out), ld_out);
+  SCB_CUDA_OK(scb_launch_pdl(gather_rows_kernel, dim3((unsigned)n_ids), dim3(128), 0,
+                             reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const __half*>(table),
+                             reinterpret_cast<const long long*>(ids), (int)dim,
+                             reinterpret_cast<__half*>(out), (long long)ld_out));
   SCB_LAUNCH_OK("gather_rows_kernel");
   return SCB_OK;
 }

@@ -1,6 +1,7 @@
 // scb_api.cu — library-wide C-ABI services: version, thread-local error text, launch counter.
 #include "scb_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = {0};
 static std::atomic<uint64_t> g_launches{0};
@@ -25,6 +26,15 @@ int scb_num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool scb_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SCB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 extern "C" {

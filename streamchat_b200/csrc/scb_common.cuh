@@ -45,6 +45,7 @@ void scb_count_launch(int n = 1);
   } while (0)
 
 int scb_num_sms();  // SM count of the current device (cached)
+bool scb_pdl_enabled();  // programmatic dependent launch for the decode chain (env SCB_PDL=0 disables)
 
 static inline size_t scb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -54,6 +55,29 @@ static inline size_t scb_align_up(size_t x, size_t a) { return (x + a - 1) / a *
 #ifdef __CUDACC__
 
 #define SCB_DEVICE __device__ __forceinline__
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its
+// predecessor drains; it must execute pdl_wait() before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t scb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = scb_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+// Device side of PDL (no-ops when the launch did not carry the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 SCB_DEVICE float warp_sum(float v) {
 #pragma unroll

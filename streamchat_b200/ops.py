@@ -179,7 +179,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         lda, ldw, sa, sw = a.stride(0), w.stride(0), 0, 0
     if lda % 8 or ldw % 8 or (batched and (sa % 8 or sw % 8)):
         raise ValueError("linear: row/batch strides of a and w must be multiples of 8 elements")
-    oshape = (bsz, m, n) if batched else (m, n)
+    n_out = n // 2 if act == L.ACT_SILU_PAIR else n
+    oshape = (bsz, m, n_out) if batched else (m, n_out)
     if out is None:
         out = torch.empty(oshape, dtype=out_dtype, device=dev)
     elif tuple(out.shape) != oshape or out.stride(-1) != 1:
@@ -203,7 +204,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     with torch.cuda.device(dev):
         L.check(L.load().scb_linear(C.byref(args), _stream(dev)), "scb_linear")
     if lead_shape is not None:
-        out = out.view(*lead_shape, n)
+        out = out.view(*lead_shape, n_out)
     return out
 
 
@@ -344,7 +345,7 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, prologue: int = L.PRO_NONE,
          gamma: Optional[torch.Tensor] = None, eps: float = 0.0, out: Optional[torch.Tensor] = None,
          out_dtype: torch.dtype = torch.float16, argmax_out: Optional[torch.Tensor] = None,
-         counters: Optional[torch.Tensor] = None) -> torch.Tensor:
+         counters: Optional[torch.Tensor] = None, epilogue: int = L.EPI_NONE) -> torch.Tensor:
     """Decode-step linear layer for 1..8 activation rows (see scb_gemv).  `argmax_out` (int64
     [rows]) fuses the greedy token choice over the stored output; `counters` (int32) are then
     incremented by one."""
@@ -352,13 +353,17 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     rows = a.shape[0]
     n, k = w.shape
     if out is None:
-        out = torch.empty((rows, n), dtype=out_dtype, device=dev)
+        out = torch.empty((rows, n // 2 if epilogue == L.EPI_SILU_PAIR else n), dtype=out_dtype, device=dev)
     args = L.GemvArgs(a=_ptr(a), w=_ptr(w), bias=_ptr(bias), residual=_ptr(residual), gamma=_ptr(gamma),
                       out=_ptr(out), n=n, k=k, lda=a.stride(0), ldw=w.stride(0),
                       ldr=residual.stride(0) if residual is not None else 0, ldo=out.stride(0),
-                      rows=rows, prologue=prologue, out_dtype=_dtype_code(out), eps=eps)
+                      rows=rows, prologue=prologue, out_dtype=_dtype_code(out), eps=eps, epilogue=epilogue)
     if argmax_out is not None:
-        ws = _workspace(dev, "gemv_argmax", L.load().scb_gemv_workspace_bytes(rows))
+        key = (dev.index, "gemv_argmax", rows)
+        ws = _workspaces.get(key)
+        if ws is None:      # zero-initialised once: the ticket word is self-resetting
+            ws = torch.zeros(L.load().scb_gemv_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+            _workspaces[key] = ws
         args.argmax_out = _ptr(argmax_out)
         args.counters = _ptr(counters)
         args.n_counters = 0 if counters is None else counters.numel()
@@ -392,21 +397,32 @@ def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], 
                            k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len_dev: torch.Tensor,
                            n_q: int, scale: float, workspace: torch.Tensor, n_splits: int = 37,
                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """RoPE + KV append + split attention + combine for ONE new token (see
-    scb_decode_attention_fused).  `workspace` is a caller-held uint8 tensor whose first 256 bytes
-    are zero (use `decode_attention_fused_workspace`)."""
+    """RoPE + KV append + split attention + combine for ONE new token of each of S sequences (see
+    scb_decode_attention_fused).  qkv [S, (n_q+2*n_kv)*hd]; caches [n_kv, max_pos, hd] (S == 1) or
+    [S, n_kv, max_pos, hd]; kv_len_dev int32 [S].  `workspace` is a caller-held uint8 tensor whose
+    first 256 bytes are zero (use `decode_attention_fused_workspace`)."""
     dev = _require_cuda(qkv, inv_freq, k_cache, v_cache, kv_len_dev, workspace, out)
-    hkv, max_pos, d = k_cache.shape
+    n_seqs = qkv.shape[0]
+    if k_cache.dim() == 3:
+        hkv, max_pos, d = k_cache.shape
+        seq_stride = 0
+    else:
+        _, hkv, max_pos, d = k_cache.shape
+        seq_stride = k_cache.stride(0)
     if out is None:
-        out = torch.empty((n_q, d), dtype=torch.float16, device=dev)
+        out = torch.empty((n_seqs, n_q, d), dtype=torch.float16, device=dev)
     args = L.DecodeAttentionFusedArgs(
         qkv=_ptr(qkv), inv_freq=_ptr(inv_freq), k_cache=_ptr(k_cache), v_cache=_ptr(v_cache), out=_ptr(out),
         kv_len_dev=_ptr(kv_len_dev), max_pos=max_pos, n_q_heads=n_q, n_kv_heads=hkv, head_dim=d,
-        n_splits=n_splits, scale=scale, theta=theta, workspace=_ptr(workspace), workspace_bytes=workspace.numel())
+        n_splits=n_splits, scale=scale, theta=theta, n_seqs=n_seqs, ld_qkv=qkv.stride(0),
+        cache_seq_stride=seq_stride, workspace=_ptr(workspace), workspace_bytes=workspace.numel())
     _call("scb_decode_attention_fused", dev, C.byref(args))
     return out
 
 
-def decode_attention_fused_workspace(dev, n_q: int, n_kv: int, head_dim: int, n_splits: int) -> torch.Tensor:
-    n = L.load().scb_decode_attention_fused_workspace_bytes(n_q, n_kv, head_dim, n_splits)
+def decode_attention_fused_workspace(dev, n_q: int, n_kv: int, head_dim: int, n_splits: int,
+                                     n_seqs: int = 1) -> torch.Tensor:
+    n = L.load().scb_decode_attention_fused_workspace_bytes(n_seqs, n_q, n_kv, head_dim, n_splits)
+    if n == 0:
+        raise ValueError("invalid decode_attention_fused configuration")
     return torch.zeros(n, dtype=torch.uint8, device=dev)

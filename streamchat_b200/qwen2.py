@@ -65,7 +65,10 @@ class Qwen2Engine:
                                  w(p + "self_attn.v_proj.bias")], 0).contiguous(),
                 o_w=w(p + "self_attn.o_proj.weight"),
                 ln2=w(p + "post_attention_layernorm.weight"),
-                gu_w=torch.cat([w(p + "mlp.gate_proj.weight"), w(p + "mlp.up_proj.weight")], 0).contiguous(),
+                # gate|up interleaved row-wise (2i = gate_i, 2i+1 = up_i) so the SiLU gate is a pair-wise
+                # epilogue of the fused projection (prefill GEMM and decode GEMV alike)
+                gu_w=torch.stack([w(p + "mlp.gate_proj.weight"), w(p + "mlp.up_proj.weight")], 1)
+                .reshape(2 * c.intermediate_size, c.hidden_size).contiguous(),
                 down_w=w(p + "mlp.down_proj.weight")))
         hd = c.head_dim
         # inv_freq exactly as HF computes it (modeling_qwen2.py:51-114): fp32 table
@@ -82,7 +85,7 @@ class Qwen2Engine:
         self._x2 = torch.zeros_like(self._x)
         self._qkv = torch.zeros((1, qkv_dim), dtype=torch.float16, device=self.device)
         self._attn = torch.zeros((c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
-        self._gu = torch.zeros((1, 2 * c.intermediate_size), dtype=torch.float16, device=self.device)
+        self._gu = torch.zeros((1, c.intermediate_size), dtype=torch.float16, device=self.device)
         self._logits = torch.zeros((1, c.vocab_size), dtype=torch.float16, device=self.device)
         self._attn_ws = ops.decode_attention_fused_workspace(self.device, c.num_attention_heads,
                                                              c.num_key_value_heads, hd, decode_splits)
@@ -136,8 +139,7 @@ class Qwen2Engine:
             ctx = ops.attention(q, k, v, scale, causal=True)
             x = ops.linear(ctx.view(T, Hq * hd), ly["o_w"], residual=x)
             y = ops.rmsnorm(x, ly["ln2"], c.rms_norm_eps)
-            gu = ops.linear(y, ly["gu_w"])
-            y = ops.silu_mul(gu)
+            y = ops.linear(y, ly["gu_w"], act=L.ACT_SILU_PAIR)
             x = ops.linear(y, ly["down_w"], residual=x)
         self.ctx_len = pos0 + T
         # final norm + lm_head on the last position only (logits_to_keep, modeling_qwen2.py:474-475)
@@ -148,7 +150,7 @@ class Qwen2Engine:
     def _decode_step_launches(self) -> None:
         """One cached decode step (142 launches for 28 layers): embeds next_id, runs every layer as
         qkv GEMV (RMSNorm fused) -> fused RoPE/append/attention/combine -> o_proj GEMV (+residual)
-        -> gate|up GEMV (RMSNorm fused) -> down GEMV (SiLU-gate fused, +residual), then the lm_head
+        -> gate|up GEMV (RMSNorm + SiLU-gate fused) -> down GEMV (+residual), then the lm_head
         GEMV with the final norm and the greedy arg-max fused; leaves logits in self._logits, the new
         token in next_id and advances the device-side [position, kv_len] state."""
         c = self.cfg
@@ -163,8 +165,9 @@ class Qwen2Engine:
                                        self.state[1:2], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
                                        out=self._attn)
             ops.gemv(self._attn.view(1, Hq * hd), ly["o_w"], residual=x, out=x2)
-            ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps, out=self._gu)
-            ops.gemv(self._gu, ly["down_w"], residual=x2, prologue=L.PRO_SILU_MUL, out=x)
+            ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps,
+                     epilogue=L.EPI_SILU_PAIR, out=self._gu)
+            ops.gemv(self._gu, ly["down_w"], residual=x2, out=x)
         ops.gemv(x, self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm, eps=c.rms_norm_eps,
                  out=self._logits, argmax_out=self.next_id, counters=self.state)
 

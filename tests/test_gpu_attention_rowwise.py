@@ -292,3 +292,49 @@ def test_decode_attention_fused(cuda, hq, hkv, d, ctx, splits, maxp):
     assert (ws[:256] == 0).all()                                        # tickets left clean
     out2 = ops.decode_attention_fused(qkv.to(cuda), inv_freq.to(cuda), 1e6, kcd, vcd, lens, hq, scale, ws, splits)
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("rows", [1, 5])
+def test_gemv_and_linear_silu_pair_epilogue(cuda, rows):
+    """gate|up interleaved weights: out[r,i] = fp16(silu(fp16 gate_i)) * fp16 up_i — decode GEMV and the
+    tcgen05 prefill GEMM must agree with each other bit for bit on the same rows and with the eager
+    formulation (modeling_qwen2.py:41-48)."""
+    from streamchat_b200 import ops, _lib
+    torch.manual_seed(rows)
+    k, inter = 512, 1536
+    gate = (torch.randn(inter, k) * 0.05).half()
+    up = (torch.randn(inter, k) * 0.05).half()
+    a = torch.randn(rows, k).half()
+    w = torch.stack([gate, up], 1).reshape(2 * inter, k).contiguous()
+    g = (a.double() @ gate.double().t()).float().half().float()
+    u = (a.double() @ up.double().t()).float().half().float()
+    ref = torch.nn.functional.silu(g).half().float() * u
+    out_v = ops.gemv(a.to(cuda), w.to(cuda), epilogue=_lib.EPI_SILU_PAIR)
+    assert out_v.shape == (rows, inter)
+    assert (out_v.float().cpu() - ref).abs().max().item() < 3e-3
+    out_m = ops.linear(a.to(cuda), w.to(cuda), act=_lib.ACT_SILU_PAIR)
+    assert out_m.shape == (rows, inter)
+    assert (out_m.float().cpu() - ref).abs().max().item() < 3e-3
+
+
+def test_decode_attention_fused_multi_sequence(cuda):
+    """Batched captions: S sequences with different lengths in one launch == S single launches."""
+    from streamchat_b200 import ops
+    torch.manual_seed(3)
+    S, hq, hkv, d, maxp, splits = 5, 28, 4, 128, 1024, 37
+    lens = [700, 1, 333, 1000, 64]
+    qkv = torch.randn(S, (hq + 2 * hkv) * d, device=cuda).half()
+    inv_freq = (1.0 / (1000000.0 ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))).to(cuda)
+    kc = torch.randn(S, hkv, maxp, d, device=cuda).half()
+    vc = torch.randn(S, hkv, maxp, d, device=cuda).half()
+    kc1, vc1 = kc.clone(), vc.clone()
+    scale = 1 / math.sqrt(d)
+    ws = ops.decode_attention_fused_workspace(cuda, hq, hkv, d, splits, n_seqs=S)
+    ld = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    out = ops.decode_attention_fused(qkv, inv_freq, 1e6, kc, vc, ld, hq, scale, ws, splits)
+    ws1 = ops.decode_attention_fused_workspace(cuda, hq, hkv, d, splits)
+    for s_ in range(S):
+        o1 = ops.decode_attention_fused(qkv[s_:s_ + 1], inv_freq, 1e6, kc1[s_], vc1[s_], ld[s_:s_ + 1], hq, scale,
+                                        ws1, splits)
+        assert torch.equal(out[s_], o1[0]), s_
+    assert torch.equal(kc, kc1) and torch.equal(vc, vc1)

@@ -1019,7 +1019,7 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
 #define SCB_DAF(HD, GG)                                                                           \
   do {                                                                                            \
     auto kern = decode_attn_fused_kernel<HD, GG>;                                                 \
-    if (smem > 48 * 1024)                                                                         \
+    if (smem > 8 * 1024) /* static o_s takes up to 32 KB of the default 48 KB */                  \
       SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                        (int)smem));                                               \
     SCB_CUDA_OK(scb_launch_pdl(kern, grid, dim3(256), smem, st,                                   \

@@ -36,6 +36,7 @@ class LlavaQwenConfig:
     mm_use_im_patch_token: bool = False
     tokenizer_model_max_length: Optional[int] = None
     max_context: int = 16384
+    max_batch: int = 5            # chunk captions decoded together (one weight pass per step)
 
     @property
     def hidden_size(self) -> int:
@@ -76,7 +77,8 @@ class LlavaQwenForCausalLM:
         self.device = torch.device(device)
         self.dtype = torch.float16
         self.vision = VisionEncoder(weights, config.vision, self.device)
-        self.llm = Qwen2Engine(weights, config.llm, self.device, max_ctx=config.max_context)
+        self.llm = Qwen2Engine(weights, config.llm, self.device, max_ctx=config.max_context,
+                               max_batch=config.max_batch)
         self._inner = _Inner(self)
 
     # ---- reference surface ---------------------------------------------------------------
@@ -154,3 +156,19 @@ class LlavaQwenForCausalLM:
                                  do_sample=do_sample, temperature=temperature,
                                  top_k=kwargs.pop("top_k", 50), top_p=kwargs.pop("top_p", None),
                                  eos_token_id=kwargs.pop("eos_token_id", None))
+
+    @torch.no_grad()
+    def generate_with_image_embedding_batch(self, inputs: torch.Tensor, image_embeddings_list: List[torch.Tensor],
+                                            modalities: Optional[List[str]] = ["image"], max_new_tokens: int = 20,
+                                            eos_token_id=None) -> List[torch.Tensor]:
+        """Greedy `generate_with_image_embedding` for several independent (prompt, features) pairs that
+        share the prompt ids — the per-chunk captions of one memory update (utiles.py:539-559).  Every
+        sequence yields exactly the ids the one-at-a-time call yields; they are decoded in lock-step so
+        each decode step streams the weights once for all of them."""
+        out: List[torch.Tensor] = []
+        B = self.llm.max_batch
+        for i in range(0, len(image_embeddings_list), B):
+            embeds = [self.prepare_inputs_embeddings_for_multimodal(inputs, None, None, None, None, [e], modalities)[4][0]
+                      for e in image_embeddings_list[i:i + B]]
+            out += self.llm.generate_batch(embeds, max_new_tokens, eos_token_id)
+        return out

@@ -115,15 +115,24 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
     merge (k-means over the merged nodes' frames + text summary).  Same positional signature as
     utiles.py:489; keyword-only extras inject determinism."""
     output_list = []
+    flat_chunks = []
     for chunk_feature in chunked_feature_list:
         dimension = chunk_feature[0].shape[-1]
-        chunk_feature = torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device)
+        flat_chunks.append(torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device))
+    if (not caption_do_sample) and len(flat_chunks) > 1 and hasattr(summarizer, "generate_with_image_embedding_batch"):
+        # greedy captions of independent chunks: same ids as one call per chunk, decoded together
         with torch.no_grad():
-            output_ids = summarizer.generate_with_image_embedding(
-                input_ids.to(summarizer.device), image_embeddings=[chunk_feature], modalities=["video"],
-                do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
-                max_new_tokens=CAPTION_TOKENS, use_cache=False)
-        output_list.append(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip())
+            ids_list = summarizer.generate_with_image_embedding_batch(
+                input_ids.to(summarizer.device), flat_chunks, modalities=["video"], max_new_tokens=CAPTION_TOKENS)
+        output_list = [tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip() for ids in ids_list]
+    else:
+        for chunk_feature in flat_chunks:
+            with torch.no_grad():
+                output_ids = summarizer.generate_with_image_embedding(
+                    input_ids.to(summarizer.device), image_embeddings=[chunk_feature], modalities=["video"],
+                    do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
+                    max_new_tokens=CAPTION_TOKENS, use_cache=False)
+            output_list.append(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip())
 
     nodes = [MultimodalTreeNode(t, text, depth=0) for (t, text) in zip(k_means_chunk_feature_list, output_list)]
     if existing_tree:

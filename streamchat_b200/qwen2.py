@@ -39,11 +39,14 @@ class Qwen2Config:
 
 class Qwen2Engine:
     def __init__(self, weights: Dict[str, torch.Tensor], cfg: Qwen2Config, device: torch.device,
-                 max_ctx: int = 16384, decode_splits: int = 37):
+                 max_ctx: int = 16384, decode_splits: int = 37, max_batch: int = 1):
         self.cfg = cfg
         self.device = torch.device(device)
         self.max_ctx = max_ctx
         self.decode_splits = decode_splits
+        self.max_batch = max_batch
+        if max_batch < 1 or max_batch > 8:
+            raise ValueError('max_batch must be in 1..8 (rows of the decode GEMV)')
         c = cfg
         if c.head_dim not in (64, 128):
             raise ValueError(f"head_dim {c.head_dim} unsupported (64 or 128)")
@@ -73,23 +76,25 @@ class Qwen2Engine:
         hd = c.head_dim
         # inv_freq exactly as HF computes it (modeling_qwen2.py:51-114): fp32 table
         self.inv_freq = (1.0 / (c.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).to(self.device)
-        self.k_cache = [torch.zeros((c.num_key_value_heads, max_ctx, hd), dtype=torch.float16, device=self.device)
+        B = max_batch
+        # one KV cache slot per concurrently decoded sequence: [B, Hkv, max_ctx, hd] per layer
+        self.k_cache = [torch.zeros((B, c.num_key_value_heads, max_ctx, hd), dtype=torch.float16, device=self.device)
                         for _ in range(c.num_hidden_layers)]
         self.v_cache = [torch.zeros_like(k) for k in self.k_cache]
-        self.ctx_len = 0
-        # decode state (device-resident so the step graph is replayable)
-        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)     # [position, kv_len]
-        self.next_id = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ctx_lens = [0] * B
+        # decode state (device-resident so the step graphs are replayable): [0] positions, [1] kv lengths
+        self.state = torch.zeros((2, B), dtype=torch.int32, device=self.device)
+        self.next_id = torch.zeros(B, dtype=torch.int64, device=self.device)
         qkv_dim = (c.num_attention_heads + 2 * c.num_key_value_heads) * hd
-        self._x = torch.zeros((1, c.hidden_size), dtype=torch.float16, device=self.device)
+        self._x = torch.zeros((B, c.hidden_size), dtype=torch.float16, device=self.device)
         self._x2 = torch.zeros_like(self._x)
-        self._qkv = torch.zeros((1, qkv_dim), dtype=torch.float16, device=self.device)
-        self._attn = torch.zeros((c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
-        self._gu = torch.zeros((1, c.intermediate_size), dtype=torch.float16, device=self.device)
-        self._logits = torch.zeros((1, c.vocab_size), dtype=torch.float16, device=self.device)
+        self._qkv = torch.zeros((B, qkv_dim), dtype=torch.float16, device=self.device)
+        self._attn = torch.zeros((B, c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
+        self._gu = torch.zeros((B, c.intermediate_size), dtype=torch.float16, device=self.device)
+        self._logits = torch.zeros((B, c.vocab_size), dtype=torch.float16, device=self.device)
         self._attn_ws = ops.decode_attention_fused_workspace(self.device, c.num_attention_heads,
-                                                             c.num_key_value_heads, hd, decode_splits)
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
+                                                             c.num_key_value_heads, hd, decode_splits, n_seqs=B)
+        self._graphs = {}
         self.graph_replays = 0
         self.profile: Optional[list] = None   # bench.py: (start event, end event, steps, bytes) per decode loop
 
@@ -100,9 +105,12 @@ class Qwen2Engine:
             n += sum(t.numel() for t in ly.values())
         return 2 * n
 
-    def decode_bytes_per_token(self, ctx: int) -> int:
+    def kv_bytes_per_token(self, ctx: int) -> int:
         c = self.cfg
-        return self.weight_bytes() + 2 * c.num_hidden_layers * c.num_key_value_heads * ctx * c.head_dim * 2
+        return 2 * c.num_hidden_layers * c.num_key_value_heads * ctx * c.head_dim * 2
+
+    def decode_bytes_per_token(self, ctx: int) -> int:
+        return self.weight_bytes() + self.kv_bytes_per_token(ctx)
 
     def prefill_flops(self, T: int) -> float:
         c = self.cfg
@@ -113,87 +121,166 @@ class Qwen2Engine:
         return c.num_hidden_layers * (per_tok * T + attn)
 
     # ---------------------------------------------------------------- prefill
-    def reset(self) -> None:
-        self.ctx_len = 0
+    @property
+    def ctx_len(self) -> int:
+        return self.ctx_lens[0]
+
+    def reset(self, slot: Optional[int] = None) -> None:
+        if slot is None:
+            self.ctx_lens = [0] * self.max_batch
+        else:
+            self.ctx_lens[slot] = 0
 
     @torch.no_grad()
-    def prefill(self, inputs_embeds: torch.Tensor) -> torch.Tensor:
-        """Append T tokens ([T, H] fp16) to the context; returns fp16 logits [1, V] of the last one."""
+    def prefill(self, inputs_embeds: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """Append T tokens ([T, H] fp16) to the context of cache slot `slot`; returns the fp16 logits
+        [1, V] of the last one (a view of row `slot` of the engine's logits buffer)."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         x = inputs_embeds.to(device=self.device, dtype=torch.float16).contiguous()
         T = x.shape[0]
-        pos0 = self.ctx_len
+        pos0 = self.ctx_lens[slot]
         if pos0 + T > self.max_ctx:
             raise ValueError(f"context {pos0 + T} exceeds max_ctx {self.max_ctx}")
         scale = hd ** -0.5
         for i, ly in enumerate(self.layers):
+            kc, vc = self.k_cache[i][slot], self.v_cache[i][slot]
             y = ops.rmsnorm(x, ly["ln1"], c.rms_norm_eps)
             qkv = ops.linear(y, ly["qkv_w"], bias=ly["qkv_b"])
-            ops.rope_append(qkv, Hq, Hkv, hd, self.inv_freq, c.rope_theta, pos_base=pos0,
-                            k_cache=self.k_cache[i], v_cache=self.v_cache[i])
+            ops.rope_append(qkv, Hq, Hkv, hd, self.inv_freq, c.rope_theta, pos_base=pos0, k_cache=kc, v_cache=vc)
             q = qkv[:, :Hq * hd].view(1, T, Hq, hd)
             kv_len = pos0 + T
-            k = self.k_cache[i][:, :kv_len].permute(1, 0, 2).unsqueeze(0)
-            v = self.v_cache[i][:, :kv_len].permute(1, 0, 2).unsqueeze(0)
+            k = kc[:, :kv_len].permute(1, 0, 2).unsqueeze(0)
+            v = vc[:, :kv_len].permute(1, 0, 2).unsqueeze(0)
             ctx = ops.attention(q, k, v, scale, causal=True)
             x = ops.linear(ctx.view(T, Hq * hd), ly["o_w"], residual=x)
             y = ops.rmsnorm(x, ly["ln2"], c.rms_norm_eps)
             y = ops.linear(y, ly["gu_w"], act=L.ACT_SILU_PAIR)
             x = ops.linear(y, ly["down_w"], residual=x)
-        self.ctx_len = pos0 + T
+        self.ctx_lens[slot] = pos0 + T
         # final norm + lm_head on the last position only (logits_to_keep, modeling_qwen2.py:474-475)
         return ops.gemv(x[T - 1:T], self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm,
-                        eps=c.rms_norm_eps, out=self._logits)
+                        eps=c.rms_norm_eps, out=self._logits[slot:slot + 1])
 
     # ---------------------------------------------------------------- decode
-    def _decode_step_launches(self) -> None:
-        """One cached decode step (142 launches for 28 layers): embeds next_id, runs every layer as
-        qkv GEMV (RMSNorm fused) -> fused RoPE/append/attention/combine -> o_proj GEMV (+residual)
-        -> gate|up GEMV (RMSNorm + SiLU-gate fused) -> down GEMV (+residual), then the lm_head
-        GEMV with the final norm and the greedy arg-max fused; leaves logits in self._logits, the new
-        token in next_id and advances the device-side [position, kv_len] state."""
+    def _decode_step_launches(self, R: int = 1) -> None:
+        """One cached decode step for the first R cache slots (5*layers + 2 launches): embeds
+        next_id[:R], runs every layer as qkv GEMV (RMSNorm fused) -> fused RoPE/append/attention/
+        combine -> o_proj GEMV (+residual) -> gate|up GEMV (RMSNorm + SiLU-gate fused) -> down GEMV
+        (+residual), then the lm_head GEMV with the final norm and the greedy arg-max fused; leaves
+        logits in self._logits[:R], the new tokens in next_id[:R] and advances the device-side
+        [position, kv_len] state.  Rows are independent: a sequence decodes to the same ids whatever R is."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         scale = hd ** -0.5
-        ops.gather_rows(self.embed, self.next_id, out=self._x)
-        x, x2 = self._x, self._x2
+        x, x2 = self._x[:R], self._x2[:R]
+        ops.gather_rows(self.embed, self.next_id[:R], out=x)
         for i, ly in enumerate(self.layers):
             ops.gemv(x, ly["qkv_w"], bias=ly["qkv_b"], prologue=L.PRO_RMSNORM, gamma=ly["ln1"],
-                     eps=c.rms_norm_eps, out=self._qkv)
-            ops.decode_attention_fused(self._qkv, self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
-                                       self.state[1:2], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
-                                       out=self._attn)
-            ops.gemv(self._attn.view(1, Hq * hd), ly["o_w"], residual=x, out=x2)
+                     eps=c.rms_norm_eps, out=self._qkv[:R])
+            ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
+                                       self.state[1, :R], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
+                                       out=self._attn[:R])
+            ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2)
             ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps,
-                     epilogue=L.EPI_SILU_PAIR, out=self._gu)
-            ops.gemv(self._gu, ly["down_w"], residual=x2, out=x)
+                     epilogue=L.EPI_SILU_PAIR, out=self._gu[:R])
+            ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x)
         ops.gemv(x, self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm, eps=c.rms_norm_eps,
-                 out=self._logits, argmax_out=self.next_id, counters=self.state)
+                 out=self._logits[:R], argmax_out=self.next_id[:R], counters=self.state.view(-1))
 
     def launches_per_decode_step(self) -> int:
         return 1 + self.cfg.num_hidden_layers * 5 + 1
 
-    def _ensure_graph(self) -> None:
-        if self._graph is not None:
-            return
-        # warm-up on a side stream (loads modules, sets func attributes), then capture
+    def _ensure_graph(self, R: int) -> "torch.cuda.CUDAGraph":
+        g = self._graphs.get(R)
+        if g is not None:
+            return g
+        # warm-up on a side stream (loads modules, sets func attributes), then capture.  Both scribble on
+        # cache rows 0.. of the first R slots, so graphs are built before any prefill of a generate call.
         saved_state, saved_id = self.state.clone(), self.next_id.clone()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
-            self.state.copy_(torch.tensor([0, 1], dtype=torch.int32))
-            self._decode_step_launches()
+            self.state[0].fill_(0)
+            self.state[1].fill_(1)
+            self._decode_step_launches(R)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
+        self.state[0].fill_(0)
+        self.state[1].fill_(1)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._decode_step_launches()
-        self._graph = g
+            self._decode_step_launches(R)
+        self._graphs[R] = g
         self.state.copy_(saved_state)
         self.next_id.copy_(saved_id)
-        # the warm-up / capture wrote K,V at positions 0..; the caller's context is rebuilt by prefill
         torch.cuda.synchronize(self.device)
+        return g
+
+    @torch.no_grad()
+    def generate_batch(self, inputs_embeds_list: List[torch.Tensor], max_new_tokens: int, eos_token_id=None,
+                       use_graph: bool = True) -> List[torch.Tensor]:
+        """Greedy generation for up to `max_batch` independent prompts: each is prefilled into its own
+        cache slot, then all decode in lock-step (one weight pass per step for all of them).  Returns a
+        list of [1, T_new] int64 tensors, each truncated after its first EOS."""
+        R = len(inputs_embeds_list)
+        if R < 1 or R > self.max_batch:
+            raise ValueError(f"{R} sequences but max_batch={self.max_batch}")
+        with torch.cuda.device(self.device):
+            graph = self._ensure_graph(R) if use_graph else None     # before prefill (see _ensure_graph)
+            self.reset()
+            lens = []
+            for s_, x in enumerate(inputs_embeds_list):
+                logits = self.prefill(x, slot=s_)
+                ops.argmax_rows(logits, out=self.next_id[s_:s_ + 1])
+                lens.append(self.ctx_lens[s_])
+            st = torch.zeros((2, self.max_batch), dtype=torch.int32)
+            st[0, :R] = torch.tensor(lens, dtype=torch.int32)
+            st[1, :R] = st[0, :R] + 1
+            self.state.copy_(st, non_blocking=True)
+            eos = set()
+            if eos_token_id is not None:
+                eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else {int(eos_token_id)}
+            out = torch.zeros((max_new_tokens, R), dtype=torch.int64, device=self.device)
+            ev0 = ev1 = None
+            replays0 = self.graph_replays
+            if self.profile is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            n_steps = 0
+            for step in range(max_new_tokens):
+                out[step].copy_(self.next_id[:R], non_blocking=True)
+                n_steps = step + 1
+                if eos and (step % 16 == 15 or step == max_new_tokens - 1):
+                    toks = out[:n_steps].t().tolist()
+                    if all(any(t in eos for t in row) for row in toks):
+                        break
+                if step == max_new_tokens - 1:
+                    break
+                if graph is not None:
+                    graph.replay()
+                    self.graph_replays += 1
+                else:
+                    self._decode_step_launches(R)
+            if ev0 is not None:
+                ev1.record()
+                n_rep = self.graph_replays - replays0
+                avg_ctx = sum(lens) / R + n_rep // 2
+                self.profile.append({"events": (ev0, ev1), "steps": n_rep, "rows": R,
+                                     "bytes": n_rep * (self.weight_bytes() + R * self.kv_bytes_per_token(int(avg_ctx)))})
+            rows = out[:n_steps].t().contiguous()
+            results = []
+            host = rows.tolist() if eos else None
+            for s_ in range(R):
+                n = n_steps
+                if eos:
+                    for j, t in enumerate(host[s_]):
+                        if t in eos:
+                            n = j + 1
+                            break
+                self.ctx_lens[s_] = lens[s_] + n - 1
+                results.append(rows[s_:s_ + 1, :n].clone())
+            return results
 
     @torch.no_grad()
     def generate(self, inputs_embeds: torch.Tensor, max_new_tokens: int, do_sample: bool = False,
@@ -201,63 +288,30 @@ class Qwen2Engine:
                  eos_token_id=None, use_graph: bool = True) -> torch.Tensor:
         """Prefill + decode; returns the NEW token ids only, [1, T_new] int64 (HF generate with
         inputs_embeds).  Greedy (do_sample False or temperature 0) is the parity path."""
+        if (not do_sample) or temperature == 0:
+            return self.generate_batch([inputs_embeds], max_new_tokens, eos_token_id, use_graph)[0]
+        # sampling path: same kernels, token drawn by torch.multinomial as HF does (hazard H2)
         with torch.cuda.device(self.device):
-            if use_graph:
-                self._ensure_graph()          # before prefill: capture scribbles on cache rows 0..1
             self.reset()
-            logits = self.prefill(inputs_embeds)
-            greedy = (not do_sample) or temperature == 0
+            logits = self.prefill(inputs_embeds, slot=0)
+            T = self.ctx_lens[0]
+            st = torch.zeros((2, self.max_batch), dtype=torch.int32)
+            st[0, 0], st[1, 0] = T, T + 1
+            self.state.copy_(st)
             eos = set()
             if eos_token_id is not None:
                 eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else {int(eos_token_id)}
-            out = torch.zeros(max_new_tokens, dtype=torch.int64, device=self.device)
-            T = self.ctx_len
-            self.state.copy_(torch.tensor([T, T + 1], dtype=torch.int32), non_blocking=True)
-            if greedy:
-                ops.argmax_rows(logits, out=self.next_id)
-            else:
-                self.next_id.copy_(self._sample(logits, temperature, top_k, top_p))
-            n_done = 0
-            ev0 = ev1 = None
-            replays0 = self.graph_replays
-            if self.profile is not None:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
+            toks = []
+            self.next_id[:1].copy_(self._sample(logits, temperature, top_k, top_p))
             for step in range(max_new_tokens):
-                out[step:step + 1].copy_(self.next_id, non_blocking=True)
-                n_done = step + 1
-                if eos and (step % 16 == 15 or step == max_new_tokens - 1):
-                    hit = [j for j, t in enumerate(out[:n_done].tolist()) if t in eos]
-                    if hit:
-                        n_done = hit[0] + 1
-                        break
-                if step == max_new_tokens - 1:
+                t = int(self.next_id[0])
+                toks.append(t)
+                if t in eos or step == max_new_tokens - 1:
                     break
-                if greedy:
-                    if use_graph:
-                        self._graph.replay()
-                        self.graph_replays += 1
-                    else:
-                        self._decode_step_launches()
-                else:
-                    # sampling path: same kernels, token drawn by torch.multinomial as HF does
-                    saved = self.state.clone()
-                    self._decode_step_launches()
-                    self.next_id.copy_(self._sample(self._logits, temperature, top_k, top_p))
-                    self.state.copy_(saved + 1)
-            if ev0 is not None:
-                ev1.record()
-                n_rep = self.graph_replays - replays0
-                self.profile.append({"events": (ev0, ev1), "steps": n_rep,
-                                     "bytes": n_rep * self.decode_bytes_per_token(T + n_rep // 2)})
-            if eos:
-                toks = out[:n_done].tolist()
-                for j, t in enumerate(toks):
-                    if t in eos:
-                        n_done = j + 1
-                        break
-            self.ctx_len = T + n_done - 1
-            return out[:n_done].unsqueeze(0).clone()
+                self._decode_step_launches(1)            # advances state, overwrites next_id with the arg-max
+                self.next_id[:1].copy_(self._sample(self._logits[:1], temperature, top_k, top_p))
+            self.ctx_lens[0] = T + len(toks) - 1
+            return torch.tensor([toks], dtype=torch.int64, device=self.device)
 
     @staticmethod
     def _sample(logits: torch.Tensor, temperature: float, top_k: Optional[int], top_p: Optional[float]) -> torch.Tensor:

@@ -235,7 +235,7 @@ def ours(args):
     roofline = None
     if dec_steps:
         achieved = dec_bytes / (dec_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "gemv_kernel (decode step: 169 of 199 launches)",
+        roofline = {"bound": "hbm", "kernel": "gemv_mma_kernel (decode step: 113 of 142 launches are GEMVs)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": None,
                     "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,

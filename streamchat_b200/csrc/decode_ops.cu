@@ -179,7 +179,7 @@ gemv_kernel(const GemvParams p) {
 //            staging overlaps the weight stream.
 //   lm_head: optional fused arg-max (block-local best, last block reduces; lowest index wins).
 // ------------------------------------------------------------------------------------------
-constexpr int kMU = 8;             // k-tiles (32 halfs each) in flight per warp
+constexpr int kMU = 8;             // k-tiles (32 halfs each) in flight per warp: 4 KB
 constexpr int kMaxMmaWarps = 16;
 
 SCB_DEVICE void mma16816(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
@@ -200,179 +200,166 @@ struct ArgmaxFuse {
   int n_counters;
 };
 
-template <int PRO>
-__global__ void __launch_bounds__(kMaxMmaWarps * 32)
+// kASmem: activation rows are staged (and transformed) in shared memory; otherwise (PRO_NONE only)
+// the A fragments are read straight from global memory through L1 (the rows are tiny and shared by
+// every warp of the SM), which leaves shared memory free and lets 32 warps per SM stream weights.
+template <int PRO, bool kASmem>
+__global__ void __launch_bounds__(kMaxMmaWarps * 32, 2)
 gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
   extern __shared__ __align__(16) unsigned char gsm[];
   const int K = p.K;
   const int lds = K + 32;                                   // row stride (halfs): +64 B breaks bank aliasing
-  __half* a_s = reinterpret_cast<__half*>(gsm);             // [R][lds]
-  float* red = reinterpret_cast<float*>(gsm + (size_t)R * lds * sizeof(__half));   // [W][8][8]
-  __shared__ float sred[kMaxMmaWarps];
-  __shared__ unsigned last_flag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = blockDim.x >> 5;
+  __half* a_s = reinterpret_cast<__half*>(gsm);             // [R][lds] when kASmem
+  float* red = reinterpret_cast<float*>(gsm + (kASmem ? (size_t)R * lds * sizeof(__half) : 0));  // [W][8][8]
+  __shared__ float sred[kMaxMmaWarps];
+  __shared__ unsigned last_flag;
   const int g = lane >> 2, t = lane & 3;
   const int n_groups = (p.N + 7) >> 3;
   const int ktiles = K >> 5;
   const int tiles_per_warp = (ktiles + W - 1) / W;
   const int kt_begin = warp * tiles_per_warp;
   const int kt_end = min(ktiles, kt_begin + tiles_per_warp);
-  const int steps_per_group = (tiles_per_warp + kMU - 1) / kMU;
 
-  // flattened iteration space of this warp: (group, step) with step covering kMU k-tiles
-  int grp = blockIdx.x;
-  int step = 0;
-  auto issue = [&](uint4 (&w)[kMU], int gq, int sq) {
-    const int row = gq * 8 + g;
-    const bool row_ok = gq < n_groups && row < p.N;
+  auto issue = [&](uint4 (&w)[kMU], int grp, int kt0) {
+    const int row = grp * 8 + g;
+    const bool row_ok = grp < n_groups && row < p.N;
     const __half* wr = p.w + (long long)row * p.ldw + t * 8;
 #pragma unroll
     for (int u = 0; u < kMU; ++u) {
-      const int kt = kt_begin + sq * kMU + u;
+      const int kt = kt0 + u;
       w[u] = (row_ok && kt < kt_end) ? ld_stream_u4(wr + kt * 32) : make_uint4(0, 0, 0, 0);
     }
   };
-  uint4 cur[kMU], nxt[kMU];
-  issue(cur, grp, 0);   // weights do not depend on the previous kernel: request them first
+  uint4 wv[kMU];
+  int grp = blockIdx.x;
+  issue(wv, grp, kt_begin);   // weights do not depend on the previous kernel: request them first
   pdl_launch_dependents();
-  pdl_wait();           // activations (and everything we write) belong to the dependency chain
+  pdl_wait();                 // activations (and everything we write) belong to the dependency chain
 
   // ---- prologue: stage (and transform) the activation rows as fp16 values
-  for (int r = 0; r < R; ++r) {
-    const __half* ar = p.a + (long long)r * p.lda;
-    __half* dst = a_s + r * lds;
-    if constexpr (PRO == PRO_RMSNORM) {
-      float ss = 0.f;
-      for (int i = tid; i < (K >> 3); i += blockDim.x) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
+  if constexpr (kASmem) {
+    for (int r = 0; r < R; ++r) {
+      const __half* ar = p.a + (long long)r * p.lda;
+      __half* dst = a_s + r * lds;
+      if constexpr (PRO == PRO_RMSNORM) {
+        float ss = 0.f;
+        for (int i = tid; i < (K >> 3); i += blockDim.x) {
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-      }
-      ss = warp_sum(ss);
-      __syncthreads();
-      if (lane == 0) sred[warp] = ss;
-      __syncthreads();
-      float tot = 0.f;
-      for (int w = 0; w < W; ++w) tot += sred[w];
-      const float rstd = rsqrtf(tot / (float)K + p.eps);
-      for (int i = tid; i < (K >> 3); i += blockDim.x) {
-        float f[8], gm[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
-        unpack8(*reinterpret_cast<const uint4*>(p.gamma + i * 8), gm);
+          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        }
+        ss = warp_sum(ss);
+        __syncthreads();
+        if (lane == 0) sred[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w = 0; w < W; ++w) tot += sred[w];
+        const float rstd = rsqrtf(tot / (float)K + p.eps);
+        for (int i = tid; i < (K >> 3); i += blockDim.x) {
+          float f[8], gm[8], o[8];
+          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
+          unpack8(*reinterpret_cast<const uint4*>(p.gamma + i * 8), gm);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(f[e] * rstd)) * gm[e];
-        uint4 q;
-        q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
-        q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(dst + i * 8) = q;
-      }
-    } else if constexpr (PRO == PRO_SILU_MUL) {
-      for (int i = tid; i < (K >> 3); i += blockDim.x) {
-        float gg[8], uu[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), gg);
-        unpack8(*reinterpret_cast<const uint4*>(ar + K + i * 8), uu);
+          for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(f[e] * rstd)) * gm[e];
+          uint4 q;
+          q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
+          q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dst + i * 8) = q;
+        }
+      } else if constexpr (PRO == PRO_SILU_MUL) {
+        for (int i = tid; i < (K >> 3); i += blockDim.x) {
+          float gg[8], uu[8], o[8];
+          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), gg);
+          unpack8(*reinterpret_cast<const uint4*>(ar + K + i * 8), uu);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          o[e] = __half2float(__float2half_rn(gg[e] / (1.f + __expf(-gg[e])))) * uu[e];
-        uint4 q;
-        q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
-        q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(dst + i * 8) = q;
+          for (int e = 0; e < 8; ++e)
+            o[e] = __half2float(__float2half_rn(gg[e] / (1.f + __expf(-gg[e])))) * uu[e];
+          uint4 q;
+          q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
+          q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dst + i * 8) = q;
+        }
+      } else {
+        for (int i = tid; i < (K >> 3); i += blockDim.x)
+          *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(ar + i * 8);
       }
-    } else {
-      for (int i = tid; i < (K >> 3); i += blockDim.x)
-        *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(ar + i * 8);
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   const bool a_ok = g < R;
-  const __half* a_row = a_s + (a_ok ? g : 0) * lds + t * 8;
-  float best_v[8];
-  int best_i[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    best_v[r] = -INFINITY;
-    best_i[r] = 0x7fffffff;
-  }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const __half* a_row = kASmem ? (a_s + (a_ok ? g : 0) * lds + t * 8)
+                               : (p.a + (long long)(a_ok ? g : 0) * p.lda + t * 8);
+  float best_v = -INFINITY;
+  int best_i = 0x7fffffff;
   while (grp < n_groups) {
-    // next (group, step) of this warp
-    int ngrp = grp, nstep = step + 1;
-    if (nstep == steps_per_group) {
-      nstep = 0;
-      ngrp = grp + gridDim.x;
-    }
-    issue(nxt, ngrp, nstep);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kt0 = kt_begin; kt0 < kt_end; kt0 += kMU) {
+      if (kt0 != kt_begin) issue(wv, grp, kt0);
 #pragma unroll
-    for (int u = 0; u < kMU; ++u) {
-      const int kt = kt_begin + step * kMU + u;
-      uint4 av = make_uint4(0, 0, 0, 0);
-      if (a_ok && kt < kt_end) av = *reinterpret_cast<const uint4*>(a_row + kt * 32);
-      mma16816(acc, av.x, av.y, cur[u].x, cur[u].y);
-      mma16816(acc, av.z, av.w, cur[u].z, cur[u].w);
+      for (int u = 0; u < kMU; ++u) {
+        const int kt = kt0 + u;
+        uint4 av = make_uint4(0, 0, 0, 0);
+        if (a_ok && kt < kt_end) av = *reinterpret_cast<const uint4*>(a_row + kt * 32);
+        mma16816(acc, av.x, av.y, wv[u].x, wv[u].y);
+        mma16816(acc, av.z, av.w, wv[u].z, wv[u].w);
+      }
     }
-    if (nstep == 0) {
-      // ---- group finished for this warp: combine the K splits in warp order, epilogue
-      // acc[0], acc[1] = out[row r = g][n = grp*8 + t*2 + {0,1}]
-      red[(warp * 8 + g) * 8 + t * 2] = acc[0];
-      red[(warp * 8 + g) * 8 + t * 2 + 1] = acc[1];
-      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-      __syncthreads();
-      if (p.silu_pair) {
-        // gate|up interleaved: threads (r, j even) and (r, j+1) hold gate_i and up_i
-        if (tid < 64) {
-          const int r = tid >> 3, j = tid & 7;
-          const int n = grp * 8 + j;
-          float v = 0.f;
-          if (r < R && n < p.N)
-            for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
-          v = __half2float(__float2half_rn(v));                     // Linear output is fp16 in HF
-          const float up = __shfl_xor_sync(0xffffffffu, v, 1);
-          if (r < R && n < p.N && (j & 1) == 0) {
-            const float sg = __half2float(__float2half_rn(v / (1.f + __expf(-v))));
-            reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + (n >> 1)] = __float2half_rn(sg * up);
-          }
-        }
-      } else if (tid < R * 8) {
+    const int ngrp = grp + gridDim.x;
+    issue(wv, ngrp, kt_begin);   // next group's first batch flies during the combine
+    // ---- combine the K splits in warp order, epilogue.
+    // acc[0], acc[1] = out[row r = g][n = grp*8 + t*2 + {0,1}]
+    red[(warp * 8 + g) * 8 + t * 2] = acc[0];
+    red[(warp * 8 + g) * 8 + t * 2 + 1] = acc[1];
+    __syncthreads();
+    if (p.silu_pair) {
+      // gate|up interleaved: threads (r, j even) and (r, j+1) hold gate_i and up_i
+      if (tid < 64) {
         const int r = tid >> 3, j = tid & 7;
         const int n = grp * 8 + j;
-        if (n < p.N) {
-          float v = 0.f;
+        float v = 0.f;
+        if (r < R && n < p.N)
           for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
-          if (p.bias) v += __half2float(p.bias[n]);
-          if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
-          if (p.out_f32) {
-            reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + n] = v;
-          } else {
-            const __half hv = __float2half_rn(v);
-            reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + n] = hv;
-            v = __half2float(hv);          // arg-max sees the stored (rounded) logits
-          }
-          if (am.out_ids) {
-            // threads r*8 .. r*8+7 hold 8 consecutive n of row r: keep the first maximum
-            if (v > best_v[0] || (v == best_v[0] && n < best_i[0])) {
-              best_v[0] = v;
-              best_i[0] = n;
-            }
-          }
+        v = __half2float(__float2half_rn(v));                     // Linear output is fp16 in HF
+        const float up = __shfl_xor_sync(0xffffffffu, v, 1);
+        if (r < R && n < p.N && (j & 1) == 0) {
+          const float sg = __half2float(__float2half_rn(v / (1.f + __expf(-v))));
+          reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + (n >> 1)] = __float2half_rn(sg * up);
         }
       }
-      __syncthreads();
+    } else if (tid < R * 8) {
+      const int r = tid >> 3, j = tid & 7;
+      const int n = grp * 8 + j;
+      if (n < p.N) {
+        float v = 0.f;
+        for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
+        if (p.bias) v += __half2float(p.bias[n]);
+        if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
+        if (p.out_f32) {
+          reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + n] = v;
+        } else {
+          const __half hv = __float2half_rn(v);
+          reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + n] = hv;
+          v = __half2float(hv);          // arg-max sees the stored (rounded) logits
+        }
+        if (am.out_ids && (v > best_v || (v == best_v && n < best_i))) {
+          best_v = v;
+          best_i = n;
+        }
+      }
     }
-#pragma unroll
-    for (int u = 0; u < kMU; ++u) cur[u] = nxt[u];
+    __syncthreads();
     grp = ngrp;
-    step = nstep;
   }
 
   if (am.out_ids) {
     // ---- fused arg-max: thread (r, j) holds the best over its column residue; reduce the 8
     // threads of each row, publish per block, the last block reduces the blocks
-    float bv = best_v[0];
-    int bi = best_i[0];
+    float bv = best_v;
+    int bi = best_i;
     if (tid < 64) {   // R <= 8 rows x 8 threads, aligned groups of 8 lanes
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
@@ -865,30 +852,34 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
       am.counters = a->counters;
       am.n_counters = a->counters ? a->n_counters : 0;
     }
-    const size_t act = (size_t)a->rows * (a->k + 32) * sizeof(__half);
-    SCB_REQUIRE(act + kMaxMmaWarps * 256 <= 220 * 1024, SCB_ERR_UNSUPPORTED,
-                "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
-    int per_sm = (int)((220 * 1024) / (act + 4096 + 1024));
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int W = (16 + per_sm - 1) / per_sm;       // >= 16 warps (64 KB of loads in flight) per SM
-    W = W <= 4 ? 4 : (W <= 8 ? 8 : 16);
-    const size_t smem = act + (size_t)W * 256;
+    // shape of the launch: enough warps to keep >= 32 per SM streaming, K split over the W warps
+    // of a block so that each warp needs only a few 4 KB batches per 8-row group
     const long long n_groups = (a->n + 7) / 8;
+    int W = 4;
+    while (W < kMaxMmaWarps && n_groups * W < (long long)sms * 32) W *= 2;
+    const bool a_smem = a->prologue != PRO_NONE;
+    const size_t act = a_smem ? (size_t)a->rows * (a->k + 32) * sizeof(__half) : 0;
+    const size_t smem = act + (size_t)W * 256;
+    SCB_REQUIRE(smem <= 220 * 1024, SCB_ERR_UNSUPPORTED,
+                "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
+    int per_sm = 32 / W;                                   // 32 warps per SM (64 registers per thread)
+    const int by_smem = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
     long long cap = (long long)sms * per_sm;
     if (cap > 2048) cap = 2048;
     const int grid = (int)(n_groups < cap ? n_groups : cap);
-#define SCB_GEMV_MMA(PRO)                                                                        \
+#define SCB_GEMV_MMA(PRO, ASM)                                                                   \
   do {                                                                                           \
-    auto kern = gemv_mma_kernel<PRO>;                                                            \
+    auto kern = gemv_mma_kernel<PRO, ASM>;                                                       \
     if (smem > 48 * 1024)                                                                        \
       SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                        (int)smem));                                              \
     SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(W * 32), smem, st, p, (int)a->rows, am));  \
   } while (0)
-    if (a->prologue == PRO_RMSNORM) SCB_GEMV_MMA(PRO_RMSNORM);
-    else if (a->prologue == PRO_SILU_MUL) SCB_GEMV_MMA(PRO_SILU_MUL);
-    else SCB_GEMV_MMA(PRO_NONE);
+    if (a->prologue == PRO_RMSNORM) SCB_GEMV_MMA(PRO_RMSNORM, true);
+    else if (a->prologue == PRO_SILU_MUL) SCB_GEMV_MMA(PRO_SILU_MUL, true);
+    else SCB_GEMV_MMA(PRO_NONE, false);
 #undef SCB_GEMV_MMA
     SCB_LAUNCH_OK("gemv_mma_kernel");
     return SCB_OK;

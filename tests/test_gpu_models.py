@@ -112,3 +112,27 @@ def test_wider_model_vs_oracle(cuda):
             margin = float(top2[0] - top2[1])
             assert margin < 4e-3 * float(ref_logits[i].abs().max()), (i, got, want, margin)
             break
+
+
+def test_batched_generation_equals_sequential(cuda, golden_dir):
+    """Chunk captions decoded together (one weight pass per step) give, per sequence, exactly the ids
+    of the one-at-a-time calls — the precondition for batching the reference's caption loop."""
+    g, W, model = _tiny(golden_dir, cuda)
+    torch.manual_seed(5)
+    ids = torch.from_numpy(g["prompt_ids"])
+    embs = [(torch.randn(n, 256) * 0.5).half().to(cuda) for n in (12, 40, 7, 25, 33)]
+    seq = [model.generate_with_image_embedding(ids, image_embeddings=[e], do_sample=False, max_new_tokens=9)
+           for e in embs]
+    bat = model.generate_with_image_embedding_batch(ids, embs, modalities=["video"], max_new_tokens=9)
+    assert len(bat) == 5
+    for a, b in zip(seq, bat):
+        assert torch.equal(a, b)
+    # EOS truncation per sequence
+    eos = int(seq[1][0, 3])
+    bat2 = model.llm.generate_batch(
+        [model.prepare_inputs_embeddings_for_multimodal(ids, None, None, None, None, [e], ["video"])[4][0] for e in embs],
+        9, eos_token_id=eos)
+    for a, b in zip(seq, bat2):
+        row = a[0].tolist()
+        n = row.index(eos) + 1 if eos in row else len(row)
+        assert b[0].tolist() == row[:n]

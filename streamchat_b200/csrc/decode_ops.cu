@@ -200,31 +200,33 @@ struct ArgmaxFuse {
   int n_counters;
 };
 
-// kASmem: activation rows are staged (and transformed) in shared memory; otherwise (PRO_NONE only)
-// the A fragments are read straight from global memory through L1 (the rows are tiny and shared by
-// every warp of the SM), which leaves shared memory free and lets 32 warps per SM stream weights.
-template <int PRO, bool kASmem>
-__global__ void __launch_bounds__(kMaxMmaWarps * 32, 2)
-gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
-  extern __shared__ __align__(16) unsigned char gsm[];
-  const int K = p.K;
-  const int lds = K + 32;                                   // row stride (halfs): +64 B breaks bank aliasing
+// Work unit = (group of 8 weight rows, K chunk).  Skinny layers (few row groups, long K: o_proj,
+// down_proj, qkv) are cut into several K chunks so that one wave of 8 blocks x 148 SMs is full;
+// the chunks of a group meet through a partial buffer and an atomic ticket — the last block to
+// arrive sums them in chunk order (deterministic) and runs the epilogue.
+constexpr int kGW = 4;             // warps per block
+
+__global__ void __launch_bounds__(kGW * 32, 8)
+gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict__ partial,
+                unsigned* __restrict__ gtickets, const ArgmaxFuse am) {
+  __shared__ float red[kGW][8][8];
+  __shared__ unsigned flag_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W = blockDim.x >> 5;
-  __half* a_s = reinterpret_cast<__half*>(gsm);             // [R][lds] when kASmem
-  float* red = reinterpret_cast<float*>(gsm + (kASmem ? (size_t)R * lds * sizeof(__half) : 0));  // [W][8][8]
-  __shared__ float sred[kMaxMmaWarps];
-  __shared__ unsigned last_flag;
   const int g = lane >> 2, t = lane & 3;
   const int n_groups = (p.N + 7) >> 3;
-  const int ktiles = K >> 5;
-  const int tiles_per_warp = (ktiles + W - 1) / W;
-  const int kt_begin = warp * tiles_per_warp;
-  const int kt_end = min(ktiles, kt_begin + tiles_per_warp);
+  const int n_units = n_groups * C;
+  const int ktiles = p.K >> 5;
 
-  auto issue = [&](uint4 (&w)[kMU], int grp, int kt0) {
-    const int row = grp * 8 + g;
-    const bool row_ok = grp < n_groups && row < p.N;
+  // tile range of (chunk c, this warp): chunk c covers [c*T/C, (c+1)*T/C), split over the warps
+  auto tile_range = [&](int c, int& b, int& e) {
+    const int cb = (int)((long long)ktiles * c / C), ce = (int)((long long)ktiles * (c + 1) / C);
+    const int per = (ce - cb + kGW - 1) / kGW;
+    b = cb + warp * per;
+    e = min(ce, b + per);
+  };
+  auto issue = [&](uint4 (&w)[kMU], int unit, int kt0, int kt_end) {
+    const int row = (unit / C) * 8 + g;
+    const bool row_ok = unit < n_units && row < p.N;
     const __half* wr = p.w + (long long)row * p.ldw + t * 8;
 #pragma unroll
     for (int u = 0; u < kMU; ++u) {
@@ -233,126 +235,96 @@ gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
     }
   };
   uint4 wv[kMU];
-  int grp = blockIdx.x;
-  issue(wv, grp, kt_begin);   // weights do not depend on the previous kernel: request them first
+  int unit = blockIdx.x;
+  int kb = 0, ke = 0;
+  if (unit < n_units) tile_range(unit % C, kb, ke);
+  issue(wv, unit, kb, ke);    // weights do not depend on the previous kernel: request them first
   pdl_launch_dependents();
   pdl_wait();                 // activations (and everything we write) belong to the dependency chain
 
-  // ---- prologue: stage (and transform) the activation rows as fp16 values
-  if constexpr (kASmem) {
-    for (int r = 0; r < R; ++r) {
-      const __half* ar = p.a + (long long)r * p.lda;
-      __half* dst = a_s + r * lds;
-      if constexpr (PRO == PRO_RMSNORM) {
-        float ss = 0.f;
-        for (int i = tid; i < (K >> 3); i += blockDim.x) {
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
-        }
-        ss = warp_sum(ss);
-        __syncthreads();
-        if (lane == 0) sred[warp] = ss;
-        __syncthreads();
-        float tot = 0.f;
-        for (int w = 0; w < W; ++w) tot += sred[w];
-        const float rstd = rsqrtf(tot / (float)K + p.eps);
-        for (int i = tid; i < (K >> 3); i += blockDim.x) {
-          float f[8], gm[8], o[8];
-          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), f);
-          unpack8(*reinterpret_cast<const uint4*>(p.gamma + i * 8), gm);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(f[e] * rstd)) * gm[e];
-          uint4 q;
-          q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
-          q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dst + i * 8) = q;
-        }
-      } else if constexpr (PRO == PRO_SILU_MUL) {
-        for (int i = tid; i < (K >> 3); i += blockDim.x) {
-          float gg[8], uu[8], o[8];
-          unpack8(*reinterpret_cast<const uint4*>(ar + i * 8), gg);
-          unpack8(*reinterpret_cast<const uint4*>(ar + K + i * 8), uu);
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o[e] = __half2float(__float2half_rn(gg[e] / (1.f + __expf(-gg[e])))) * uu[e];
-          uint4 q;
-          q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
-          q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dst + i * 8) = q;
-        }
-      } else {
-        for (int i = tid; i < (K >> 3); i += blockDim.x)
-          *reinterpret_cast<uint4*>(dst + i * 8) = *reinterpret_cast<const uint4*>(ar + i * 8);
-      }
-    }
-    __syncthreads();
-  }
-
   const bool a_ok = g < R;
-  const __half* a_row = kASmem ? (a_s + (a_ok ? g : 0) * lds + t * 8)
-                               : (p.a + (long long)(a_ok ? g : 0) * p.lda + t * 8);
+  const __half* a_row = p.a + (long long)(a_ok ? g : 0) * p.lda + t * 8;   // read through L1 (tiny, shared)
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
-  while (grp < n_groups) {
+  while (unit < n_units) {
+    const int grp = unit / C, c = unit - grp * C;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kt0 = kt_begin; kt0 < kt_end; kt0 += kMU) {
-      if (kt0 != kt_begin) issue(wv, grp, kt0);
+    for (int kt0 = kb; kt0 < ke; kt0 += kMU) {
+      if (kt0 != kb) issue(wv, unit, kt0, ke);
 #pragma unroll
       for (int u = 0; u < kMU; ++u) {
         const int kt = kt0 + u;
         uint4 av = make_uint4(0, 0, 0, 0);
-        if (a_ok && kt < kt_end) av = *reinterpret_cast<const uint4*>(a_row + kt * 32);
+        if (a_ok && kt < ke) av = __ldg(reinterpret_cast<const uint4*>(a_row + kt * 32));
         mma16816(acc, av.x, av.y, wv[u].x, wv[u].y);
         mma16816(acc, av.z, av.w, wv[u].z, wv[u].w);
       }
     }
-    const int ngrp = grp + gridDim.x;
-    issue(wv, ngrp, kt_begin);   // next group's first batch flies during the combine
-    // ---- combine the K splits in warp order, epilogue.
-    // acc[0], acc[1] = out[row r = g][n = grp*8 + t*2 + {0,1}]
-    red[(warp * 8 + g) * 8 + t * 2] = acc[0];
-    red[(warp * 8 + g) * 8 + t * 2 + 1] = acc[1];
+    const int nunit = unit + gridDim.x;
+    int nkb = 0, nke = 0;
+    if (nunit < n_units) tile_range(nunit % C, nkb, nke);
+    issue(wv, nunit, nkb, nke);   // next unit's first batch flies during the combine
+    // ---- combine the warps in order: acc[0], acc[1] = out[row g][n = grp*8 + t*2 + {0,1}]
+    red[warp][g][t * 2] = acc[0];
+    red[warp][g][t * 2 + 1] = acc[1];
     __syncthreads();
+    const int r = tid >> 3, j = tid & 7;
+    const int n = grp * 8 + j;
+    float v = 0.f;
+    bool have = false;                    // this thread holds a finished output value
+    if (tid < 64 && r < R) {
+#pragma unroll
+      for (int w = 0; w < kGW; ++w) v += red[w][r][j];
+      have = (C == 1);
+    }
+    if (C > 1) {
+      if (tid < 64 && r < R) partial[((long long)grp * C + c) * 64 + tid] = v;
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned tk = atomicAdd(&gtickets[grp], 1u);
+        flag_s = (tk == (unsigned)C - 1u) ? 1u : 0u;
+      }
+      __syncthreads();
+      if (flag_s) {
+        __threadfence();
+        if (tid < 64 && r < R) {
+          v = 0.f;
+          for (int cc = 0; cc < C; ++cc) v += __ldcg(partial + ((long long)grp * C + cc) * 64 + tid);
+          have = true;
+        }
+        if (tid == 0) gtickets[grp] = 0;
+      }
+    }
+    // ---- epilogue (warp-uniform branch on silu_pair; `have` only where a value is final)
     if (p.silu_pair) {
-      // gate|up interleaved: threads (r, j even) and (r, j+1) hold gate_i and up_i
       if (tid < 64) {
-        const int r = tid >> 3, j = tid & 7;
-        const int n = grp * 8 + j;
-        float v = 0.f;
-        if (r < R && n < p.N)
-          for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
-        v = __half2float(__float2half_rn(v));                     // Linear output is fp16 in HF
-        const float up = __shfl_xor_sync(0xffffffffu, v, 1);
-        if (r < R && n < p.N && (j & 1) == 0) {
-          const float sg = __half2float(__float2half_rn(v / (1.f + __expf(-v))));
+        const float gt = __half2float(__float2half_rn(v));       // Linear output is fp16 in HF
+        const float up = __shfl_xor_sync(0xffffffffu, gt, 1);
+        if (have && n < p.N && (j & 1) == 0) {
+          const float sg = __half2float(__float2half_rn(gt / (1.f + __expf(-gt))));
           reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + (n >> 1)] = __float2half_rn(sg * up);
         }
       }
-    } else if (tid < R * 8) {
-      const int r = tid >> 3, j = tid & 7;
-      const int n = grp * 8 + j;
-      if (n < p.N) {
-        float v = 0.f;
-        for (int w = 0; w < W; ++w) v += red[(w * 8 + r) * 8 + j];
-        if (p.bias) v += __half2float(p.bias[n]);
-        if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
-        if (p.out_f32) {
-          reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + n] = v;
-        } else {
-          const __half hv = __float2half_rn(v);
-          reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + n] = hv;
-          v = __half2float(hv);          // arg-max sees the stored (rounded) logits
-        }
-        if (am.out_ids && (v > best_v || (v == best_v && n < best_i))) {
-          best_v = v;
-          best_i = n;
-        }
+    } else if (have && n < p.N) {
+      if (p.bias) v += __half2float(p.bias[n]);
+      if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
+      if (p.out_f32) {
+        reinterpret_cast<float*>(p.out)[(long long)r * p.ldo + n] = v;
+      } else {
+        const __half hv = __float2half_rn(v);
+        reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + n] = hv;
+        v = __half2float(hv);          // arg-max sees the stored (rounded) logits
+      }
+      if (am.out_ids && (v > best_v || (v == best_v && n < best_i))) {
+        best_v = v;
+        best_i = n;
       }
     }
-    __syncthreads();
-    grp = ngrp;
+    __syncthreads();   // red / flag_s reuse
+    unit = nunit;
+    kb = nkb;
+    ke = nke;
   }
 
   if (am.out_ids) {
@@ -379,29 +351,28 @@ gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
     __syncthreads();
     if (tid == 0) {
       const unsigned tk = atomicAdd(am.ticket, 1u);
-      last_flag = (tk == gridDim.x - 1) ? 1u : 0u;
+      flag_s = (tk == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (last_flag) {
+    if (flag_s) {
       __threadfence();
-      // warp r (strided) reduces row r over all blocks
-      for (int row = warp; row < R; row += W) {
-        float v = -INFINITY;
+      for (int row = warp; row < R; row += kGW) {
+        float bv2 = -INFINITY;
         int ix = 0x7fffffff;
         for (int b = lane; b < (int)gridDim.x; b += 32) {
           const float ov = __ldcg(am.blk_val + (long long)b * R + row);
           const int oi = __ldcg(am.blk_idx + (long long)b * R + row);
-          if (ov > v || (ov == v && oi < ix)) {
-            v = ov;
+          if (ov > bv2 || (ov == bv2 && oi < ix)) {
+            bv2 = ov;
             ix = oi;
           }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const float ov = __shfl_xor_sync(0xffffffffu, bv2, o);
           const int oi = __shfl_xor_sync(0xffffffffu, ix, o);
-          if (ov > v || (ov == v && oi < ix)) {
-            v = ov;
+          if (ov > bv2 || (ov == bv2 && oi < ix)) {
+            bv2 = ov;
             ix = oi;
           }
         }
@@ -409,7 +380,7 @@ gemv_mma_kernel(const GemvParams p, const int R, const ArgmaxFuse am) {
       }
       if (tid == 0) {
         *am.ticket = 0;
-        for (int c = 0; c < am.n_counters; ++c) am.counters[c] += 1;
+        for (int cc = 0; cc < am.n_counters; ++cc) am.counters[cc] += 1;
       }
     }
   }
@@ -559,6 +530,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   float* q_s = dsm;                 // [G][HD] rotated q, pre-scaled by scale*log2(e)
   float* s_s = dsm + G * HD;        // [G][per_max] scores -> probabilities
   __shared__ float m_s[G], l_s[G];
+  __shared__ float m_sp[G * 64], l_sp[G * 64];   // per-split statistics for the combine (n_splits <= 64)
   __shared__ float o_s[8][G][HD];   // per-warp partial outputs
   __shared__ unsigned last_flag;
   const int hk = blockIdx.x, split = blockIdx.y, n_splits = gridDim.y;
@@ -751,19 +723,46 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   __syncthreads();
   if (!last_flag) return;
   __threadfence();
+  // stage the per-split statistics of the G heads (one round trip), turn them into weights
+  float* w_s = s_s;                      // [G][n_splits] reuse of the score buffer (n_splits <= per_max*...)
+  __shared__ float inv_l[G];
+  for (int idx = tid; idx < G * n_splits; idx += 256) {
+    const int h = idx / n_splits, sp = idx % n_splits;
+    const long long base = (long long)(hk * G + h) * n_splits + sp;
+    m_sp[idx] = __ldcg(part_m + base);
+    l_sp[idx] = __ldcg(part_l + base);
+  }
+  __syncthreads();
+  if (warp < G) {
+    float mm = -INFINITY;
+    for (int sp = lane; sp < n_splits; sp += 32) mm = fmaxf(mm, m_sp[warp * n_splits + sp]);
+    mm = warp_max(mm);
+    float ll = 0.f;
+    for (int sp = lane; sp < n_splits; sp += 32) {
+      const float pm = m_sp[warp * n_splits + sp];
+      const float scl = (pm == -INFINITY) ? 0.f : exp2f(pm - mm);
+      w_s[warp * n_splits + sp] = scl;
+      ll = fmaf(l_sp[warp * n_splits + sp], scl, ll);
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) inv_l[warp] = ll > 0.f ? 1.f / ll : 0.f;
+  }
+  __syncthreads();
   for (int idx = tid; idx < G * HD; idx += 256) {
     const int h = idx / HD, d = idx % HD;
-    const long long base = (long long)(hk * G + h) * n_splits;
-    float mm = -INFINITY;
-    for (int sp = 0; sp < n_splits; ++sp) mm = fmaxf(mm, __ldcg(part_m + base + sp));
-    float ll = 0.f, oo = 0.f;
-    for (int sp = 0; sp < n_splits; ++sp) {
-      const float pm = __ldcg(part_m + base + sp);
-      const float scl = (pm == -INFINITY) ? 0.f : exp2f(pm - mm);
-      ll = fmaf(__ldcg(part_l + base + sp), scl, ll);
-      oo = fmaf(__ldcg(part_o + (base + sp) * HD + d), scl, oo);
+    const float* po = part_o + ((long long)(hk * G + h) * n_splits) * HD + d;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= n_splits; sp += 4) {    // four independent loads in flight
+      const float a0 = __ldcg(po + (long long)(sp + 0) * HD), a1 = __ldcg(po + (long long)(sp + 1) * HD);
+      const float a2 = __ldcg(po + (long long)(sp + 2) * HD), a3 = __ldcg(po + (long long)(sp + 3) * HD);
+      o0 = fmaf(a0, w_s[h * n_splits + sp + 0], o0);
+      o1 = fmaf(a1, w_s[h * n_splits + sp + 1], o1);
+      o2 = fmaf(a2, w_s[h * n_splits + sp + 2], o2);
+      o3 = fmaf(a3, w_s[h * n_splits + sp + 3], o3);
     }
-    out[(long long)(hk * G + h) * HD + d] = __float2half_rn(ll > 0.f ? oo / ll : 0.f);
+    for (; sp < n_splits; ++sp) o0 = fmaf(__ldcg(po + (long long)sp * HD), w_s[h * n_splits + sp], o0);
+    out[(long long)(hk * G + h) * HD + d] = __float2half_rn(((o0 + o1) + (o2 + o3)) * inv_l[h]);
   }
   if (tid == 0) tickets[hk] = 0;
 }
@@ -792,10 +791,17 @@ int launch_gemv(const GemvParams& p, int prologue, int grid, size_t smem, cudaSt
 
 extern "C" {
 
+// workspace layout: [0,256) arg-max ticket | per-block arg-max (value,index) for 2048 blocks x 8 rows
+//                   | group tickets (kMaxSplitGroups u32) | K-chunk partials
+constexpr int kMaxSplitGroups = 4096;
+constexpr int kMaxChunks = 8;
+constexpr size_t kWsArgmax = 256 + (size_t)2048 * 8 * (sizeof(float) + sizeof(int));
+constexpr size_t kWsTickets = (size_t)kMaxSplitGroups * sizeof(unsigned);
+constexpr size_t kWsPartial = (size_t)kMaxSplitGroups * kMaxChunks * 64 * sizeof(float);
+
 size_t scb_gemv_workspace_bytes(int32_t rows) {
   if (rows < 1 || rows > 8) return 0;
-  // fused arg-max scratch: ticket + per-block (value, index) for up to 2048 blocks
-  return 256 + (size_t)2048 * rows * (sizeof(float) + sizeof(int));
+  return kWsArgmax + kWsTickets + kWsPartial;
 }
 
 int scb_gemv(const scb_gemv_args* a, void* stream) {
@@ -836,59 +842,60 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   const int sms = scb_num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-  if (a->k % 32 == 0) {
-    // ---- tensor-core streaming path
-    ArgmaxFuse am{};
-    if (a->argmax_out) {
-      const size_t need = scb_gemv_workspace_bytes(a->rows);
-      SCB_REQUIRE(a->workspace && a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
-                  "scb_gemv: fused arg-max needs a %zu B workspace", need);
-      SCB_REQUIRE(!p.out_f32 || true, SCB_ERR_INVALID_ARG, "unreachable");
-      char* ws = reinterpret_cast<char*>(a->workspace);
-      am.ticket = reinterpret_cast<unsigned*>(ws);
-      am.blk_val = reinterpret_cast<float*>(ws + 256);
-      am.blk_idx = reinterpret_cast<int*>(ws + 256 + (size_t)2048 * a->rows * sizeof(float));
-      am.out_ids = reinterpret_cast<long long*>(a->argmax_out);
-      am.counters = a->counters;
-      am.n_counters = a->counters ? a->n_counters : 0;
-    }
-    // shape of the launch: enough warps to keep >= 32 per SM streaming, K split over the W warps
-    // of a block so that each warp needs only a few 4 KB batches per 8-row group
+  if (a->k % 32 == 0 && a->prologue == PRO_NONE) {
+    // ---- tensor-core streaming path (activations already normalised / gated by the caller)
     const long long n_groups = (a->n + 7) / 8;
-    int W = 4;
-    while (W < kMaxMmaWarps && n_groups * W < (long long)sms * 32) W *= 2;
-    const bool a_smem = a->prologue != PRO_NONE;
-    const size_t act = a_smem ? (size_t)a->rows * (a->k + 32) * sizeof(__half) : 0;
-    const size_t smem = act + (size_t)W * 256;
-    SCB_REQUIRE(smem <= 220 * 1024, SCB_ERR_UNSUPPORTED,
-                "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
-    int per_sm = 32 / W;                                   // 32 warps per SM (64 registers per thread)
-    const int by_smem = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > by_smem) per_sm = by_smem;
-    if (per_sm < 1) per_sm = 1;
-    long long cap = (long long)sms * per_sm;
-    if (cap > 2048) cap = 2048;
-    const int grid = (int)(n_groups < cap ? n_groups : cap);
-#define SCB_GEMV_MMA(PRO, ASM)                                                                   \
-  do {                                                                                           \
-    auto kern = gemv_mma_kernel<PRO, ASM>;                                                       \
-    if (smem > 48 * 1024)                                                                        \
-      SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                       (int)smem));                                              \
-    SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(W * 32), smem, st, p, (int)a->rows, am));  \
-  } while (0)
-    if (a->prologue == PRO_RMSNORM) SCB_GEMV_MMA(PRO_RMSNORM, true);
-    else if (a->prologue == PRO_SILU_MUL) SCB_GEMV_MMA(PRO_SILU_MUL, true);
-    else SCB_GEMV_MMA(PRO_NONE, false);
-#undef SCB_GEMV_MMA
+    const int ktiles = (int)(a->k / 32);
+    const long long wave = (long long)sms * 8;             // 8 blocks of 4 warps per SM
+    // K chunks: fill whole waves (skinny layers), keep >= 2 batches of 8 tiles per warp
+    int C = 1;
+    if (n_groups <= kMaxSplitGroups && a->workspace) {
+      double best_eff = 0.0;
+      for (int c = 1; c <= kMaxChunks; ++c) {
+        if (c > 1 && ktiles / (c * kGW) < 2 * kMU) break;
+        const long long units = n_groups * c;
+        const double eff = (double)units / (double)(((units + wave - 1) / wave) * wave);
+        if (eff > best_eff + 0.02) {
+          best_eff = eff;
+          C = c;
+        }
+      }
+    }
+    ArgmaxFuse am{};
+    float* partial = nullptr;
+    unsigned* gtickets = nullptr;
+    if (a->workspace) {
+      const size_t need = scb_gemv_workspace_bytes(a->rows);
+      SCB_REQUIRE(a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
+                  "scb_gemv: workspace %zu B < required %zu B", a->workspace_bytes, need);
+      char* ws = reinterpret_cast<char*>(a->workspace);
+      gtickets = reinterpret_cast<unsigned*>(ws + kWsArgmax);
+      partial = reinterpret_cast<float*>(ws + kWsArgmax + kWsTickets);
+      if (a->argmax_out) {
+        am.ticket = reinterpret_cast<unsigned*>(ws);
+        am.blk_val = reinterpret_cast<float*>(ws + 256);
+        am.blk_idx = reinterpret_cast<int*>(ws + 256 + (size_t)2048 * 8 * sizeof(float));
+        am.out_ids = reinterpret_cast<long long*>(a->argmax_out);
+        am.counters = a->counters;
+        am.n_counters = a->counters ? a->n_counters : 0;
+      }
+    } else {
+      SCB_REQUIRE(!a->argmax_out, SCB_ERR_WORKSPACE, "scb_gemv: fused arg-max needs the workspace");
+    }
+    const long long units = n_groups * C;
+    long long cap = wave < 2048 ? wave : 2048;
+    const int grid = (int)(units < cap ? units : cap);
+    SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel, dim3(grid), dim3(kGW * 32), 0, st, p, (int)a->rows, C,
+                               partial, gtickets, am));
     SCB_LAUNCH_OK("gemv_mma_kernel");
     return SCB_OK;
   }
 
   // ---- SIMT path for k not a multiple of 32
   SCB_REQUIRE(a->rows == 1 || a->rows == 2 || a->rows == 4, SCB_ERR_UNSUPPORTED,
-              "scb_gemv: k %% 32 != 0 supports rows 1, 2 or 4 only");
-  SCB_REQUIRE(!a->argmax_out, SCB_ERR_UNSUPPORTED, "scb_gemv: fused arg-max needs k %% 32 == 0");
+              "scb_gemv: the fused-prologue / k %% 32 != 0 path supports rows 1, 2 or 4 only");
+  SCB_REQUIRE(!a->argmax_out && a->epilogue == 0, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: fused arg-max / SiLU-pair need k %% 32 == 0 and no prologue");
   const size_t smem = (size_t)a->rows * a->k * sizeof(__half);
   SCB_REQUIRE(smem <= 200 * 1024, SCB_ERR_UNSUPPORTED,
               "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
@@ -987,8 +994,8 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
   const int G = a->n_q_heads / a->n_kv_heads;
   SCB_REQUIRE(G == 1 || G == 2 || G == 4 || G == 7 || G == 8, SCB_ERR_UNSUPPORTED,
               "scb_decode_attention_fused: group size %d unsupported (1,2,4,7,8)", G);
-  SCB_REQUIRE(a->n_splits >= 1 && a->n_splits <= 1024, SCB_ERR_INVALID_ARG,
-              "scb_decode_attention_fused: n_splits out of range");
+  SCB_REQUIRE(a->n_splits >= 1 && a->n_splits <= 64, SCB_ERR_INVALID_ARG,
+              "scb_decode_attention_fused: n_splits out of range (1..64)");
   SCB_REQUIRE(a->n_seqs >= 1 && a->n_seqs * a->n_kv_heads <= 64, SCB_ERR_INVALID_ARG,
               "scb_decode_attention_fused: n_seqs=%d out of range (n_seqs * n_kv_heads <= 64)", a->n_seqs);
   const size_t need = scb_decode_attention_fused_workspace_bytes(a->n_seqs, a->n_q_heads, a->n_kv_heads,
@@ -1001,7 +1008,8 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
   float* part_l = part_m + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   float* part_o = part_l + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   const int per_max = (int)((a->max_pos + a->n_splits - 1) / a->n_splits);
-  const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_max);
+  const int per_alloc = per_max > a->n_splits ? per_max : a->n_splits;   // the combine reuses the score buffer
+  const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_alloc);
   SCB_REQUIRE(smem <= 160 * 1024, SCB_ERR_UNSUPPORTED,
               "scb_decode_attention_fused: max_pos/n_splits too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -72,6 +72,8 @@ norm_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restri
             long long ld_out, const __half* __restrict__ cls, const __half* __restrict__ pos,
             int tokens_per_img) {
   __shared__ float red[kNormThreads / 32];
+  pdl_launch_dependents();
+  pdl_wait();   // decode chain: x comes from the preceding GEMV
   const long long row = blockIdx.x;
   const int nvec = D >> 3;
   float v[kNormMaxChunks][8];
@@ -356,8 +358,9 @@ static int norm_common(int kind, const void* x, int64_t ld_x, const void* gamma,
     norm_kernel<0><<<(unsigned)rows, kNormThreads, 0, st>>>(xh, ld_x, g, b, eps, dim, o, ld_out,
                                                             nullptr, nullptr, 0);
   else if (kind == 1)
-    norm_kernel<1><<<(unsigned)rows, kNormThreads, 0, st>>>(xh, ld_x, g, b, eps, dim, o, ld_out,
-                                                            nullptr, nullptr, 0);
+    SCB_CUDA_OK(scb_launch_pdl(norm_kernel<1>, dim3((unsigned)rows), dim3(kNormThreads), 0, st, xh,
+                               (long long)ld_x, g, b, eps, (int)dim, o, (long long)ld_out,
+                               (const __half*)nullptr, (const __half*)nullptr, 0));
   else
     norm_kernel<2><<<(unsigned)rows, kNormThreads, 0, st>>>(
         xh, ld_x, g, b, eps, dim, o, ld_out, reinterpret_cast<const __half*>(cls),

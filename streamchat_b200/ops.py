@@ -358,17 +358,17 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
                       out=_ptr(out), n=n, k=k, lda=a.stride(0), ldw=w.stride(0),
                       ldr=residual.stride(0) if residual is not None else 0, ldo=out.stride(0),
                       rows=rows, prologue=prologue, out_dtype=_dtype_code(out), eps=eps, epilogue=epilogue)
+    key = (dev.index, "gemv_ws")
+    ws = _workspaces.get(key)
+    if ws is None:      # zero-initialised once: tickets are self-resetting
+        ws = torch.zeros(L.load().scb_gemv_workspace_bytes(8), dtype=torch.uint8, device=dev)
+        _workspaces[key] = ws
+    args.workspace = _ptr(ws)
+    args.workspace_bytes = ws.numel()
     if argmax_out is not None:
-        key = (dev.index, "gemv_argmax", rows)
-        ws = _workspaces.get(key)
-        if ws is None:      # zero-initialised once: the ticket word is self-resetting
-            ws = torch.zeros(L.load().scb_gemv_workspace_bytes(rows), dtype=torch.uint8, device=dev)
-            _workspaces[key] = ws
         args.argmax_out = _ptr(argmax_out)
         args.counters = _ptr(counters)
         args.n_counters = 0 if counters is None else counters.numel()
-        args.workspace = _ptr(ws)
-        args.workspace_bytes = ws.numel()
     _call("scb_gemv", dev, C.byref(args))
     return out
 

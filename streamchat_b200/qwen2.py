@@ -88,6 +88,7 @@ class Qwen2Engine:
         qkv_dim = (c.num_attention_heads + 2 * c.num_key_value_heads) * hd
         self._x = torch.zeros((B, c.hidden_size), dtype=torch.float16, device=self.device)
         self._x2 = torch.zeros_like(self._x)
+        self._nrm = torch.zeros_like(self._x)
         self._qkv = torch.zeros((B, qkv_dim), dtype=torch.float16, device=self.device)
         self._attn = torch.zeros((B, c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
         self._gu = torch.zeros((B, c.intermediate_size), dtype=torch.float16, device=self.device)
@@ -159,37 +160,37 @@ class Qwen2Engine:
             x = ops.linear(y, ly["down_w"], residual=x)
         self.ctx_lens[slot] = pos0 + T
         # final norm + lm_head on the last position only (logits_to_keep, modeling_qwen2.py:474-475)
-        return ops.gemv(x[T - 1:T], self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm,
-                        eps=c.rms_norm_eps, out=self._logits[slot:slot + 1])
+        last = ops.rmsnorm(x[T - 1:T], self.final_norm, c.rms_norm_eps)
+        return ops.gemv(last, self.lm_head, out=self._logits[slot:slot + 1])
 
     # ---------------------------------------------------------------- decode
     def _decode_step_launches(self, R: int = 1) -> None:
-        """One cached decode step for the first R cache slots (5*layers + 2 launches): embeds
-        next_id[:R], runs every layer as qkv GEMV (RMSNorm fused) -> fused RoPE/append/attention/
-        combine -> o_proj GEMV (+residual) -> gate|up GEMV (RMSNorm + SiLU-gate fused) -> down GEMV
-        (+residual), then the lm_head GEMV with the final norm and the greedy arg-max fused; leaves
+        """One cached decode step for the first R cache slots (7*layers + 3 launches): embeds
+        next_id[:R], runs every layer as RMSNorm -> qkv GEMV -> fused RoPE/append/attention/combine ->
+        o_proj GEMV (+residual) -> RMSNorm -> gate|up GEMV (SiLU-gate fused) -> down GEMV (+residual),
+        then the final norm and the lm_head GEMV with the greedy arg-max fused; leaves
         logits in self._logits[:R], the new tokens in next_id[:R] and advances the device-side
         [position, kv_len] state.  Rows are independent: a sequence decodes to the same ids whatever R is."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         scale = hd ** -0.5
-        x, x2 = self._x[:R], self._x2[:R]
+        x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
         ops.gather_rows(self.embed, self.next_id[:R], out=x)
         for i, ly in enumerate(self.layers):
-            ops.gemv(x, ly["qkv_w"], bias=ly["qkv_b"], prologue=L.PRO_RMSNORM, gamma=ly["ln1"],
-                     eps=c.rms_norm_eps, out=self._qkv[:R])
+            ops.rmsnorm(x, ly["ln1"], c.rms_norm_eps, out=nrm)
+            ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
                                        self.state[1, :R], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
                                        out=self._attn[:R])
             ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2)
-            ops.gemv(x2, ly["gu_w"], prologue=L.PRO_RMSNORM, gamma=ly["ln2"], eps=c.rms_norm_eps,
-                     epilogue=L.EPI_SILU_PAIR, out=self._gu[:R])
+            ops.rmsnorm(x2, ly["ln2"], c.rms_norm_eps, out=nrm)
+            ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R])
             ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x)
-        ops.gemv(x, self.lm_head, prologue=L.PRO_RMSNORM, gamma=self.final_norm, eps=c.rms_norm_eps,
-                 out=self._logits[:R], argmax_out=self.next_id[:R], counters=self.state.view(-1))
+        ops.rmsnorm(x, self.final_norm, c.rms_norm_eps, out=nrm)
+        ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R], counters=self.state.view(-1))
 
     def launches_per_decode_step(self) -> int:
-        return 1 + self.cfg.num_hidden_layers * 5 + 1
+        return 1 + self.cfg.num_hidden_layers * 7 + 2
 
     def _ensure_graph(self, R: int) -> "torch.cuda.CUDAGraph":
         g = self._graphs.get(R)

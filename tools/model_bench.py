@@ -1,0 +1,53 @@
+"""Times the two tensor-core stages at the bench shapes: CLIP encode (frames) and Qwen2 prefill (tokens).
+   python tools/model_bench.py [frames] [tokens] [--once]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from streamchat_b200.longva.model.builder import SYNTHETIC, random_weights  # noqa: E402
+from streamchat_b200.qwen2 import Qwen2Engine  # noqa: E402
+from streamchat_b200.vision import VisionEncoder  # noqa: E402
+
+dev = torch.device("cuda:0")
+cfg = SYNTHETIC["longva7b"]
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 5824
+once = "--once" in sys.argv
+W = random_weights(cfg, dev, seed=0)
+vis = VisionEncoder(W, cfg.vision, dev, max_frames_per_pass=64)
+eng = Qwen2Engine({k: v for k, v in W.items() if not k.startswith("model.vision_tower")}, cfg.llm, dev, max_ctx=32768)
+del W
+
+
+def timed(fn, iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+if frames:
+    px = torch.randn(frames, 3, 336, 336, device=dev).half()
+    if not once:
+        vis.encode_images(px)
+    ms = timed(lambda: vis.encode_images(px), 1 if once else 5)
+    fl = vis.flops_per_frame() * frames
+    print(f"encode_images {frames} frames: {ms:.2f} ms  {frames / ms * 1e3:.0f} frames/s  {fl / ms / 1e9:.0f} TFLOP/s "
+          f"({vis.flops_per_frame() / 1e9:.2f} GF/frame)")
+if tokens:
+    x = (torch.randn(tokens, cfg.llm.hidden_size, device=dev) * 0.02).half()
+
+    def pf():
+        eng.reset()
+        eng.prefill(x)
+    if not once:
+        pf()
+    ms = timed(pf, 1 if once else 3)
+    fl = eng.prefill_flops(tokens)
+    print(f"prefill {tokens} tokens: {ms:.2f} ms  {fl / ms / 1e9:.0f} TFLOP/s")

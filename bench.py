@@ -123,20 +123,15 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
         feats = sess.ingest(seg)
         sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
     if world > 1:
-        # the one exchange step: all-gather the per-rank memory embeddings (root-node text embeddings
-        # [max_roots, 1024] fp32 + validity) so every rank searches the global index
-        roots = sess.long_memory_tree
-        max_roots = 16
-        emb = torch.zeros((max_roots, 1025), dtype=torch.float32, device=device)
-        for i, node in enumerate(roots[:max_roots]):
-            emb[i, :1024] = M_embed(sess, node)
-            emb[i, 1024] = 1.0
-        gathered = torch.empty((world * max_roots, 1025), dtype=torch.float32, device=device)
-        dist.all_gather_into_tensor(gathered, emb)
+        # the one exchange step (§8e): all-gather the per-rank memory embeddings (root-node text
+        # embeddings) so every rank's retrieval sees the global index; top-k is computed redundantly
+        from streamchat_b200.distributed import gather_memory_embeddings, live_rows, pack_memory_embeddings
+        embs = [M_embed(sess, node) for node in sess.long_memory_tree]
+        packed = pack_memory_embeddings(embs, 16, 1024, device)
+        index, owner, local = live_rows(gather_memory_embeddings(packed))
         q = sess.embedding_model(sess.embedding_tokenizer, QUESTION)
-        valid = gathered[:, 1024] > 0
-        scores, idx = ops.cosine_topk(gathered[valid][:, :1024].contiguous(), q, k=1)
-        sess.global_best = (scores, idx)
+        scores, idx = ops.cosine_topk(index, q, k=1)
+        sess.global_best = (scores, owner[idx[0, 0]], local[idx[0, 0]])
     text, ids = sess.answer(QUESTION)
     if e2e:
         ids_host = ids.cpu()                                                  # device -> host read of the result

@@ -209,6 +209,12 @@ int scb_rope_append(void* qkv, int64_t ld_qkv, int64_t rows, int32_t n_q_heads, 
 int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_t dim, void* out,
                     int64_t ld_out, void* stream);
 
+/* Decode-step entry: embed_tokens lookup fused with the first layer's input RMSNorm
+ * (modeling_qwen2.py:249-263): out[r] = table[ids[r]], norm_out[r] = RMSNorm(out[r]) * gamma. */
+int scb_gather_rows_rmsnorm(const void* table, const int64_t* ids, int64_t n_ids, int32_t dim, void* out,
+                            int64_t ld_out, const void* gamma, float eps, void* norm_out,
+                            int64_t ld_norm, void* stream);
+
 /* Greedy token choice: arg-max per row of logits (fp16 or fp32), lowest index wins ties —
  * torch.argmax over the fp16 lm_head output as HF generate does.  If counters != NULL the
  * n_counters device int32 values it points to are each incremented by one (position / length
@@ -278,6 +284,17 @@ typedef struct scb_gemv_args {
                            * (Qwen2 MLP gate, modeling_qwen2.py:41-48, fused into the gate|up layer) */
   void* workspace;
   size_t workspace_bytes;
+  /* optional (k % 32 == 0, no prologue, fp16 out): the last block to finish writes
+   * post_norm_out[r, :] = RMSNorm(out[r, :]) * post_norm_gamma (the next layer's input norm) */
+  const void* post_norm_gamma;
+  void* post_norm_out;
+  int64_t post_norm_ld;
+  float post_norm_eps;
+  int32_t _pad3;
+  /* optional: blocks that run out of work prefetch [prefetch, prefetch + prefetch_bytes) into L2
+   * (the next kernel's weights) */
+  const void* prefetch;
+  int64_t prefetch_bytes;
 } scb_gemv_args;
 
 size_t scb_gemv_workspace_bytes(int32_t rows);
@@ -325,6 +342,8 @@ typedef struct scb_decode_attention_fused_args {
   int64_t cache_seq_stride;  /* elements between the sequences' caches */
   void* workspace;
   size_t workspace_bytes;
+  const void* prefetch;      /* optional: pulled into L2 while the attention runs (next layer weights) */
+  int64_t prefetch_bytes;
 } scb_decode_attention_fused_args;
 
 size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_heads,

@@ -79,6 +79,9 @@ class GemvArgs(C.Structure):
         ("rows", C.c_int32), ("prologue", C.c_int32), ("out_dtype", C.c_int32), ("eps", C.c_float),
         ("argmax_out", C.c_void_p), ("counters", C.c_void_p), ("n_counters", C.c_int32), ("epilogue", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("post_norm_gamma", C.c_void_p), ("post_norm_out", C.c_void_p), ("post_norm_ld", C.c_int64),
+        ("post_norm_eps", C.c_float), ("_pad3", C.c_int32),
+        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 
@@ -100,6 +103,7 @@ class DecodeAttentionFusedArgs(C.Structure):
         ("scale", C.c_float), ("theta", C.c_float), ("n_seqs", C.c_int32), ("_pad", C.c_int32),
         ("ld_qkv", C.c_int64), ("cache_seq_stride", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 
@@ -132,6 +136,7 @@ SYMBOLS = {
     "scb_silu_mul": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _vp]),
     "scb_rope_append": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _f, _vp, _vp, _vp, _i64, _vp]),
     "scb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "scb_gather_rows_rmsnorm": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _f, _vp, _i64, _vp]),
     "scb_argmax_rows": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
 }
 

@@ -43,6 +43,16 @@ struct GemvParams {
   int out_f32;
   int silu_pair;  // rows (2i, 2i+1) of w are (gate_i, up_i): out[r][i] = fp16(silu(gate)) * up
   float eps;
+  // fused RMSNorm of the finished output rows by the last block to leave the kernel (decode chain:
+  // the next layer's input norm), and an L2 prefetch of the next kernel's weights issued by blocks
+  // that ran out of work (fills the launch gap / ramp-up of the next kernel with useful traffic)
+  const __half* pn_gamma;
+  __half* pn_out;
+  long long pn_ld;
+  float pn_eps;
+  unsigned* done_ticket;
+  const char* next_w;
+  long long next_w_bytes;
 };
 
 template <int R, int PRO>
@@ -327,6 +337,60 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
     ke = nke;
   }
 
+  // ---- tail 1: blocks that ran out of work pull the next kernel's weights into L2
+  if (p.next_w) {
+    const long long per_blk = (p.next_w_bytes / gridDim.x) & ~127ll;
+    const char* base = p.next_w + (long long)blockIdx.x * per_blk;
+    for (long long off = (long long)tid * 128; off < per_blk; off += (long long)kGW * 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+  }
+  // ---- tail 2: the last block to finish normalises the complete output rows (RMSNorm, HF order)
+  if (p.pn_out) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned tk = atomicAdd(p.done_ticket, 1u);
+      flag_s = (tk == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (flag_s) {
+      __threadfence();
+      float* sred = &red[0][0][0];
+      const __half* o16 = reinterpret_cast<const __half*>(p.out);
+      for (int r = 0; r < R; ++r) {
+        float ss = 0.f;
+        for (int i = tid; i < (p.N >> 3); i += kGW * 32) {
+          float f[8];
+          const uint4 q = __ldcg(reinterpret_cast<const uint4*>(o16 + (long long)r * p.ldo + i * 8));
+          unpack8(q, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+        }
+        ss = warp_sum(ss);
+        __syncthreads();
+        if (lane == 0) sred[warp] = ss;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGW; ++w) tot += sred[w];
+        const float rstd = rsqrtf(tot / (float)p.N + p.pn_eps);
+        for (int i = tid; i < (p.N >> 3); i += kGW * 32) {
+          float f[8], gm[8], o[8];
+          unpack8(__ldcg(reinterpret_cast<const uint4*>(o16 + (long long)r * p.ldo + i * 8)), f);
+          unpack8(*reinterpret_cast<const uint4*>(p.pn_gamma + i * 8), gm);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(f[e] * rstd)) * gm[e];
+          uint4 q;
+          q.x = f2_to_h2(o[0], o[1]); q.y = f2_to_h2(o[2], o[3]);
+          q.z = f2_to_h2(o[4], o[5]); q.w = f2_to_h2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(p.pn_out + (long long)r * p.pn_ld + i * 8) = q;
+        }
+      }
+      if (tid == 0) *p.done_ticket = 0;
+    }
+    __syncthreads();
+  }
+
   if (am.out_ids) {
     // ---- fused arg-max: thread (r, j) holds the best over its column residue; reduce the 8
     // threads of each row, publish per block, the last block reduces the blocks
@@ -524,7 +588,8 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
                          int n_q, int n_kv, int per_max, float* __restrict__ part_m,
                          float* __restrict__ part_l, float* __restrict__ part_o,
                          unsigned* __restrict__ tickets, __half* __restrict__ out, long long ld_qkv,
-                         long long cache_seq_stride) {
+                         long long cache_seq_stride, const char* __restrict__ next_w,
+                         long long next_w_bytes) {
   constexpr int HALF = HD / 2;
   extern __shared__ __align__(16) float dsm[];
   float* q_s = dsm;                 // [G][HD] rotated q, pre-scaled by scale*log2(e)
@@ -552,12 +617,18 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   const int begin = split * per, end = min(kv_len, begin + per);
   const int n_local = max(0, end - begin);
 
-  // ---- RoPE of this group's q rows (every block recomputes: G*HD/2 pairs)
+  // ---- cos/sin of the new position once per block (HALF angles), then RoPE of the G q rows
+  __shared__ float cs_s[HALF], sn_s[HALF];
+  if (tid < HALF) {
+    const float f = inv_freq ? inv_freq[tid] : powf(theta, -(float)(2 * tid) / (float)HD);
+    const float ang = (float)pos * f;
+    cs_s[tid] = __half2float(__float2half_rn(cosf(ang)));
+    sn_s[tid] = __half2float(__float2half_rn(sinf(ang)));
+  }
+  __syncthreads();
   for (int idx = tid; idx < G * HALF; idx += 256) {
     const int h = idx / HALF, i = idx % HALF;
-    const float f = inv_freq ? inv_freq[i] : powf(theta, -(float)(2 * i) / (float)HD);
-    const float ang = (float)pos * f;
-    const float c = __half2float(__float2half_rn(cosf(ang))), sn = __half2float(__float2half_rn(sinf(ang)));
+    const float c = cs_s[i], sn = sn_s[i];
     const __half* qp = qkv + (long long)(hk * G + h) * HD;
     const float x1 = __half2float(qp[i]), x2 = __half2float(qp[i + HALF]);
     const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
@@ -572,9 +643,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
     __half* kc = k_cache + ((long long)hk * max_pos + pos) * HD;
     __half* vc = v_cache + ((long long)hk * max_pos + pos) * HD;
     for (int i = tid; i < HALF; i += 256) {
-      const float f = inv_freq ? inv_freq[i] : powf(theta, -(float)(2 * i) / (float)HD);
-      const float ang = (float)pos * f;
-      const float c = __half2float(__float2half_rn(cosf(ang))), sn = __half2float(__float2half_rn(sinf(ang)));
+      const float c = cs_s[i], sn = sn_s[i];
       const float x1 = __half2float(kp[i]), x2 = __half2float(kp[i + HALF]);
       const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
       const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
@@ -585,20 +654,20 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   __syncthreads();   // q_s ready; the appended row is visible to this block
 
-  // ---- phase 1: scores.  A quad of threads owns a position: thread j reads the 16-byte chunks
-  // j, j+4, j+8, ... of the K row (the quad covers 64 contiguous bytes per load), all loads of
-  // the row are in flight at once, partial dots meet with two shuffles.
+  // ---- phase 1: scores.  A pair of threads owns a position: thread j reads the 16-byte chunks
+  // j, j+2, j+4, ... of the K row, all of them in flight at once (128 positions per pass), partial
+  // dots meet with one shuffle.
   {
-    constexpr int CH = HD / 32;           // 16-byte chunks per thread
-    const int quad = tid >> 2, j = tid & 3;
+    constexpr int CH = HD / 16;           // 16-byte chunks per thread
+    const int pr = tid >> 1, j = tid & 1;
     const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD;
-    for (int p0 = 0; p0 < n_local; p0 += 64) {
-      const int pl = p0 + quad;
+    for (int p0 = 0; p0 < n_local; p0 += 128) {
+      const int pl = p0 + pr;
       const bool ok = pl < n_local;
       uint4 kv4[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c)
-        kv4[c] = ok ? *reinterpret_cast<const uint4*>(kb + (long long)pl * HD + (c * 4 + j) * 8)
+        kv4[c] = ok ? *reinterpret_cast<const uint4*>(kb + (long long)pl * HD + (c * 2 + j) * 8)
                     : make_uint4(0, 0, 0, 0);
       float sc[G];
 #pragma unroll
@@ -607,7 +676,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
       for (int c = 0; c < CH; ++c) {
         float kf[8];
         unpack8(kv4[c], kf);
-        const int d0 = (c * 4 + j) * 8;
+        const int d0 = (c * 2 + j) * 8;
 #pragma unroll
         for (int h = 0; h < G; ++h) {
           const float4 qa = *reinterpret_cast<const float4*>(q_s + h * HD + d0);
@@ -619,10 +688,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
         }
       }
 #pragma unroll
-      for (int h = 0; h < G; ++h) {
-        sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 1);
-        sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 2);
-      }
+      for (int h = 0; h < G; ++h) sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 1);
       if (ok && j == 0) {
 #pragma unroll
         for (int h = 0; h < G; ++h) s_s[h * per_max + pl] = sc[h];
@@ -753,13 +819,17 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
     const float* po = part_o + ((long long)(hk * G + h) * n_splits) * HD + d;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
     int sp = 0;
-    for (; sp + 4 <= n_splits; sp += 4) {    // four independent loads in flight
-      const float a0 = __ldcg(po + (long long)(sp + 0) * HD), a1 = __ldcg(po + (long long)(sp + 1) * HD);
-      const float a2 = __ldcg(po + (long long)(sp + 2) * HD), a3 = __ldcg(po + (long long)(sp + 3) * HD);
-      o0 = fmaf(a0, w_s[h * n_splits + sp + 0], o0);
-      o1 = fmaf(a1, w_s[h * n_splits + sp + 1], o1);
-      o2 = fmaf(a2, w_s[h * n_splits + sp + 2], o2);
-      o3 = fmaf(a3, w_s[h * n_splits + sp + 3], o3);
+    for (; sp + 8 <= n_splits; sp += 8) {    // eight independent L2 loads in flight
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = __ldcg(po + (long long)(sp + u) * HD);
+#pragma unroll
+      for (int u = 0; u < 8; u += 4) {
+        o0 = fmaf(a[u + 0], w_s[h * n_splits + sp + u + 0], o0);
+        o1 = fmaf(a[u + 1], w_s[h * n_splits + sp + u + 1], o1);
+        o2 = fmaf(a[u + 2], w_s[h * n_splits + sp + u + 2], o2);
+        o3 = fmaf(a[u + 3], w_s[h * n_splits + sp + u + 3], o3);
+      }
     }
     for (; sp < n_splits; ++sp) o0 = fmaf(__ldcg(po + (long long)sp * HD), w_s[h * n_splits + sp], o0);
     out[(long long)(hk * G + h) * HD + d] = __float2half_rn(((o0 + o1) + (o2 + o3)) * inv_l[h]);
@@ -839,6 +909,13 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   p.out_f32 = a->out_dtype == SCB_F32;
   p.silu_pair = a->epilogue == 1;
   p.eps = a->eps;
+  p.pn_gamma = reinterpret_cast<const __half*>(a->post_norm_gamma);
+  p.pn_out = reinterpret_cast<__half*>(a->post_norm_out);
+  p.pn_ld = a->post_norm_ld;
+  p.pn_eps = a->post_norm_eps;
+  p.done_ticket = nullptr;
+  p.next_w = reinterpret_cast<const char*>(a->prefetch);
+  p.next_w_bytes = a->prefetch_bytes;
   const int sms = scb_num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
@@ -852,7 +929,7 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
     if (n_groups <= kMaxSplitGroups && a->workspace) {
       double best_eff = 0.0;
       for (int c = 1; c <= kMaxChunks; ++c) {
-        if (c > 1 && ktiles / (c * kGW) < 2 * kMU) break;
+        if (c > 1 && ktiles / (c * kGW) < kMU) break;   // at least one full 4 KB batch per warp
         const long long units = n_groups * c;
         const double eff = (double)units / (double)(((units + wave - 1) / wave) * wave);
         if (eff > best_eff + 0.02) {
@@ -871,6 +948,7 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
       char* ws = reinterpret_cast<char*>(a->workspace);
       gtickets = reinterpret_cast<unsigned*>(ws + kWsArgmax);
       partial = reinterpret_cast<float*>(ws + kWsArgmax + kWsTickets);
+      p.done_ticket = reinterpret_cast<unsigned*>(ws + 128);
       if (a->argmax_out) {
         am.ticket = reinterpret_cast<unsigned*>(ws);
         am.blk_val = reinterpret_cast<float*>(ws + 256);
@@ -880,8 +958,12 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
         am.n_counters = a->counters ? a->n_counters : 0;
       }
     } else {
-      SCB_REQUIRE(!a->argmax_out, SCB_ERR_WORKSPACE, "scb_gemv: fused arg-max needs the workspace");
+      SCB_REQUIRE(!a->argmax_out && !a->post_norm_out, SCB_ERR_WORKSPACE,
+                  "scb_gemv: fused arg-max / post-norm need the workspace");
     }
+    SCB_REQUIRE(!a->post_norm_out || (a->post_norm_gamma && a->out_dtype == SCB_F16 && a->epilogue == 0 &&
+                                      a->n % 8 == 0 && a->ldo % 8 == 0 && a->post_norm_ld % 8 == 0),
+                SCB_ERR_INVALID_ARG, "scb_gemv: post-norm needs gamma, fp16 out, n %% 8 == 0, aligned rows");
     const long long units = n_groups * C;
     long long cap = wave < 2048 ? wave : 2048;
     const int grid = (int)(units < cap ? units : cap);
@@ -894,8 +976,8 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
   // ---- SIMT path for k not a multiple of 32
   SCB_REQUIRE(a->rows == 1 || a->rows == 2 || a->rows == 4, SCB_ERR_UNSUPPORTED,
               "scb_gemv: the fused-prologue / k %% 32 != 0 path supports rows 1, 2 or 4 only");
-  SCB_REQUIRE(!a->argmax_out && a->epilogue == 0, SCB_ERR_UNSUPPORTED,
-              "scb_gemv: fused arg-max / SiLU-pair need k %% 32 == 0 and no prologue");
+  SCB_REQUIRE(!a->argmax_out && a->epilogue == 0 && !a->post_norm_out, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: fused arg-max / SiLU-pair / post-norm need k %% 32 == 0 and no prologue");
   const size_t smem = (size_t)a->rows * a->k * sizeof(__half);
   SCB_REQUIRE(smem <= 200 * 1024, SCB_ERR_UNSUPPORTED,
               "scb_gemv: rows*k=%lld does not fit in shared memory", (long long)a->rows * a->k);
@@ -1028,7 +1110,9 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
                                a->kv_len_dev, sl2, (int)a->n_q_heads, (int)a->n_kv_heads, per_max,\
                                part_m, part_l, part_o, tickets,                                   \
                                reinterpret_cast<__half*>(a->out), (long long)a->ld_qkv,           \
-                               (long long)a->cache_seq_stride));                                  \
+                               (long long)a->cache_seq_stride,                                    \
+                               reinterpret_cast<const char*>(a->prefetch),                        \
+                               (long long)a->prefetch_bytes));                                    \
   } while (0)
   if (a->head_dim == 128) {
     switch (G) {

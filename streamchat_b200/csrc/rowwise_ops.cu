@@ -263,6 +263,49 @@ __global__ void gather_rows_kernel(const __half* __restrict__ table, const long 
 }
 
 // ------------------------------------------------------------------------------------------
+// Embedding gather fused with the first RMSNorm of the decode step: out[r] = table[ids[r]],
+// norm_out[r] = RMSNorm(out[r]) * gamma (HF order).  One block per row, row in registers.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads)
+gather_rmsnorm_kernel(const __half* __restrict__ table, const long long* __restrict__ ids, int D,
+                      __half* __restrict__ out, long long ld_out, const __half* __restrict__ gamma,
+                      float eps, __half* __restrict__ norm_out, long long ld_norm) {
+  __shared__ float red[kNormThreads / 32];
+  pdl_launch_dependents();
+  pdl_wait();   // ids come from the previous decode step's fused arg-max
+  const long long row = blockIdx.x;
+  const long long id = ids[row];
+  const int nvec = D >> 3;
+  float v[kNormMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (id >= 0) q = *reinterpret_cast<const uint4*>(table + id * D + i * 8);
+      *reinterpret_cast<uint4*>(out + row * ld_out + i * 8) = q;
+      unpack8(q, v[c]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(v[c][e], v[c][e], s);
+    }
+  }
+  s = block_sum(s, red);
+  const float rstd = rsqrtf(s / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      float g[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + i * 8), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = __half2float(__float2half_rn(v[c][e] * rstd)) * g[e];
+      *reinterpret_cast<uint4*>(norm_out + row * ld_norm + i * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Arg-max over rows of fp32 logits, lowest index wins ties (greedy decoding,
 // generation/utils.py greedy branch == torch.argmax).  One block per row.
 // ------------------------------------------------------------------------------------------
@@ -455,6 +498,24 @@ int scb_gather_rows(const void* table, const int64_t* ids, int64_t n_ids, int32_
                              reinterpret_cast<const long long*>(ids), (int)dim,
                              reinterpret_cast<__half*>(out), (long long)ld_out));
   SCB_LAUNCH_OK("gather_rows_kernel");
+  return SCB_OK;
+}
+
+int scb_gather_rows_rmsnorm(const void* table, const int64_t* ids, int64_t n_ids, int32_t dim, void* out,
+                            int64_t ld_out, const void* gamma, float eps, void* norm_out,
+                            int64_t ld_norm, void* stream) {
+  SCB_REQUIRE(table && ids && out && gamma && norm_out && n_ids >= 1 && dim % 8 == 0 && ld_out % 8 == 0 &&
+                  ld_norm % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks && aligned16(table) &&
+                  aligned16(out) && aligned16(gamma) && aligned16(norm_out),
+              SCB_ERR_INVALID_ARG, "scb_gather_rows_rmsnorm: bad arguments");
+  SCB_CUDA_OK(scb_launch_pdl(gather_rmsnorm_kernel, dim3((unsigned)n_ids), dim3(kNormThreads), 0,
+                             reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const __half*>(table),
+                             reinterpret_cast<const long long*>(ids), (int)dim,
+                             reinterpret_cast<__half*>(out), (long long)ld_out,
+                             reinterpret_cast<const __half*>(gamma), eps,
+                             reinterpret_cast<__half*>(norm_out), (long long)ld_norm));
+  SCB_LAUNCH_OK("gather_rmsnorm_kernel");
   return SCB_OK;
 }
 

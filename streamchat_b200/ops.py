@@ -330,6 +330,14 @@ def gather_rows(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tens
     return out
 
 
+def gather_rows_rmsnorm(table: torch.Tensor, ids: torch.Tensor, gamma: torch.Tensor, eps: float,
+                        out: torch.Tensor, norm_out: torch.Tensor) -> None:
+    dev = _require_cuda(table, ids, gamma, out, norm_out)
+    ids = ids.reshape(-1)
+    _call("scb_gather_rows_rmsnorm", dev, _ptr(table), _ptr(ids), ids.numel(), table.shape[1], _ptr(out),
+          out.stride(0), _ptr(gamma), eps, _ptr(norm_out), norm_out.stride(0))
+
+
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
                 counter: Optional[torch.Tensor] = None) -> torch.Tensor:
     dev = _require_cuda(logits, out, counter)
@@ -345,10 +353,14 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, prologue: int = L.PRO_NONE,
          gamma: Optional[torch.Tensor] = None, eps: float = 0.0, out: Optional[torch.Tensor] = None,
          out_dtype: torch.dtype = torch.float16, argmax_out: Optional[torch.Tensor] = None,
-         counters: Optional[torch.Tensor] = None, epilogue: int = L.EPI_NONE) -> torch.Tensor:
+         counters: Optional[torch.Tensor] = None, epilogue: int = L.EPI_NONE,
+         post_norm: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+         prefetch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Decode-step linear layer for 1..8 activation rows (see scb_gemv).  `argmax_out` (int64
     [rows]) fuses the greedy token choice over the stored output; `counters` (int32) are then
-    incremented by one."""
+    incremented by one.  `post_norm=(gamma, out_tensor, eps)` makes the last block write
+    RMSNorm(out)*gamma into out_tensor; `prefetch` is a tensor (the next kernel's weights) pulled into
+    L2 by blocks that finish early."""
     dev = _require_cuda(a, w, bias, residual, gamma, out, argmax_out, counters)
     rows = a.shape[0]
     n, k = w.shape
@@ -365,6 +377,12 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
         _workspaces[key] = ws
     args.workspace = _ptr(ws)
     args.workspace_bytes = ws.numel()
+    if post_norm is not None:
+        pg, po, pe = post_norm
+        args.post_norm_gamma, args.post_norm_out, args.post_norm_ld, args.post_norm_eps = _ptr(pg), _ptr(po), po.stride(0), pe
+    if prefetch is not None:
+        args.prefetch = _ptr(prefetch)
+        args.prefetch_bytes = min(prefetch.numel() * prefetch.element_size(), 48 << 20)
     if argmax_out is not None:
         args.argmax_out = _ptr(argmax_out)
         args.counters = _ptr(counters)
@@ -396,7 +414,7 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
 def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], theta: float,
                            k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len_dev: torch.Tensor,
                            n_q: int, scale: float, workspace: torch.Tensor, n_splits: int = 37,
-                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, prefetch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """RoPE + KV append + split attention + combine for ONE new token of each of S sequences (see
     scb_decode_attention_fused).  qkv [S, (n_q+2*n_kv)*hd]; caches [n_kv, max_pos, hd] (S == 1) or
     [S, n_kv, max_pos, hd]; kv_len_dev int32 [S].  `workspace` is a caller-held uint8 tensor whose
@@ -416,6 +434,9 @@ def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], 
         kv_len_dev=_ptr(kv_len_dev), max_pos=max_pos, n_q_heads=n_q, n_kv_heads=hkv, head_dim=d,
         n_splits=n_splits, scale=scale, theta=theta, n_seqs=n_seqs, ld_qkv=qkv.stride(0),
         cache_seq_stride=seq_stride, workspace=_ptr(workspace), workspace_bytes=workspace.numel())
+    if prefetch is not None:
+        args.prefetch = _ptr(prefetch)
+        args.prefetch_bytes = min(prefetch.numel() * prefetch.element_size(), 48 << 20)
     _call("scb_decode_attention_fused", dev, C.byref(args))
     return out
 

@@ -165,32 +165,37 @@ class Qwen2Engine:
 
     # ---------------------------------------------------------------- decode
     def _decode_step_launches(self, R: int = 1) -> None:
-        """One cached decode step for the first R cache slots (7*layers + 3 launches): embeds
-        next_id[:R], runs every layer as RMSNorm -> qkv GEMV -> fused RoPE/append/attention/combine ->
-        o_proj GEMV (+residual) -> RMSNorm -> gate|up GEMV (SiLU-gate fused) -> down GEMV (+residual),
-        then the final norm and the lm_head GEMV with the greedy arg-max fused; leaves
+        """One cached decode step for the first R cache slots (5*layers + 2 launches): embedding
+        gather (+ first RMSNorm), then per layer qkv GEMV -> fused RoPE/append/attention/combine ->
+        o_proj GEMV (+residual, + post-attention RMSNorm by its last block) -> gate|up GEMV (SiLU-gate
+        fused) -> down GEMV (+residual, + the next layer's input RMSNorm), then the lm_head GEMV with
+        the greedy arg-max fused.  Every kernel prefetches the next one's weights into L2.  Leaves
         logits in self._logits[:R], the new tokens in next_id[:R] and advances the device-side
         [position, kv_len] state.  Rows are independent: a sequence decodes to the same ids whatever R is."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         scale = hd ** -0.5
         x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
-        ops.gather_rows(self.embed, self.next_id[:R], out=x)
+        eps = c.rms_norm_eps
+        L0 = self.layers[0]
+        ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
+        n_layers = len(self.layers)
         for i, ly in enumerate(self.layers):
-            ops.rmsnorm(x, ly["ln1"], c.rms_norm_eps, out=nrm)
+            nxt_gamma = self.layers[i + 1]["ln1"] if i + 1 < n_layers else self.final_norm
+            nxt_w = self.layers[i + 1]["qkv_w"] if i + 1 < n_layers else self.lm_head
             ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
                                        self.state[1, :R], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
-                                       out=self._attn[:R])
-            ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2)
-            ops.rmsnorm(x2, ly["ln2"], c.rms_norm_eps, out=nrm)
-            ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R])
-            ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x)
-        ops.rmsnorm(x, self.final_norm, c.rms_norm_eps, out=nrm)
+                                       out=self._attn[:R], prefetch=ly["o_w"])
+            ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2,
+                     post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
+            ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])
+            ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x, post_norm=(nxt_gamma, nrm, eps),
+                     prefetch=nxt_w)
         ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R], counters=self.state.view(-1))
 
     def launches_per_decode_step(self) -> int:
-        return 1 + self.cfg.num_hidden_layers * 7 + 2
+        return 1 + self.cfg.num_hidden_layers * 5 + 1
 
     def _ensure_graph(self, R: int) -> "torch.cuda.CUDAGraph":
         g = self._graphs.get(R)

@@ -184,7 +184,8 @@ def test_rope_append(cuda):
 
 @pytest.mark.parametrize("rows,n,k,pro", [(1, 4608, 3584, 1), (1, 3584, 3584, 0), (1, 3584, 18944, 2),
                                           (2, 1000, 512, 0), (4, 300, 1024, 1), (1, 152064, 3584, 1),
-                                          (5, 3584, 18944, 2), (8, 4608, 3584, 1), (3, 37888, 3584, 1),
+                                          (5, 3584, 18944, 0), (8, 4608, 3584, 0), (3, 37888, 3584, 0),
+                                          (4, 3584, 18944, 2), (2, 4608, 3584, 1),
                                           (7, 1003, 96, 0), (1, 77, 32, 0), (2, 50, 40, 0)])
 def test_gemv(cuda, rows, n, k, pro):
     from streamchat_b200 import ops
@@ -338,3 +339,28 @@ def test_decode_attention_fused_multi_sequence(cuda):
                                         ws1, splits)
         assert torch.equal(out[s_], o1[0]), s_
     assert torch.equal(kc, kc1) and torch.equal(vc, vc1)
+
+
+def test_gemv_post_norm_prefetch_and_gather_norm(cuda):
+    """Decode-chain fusions: RMSNorm of the finished GEMV output by the last block, L2 prefetch of the
+    next weights (no functional effect), embedding gather fused with the first norm."""
+    from streamchat_b200 import ops
+    torch.manual_seed(8)
+    for rows, n, k in ((1, 3584, 3584), (5, 3584, 18944), (3, 256, 512)):
+        a = torch.randn(rows, k, device=cuda).half()
+        w = (torch.randn(n, k, device=cuda) * 0.02).half()
+        res = torch.randn(rows, n, device=cuda).half()
+        gamma = (1 + 0.1 * torch.randn(n, device=cuda)).half()
+        nxt = torch.randn(1000, 64, device=cuda).half()
+        nrm = torch.zeros(rows, n, device=cuda, dtype=torch.float16)
+        out = ops.gemv(a, w, residual=res, post_norm=(gamma, nrm, 1e-6), prefetch=nxt)
+        plain = ops.gemv(a, w, residual=res)
+        assert torch.equal(out, plain)
+        assert torch.equal(nrm, ops.rmsnorm(out, gamma, 1e-6))
+    table = torch.randn(50, 256, device=cuda).half()
+    ids = torch.tensor([3, 49, 0], dtype=torch.int64, device=cuda)
+    gamma = (1 + 0.1 * torch.randn(256, device=cuda)).half()
+    x = torch.zeros(3, 256, device=cuda, dtype=torch.float16)
+    nrm = torch.zeros_like(x)
+    ops.gather_rows_rmsnorm(table, ids, gamma, 1e-6, out=x, norm_out=nrm)
+    assert torch.equal(x, table[ids]) and torch.equal(nrm, ops.rmsnorm(x, gamma, 1e-6))

@@ -18,6 +18,7 @@
 //                      Algorithmic bytes: 2 * n_kv * ctx * head_dim * 2.
 #include "scb_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -214,9 +215,8 @@ struct ArgmaxFuse {
 // down_proj, qkv) are cut into several K chunks so that one wave of 8 blocks x 148 SMs is full;
 // the chunks of a group meet through a partial buffer and an atomic ticket — the last block to
 // arrive sums them in chunk order (deterministic) and runs the epilogue.
-constexpr int kGW = 4;             // warps per block
-
-__global__ void __launch_bounds__(kGW * 32, 8)
+template <int kGW>
+__global__ void __launch_bounds__(kGW * 32, 32 / kGW)
 gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict__ partial,
                 unsigned* __restrict__ gtickets, const ArgmaxFuse am) {
   __shared__ float red[kGW][8][8];
@@ -867,6 +867,7 @@ constexpr int kMaxSplitGroups = 4096;
 constexpr int kMaxChunks = 8;
 constexpr size_t kWsArgmax = 256 + (size_t)2048 * 8 * (sizeof(float) + sizeof(int));
 constexpr size_t kWsTickets = (size_t)kMaxSplitGroups * sizeof(unsigned);
+constexpr int kGWDefault = 8;   // sweep on B200 (tools/gemv_sweep.py): 8 warps per block, no K chunking
 constexpr size_t kWsPartial = (size_t)kMaxSplitGroups * kMaxChunks * 64 * sizeof(float);
 
 size_t scb_gemv_workspace_bytes(int32_t rows) {
@@ -923,21 +924,23 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
     // ---- tensor-core streaming path (activations already normalised / gated by the caller)
     const long long n_groups = (a->n + 7) / 8;
     const int ktiles = (int)(a->k / 32);
-    const long long wave = (long long)sms * 8;             // 8 blocks of 4 warps per SM
-    // K chunks: fill whole waves (skinny layers), keep >= 2 batches of 8 tiles per warp
-    int C = 1;
-    if (n_groups <= kMaxSplitGroups && a->workspace) {
-      double best_eff = 0.0;
-      for (int c = 1; c <= kMaxChunks; ++c) {
-        if (c > 1 && ktiles / (c * kGW) < kMU) break;   // at least one full 4 KB batch per warp
-        const long long units = n_groups * c;
-        const double eff = (double)units / (double)(((units + wave - 1) / wave) * wave);
-        if (eff > best_eff + 0.02) {
-          best_eff = eff;
-          C = c;
-        }
-      }
+    static int env_w = -1, env_c = -1;
+    if (env_w < 0) {
+      const char* e = getenv("SCB_GEMV_W");
+      env_w = e ? atoi(e) : 0;
+      e = getenv("SCB_GEMV_C");
+      env_c = e ? atoi(e) : 0;
     }
+    const int GW = (env_w == 8 || env_w == 16 || env_w == 32) ? env_w : kGWDefault;
+    const long long wave = (long long)sms * (32 / GW);     // 32 warps per SM
+    // K chunks: fill whole waves (skinny layers), keep >= 2 batches of 8 tiles per warp
+    // K chunking (C > 1) only pays when a layer has far fewer row groups than block slots; on the
+    // Qwen2-7B shapes the ticket round trip costs more than it gains (profiles/r01_gemv_sweep.txt)
+    int C = 1;
+    if (n_groups * 4 < wave && n_groups <= kMaxSplitGroups && a->workspace) {
+      while (C < kMaxChunks && n_groups * C * 2 <= wave && ktiles / (2 * C * GW) >= kMU) C *= 2;
+    }
+    if (env_c >= 1 && env_c <= kMaxChunks && n_groups <= kMaxSplitGroups && a->workspace) C = env_c;
     ArgmaxFuse am{};
     float* partial = nullptr;
     unsigned* gtickets = nullptr;
@@ -967,8 +970,14 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
     const long long units = n_groups * C;
     long long cap = wave < 2048 ? wave : 2048;
     const int grid = (int)(units < cap ? units : cap);
-    SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel, dim3(grid), dim3(kGW * 32), 0, st, p, (int)a->rows, C,
-                               partial, gtickets, am));
+    if (GW == 4)
+      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<4>, dim3(grid), dim3(128), 0, st, p, (int)a->rows, C, partial, gtickets, am));
+    else if (GW == 8)
+      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<8>, dim3(grid), dim3(256), 0, st, p, (int)a->rows, C, partial, gtickets, am));
+    else if (GW == 16)
+      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<16>, dim3(grid), dim3(512), 0, st, p, (int)a->rows, C, partial, gtickets, am));
+    else
+      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<32>, dim3(grid), dim3(1024), 0, st, p, (int)a->rows, C, partial, gtickets, am));
     SCB_LAUNCH_OK("gemv_mma_kernel");
     return SCB_OK;
   }

@@ -215,6 +215,135 @@ kmeans_assign_partial(const T* __restrict__ x, const float* __restrict__ cent, i
 }
 
 // ------------------------------------------------------------------------------------------
+// assign_partial_async — the vector path at HBM speed.  Same tiling as above, but the point
+// vectors travel global -> shared with cp.async (16 B per thread, L1 bypass) through a private
+// ring of kST stages per thread: three stages (12 loads of 16 B per thread, 96 KB per SM) are in
+// flight while the fourth is consumed, without spending registers on them; a thread only ever
+// reads back its own slots, so the ring needs cp.async.wait_group and no block barrier.  Warps
+// reduce their partial sums on their own and write them per warp:
+//   partial[b][tile*8 + warp][n][k]          (summed in a fixed order by assign_final)
+// ------------------------------------------------------------------------------------------
+constexpr int kST = 4;
+
+SCB_DEVICE void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+SCB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SCB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, bool kEps, int KT>
+__global__ void __launch_bounds__(kThreads, 2)
+kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ cent, int n_points,
+                            int n_clusters, long long dim, int tile_cols, int points_per_split,
+                            float eps, float* __restrict__ partial) {
+  constexpr int E = PVec<T>::kElems;
+  constexpr int NP = PVec<T>::kPairs;
+  extern __shared__ __align__(16) float cs[];          // [KT][tile_cols] then the x ring
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.z;
+  const int n_tiles = gridDim.x;
+  uint4* xs = reinterpret_cast<uint4*>(cs + (size_t)KT * tile_cols);   // [kST][kPG][kThreads]
+  const long long col0 = (long long)tile * tile_cols;
+  const int ncols = (int)min((long long)tile_cols, dim - col0);
+  const int n_begin = blockIdx.y * points_per_split;
+  const int n_end = min(n_points, n_begin + points_per_split);
+  const float* cb = cent + (long long)b * n_clusters * dim + col0;
+  const u64 eps2 = pack2(eps, eps);
+  const int passes = (ncols + kThreads * E - 1) / (kThreads * E);
+  const int n_pg = (n_end - n_begin + kPG - 1) / kPG;
+  const int n_it = n_pg * passes;
+
+  auto issue = [&](int it) {
+    if (it < n_it) {
+      const int pg = it / passes, pass = it - pg * passes;
+      const int c = (pass * kThreads + tid) * E;
+      if (c < ncols) {
+#pragma unroll
+        for (int p = 0; p < kPG; ++p) {
+          int n = n_begin + pg * kPG + p;
+          if (n >= n_end) n = n_end - 1;   // clamped duplicate, discarded below
+          cp_async16(xs + ((it % kST) * kPG + p) * kThreads + tid, x + (long long)n * dim + col0 + c);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (int k0 = 0; k0 < n_clusters; k0 += KT) {
+    const int kt = min(KT, n_clusters - k0);
+#pragma unroll
+    for (int s = 0; s < kST - 1; ++s) issue(s);        // the points do not wait for the centroids
+    {
+      const int n4 = ncols >> 2;
+      for (int i = tid; i < kt * n4; i += kThreads) {
+        const int k = i / n4, c = (i - k * n4) << 2;
+        *reinterpret_cast<float4*>(cs + k * tile_cols + c) =
+            *reinterpret_cast<const float4*>(cb + (long long)(k0 + k) * dim + c);
+      }
+    }
+    __syncthreads();
+
+    u64 acc[kPG][KT];
+#pragma unroll
+    for (int p = 0; p < kPG; ++p)
+#pragma unroll
+      for (int k = 0; k < KT; ++k) acc[p][k] = 0ull;
+
+    for (int it = 0; it < n_it; ++it) {
+      issue(it + kST - 1);
+      cp_async_wait<kST - 1>();                          // stage `it` has landed (own slots only)
+      const int pg = it / passes, pass = it - pg * passes;
+      const int c = (pass * kThreads + tid) * E;
+      if (c < ncols) {
+        u64 xv[kPG][NP];
+#pragma unroll
+        for (int p = 0; p < kPG; ++p)
+          PVec<T>::unpack(xs[((it % kST) * kPG + p) * kThreads + tid], xv[p]);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          if (k < kt) {
+            u64 cv[NP];
+            const float* cp = cs + k * tile_cols + c;
+#pragma unroll
+            for (int j = 0; j < NP; j += 2) {
+              ulonglong2 t = *reinterpret_cast<const ulonglong2*>(cp + j * 2);
+              cv[j] = t.x;
+              cv[j + 1] = t.y;
+            }
+#pragma unroll
+            for (int p = 0; p < kPG; ++p)
+#pragma unroll
+              for (int j = 0; j < NP; ++j) {
+                u64 d = sub2(xv[p][j], cv[j]);
+                if constexpr (kEps) d = add2(d, eps2);
+                sqacc2(acc[p][k], d);
+              }
+          }
+        }
+      }
+      if (pass == passes - 1) {
+        // point group finished: warp-level sums, one writer lane, no block barrier
+        const int p0 = n_begin + pg * kPG;
+#pragma unroll
+        for (int p = 0; p < kPG; ++p)
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            float2 a = unpack2(acc[p][k]);
+            const float v = warp_sum(a.x + a.y);
+            acc[p][k] = 0ull;
+            if (lane == 0 && k < kt && p0 + p < n_end)
+              partial[((((long long)b * n_tiles + tile) * (kThreads / 32) + warp) * n_points + p0 + p) *
+                          n_clusters + k0 + k] = v;
+          }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // centroid tile reuse by the next cluster tile
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // assign_final: one block per batch entry.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -224,21 +353,28 @@ kmeans_assign_final(const float* __restrict__ partial, const float* __restrict__
                     int* __restrict__ order, int* __restrict__ starts) {
   const int b = blockIdx.x, tid = threadIdx.x;
   __shared__ int cnt[kMaxClusters + 1];
-  for (int n = tid; n < n_points; n += kThreads) {
-    float best = INFINITY;
-    int bi = 0;
-    for (int k = 0; k < n_clusters; ++k) {
-      float s = 0.f;
-      for (int sl = 0; sl < n_slices; ++sl)
-        s += partial[(((long long)b * n_slices + sl) * n_points + n) * n_clusters + k];
-      float d = sqrtf(s);
-      if (k == 0 || d < best) {  // first minimum wins (torch.argmin; NaN-free inputs assumed)
-        best = d;
-        bi = k;
+  // one warp per point: lanes stride over the partial slices (fixed order -> deterministic sums)
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int n = warp; n < n_points; n += kThreads / 32) {
+      float best = INFINITY;
+      int bi = 0;
+      for (int k = 0; k < n_clusters; ++k) {
+        float s = 0.f;
+        for (int sl = lane; sl < n_slices; sl += 32)
+          s += partial[(((long long)b * n_slices + sl) * n_points + n) * n_clusters + k];
+        s = warp_sum(s);
+        const float d = sqrtf(s);
+        if (k == 0 || d < best) {  // first minimum wins (torch.argmin; NaN-free inputs assumed)
+          best = d;
+          bi = k;
+        }
+      }
+      if (lane == 0) {
+        labels[(long long)b * n_points + n] = bi;
+        if (out_dist) out_dist[(long long)b * n_points + n] = best;
       }
     }
-    labels[(long long)b * n_points + n] = bi;
-    if (out_dist) out_dist[(long long)b * n_points + n] = best;
   }
   if (order == nullptr) return;
   __syncthreads();
@@ -371,6 +507,8 @@ struct Plan {
   int tile_cols, n_tiles;         // assign: centroid tile (columns) and tile count
   int points_per_split, n_splits; // assign: points per block
   size_t assign_smem;
+  int n_slices;                   // partial-sum slices summed by assign_final
+  int kt_async = 8;
   int n_chunks;                   // update: column chunks
   size_t partial_off, order_off, starts_off, shiftp_off, total;
 };
@@ -383,12 +521,19 @@ Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esi
   const long long cols_per_pass = (long long)kThreads * ce;
   const long long passes = (dim + cols_per_pass - 1) / cols_per_pass;
   const int kt = n_clusters < kKT ? n_clusters : kKT;
-  long long tile_passes = kTileBytes / ((long long)kt * 4 * cols_per_pass);
+  const long long tile_budget = p.vec ? (40 * 1024) : kTileBytes;   // vec: tile + 64 KB ring, 2 blocks / SM
+  long long tile_passes = tile_budget / ((long long)kt * 4 * cols_per_pass);
   if (tile_passes < 1) tile_passes = 1;
   if (tile_passes > passes) tile_passes = passes;
   p.tile_cols = (int)(tile_passes * cols_per_pass);
   p.n_tiles = (int)((dim + p.tile_cols - 1) / p.tile_cols);
   p.assign_smem = (size_t)kt * p.tile_cols * sizeof(float);
+  p.n_slices = p.n_tiles;
+  if (p.vec) {   // cp.async kernel: exact cluster tile, per-thread x ring, per-warp partial slices
+    p.kt_async = n_clusters <= 4 ? 4 : (n_clusters == 5 ? 5 : 8);
+    p.assign_smem = (size_t)p.kt_async * p.tile_cols * sizeof(float) + (size_t)kST * kPG * kThreads * 16;
+    p.n_slices = p.n_tiles * (kThreads / 32);
+  }
   // split the points so that ~4 blocks per SM exist (each split re-reads the centroid tile from L2)
   const int n_groups = (n_points + kPG - 1) / kPG;
   long long splits = (148LL * 4 + (long long)p.n_tiles * n_batch - 1) / ((long long)p.n_tiles * n_batch);
@@ -400,7 +545,7 @@ Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esi
   p.n_chunks = (int)passes;
   size_t off = 0;
   p.partial_off = off;
-  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * p.n_tiles * n_points * n_clusters, 256);
+  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * p.n_slices * n_points * n_clusters, 256);
   p.order_off = off;
   off = scb_align_up(off + sizeof(int) * (size_t)n_batch * n_points, 256);
   p.starts_off = off;
@@ -439,16 +584,30 @@ int run(const scb_kmeans_step_args* a, cudaStream_t st) {
                                               p.tile_cols, p.points_per_split, a->dist_eps,        \
                                               partial);                                            \
   } while (0)
+#define SCB_KM_ASYNC(EPS, KT)                                                                      \
+  do {                                                                                             \
+    auto kern = kmeans_assign_partial_async<T, EPS, KT>;                                           \
+    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                     (int)p.assign_smem));                                         \
+    kern<<<g1, kThreads, p.assign_smem, st>>>(x, a->centroids, a->n_points, a->n_clusters, a->dim, \
+                                              p.tile_cols, p.points_per_split, a->dist_eps,        \
+                                              partial);                                            \
+  } while (0)
   if (p.vec) {
-    if (eps) SCB_KM_ASSIGN(true, true); else SCB_KM_ASSIGN(true, false);
+    if (eps) {
+      if (p.kt_async == 4) SCB_KM_ASYNC(true, 4); else if (p.kt_async == 5) SCB_KM_ASYNC(true, 5); else SCB_KM_ASYNC(true, 8);
+    } else {
+      if (p.kt_async == 4) SCB_KM_ASYNC(false, 4); else if (p.kt_async == 5) SCB_KM_ASYNC(false, 5); else SCB_KM_ASYNC(false, 8);
+    }
   } else {
     if (eps) SCB_KM_ASSIGN(false, true); else SCB_KM_ASSIGN(false, false);
   }
 #undef SCB_KM_ASSIGN
+#undef SCB_KM_ASYNC
   SCB_LAUNCH_OK("kmeans_assign_partial");
 
   kmeans_assign_final<<<a->n_batch, kThreads, 0, st>>>(
-      partial, a->weights, a->n_points, a->n_clusters, p.n_tiles, a->out_labels, a->out_dist,
+      partial, a->weights, a->n_points, a->n_clusters, p.n_slices, a->out_labels, a->out_dist,
       a->do_update ? a->out_wsum : nullptr, a->do_update ? order : nullptr, starts);
   SCB_LAUNCH_OK("kmeans_assign_final");
   if (!a->do_update) return SCB_OK;

@@ -245,7 +245,8 @@ def test_gemv_fused_argmax(cuda, rows):
     gamma = (1 + 0.1 * torch.randn(k, device=cuda)).half()
     ids = torch.full((rows,), -1, dtype=torch.int64, device=cuda)
     cnt = torch.tensor([10, 11], dtype=torch.int32, device=cuda)
-    out = ops.gemv(a, w, prologue=_lib.PRO_RMSNORM, gamma=gamma, eps=1e-6, argmax_out=ids, counters=cnt)
+    a = ops.rmsnorm(a, gamma, 1e-6)
+    out = ops.gemv(a, w, argmax_out=ids, counters=cnt)
     assert out.dtype == torch.float16
     assert ids.tolist() == torch.argmax(out.float(), dim=1).tolist()      # over the stored fp16 logits
     assert cnt.tolist() == [11, 12]
@@ -255,7 +256,7 @@ def test_gemv_fused_argmax(cuda, rows):
     lo, hi = 5, n - 3
     w2[lo] = w[best]
     w2[hi] = w[best]
-    out2 = ops.gemv(a, w2, prologue=_lib.PRO_RMSNORM, gamma=gamma, eps=1e-6, argmax_out=ids, counters=cnt)
+    out2 = ops.gemv(a, w2, argmax_out=ids, counters=cnt)
     assert int(ids[0]) == min(lo, best) and ids.tolist() == torch.argmax(out2.float(), dim=1).tolist()
     assert cnt.tolist() == [12, 13]
 

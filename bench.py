@@ -107,6 +107,22 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+STAGE_EVENTS = []   # (stage name, start event, end event) of the last timed region
+
+
+def _stage(name):
+    class _S:
+        def __enter__(self_):
+            self_.e0 = torch.cuda.Event(enable_timing=True)
+            self_.e1 = torch.cuda.Event(enable_timing=True)
+            self_.e0.record()
+
+        def __exit__(self_, *a):
+            self_.e1.record()
+            STAGE_EVENTS.append((name, self_.e0, self_.e1))
+    return _S()
+
+
 def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, device, e2e: bool):
     """One step.  Returns (answer ids tensor, h2d bytes, d2h bytes)."""
     import torch.distributed as dist
@@ -120,8 +136,10 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
             h2d += seg.numel() * seg.element_size()
         else:
             seg = frames_dev[s0:s0 + segment]
-        feats = sess.ingest(seg)
-        sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
+        with _stage("encode"):
+            feats = sess.ingest(seg)
+        with _stage("memory_update"):
+            sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
     if world > 1:
         # the one exchange step (§8e): all-gather the per-rank memory embeddings (root-node text
         # embeddings) so every rank's retrieval sees the global index; top-k is computed redundantly
@@ -132,7 +150,8 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
         q = sess.embedding_model(sess.embedding_tokenizer, QUESTION)
         scores, idx = ops.cosine_topk(index, q, k=1)
         sess.global_best = (scores, owner[idx[0, 0]], local[idx[0, 0]])
-    text, ids = sess.answer(QUESTION)
+    with _stage("answer"):
+        text, ids = sess.answer(QUESTION)
     if e2e:
         ids_host = ids.cpu()                                                  # device -> host read of the result
         d2h += ids_host.numel() * ids_host.element_size()
@@ -187,6 +206,7 @@ def ours(args):
 
     def timed(e2e: bool, steps: int):
         model.llm.profile = []
+        STAGE_EVENTS.clear()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
@@ -213,6 +233,9 @@ def ours(args):
     sampler.start()
     ms, _, _, launches, prof = timed(False, args.steps)
     clocks = sampler.stop()
+    breakdown = {}
+    for name, a0, a1 in STAGE_EVENTS:
+        breakdown[name] = breakdown.get(name, 0.0) + a0.elapsed_time(a1) / args.steps
     ms_e2e, h2d, d2h, _, _ = timed(True, args.steps)
 
     total_frames = n_frames * world * args.steps
@@ -250,6 +273,7 @@ def ours(args):
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "impl": "ours",
+        "breakdown_ms_per_step": breakdown,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n_frames, args, tiny)

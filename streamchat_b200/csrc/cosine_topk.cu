@@ -188,17 +188,44 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
   if (!is_last_s) return;
   __threadfence();
 
-  // ---- final merge by the last block of this query: 8 warps split the block lists
+  // ---- final merge by the last block of this query.  The gx*k candidates are read 32 at a time
+  // per warp with coalesced L2 loads (one round trip per chunk, next chunk requested before the
+  // current one is consumed); only candidates that beat the warp's current k-th entry are inserted.
   list.s = -INFINITY;
   list.i = -1;
-  for (int b = warp; b < gx; b += kWarps) {
-    const float* cs = cand_s + ((long long)qi * gx + b) * k;
-    const long long* ci = cand_i + ((long long)qi * gx + b) * k;
-    for (int j = 0; j < k; ++j) {
-      float s = __ldcg(cs + j);
-      long long i = __ldcg(ci + j);
-      if (i < 0) break;
-      topk_insert(list, s, i, k, lane);
+  {
+    const int n_cand = gx * k;
+    const float* cs = cand_s + (long long)qi * n_cand;
+    const long long* ci = cand_i + (long long)qi * n_cand;
+    int c0 = warp * 32;
+    float ns = -INFINITY;
+    long long ni = -1;
+    if (c0 + lane < n_cand) {
+      ns = __ldcg(cs + c0 + lane);
+      ni = __ldcg(ci + c0 + lane);
+    }
+    while (c0 < n_cand) {
+      const float s_l = ns;
+      const long long i_l = ni;
+      const int c1 = c0 + kWarps * 32;
+      ns = -INFINITY;
+      ni = -1;
+      if (c1 + lane < n_cand) {
+        ns = __ldcg(cs + c1 + lane);
+        ni = __ldcg(ci + c1 + lane);
+      }
+      // threshold = current k-th entry (lane k-1); candidates not ranking before it cannot enter
+      const float th_s = __shfl_sync(0xffffffffu, list.s, k - 1);
+      const long long th_i = __shfl_sync(0xffffffffu, list.i, k - 1);
+      unsigned live = __ballot_sync(0xffffffffu, i_l >= 0 && (th_i < 0 || ranks_before(s_l, i_l, th_s, th_i)));
+      while (live) {
+        const int src = __ffs(live) - 1;
+        live &= live - 1;
+        const float s = __shfl_sync(0xffffffffu, s_l, src);
+        const long long i = __shfl_sync(0xffffffffu, i_l, src);
+        topk_insert(list, s, i, k, lane);
+      }
+      c0 = c1;
     }
   }
   __syncthreads();  // m_s/m_i reuse
@@ -250,7 +277,7 @@ int launch(const scb_cosine_topk_args* a, cudaStream_t st) {
   SCB_CUDA_OK(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * a->n_queries, st));
 
   const int sms = scb_num_sms();
-  long long want = (a->n_rows + kWarps - 1) / kWarps;  // one row per warp at least
+  long long want = (a->n_rows + kWarps * 4 - 1) / (kWarps * 4);  // >= 4 rows per warp: fewer candidates to merge
   int gx = (int)(want < 1 ? 1 : (want > (long long)sms * 4 ? (long long)sms * 4 : want));
   if (gx > kMaxGx) gx = kMaxGx;
   dim3 grid(gx, a->n_queries);

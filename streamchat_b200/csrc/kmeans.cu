@@ -219,9 +219,9 @@ kmeans_assign_partial(const T* __restrict__ x, const float* __restrict__ cent, i
 // vectors travel global -> shared with cp.async (16 B per thread, L1 bypass) through a private
 // ring of kST stages per thread: three stages (12 loads of 16 B per thread, 96 KB per SM) are in
 // flight while the fourth is consumed, without spending registers on them; a thread only ever
-// reads back its own slots, so the ring needs cp.async.wait_group and no block barrier.  Warps
-// reduce their partial sums on their own and write them per warp:
-//   partial[b][tile*8 + warp][n][k]          (summed in a fixed order by assign_final)
+// reads back its own slots, so the ring needs cp.async.wait_group and no block barrier.  A warp
+// owns whole point groups and reduces over its lanes once per group:
+//   partial[b][tile][n][k]                   (summed in a fixed order by assign_final)
 // ------------------------------------------------------------------------------------------
 constexpr int kST = 4;
 
@@ -239,6 +239,7 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
                             float eps, float* __restrict__ partial) {
   constexpr int E = PVec<T>::kElems;
   constexpr int NP = PVec<T>::kPairs;
+  constexpr int NW = kThreads / 32;
   extern __shared__ __align__(16) float cs[];          // [KT][tile_cols] then the x ring
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, b = blockIdx.z;
@@ -250,18 +251,22 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
   const int n_end = min(n_points, n_begin + points_per_split);
   const float* cb = cent + (long long)b * n_clusters * dim + col0;
   const u64 eps2 = pack2(eps, eps);
-  const int passes = (ncols + kThreads * E - 1) / (kThreads * E);
+  // a WARP owns whole point groups (4 points) and walks the tile's columns in `passes` steps of
+  // 32 lanes x 16 B, so the lane reduction happens once per point group, not once per load
+  const int passes = (ncols + 32 * E - 1) / (32 * E);
   const int n_pg = (n_end - n_begin + kPG - 1) / kPG;
-  const int n_it = n_pg * passes;
+  const int n_pg_w = n_pg > warp ? (n_pg - warp + NW - 1) / NW : 0;
+  const int n_it = n_pg_w * passes;
 
   auto issue = [&](int it) {
     if (it < n_it) {
-      const int pg = it / passes, pass = it - pg * passes;
-      const int c = (pass * kThreads + tid) * E;
+      const int pgi = it / passes, pass = it - pgi * passes;
+      const int c = (pass * 32 + lane) * E;
       if (c < ncols) {
+        const int p0 = n_begin + (warp + pgi * NW) * kPG;
 #pragma unroll
         for (int p = 0; p < kPG; ++p) {
-          int n = n_begin + pg * kPG + p;
+          int n = p0 + p;
           if (n >= n_end) n = n_end - 1;   // clamped duplicate, discarded below
           cp_async16(xs + ((it % kST) * kPG + p) * kThreads + tid, x + (long long)n * dim + col0 + c);
         }
@@ -293,8 +298,8 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
     for (int it = 0; it < n_it; ++it) {
       issue(it + kST - 1);
       cp_async_wait<kST - 1>();                          // stage `it` has landed (own slots only)
-      const int pg = it / passes, pass = it - pg * passes;
-      const int c = (pass * kThreads + tid) * E;
+      const int pgi = it / passes, pass = it - pgi * passes;
+      const int c = (pass * 32 + lane) * E;
       if (c < ncols) {
         u64 xv[kPG][NP];
 #pragma unroll
@@ -323,8 +328,8 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
         }
       }
       if (pass == passes - 1) {
-        // point group finished: warp-level sums, one writer lane, no block barrier
-        const int p0 = n_begin + pg * kPG;
+        // point group finished for this warp: xor-tree over the lanes, lane 0 writes
+        const int p0 = n_begin + (warp + pgi * NW) * kPG;
 #pragma unroll
         for (int p = 0; p < kPG; ++p)
 #pragma unroll
@@ -333,8 +338,7 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
             const float v = warp_sum(a.x + a.y);
             acc[p][k] = 0ull;
             if (lane == 0 && k < kt && p0 + p < n_end)
-              partial[((((long long)b * n_tiles + tile) * (kThreads / 32) + warp) * n_points + p0 + p) *
-                          n_clusters + k0 + k] = v;
+              partial[(((long long)b * n_tiles + tile) * n_points + p0 + p) * n_clusters + k0 + k] = v;
           }
       }
     }
@@ -438,6 +442,25 @@ kmeans_update_partial(const T* __restrict__ x, const float* __restrict__ weights
     if (active) {
       int i = beg;
       if constexpr (kVec) {
+        // the grid has only D/2048 blocks (~14 warps per SM at 516 096 dims), so every thread keeps
+        // 16 independent 16-byte loads in flight (~110 KB per SM) to cover the HBM latency
+        for (; i + 16 <= end; i += 16) {
+          uint4 r[16];
+          float w[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int n = sm_order[i + u];
+            r[u] = ld_stream_u4(x + (long long)n * dim + col);
+            w[u] = weights ? weights[n] : 1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            float f[E];
+            PVec<T>::to_float(r[u], f);
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] = fmaf(w[u], f[e], acc[e]);
+          }
+        }
         for (; i + 4 <= end; i += 4) {  // four independent 16-byte loads in flight
           uint4 r[4];
           float w[4];
@@ -532,7 +555,6 @@ Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esi
   if (p.vec) {   // cp.async kernel: exact cluster tile, per-thread x ring, per-warp partial slices
     p.kt_async = n_clusters <= 4 ? 4 : (n_clusters == 5 ? 5 : 8);
     p.assign_smem = (size_t)p.kt_async * p.tile_cols * sizeof(float) + (size_t)kST * kPG * kThreads * 16;
-    p.n_slices = p.n_tiles * (kThreads / 32);
   }
   // split the points so that ~4 blocks per SM exist (each split re-reads the centroid tile from L2)
   const int n_groups = (n_points + kPG - 1) / kPG;

@@ -312,7 +312,7 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
         const float gt = __half2float(__float2half_rn(v));       // Linear output is fp16 in HF
         const float up = __shfl_xor_sync(0xffffffffu, gt, 1);
         if (have && n < p.N && (j & 1) == 0) {
-          const float sg = __half2float(__float2half_rn(gt / (1.f + __expf(-gt))));
+          const float sg = __half2float(__float2half_rn(__fdividef(gt, 1.f + __expf(-gt))));
           reinterpret_cast<__half*>(p.out)[(long long)r * p.ldo + (n >> 1)] = __float2half_rn(sg * up);
         }
       }

@@ -192,7 +192,7 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, long long ld_gu, 
     unpack8(*reinterpret_cast<const uint4*>(gu + m * ld_gu + I + i), u);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float s = __half2float(__float2half_rn(g[e] / (1.f + __expf(-g[e]))));
+      const float s = __half2float(__float2half_rn(__fdividef(g[e], 1.f + __expf(-g[e]))));
       o[e] = s * u[e];
     }
     *reinterpret_cast<uint4*>(out + m * ld_out + i) = pack8(o);

@@ -36,7 +36,7 @@ class LlavaQwenConfig:
     mm_use_im_patch_token: bool = False
     tokenizer_model_max_length: Optional[int] = None
     max_context: int = 16384
-    max_batch: int = 5            # chunk captions decoded together (one weight pass per step)
+    max_batch: int = 6            # chunk captions (+ a pending summary) decoded together, one weight pass per step
 
     @property
     def hidden_size(self) -> int:
@@ -158,17 +158,29 @@ class LlavaQwenForCausalLM:
                                  eos_token_id=kwargs.pop("eos_token_id", None))
 
     @torch.no_grad()
+    def generate_requests(self, requests, modalities: Optional[List[str]] = ["image"], eos_token_id=None):
+        """Greedy generation for several independent requests `(input_ids, image_embeddings | None,
+        max_new_tokens)` — e.g. the per-chunk captions of one memory update (utiles.py:539-559) plus a
+        pending text summary (utiles.py:594-605).  Each request yields exactly the ids the
+        one-at-a-time `generate_with_image_embedding` call yields; they are decoded in lock-step so every
+        decode step streams the weights once for all of them."""
+        out: List[Optional[torch.Tensor]] = [None] * len(requests)
+        B = self.llm.max_batch
+        for i in range(0, len(requests), B):
+            embeds, budgets = [], []
+            for ids, img, max_new in requests[i:i + B]:
+                if img is not None:
+                    x = self.prepare_inputs_embeddings_for_multimodal(ids, None, None, None, None, img, modalities)[4][0]
+                else:
+                    x = self._inner.embed_tokens(ids.to(self.device))[0]
+                embeds.append(x)
+                budgets.append(int(max_new))
+            res = self.llm.generate_batch(embeds, budgets, eos_token_id)
+            out[i:i + len(res)] = res
+        return out
+
     def generate_with_image_embedding_batch(self, inputs: torch.Tensor, image_embeddings_list: List[torch.Tensor],
                                             modalities: Optional[List[str]] = ["image"], max_new_tokens: int = 20,
                                             eos_token_id=None) -> List[torch.Tensor]:
-        """Greedy `generate_with_image_embedding` for several independent (prompt, features) pairs that
-        share the prompt ids — the per-chunk captions of one memory update (utiles.py:539-559).  Every
-        sequence yields exactly the ids the one-at-a-time call yields; they are decoded in lock-step so
-        each decode step streams the weights once for all of them."""
-        out: List[torch.Tensor] = []
-        B = self.llm.max_batch
-        for i in range(0, len(image_embeddings_list), B):
-            embeds = [self.prepare_inputs_embeddings_for_multimodal(inputs, None, None, None, None, [e], modalities)[4][0]
-                      for e in image_embeddings_list[i:i + B]]
-            out += self.llm.generate_batch(embeds, max_new_tokens, eos_token_id)
-        return out
+        return self.generate_requests([(inputs, [e], max_new_tokens) for e in image_embeddings_list],
+                                      modalities, eos_token_id)

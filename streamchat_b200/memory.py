@@ -35,15 +35,41 @@ SUMMARY_TOKENS = 256   # max_new_tokens of the merge summary (utiles.py:604)
 
 
 class MultimodalTreeNode:
+    """utiles.py:48-56.  `text` may be PENDING: a merge node's summary is a greedy generation that
+    nothing needs until the next merge or a search, so it is deferred and decoded together with the
+    next update's captions (same ids, one weight pass per step); reading `.text` earlier resolves it
+    on the spot."""
+
     def __init__(self, centroids, text, text_distance=None, image_distance=None, labels=None, depth=0):
         self.centroids = centroids
-        self.text = text
+        self._text = text
+        self._pending = None        # (summarizer, tokenizer, input_ids, max_new_tokens)
         self.text_distance = text_distance
         self.image_distance = image_distance
         self.labels = labels
         self.children = []
         self.depth = depth
         self.text_embedding = None  # cached [D] embedding of `text` (not in the reference)
+
+    @property
+    def text(self):
+        if self._pending is not None:
+            summarizer, tokenizer, ids, max_new = self._pending
+            with torch.no_grad():
+                out = summarizer.generate_with_image_embedding(
+                    ids.to(summarizer.device), image_embeddings=None, modalities=["video"], do_sample=False,
+                    temperature=0, top_p=None, max_new_tokens=max_new, use_cache=False)
+            self.set_text(tokenizer.batch_decode(out, skip_special_tokens=True)[0].strip())
+        return self._text
+
+    @text.setter
+    def text(self, value):
+        self.set_text(value)
+
+    def set_text(self, value):
+        self._text = value
+        self._pending = None
+        self.text_embedding = None
 
 
 def calculate_forgetting_probabilities(length, tau=10):
@@ -119,12 +145,20 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
     for chunk_feature in chunked_feature_list:
         dimension = chunk_feature[0].shape[-1]
         flat_chunks.append(torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device))
-    if (not caption_do_sample) and len(flat_chunks) > 1 and hasattr(summarizer, "generate_with_image_embedding_batch"):
-        # greedy captions of independent chunks: same ids as one call per chunk, decoded together
+    batched = (not caption_do_sample) and hasattr(summarizer, "generate_requests")
+    pending = [n for n in (existing_tree or []) if getattr(n, "_pending", None) is not None] if batched else []
+    if batched and (len(flat_chunks) + len(pending) > 1):
+        # greedy captions of independent chunks (+ summaries deferred by earlier merges): same ids as
+        # one call each, decoded together
+        ids_dev = input_ids.to(summarizer.device)
+        reqs = [(n._pending[2].to(summarizer.device), None, n._pending[3]) for n in pending]
+        reqs += [(ids_dev, [c], CAPTION_TOKENS) for c in flat_chunks]
         with torch.no_grad():
-            ids_list = summarizer.generate_with_image_embedding_batch(
-                input_ids.to(summarizer.device), flat_chunks, modalities=["video"], max_new_tokens=CAPTION_TOKENS)
-        output_list = [tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip() for ids in ids_list]
+            ids_list = summarizer.generate_requests(reqs, modalities=["video"])
+        for n, ids in zip(pending, ids_list[:len(pending)]):
+            n.set_text(tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip())
+        output_list = [tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip()
+                       for ids in ids_list[len(pending):]]
     else:
         for chunk_feature in flat_chunks:
             with torch.no_grad():
@@ -158,13 +192,18 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
             from .longva.conversation import conv_templates as _ct
             conv_templates = _ct
         summarize_ids = make_summary_prompt(caption_list, tokenizer, conv_templates)
-        with torch.no_grad():
-            output_ids = summarizer.generate_with_image_embedding(
-                summarize_ids.to(summarizer.device), image_embeddings=None, modalities=["video"],
-                do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
-                max_new_tokens=SUMMARY_TOKENS, use_cache=False)
-        summarize_text = tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip()
-        new_node = MultimodalTreeNode(new_centroids, summarize_text, depth=chunk[0].depth + 1)
+        if batched:
+            # deferred: resolved together with the next update's captions, or on first read of .text
+            new_node = MultimodalTreeNode(new_centroids, None, depth=chunk[0].depth + 1)
+            new_node._pending = (summarizer, tokenizer, summarize_ids, SUMMARY_TOKENS)
+        else:
+            with torch.no_grad():
+                output_ids = summarizer.generate_with_image_embedding(
+                    summarize_ids.to(summarizer.device), image_embeddings=None, modalities=["video"],
+                    do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
+                    max_new_tokens=SUMMARY_TOKENS, use_cache=False)
+            summarize_text = tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip()
+            new_node = MultimodalTreeNode(new_centroids, summarize_text, depth=chunk[0].depth + 1)
         for node in chunk:
             new_node.children.append(node)
         nodes[start_index: start_index + interval] = [new_node]

@@ -177,6 +177,8 @@ class Qwen2Engine:
         scale = hd ** -0.5
         x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
         eps = c.rms_norm_eps
+        # KV splits: ~2 blocks per SM in ONE wave whatever the batch is (fewer partials to combine)
+        splits = max(8, min(self.decode_splits, 296 // (R * Hkv)))
         L0 = self.layers[0]
         ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
         n_layers = len(self.layers)
@@ -185,7 +187,7 @@ class Qwen2Engine:
             nxt_w = self.layers[i + 1]["qkv_w"] if i + 1 < n_layers else self.lm_head
             ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
-                                       self.state[1, :R], Hq, scale, self._attn_ws, n_splits=self.decode_splits,
+                                       self.state[1, :R], Hq, scale, self._attn_ws, n_splits=splits,
                                        out=self._attn[:R], prefetch=ly["o_w"])
             ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2,
                      post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
@@ -224,68 +226,79 @@ class Qwen2Engine:
         return g
 
     @torch.no_grad()
-    def generate_batch(self, inputs_embeds_list: List[torch.Tensor], max_new_tokens: int, eos_token_id=None,
+    def generate_batch(self, inputs_embeds_list: List[torch.Tensor], max_new_tokens, eos_token_id=None,
                        use_graph: bool = True) -> List[torch.Tensor]:
         """Greedy generation for up to `max_batch` independent prompts: each is prefilled into its own
-        cache slot, then all decode in lock-step (one weight pass per step for all of them).  Returns a
-        list of [1, T_new] int64 tensors, each truncated after its first EOS."""
-        R = len(inputs_embeds_list)
-        if R < 1 or R > self.max_batch:
-            raise ValueError(f"{R} sequences but max_batch={self.max_batch}")
+        cache slot, then all decode in lock-step (one weight pass per step for all of them).
+        `max_new_tokens` is an int or one int per prompt; sequences with a larger budget take the lower
+        slots so that finished ones drop off the end and the step shrinks to the rows still running.
+        Returns a list (in the caller's order) of [1, T_new] int64 tensors, each truncated after its
+        first EOS.  Rows are independent: every sequence gets the ids it would get alone."""
+        n = len(inputs_embeds_list)
+        if n < 1 or n > self.max_batch:
+            raise ValueError(f"{n} sequences but max_batch={self.max_batch}")
+        budgets = [int(max_new_tokens)] * n if isinstance(max_new_tokens, int) else [int(b) for b in max_new_tokens]
+        if len(budgets) != n or min(budgets) < 1:
+            raise ValueError("max_new_tokens must be a positive int or one per sequence")
+        order = sorted(range(n), key=lambda i: -budgets[i])           # slot s holds caller's sequence order[s]
         with torch.cuda.device(self.device):
-            graph = self._ensure_graph(R) if use_graph else None     # before prefill (see _ensure_graph)
+            if use_graph:
+                for r in sorted({sum(1 for b in budgets if b > t) for t in [0] + budgets} - {0}):
+                    self._ensure_graph(r)                               # before prefill (see _ensure_graph)
             self.reset()
             lens = []
-            for s_, x in enumerate(inputs_embeds_list):
-                logits = self.prefill(x, slot=s_)
+            for s_, i in enumerate(order):
+                logits = self.prefill(inputs_embeds_list[i], slot=s_)
                 ops.argmax_rows(logits, out=self.next_id[s_:s_ + 1])
                 lens.append(self.ctx_lens[s_])
             st = torch.zeros((2, self.max_batch), dtype=torch.int32)
-            st[0, :R] = torch.tensor(lens, dtype=torch.int32)
-            st[1, :R] = st[0, :R] + 1
+            st[0, :n] = torch.tensor(lens, dtype=torch.int32)
+            st[1, :n] = st[0, :n] + 1
             self.state.copy_(st, non_blocking=True)
             eos = set()
             if eos_token_id is not None:
                 eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else {int(eos_token_id)}
-            out = torch.zeros((max_new_tokens, R), dtype=torch.int64, device=self.device)
+            slot_budget = [budgets[i] for i in order]
+            total = slot_budget[0]
+            out = torch.zeros((total, n), dtype=torch.int64, device=self.device)
             ev0 = ev1 = None
-            replays0 = self.graph_replays
             if self.profile is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            n_steps = 0
-            for step in range(max_new_tokens):
-                out[step].copy_(self.next_id[:R], non_blocking=True)
+            n_steps, prof_bytes, prof_steps = 0, 0, 0
+            for step in range(total):
+                R = sum(1 for b in slot_budget if b > step)              # rows still running
+                out[step, :R].copy_(self.next_id[:R], non_blocking=True)
                 n_steps = step + 1
-                if eos and (step % 16 == 15 or step == max_new_tokens - 1):
+                if eos and (step % 16 == 15 or step == total - 1):
                     toks = out[:n_steps].t().tolist()
-                    if all(any(t in eos for t in row) for row in toks):
+                    if all(any(t in eos for t in row[:slot_budget[s_]]) for s_, row in enumerate(toks)):
                         break
-                if step == max_new_tokens - 1:
+                if step == total - 1:
                     break
-                if graph is not None:
-                    graph.replay()
+                Rn = sum(1 for b in slot_budget if b > step + 1)         # rows that need another token
+                if use_graph:
+                    self._graphs[Rn].replay()
                     self.graph_replays += 1
                 else:
-                    self._decode_step_launches(R)
+                    self._decode_step_launches(Rn)
+                prof_steps += 1
+                prof_bytes += self.weight_bytes() + sum(self.kv_bytes_per_token(lens[s_] + step) for s_ in range(Rn))
             if ev0 is not None:
                 ev1.record()
-                n_rep = self.graph_replays - replays0
-                avg_ctx = sum(lens) / R + n_rep // 2
-                self.profile.append({"events": (ev0, ev1), "steps": n_rep, "rows": R,
-                                     "bytes": n_rep * (self.weight_bytes() + R * self.kv_bytes_per_token(int(avg_ctx)))})
+                self.profile.append({"events": (ev0, ev1), "steps": prof_steps, "rows": n, "bytes": prof_bytes})
             rows = out[:n_steps].t().contiguous()
-            results = []
             host = rows.tolist() if eos else None
-            for s_ in range(R):
-                n = n_steps
+            results: List[Optional[torch.Tensor]] = [None] * n
+            for s_, i in enumerate(order):
+                m = min(n_steps, slot_budget[s_])
                 if eos:
-                    for j, t in enumerate(host[s_]):
+                    for j, t in enumerate(host[s_][:m]):
                         if t in eos:
-                            n = j + 1
+                            m = j + 1
                             break
-                self.ctx_lens[s_] = lens[s_] + n - 1
-                results.append(rows[s_:s_ + 1, :n].clone())
+                self.ctx_lens[s_] = lens[s_] + m - 1
+                results[i] = rows[s_:s_ + 1, :m].clone()
             return results
 
     @torch.no_grad()

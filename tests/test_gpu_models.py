@@ -136,3 +136,21 @@ def test_batched_generation_equals_sequential(cuda, golden_dir):
         row = a[0].tolist()
         n = row.index(eos) + 1 if eos in row else len(row)
         assert b[0].tolist() == row[:n]
+
+
+def test_mixed_budget_requests_equal_sequential(cuda, golden_dir):
+    """Captions (short budget, with image features) and a deferred text summary (long budget, text only)
+    decoded in one batch: rows drop out as they finish; ids equal the one-at-a-time calls."""
+    g, W, model = _tiny(golden_dir, cuda)
+    torch.manual_seed(6)
+    ids = torch.from_numpy(g["prompt_ids"])
+    tids = torch.tensor([[12, 13, 14, 15, 16, 17, 18]])
+    embs = [(torch.randn(n, 256) * 0.5).half().to(cuda) for n in (12, 40, 7)]
+    seq = [model.generate_with_image_embedding(tids, image_embeddings=None, do_sample=False, max_new_tokens=14)]
+    seq += [model.generate_with_image_embedding(ids, image_embeddings=[e], do_sample=False, max_new_tokens=6) for e in embs]
+    reqs = [(ids, [embs[0]], 6), (tids, None, 14), (ids, [embs[1]], 6), (ids, [embs[2]], 6)]
+    bat = model.generate_requests(reqs, modalities=["video"])
+    assert [tuple(b.shape) for b in bat] == [(1, 6), (1, 14), (1, 6), (1, 6)]
+    assert torch.equal(bat[1], seq[0])
+    for got, want in zip([bat[0], bat[2], bat[3]], seq[1:]):
+        assert torch.equal(got, want)

@@ -50,6 +50,12 @@ SCB_DEVICE uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   return d;
 }
 
+SCB_DEVICE float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   __half* out;
   long long o_stride_b, o_stride_t, o_stride_h;
@@ -220,6 +226,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       mbar_wait(s_full, ph);
       tc_fence_after();
       const int key0 = j * kBKV;
+      // Interior blocks (every key visible to every row of the warp) take a mask-free path: the
+      // softmax warps are instruction-bound, so per-element compares are not free.
+      const bool full_blk = __all_sync(0xffffffffu, key0 + kBKV - 1 <= key_limit);
       // ---- pass 1: row maximum of this block
       float m_blk = -INFINITY;
 #pragma unroll 1
@@ -227,9 +236,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (full_blk) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + c0 + i <= key_limit) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2)
+            m_blk = fmaxf(m_blk, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c0 + i <= key_limit) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        }
       }
       const float m_new = fmaxf(m_run, m_blk);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
@@ -243,17 +258,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
         tmem_ld_wait();
         uint32_t packed[16];
+        if (full_blk) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (key0 + c0 + i <= key_limit) p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
-          if (key0 + c0 + i + 1 <= key_limit)
-            p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          // the row sum uses the rounded probabilities the tensor core will see
-          const float2 back = __half22float2(hp);
-          l_blk += back.x + back.y;
-          packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
+            l_blk += p0 + p1;
+            packed[i >> 1] = f2_to_h2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = 0.f, p1 = 0.f;
+            if (key0 + c0 + i <= key_limit) p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
+            if (key0 + c0 + i + 1 <= key_limit)
+              p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
+            l_blk += p0 + p1;
+            packed[i >> 1] = f2_to_h2(p0, p1);
+          }
         }
         uint8_t* tile = sp + (c0 / 64) * (kBQ * 128) + r * 128;
 #pragma unroll

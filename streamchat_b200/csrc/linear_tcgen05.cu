@@ -211,9 +211,17 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (col0 + j < ep.n) f[j] += __half2float(ep.bias[col0 + j]);
             }
           }
-          if (ep.act != SCB_ACT_NONE && ep.act != SCB_ACT_SILU_PAIR) {
+          // one tight loop per activation: a per-element switch unrolled 32x (with erff inlined in
+          // every copy) overflowed the instruction cache and made the epilogue 9x slower than the MMA
+          if (ep.act == SCB_ACT_QUICK_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-1.702f * f[j]));
+          } else if (ep.act == SCB_ACT_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
+          } else if (ep.act == SCB_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
           }
           if (ep.residual) {
             const __half* rp = ep.residual + (long long)b * ep.stride_r + row * ep.ldr + col0;

@@ -36,7 +36,7 @@ class LlavaQwenConfig:
     mm_use_im_patch_token: bool = False
     tokenizer_model_max_length: Optional[int] = None
     max_context: int = 16384
-    max_batch: int = 6            # chunk captions (+ a pending summary) decoded together, one weight pass per step
+    max_batch: int = 8            # memory captions / summaries decoded together, one weight pass per step
 
     @property
     def hidden_size(self) -> int:

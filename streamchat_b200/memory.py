@@ -35,15 +35,16 @@ SUMMARY_TOKENS = 256   # max_new_tokens of the merge summary (utiles.py:604)
 
 
 class MultimodalTreeNode:
-    """utiles.py:48-56.  `text` may be PENDING: a merge node's summary is a greedy generation that
-    nothing needs until the next merge or a search, so it is deferred and decoded together with the
-    next update's captions (same ids, one weight pass per step); reading `.text` earlier resolves it
-    on the spot."""
+    """utiles.py:48-56.  `text` may be PENDING: captions and merge summaries are greedy generations
+    whose result nothing reads until the next summary prompt or a tree search, and neither the tree
+    shape nor the centroids depend on them — so they are recorded as recipes and generated later in
+    large lock-step batches (`resolve_pending`; same ids, one weight pass per decode step for up to
+    `max_batch` sequences).  Reading `.text` earlier resolves the node (and what it depends on)."""
 
     def __init__(self, centroids, text, text_distance=None, image_distance=None, labels=None, depth=0):
         self.centroids = centroids
         self._text = text
-        self._pending = None        # (summarizer, tokenizer, input_ids, max_new_tokens)
+        self._pending = None        # dict recipe, see fast_building_memory_tree_summarize_token
         self.text_distance = text_distance
         self.image_distance = image_distance
         self.labels = labels
@@ -54,12 +55,7 @@ class MultimodalTreeNode:
     @property
     def text(self):
         if self._pending is not None:
-            summarizer, tokenizer, ids, max_new = self._pending
-            with torch.no_grad():
-                out = summarizer.generate_with_image_embedding(
-                    ids.to(summarizer.device), image_embeddings=None, modalities=["video"], do_sample=False,
-                    temperature=0, top_p=None, max_new_tokens=max_new, use_cache=False)
-            self.set_text(tokenizer.batch_decode(out, skip_special_tokens=True)[0].strip())
+            resolve_pending([self])
         return self._text
 
     @text.setter
@@ -70,6 +66,46 @@ class MultimodalTreeNode:
         self._text = value
         self._pending = None
         self.text_embedding = None
+
+
+def _collect_pending(nodes, out):
+    for n in nodes:
+        if n._pending is not None:
+            out.append(n)
+        _collect_pending(n.children, out)
+
+
+def resolve_pending(nodes) -> int:
+    """Generate every pending caption / summary reachable from `nodes`: captions first (batched),
+    then summaries level by level (a summary prompt quotes its children's texts, utiles.py:506-523).
+    Returns the number of texts generated."""
+    todo: list = []
+    _collect_pending(nodes, todo)
+    todo = list({id(n): n for n in todo}.values())
+    done = 0
+    while todo:
+        ready = [n for n in todo if n._pending["kind"] == "caption"]
+        if not ready:
+            ready = [n for n in todo if all(c._pending is None for c in n._pending["children"])]
+        if not ready:
+            raise RuntimeError("pending memory texts form a cycle")
+        summarizer, tokenizer = ready[0]._pending["summarizer"], ready[0]._pending["tokenizer"]
+        reqs = []
+        for n in ready:
+            r = n._pending
+            if r["kind"] == "caption":
+                reqs.append((r["input_ids"].to(summarizer.device), [r["features"]], r["max_new"]))
+            else:
+                ids = make_summary_prompt([c._text for c in r["children"]], tokenizer, r["conv_templates"])
+                reqs.append((ids.to(summarizer.device), None, r["max_new"]))
+        with torch.no_grad():
+            ids_list = summarizer.generate_requests(reqs, modalities=["video"])
+        for n, ids in zip(ready, ids_list):
+            n.set_text(tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip())
+        done += len(ready)
+        ready_ids = {id(n) for n in ready}
+        todo = [n for n in todo if id(n) not in ready_ids]
+    return done
 
 
 def calculate_forgetting_probabilities(length, tau=10):
@@ -136,39 +172,37 @@ def make_summary_prompt(caption_list, tokenizer, conv_templates):
 def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_clusters, interval, summarizer,
                                               input_ids, tokenizer, chunked_feature_list, existing_tree=None,
                                               *, caption_do_sample=True, kmeans_init_indices=None,
-                                              conv_templates=None):
+                                              conv_templates=None, lazy_text=True):
     """One memory-tree update: caption every new chunk, append depth-0 nodes, perform at most one
     merge (k-means over the merged nodes' frames + text summary).  Same positional signature as
-    utiles.py:489; keyword-only extras inject determinism."""
-    output_list = []
+    utiles.py:489; keyword-only extras inject determinism.  With a greedy captioner that offers
+    `generate_requests` (the sm_100a engine) and `lazy_text`, captions and summaries are deferred and
+    generated in lock-step batches by `resolve_pending` — identical ids, far fewer weight passes."""
+    if conv_templates is None:
+        from .longva.conversation import conv_templates as _ct
+        conv_templates = _ct
     flat_chunks = []
     for chunk_feature in chunked_feature_list:
         dimension = chunk_feature[0].shape[-1]
         flat_chunks.append(torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device))
-    batched = (not caption_do_sample) and hasattr(summarizer, "generate_requests")
-    pending = [n for n in (existing_tree or []) if getattr(n, "_pending", None) is not None] if batched else []
-    if batched and (len(flat_chunks) + len(pending) > 1):
-        # greedy captions of independent chunks (+ summaries deferred by earlier merges): same ids as
-        # one call each, decoded together
-        ids_dev = input_ids.to(summarizer.device)
-        reqs = [(n._pending[2].to(summarizer.device), None, n._pending[3]) for n in pending]
-        reqs += [(ids_dev, [c], CAPTION_TOKENS) for c in flat_chunks]
-        with torch.no_grad():
-            ids_list = summarizer.generate_requests(reqs, modalities=["video"])
-        for n, ids in zip(pending, ids_list[:len(pending)]):
-            n.set_text(tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip())
-        output_list = [tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip()
-                       for ids in ids_list[len(pending):]]
+    lazy = (not caption_do_sample) and hasattr(summarizer, "generate_requests") and lazy_text
+    nodes = []
+    if lazy:
+        # greedy captions are recipes until somebody needs the text (see MultimodalTreeNode)
+        for t, feats in zip(k_means_chunk_feature_list, flat_chunks):
+            n = MultimodalTreeNode(t, None, depth=0)
+            n._pending = {"kind": "caption", "summarizer": summarizer, "tokenizer": tokenizer,
+                          "input_ids": input_ids, "features": feats, "max_new": CAPTION_TOKENS}
+            nodes.append(n)
     else:
-        for chunk_feature in flat_chunks:
+        for t, chunk_feature in zip(k_means_chunk_feature_list, flat_chunks):
             with torch.no_grad():
                 output_ids = summarizer.generate_with_image_embedding(
                     input_ids.to(summarizer.device), image_embeddings=[chunk_feature], modalities=["video"],
                     do_sample=caption_do_sample, temperature=0.1 if caption_do_sample else 0, top_p=None,
                     max_new_tokens=CAPTION_TOKENS, use_cache=False)
-            output_list.append(tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip())
-
-    nodes = [MultimodalTreeNode(t, text, depth=0) for (t, text) in zip(k_means_chunk_feature_list, output_list)]
+            nodes.append(MultimodalTreeNode(t, tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip(),
+                                            depth=0))
     if existing_tree:
         nodes = existing_tree + nodes
 
@@ -182,21 +216,18 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
     if chunk_length % interval >= 0 and len(nodes) > 0 and chunk_length >= interval:   # utiles.py:575
         chunk = nodes[start_index: start_index + interval]
         combined_centroids = torch.cat([n.centroids for n in chunk], dim=0)
-        caption_list = [n.text for n in chunk]
         if combined_centroids.shape[0] > num_clusters:
             new_centroids, _ = weighted_kmeans_feature(combined_centroids, num_clusters,
                                                        init_indices=kmeans_init_indices)
         else:
             new_centroids = combined_centroids
-        if conv_templates is None:
-            from .longva.conversation import conv_templates as _ct
-            conv_templates = _ct
-        summarize_ids = make_summary_prompt(caption_list, tokenizer, conv_templates)
-        if batched:
-            # deferred: resolved together with the next update's captions, or on first read of .text
+        if lazy:
             new_node = MultimodalTreeNode(new_centroids, None, depth=chunk[0].depth + 1)
-            new_node._pending = (summarizer, tokenizer, summarize_ids, SUMMARY_TOKENS)
+            new_node._pending = {"kind": "summary", "summarizer": summarizer, "tokenizer": tokenizer,
+                                 "children": list(chunk), "conv_templates": conv_templates,
+                                 "max_new": SUMMARY_TOKENS}
         else:
+            summarize_ids = make_summary_prompt([n.text for n in chunk], tokenizer, conv_templates)
             with torch.no_grad():
                 output_ids = summarizer.generate_with_image_embedding(
                     summarize_ids.to(summarizer.device), image_embeddings=None, modalities=["video"],
@@ -250,6 +281,7 @@ def fast_search_tree_multi_modal_with_embedding(all_nodes, query, image_embeddin
     path_features: List[torch.Tensor] = []
     path_text: List[str] = []
     redundant_nodes = []
+    resolve_pending(all_nodes)          # every node text the walk may read, in batched generations
     query_embedding = embed_text(model, tokenizer, query)
     for node in all_nodes:
         current_node = node

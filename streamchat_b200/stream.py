@@ -40,6 +40,7 @@ class StreamConfig:
     temperature: float = 0.0          # 0 -> greedy (parity runs, hazard H2); the script uses 0.2
     answer_tokens: int = 256
     caption_do_sample: bool = False   # the reference samples captions at T=0.1 (utiles.py:551-552)
+    lazy_text: bool = True            # defer greedy captions / summaries and generate them in batches
 
 
 class HashTextEmbedder:
@@ -111,7 +112,7 @@ class StreamingSession:
         self.long_memory_tree = M.fast_building_memory_tree_summarize_token(
             kmeans_chunks, c.num_clusters, c.interval, self.summarizer, self._caption_ids, self.tokenizer,
             chunks, self.long_memory_tree, caption_do_sample=c.caption_do_sample,
-            kmeans_init_indices=kmeans_init_indices, conv_templates=conv_templates)
+            kmeans_init_indices=kmeans_init_indices, conv_templates=conv_templates, lazy_text=c.lazy_text)
         assert len(self.short_memory_buffer) > 0, "No memory ?"
         return self.long_memory_tree, self.short_memory_buffer
 

@@ -88,7 +88,9 @@ def test_streaming_session_tiny_end_to_end(cuda):
         g = torch.Generator(device=cuda).manual_seed(0)
         frames = torch.randn(60, 3, 56, 56, device=cuda, dtype=torch.float16, generator=g)
         outs = []
-        for _ in range(2):
+        texts = []
+        for lazy in (True, False, True):
+            cfg.lazy_text = lazy
             np.random.seed(7)
             sess = StreamingSession(model, tokenizer, HashTextEmbedder(1024, cuda), None, None, cfg)
             for s0 in range(0, 60, 20):
@@ -101,6 +103,11 @@ def test_streaming_session_tiny_end_to_end(cuda):
             text, ids = sess.answer("what did I see?")
             assert ids.shape == (1, 10)
             outs.append(ids.cpu())
-        assert torch.equal(outs[0], outs[1])                             # deterministic end to end
+            flat = {}
+            _collect(sess.long_memory_tree, "n", flat)
+            texts.append({k: v.text for k, v in flat.items()})
+        # deferred + batched memory texts == one generation per chunk, and runs are deterministic
+        assert texts[0] == texts[1] == texts[2]
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     finally:
         M.CAPTION_TOKENS, M.SUMMARY_TOKENS = 128, 256

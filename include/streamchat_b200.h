@@ -269,7 +269,7 @@ typedef struct scb_gemv_args {
   void* out;              /* [rows, ldo] */
   int64_t n, k;
   int64_t lda, ldw, ldr, ldo;
-  int32_t rows;           /* 1..8 (k % 32 == 0), else 1, 2 or 4 */
+  int32_t rows;           /* 1..16 (k % 32 == 0, no prologue), else 1, 2 or 4 */
   int32_t prologue;       /* scb_gemv_prologue */
   int32_t out_dtype;      /* scb_dtype */
   float eps;

@@ -193,13 +193,14 @@ gemv_kernel(const GemvParams p) {
 constexpr int kMU = 8;             // k-tiles (32 halfs each) in flight per warp: 4 KB
 constexpr int kMaxMmaWarps = 16;
 
-SCB_DEVICE void mma16816(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  // rows 8..15 of A are zero (a1 = a3 = 0)
+SCB_DEVICE void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                         uint32_t b1) {
+  // a0/a2: activation row g (k low / high half), a1/a3: activation row g+8 (zero when rows <= 8)
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
       "{%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 struct ArgmaxFuse {
@@ -215,11 +216,13 @@ struct ArgmaxFuse {
 // down_proj, qkv) are cut into several K chunks so that one wave of 8 blocks x 148 SMs is full;
 // the chunks of a group meet through a partial buffer and an atomic ticket — the last block to
 // arrive sums them in chunk order (deterministic) and runs the epilogue.
-template <int kGW>
-__global__ void __launch_bounds__(kGW * 32, 32 / kGW)
+// kHi: activation rows 8..15 are live (batches of 9..16 sequences); costs a few registers, so the
+// <= 8 row variant keeps the 64-register / 32-warps-per-SM budget and the wide one runs 24 warps.
+template <int kGW, bool kHi>
+__global__ void __launch_bounds__(kGW * 32, kHi ? (24 / kGW > 0 ? 24 / kGW : 1) : 32 / kGW)
 gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict__ partial,
                 unsigned* __restrict__ gtickets, const ArgmaxFuse am) {
-  __shared__ float red[kGW][8][8];
+  __shared__ float red[kGW][16][8];
   __shared__ unsigned flag_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -252,8 +255,9 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
   pdl_launch_dependents();
   pdl_wait();                 // activations (and everything we write) belong to the dependency chain
 
-  const bool a_ok = g < R;
+  const bool a_ok = g < R, a_ok2 = kHi && (g + 8 < R);   // rows 8..15 of the MMA carry sequences 8..15
   const __half* a_row = p.a + (long long)(a_ok ? g : 0) * p.lda + t * 8;   // read through L1 (tiny, shared)
+  const __half* a_row2 = p.a + (long long)(a_ok2 ? g + 8 : 0) * p.lda + t * 8;
   float best_v = -INFINITY;
   int best_i = 0x7fffffff;
   while (unit < n_units) {
@@ -264,10 +268,12 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
 #pragma unroll
       for (int u = 0; u < kMU; ++u) {
         const int kt = kt0 + u;
-        uint4 av = make_uint4(0, 0, 0, 0);
+        uint4 av = make_uint4(0, 0, 0, 0), av2 = make_uint4(0, 0, 0, 0);
         if (a_ok && kt < ke) av = __ldg(reinterpret_cast<const uint4*>(a_row + kt * 32));
-        mma16816(acc, av.x, av.y, wv[u].x, wv[u].y);
-        mma16816(acc, av.z, av.w, wv[u].z, wv[u].w);
+        if constexpr (kHi)
+          if (a_ok2 && kt < ke) av2 = __ldg(reinterpret_cast<const uint4*>(a_row2 + kt * 32));
+        mma16816(acc, av.x, av2.x, av.y, av2.y, wv[u].x, wv[u].y);
+        mma16816(acc, av.z, av2.z, av.w, av2.w, wv[u].z, wv[u].w);
       }
     }
     const int nunit = unit + gridDim.x;
@@ -277,18 +283,20 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
     // ---- combine the warps in order: acc[0], acc[1] = out[row g][n = grp*8 + t*2 + {0,1}]
     red[warp][g][t * 2] = acc[0];
     red[warp][g][t * 2 + 1] = acc[1];
+    red[warp][g + 8][t * 2] = acc[2];
+    red[warp][g + 8][t * 2 + 1] = acc[3];
     __syncthreads();
-    const int r = tid >> 3, j = tid & 7;
+    const int r = tid >> 3, j = tid & 7;  // threads 0..127: (row r of 16, column j of the 8-row group)
     const int n = grp * 8 + j;
     float v = 0.f;
     bool have = false;                    // this thread holds a finished output value
-    if (tid < 64 && r < R) {
+    if (tid < 128 && r < R) {
 #pragma unroll
       for (int w = 0; w < kGW; ++w) v += red[w][r][j];
       have = (C == 1);
     }
     if (C > 1) {
-      if (tid < 64 && r < R) partial[((long long)grp * C + c) * 64 + tid] = v;
+      if (tid < 128 && r < R) partial[((long long)grp * C + c) * 128 + tid] = v;
       __threadfence();
       __syncthreads();
       if (tid == 0) {
@@ -298,9 +306,9 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
       __syncthreads();
       if (flag_s) {
         __threadfence();
-        if (tid < 64 && r < R) {
+        if (tid < 128 && r < R) {
           v = 0.f;
-          for (int cc = 0; cc < C; ++cc) v += __ldcg(partial + ((long long)grp * C + cc) * 64 + tid);
+          for (int cc = 0; cc < C; ++cc) v += __ldcg(partial + ((long long)grp * C + cc) * 128 + tid);
           have = true;
         }
         if (tid == 0) gtickets[grp] = 0;
@@ -308,7 +316,7 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
     }
     // ---- epilogue (warp-uniform branch on silu_pair; `have` only where a value is final)
     if (p.silu_pair) {
-      if (tid < 64) {
+      if (tid < 128) {
         const float gt = __half2float(__float2half_rn(v));       // Linear output is fp16 in HF
         const float up = __shfl_xor_sync(0xffffffffu, gt, 1);
         if (have && n < p.N && (j & 1) == 0) {
@@ -396,7 +404,7 @@ gemv_mma_kernel(const GemvParams p, const int R, const int C, float* __restrict_
     // threads of each row, publish per block, the last block reduces the blocks
     float bv = best_v;
     int bi = best_i;
-    if (tid < 64) {   // R <= 8 rows x 8 threads, aligned groups of 8 lanes
+    if (tid < 128) {  // R <= 16 rows x 8 threads, aligned groups of 8 lanes
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -865,21 +873,21 @@ extern "C" {
 //                   | group tickets (kMaxSplitGroups u32) | K-chunk partials
 constexpr int kMaxSplitGroups = 4096;
 constexpr int kMaxChunks = 8;
-constexpr size_t kWsArgmax = 256 + (size_t)2048 * 8 * (sizeof(float) + sizeof(int));
+constexpr size_t kWsArgmax = 256 + (size_t)2048 * 16 * (sizeof(float) + sizeof(int));
 constexpr size_t kWsTickets = (size_t)kMaxSplitGroups * sizeof(unsigned);
 constexpr int kGWDefault = 8;   // sweep on B200 (tools/gemv_sweep.py): 8 warps per block, no K chunking
-constexpr size_t kWsPartial = (size_t)kMaxSplitGroups * kMaxChunks * 64 * sizeof(float);
+constexpr size_t kWsPartial = (size_t)kMaxSplitGroups * kMaxChunks * 128 * sizeof(float);
 
 size_t scb_gemv_workspace_bytes(int32_t rows) {
-  if (rows < 1 || rows > 8) return 0;
+  if (rows < 1 || rows > 16) return 0;
   return kWsArgmax + kWsTickets + kWsPartial;
 }
 
 int scb_gemv(const scb_gemv_args* a, void* stream) {
   SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_gemv: args is NULL");
   SCB_REQUIRE(a->a && a->w && a->out, SCB_ERR_INVALID_ARG, "scb_gemv: NULL buffer");
-  SCB_REQUIRE(a->rows >= 1 && a->rows <= 8, SCB_ERR_UNSUPPORTED,
-              "scb_gemv: rows=%d (1..8; larger batches use scb_linear)", a->rows);
+  SCB_REQUIRE(a->rows >= 1 && a->rows <= 16, SCB_ERR_UNSUPPORTED,
+              "scb_gemv: rows=%d (1..16; larger batches use scb_linear)", a->rows);
   SCB_REQUIRE(a->n >= 1 && a->k >= 8 && a->k % 8 == 0, SCB_ERR_INVALID_ARG,
               "scb_gemv: n=%lld k=%lld (k must be a multiple of 8)", (long long)a->n, (long long)a->k);
   SCB_REQUIRE(a->prologue >= PRO_NONE && a->prologue <= PRO_SILU_MUL, SCB_ERR_UNSUPPORTED,
@@ -955,7 +963,7 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
       if (a->argmax_out) {
         am.ticket = reinterpret_cast<unsigned*>(ws);
         am.blk_val = reinterpret_cast<float*>(ws + 256);
-        am.blk_idx = reinterpret_cast<int*>(ws + 256 + (size_t)2048 * 8 * sizeof(float));
+        am.blk_idx = reinterpret_cast<int*>(ws + 256 + (size_t)2048 * 16 * sizeof(float));
         am.out_ids = reinterpret_cast<long long*>(a->argmax_out);
         am.counters = a->counters;
         am.n_counters = a->counters ? a->n_counters : 0;
@@ -970,14 +978,15 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
     const long long units = n_groups * C;
     long long cap = wave < 2048 ? wave : 2048;
     const int grid = (int)(units < cap ? units : cap);
-    if (GW == 4)
-      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<4>, dim3(grid), dim3(128), 0, st, p, (int)a->rows, C, partial, gtickets, am));
-    else if (GW == 8)
-      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<8>, dim3(grid), dim3(256), 0, st, p, (int)a->rows, C, partial, gtickets, am));
-    else if (GW == 16)
-      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<16>, dim3(grid), dim3(512), 0, st, p, (int)a->rows, C, partial, gtickets, am));
-    else
-      SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<32>, dim3(grid), dim3(1024), 0, st, p, (int)a->rows, C, partial, gtickets, am));
+#define SCB_GEMV_GO(GWV, HI)                                                                          \
+  SCB_CUDA_OK(scb_launch_pdl(gemv_mma_kernel<GWV, HI>, dim3(grid), dim3(GWV * 32), 0, st, p, (int)a->rows, \
+                             C, partial, gtickets, am))
+    const bool hi = a->rows > 8;
+    if (GW == 4) { if (hi) SCB_GEMV_GO(4, true); else SCB_GEMV_GO(4, false); }
+    else if (GW == 8) { if (hi) SCB_GEMV_GO(8, true); else SCB_GEMV_GO(8, false); }
+    else if (GW == 16) { if (hi) SCB_GEMV_GO(16, true); else SCB_GEMV_GO(16, false); }
+    else { if (hi) SCB_GEMV_GO(32, true); else SCB_GEMV_GO(32, false); }
+#undef SCB_GEMV_GO
     SCB_LAUNCH_OK("gemv_mma_kernel");
     return SCB_OK;
   }

@@ -373,7 +373,7 @@ def gemv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     key = (dev.index, "gemv_ws")
     ws = _workspaces.get(key)
     if ws is None:      # zero-initialised once: tickets are self-resetting
-        ws = torch.zeros(L.load().scb_gemv_workspace_bytes(8), dtype=torch.uint8, device=dev)
+        ws = torch.zeros(L.load().scb_gemv_workspace_bytes(16), dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
     args.workspace = _ptr(ws)
     args.workspace_bytes = ws.numel()

@@ -45,8 +45,8 @@ class Qwen2Engine:
         self.max_ctx = max_ctx
         self.decode_splits = decode_splits
         self.max_batch = max_batch
-        if max_batch < 1 or max_batch > 8:
-            raise ValueError('max_batch must be in 1..8 (rows of the decode GEMV)')
+        if max_batch < 1 or max_batch > 16:
+            raise ValueError('max_batch must be in 1..16 (rows of the decode GEMV)')
         c = cfg
         if c.head_dim not in (64, 128):
             raise ValueError(f"head_dim {c.head_dim} unsupported (64 or 128)")

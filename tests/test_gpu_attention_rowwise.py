@@ -185,6 +185,7 @@ def test_rope_append(cuda):
 @pytest.mark.parametrize("rows,n,k,pro", [(1, 4608, 3584, 1), (1, 3584, 3584, 0), (1, 3584, 18944, 2),
                                           (2, 1000, 512, 0), (4, 300, 1024, 1), (1, 152064, 3584, 1),
                                           (5, 3584, 18944, 0), (8, 4608, 3584, 0), (3, 37888, 3584, 0),
+                                          (13, 3584, 18944, 0), (16, 4608, 3584, 0), (9, 1000, 512, 0),
                                           (4, 3584, 18944, 2), (2, 4608, 3584, 1),
                                           (7, 1003, 96, 0), (1, 77, 32, 0), (2, 50, 40, 0)])
 def test_gemv(cuda, rows, n, k, pro):
@@ -235,7 +236,7 @@ def test_decode_attention(cuda, hq, hkv, d, ctx, splits):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("rows", [1, 5])
+@pytest.mark.parametrize("rows", [1, 5, 16])
 def test_gemv_fused_argmax(cuda, rows):
     from streamchat_b200 import ops, _lib
     torch.manual_seed(rows)
@@ -296,7 +297,7 @@ def test_decode_attention_fused(cuda, hq, hkv, d, ctx, splits, maxp):
     assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("rows", [1, 5])
+@pytest.mark.parametrize("rows", [1, 5, 12])
 def test_gemv_and_linear_silu_pair_epilogue(cuda, rows):
     """gate|up interleaved weights: out[r,i] = fp16(silu(fp16 gate_i)) * fp16 up_i — decode GEMV and the
     tcgen05 prefill GEMM must agree with each other bit for bit on the same rows and with the eager

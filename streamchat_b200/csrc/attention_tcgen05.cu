@@ -71,12 +71,14 @@ struct ACfg {
   static constexpr int kQBytes = kBQ * D * 2;
   static constexpr int kKBytes = kBKV * D * 2;
   static constexpr int kPBytes = kBQ * kBKV * 2;
-  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 128;
-  static constexpr int kTmemCols = 256;                // S: [0,kBKV)  O_j: [128,128+D)
+  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 192;
+  // S is double-buffered: S_{j+1} is computed while the softmax works on S_j.
+  //   S0: [0,128)  S1: [128,256)  O_j: [256,256+D)   -> 512 columns, one CTA per SM
+  static constexpr int kTmemCols = 512;
 };
 
 template <int D, int kBKV>
-__global__ void __launch_bounds__(kAttnThreads, (D == 64) ? 2 : 1)
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
                          const __grid_constant__ CUtensorMap map_k,
                          const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
@@ -95,12 +97,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
   uint64_t* k_empty = bars + 3;            // [2]
   uint64_t* v_full = bars + 5;             // [2]
   uint64_t* v_empty = bars + 7;            // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* o_full = bars + 12;
-  uint64_t* o_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* s_full = bars + 9;             // [2]
+  uint64_t* s_empty = bars + 11;           // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* o_full = bars + 14;
+  uint64_t* o_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBQ;
@@ -124,8 +126,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
+    for (int sb = 0; sb < 2; ++sb) {
+      mbar_init(&s_full[sb], 1);
+      mbar_init(&s_empty[sb], 4);
+    }
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
@@ -139,8 +143,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_s = tmem_base;          // + 128 * (j & 1)
+  const uint32_t tmem_o = tmem_base + 256;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -169,8 +173,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, D, 0, 1);  // B = V is MN-major
       auto issue_s = [&](int j) {
-        const int st = j % kKVStages;
+        const int st = j % kKVStages, sb = j & 1;
         mbar_wait(&k_full[st], (uint32_t)(j / kKVStages) & 1u);
+        if (j >= 2) mbar_wait(&s_empty[sb], (uint32_t)((j >> 1) - 1) & 1u);   // softmax done with S_{j-2}
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -179,20 +184,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
           const uint64_t db =
               umma_desc_k_sw128(smem_u32(sk + st * C::kKBytes + (kk / 4) * (kBKV * 128))) +
               (uint64_t)((kk % 4) * 2);
-          umma_f16_ss(tmem_s, da, db, idesc_s, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_s + (uint32_t)(sb * 128), da, db, idesc_s, kk != 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+        umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
+      if (n_blocks > 1) issue_s(1);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j % kKVStages;
-        if (j + 1 < n_blocks) {
-          mbar_wait(s_empty, (uint32_t)j & 1u);  // softmax finished reading S_j
-          tc_fence_after();
-          issue_s(j + 1);
-        }
         mbar_wait(&v_full[st], (uint32_t)(j / kKVStages) & 1u);
         mbar_wait(p_full, (uint32_t)j & 1u);
         if (j > 0) mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);
@@ -207,6 +208,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         }
         umma_commit(&v_empty[st]);
         umma_commit(o_full);
+        if (j + 2 < n_blocks) issue_s(j + 2);   // keeps the tensor pipe busy under the next softmax
       }
     }
   } else {
@@ -221,9 +223,28 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
     for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
     const int key_limit = p.causal ? min(p.kv_len - 1, qpos + causal_off) : p.kv_len - 1;
 
+    // O_{j-1} = P_{j-1}·V_{j-1} is folded into the register accumulator AFTER pass 1 of block j, so
+    // the P·V MMA runs under that pass instead of stalling the softmax warps.
+    auto fold_o = [&](int jj) {
+      mbar_wait(o_full, (uint32_t)jj & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_o + lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c0 + i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    };
+
     for (int j = 0; j < n_blocks; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(s_full, ph);
+      const int sb = j & 1;
+      const uint32_t tmem_sj = tmem_s + (uint32_t)(sb * 128);
+      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       const int key0 = j * kBKV;
       // Interior blocks (every key visible to every row of the warp) take a mask-free path: the
@@ -234,7 +255,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
 #pragma unroll 1
       for (int c0 = 0; c0 < kBKV; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
+        tmem_ld_32x32b_x32(tmem_sj + lane_addr + (uint32_t)c0, v);
         tmem_ld_wait();
         if (full_blk) {
 #pragma unroll
@@ -250,12 +271,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = exp2f((m_run - m_use) * p.scale_log2);  // m_run == -inf -> 0
       const float mb = m_use * p.scale_log2;
+      if (j > 0) fold_o(j - 1);          // also guarantees P·V_{j-1} has finished reading the P tile
+#pragma unroll
+      for (int i = 0; i < D; ++i) o_acc[i] *= alpha;
       // ---- pass 2: P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
       float l_blk = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < kBKV; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + (uint32_t)c0, v);
+        tmem_ld_32x32b_x32(tmem_sj + lane_addr + (uint32_t)c0, v);
         tmem_ld_wait();
         uint32_t packed[16];
         if (full_blk) {
@@ -285,31 +309,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
               make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
         }
       }
-      // S fully consumed -> the issuer may overwrite it with S_{j+1}
+      // S_j fully consumed -> the issuer may overwrite this buffer with S_{j+2}; P_j is ready
       tc_fence_before();
       fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor core
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
+        mbar_arrive(&s_empty[sb]);
         mbar_arrive(p_full);
       }
       l_run = l_run * alpha + l_blk;
       m_run = m_new;
-      // ---- O = O*alpha + P·V
-      mbar_wait(o_full, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] = fmaf(o_acc[c0 + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
     }
+    if (n_blocks > 0) fold_o(n_blocks - 1);
 
     if (qpos < p.q_len) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;

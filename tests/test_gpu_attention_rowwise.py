@@ -314,10 +314,11 @@ def test_gemv_and_linear_silu_pair_epilogue(cuda, rows):
     ref = torch.nn.functional.silu(g).half().float() * u
     out_v = ops.gemv(a.to(cuda), w.to(cuda), epilogue=_lib.EPI_SILU_PAIR)
     assert out_v.shape == (rows, inter)
-    assert (out_v.float().cpu() - ref).abs().max().item() < 3e-3
+    tol = 2e-3 * (ref.abs() + 1)          # fp16 output: half an ulp of the value
+    assert ((out_v.float().cpu() - ref).abs() <= tol).all()
     out_m = ops.linear(a.to(cuda), w.to(cuda), act=_lib.ACT_SILU_PAIR)
     assert out_m.shape == (rows, inter)
-    assert (out_m.float().cpu() - ref).abs().max().item() < 3e-3
+    assert ((out_m.float().cpu() - ref).abs() <= tol).all()
 
 
 def test_decode_attention_fused_multi_sequence(cuda):

@@ -272,8 +272,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       const float alpha = exp2f((m_run - m_use) * p.scale_log2);  // m_run == -inf -> 0
       const float mb = m_use * p.scale_log2;
       if (j > 0) fold_o(j - 1);          // also guarantees P·V_{j-1} has finished reading the P tile
+      if (__any_sync(0xffffffffu, alpha != 1.f)) {   // the running max rarely moves after the first blocks
 #pragma unroll
-      for (int i = 0; i < D; ++i) o_acc[i] *= alpha;
+        for (int i = 0; i < D; ++i) o_acc[i] *= alpha;
+      }
       // ---- pass 2: P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
       float l_blk = 0.f;
 #pragma unroll 1
@@ -283,13 +285,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         tmem_ld_wait();
         uint32_t packed[16];
         if (full_blk) {
+          // packed fp32x2 FMA for the scale/shift (half the FMA-pipe instructions), MUFU ex2
+          unsigned long long sc2, mb2, l2 = 0ull;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(p.scale_log2));
+          asm("mov.b64 %0, {%1, %1};" : "=l"(mb2) : "f"(-mb));
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
-            l_blk += p0 + p1;
+            unsigned long long x2, e2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(v[i]), "r"(v[i + 1]));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(x2), "l"(sc2), "l"(mb2));
+            float x0, x1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(p0), "f"(p1));
+            asm("add.f32x2 %0, %0, %1;" : "+l"(l2) : "l"(e2));
             packed[i >> 1] = f2_to_h2(p0, p1);
           }
+          float la, lb;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(la), "=f"(lb) : "l"(l2));
+          l_blk += la + lb;
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {

@@ -191,10 +191,20 @@ class Qwen2Engine:
                                        out=self._attn[:R], prefetch=ly["o_w"])
             ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2,
                      post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
-            ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])
+            if R > 8:
+                # wide batches: the A-fragment reads of the streaming GEMV (R x K per 8 weight rows) outgrow
+                # L1; the tcgen05 GEMM streams the same weights through TMA with the activations in smem
+                ops.linear(nrm, ly["gu_w"], act=L.ACT_SILU_PAIR, out=self._gu[:R])
+            else:
+                ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])
             ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x, post_norm=(nxt_gamma, nrm, eps),
                      prefetch=nxt_w)
-        ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R], counters=self.state.view(-1))
+        if R > 8:
+            ops.linear(nrm, self.lm_head, out=self._logits[:R])
+            ops.argmax_rows(self._logits[:R], out=self.next_id[:R], counter=self.state.view(-1))
+        else:
+            ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R],
+                     counters=self.state.view(-1))
 
     def launches_per_decode_step(self) -> int:
         return 1 + self.cfg.num_hidden_layers * 5 + 1

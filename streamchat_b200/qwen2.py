@@ -178,7 +178,9 @@ class Qwen2Engine:
         x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
         eps = c.rms_norm_eps
         # KV splits: ~2 blocks per SM in ONE wave whatever the batch is (fewer partials to combine)
-        splits = max(2, min(self.decode_splits, 296 // (R * Hkv)))
+        G = Hq // Hkv
+        smem_min = -(-self.max_ctx * G * 4 // (96 * 1024))       # per-split score buffer must fit in shared memory
+        splits = max(2, smem_min, min(self.decode_splits, 296 // (R * Hkv)))
         L0 = self.layers[0]
         ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
         n_layers = len(self.layers)

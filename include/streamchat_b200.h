@@ -344,6 +344,8 @@ typedef struct scb_decode_attention_fused_args {
   size_t workspace_bytes;
   const void* prefetch;      /* optional: pulled into L2 while the attention runs (next layer weights) */
   int64_t prefetch_bytes;
+  int64_t ctx_cap;           /* optional upper bound of every kv_len (0 = max_pos): sizes the per-split
+                              * score buffer in shared memory */
 } scb_decode_attention_fused_args;
 
 size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_heads,

@@ -103,7 +103,7 @@ class DecodeAttentionFusedArgs(C.Structure):
         ("scale", C.c_float), ("theta", C.c_float), ("n_seqs", C.c_int32), ("_pad", C.c_int32),
         ("ld_qkv", C.c_int64), ("cache_seq_stride", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
+        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64), ("ctx_cap", C.c_int64),
     ]
 
 

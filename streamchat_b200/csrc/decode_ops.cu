@@ -589,7 +589,7 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ part_m,
 //   phase 3  thread = (dim, position half): P·V with coalesced V reads        -> reads V once
 // ------------------------------------------------------------------------------------------
 template <int HD, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict__ inv_freq,
                          float theta, __half* __restrict__ k_cache, __half* __restrict__ v_cache,
                          long long max_pos, const int* __restrict__ len_dev, float scale_log2,
@@ -623,7 +623,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   const int pos = kv_len - 1;       // position of the token being decoded
   const int per = (kv_len + n_splits - 1) / n_splits;
   const int begin = split * per, end = min(kv_len, begin + per);
-  const int n_local = max(0, end - begin);
+  const int n_local = min(per_max, max(0, end - begin));   // per_max bounds the score buffer (host guarantees kv_len <= ctx_cap)
 
   // ---- cos/sin of the new position once per block (HALF angles), then RoPE of the G q rows
   __shared__ float cs_s[HALF], sn_s[HALF];
@@ -1107,7 +1107,10 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
   float* part_m = reinterpret_cast<float*>(ws + 256);
   float* part_l = part_m + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   float* part_o = part_l + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
-  const int per_max = (int)((a->max_pos + a->n_splits - 1) / a->n_splits);
+  // score-buffer sizing: the caller may bound the live context (ctx_cap <= max_pos) so that short
+  // contexts do not pay shared memory (and occupancy) for the cache capacity
+  const long long cap = (a->ctx_cap > 0 && a->ctx_cap < a->max_pos) ? a->ctx_cap : a->max_pos;
+  const int per_max = (int)((cap + a->n_splits - 1) / a->n_splits);
   const int per_alloc = per_max > a->n_splits ? per_max : a->n_splits;   // the combine reuses the score buffer
   const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_alloc);
   SCB_REQUIRE(smem <= 160 * 1024, SCB_ERR_UNSUPPORTED,

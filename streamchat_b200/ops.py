@@ -414,7 +414,8 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
 def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], theta: float,
                            k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len_dev: torch.Tensor,
                            n_q: int, scale: float, workspace: torch.Tensor, n_splits: int = 37,
-                           out: Optional[torch.Tensor] = None, prefetch: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, prefetch: Optional[torch.Tensor] = None,
+                           ctx_cap: int = 0) -> torch.Tensor:
     """RoPE + KV append + split attention + combine for ONE new token of each of S sequences (see
     scb_decode_attention_fused).  qkv [S, (n_q+2*n_kv)*hd]; caches [n_kv, max_pos, hd] (S == 1) or
     [S, n_kv, max_pos, hd]; kv_len_dev int32 [S].  `workspace` is a caller-held uint8 tensor whose
@@ -434,6 +435,7 @@ def decode_attention_fused(qkv: torch.Tensor, inv_freq: Optional[torch.Tensor], 
         kv_len_dev=_ptr(kv_len_dev), max_pos=max_pos, n_q_heads=n_q, n_kv_heads=hkv, head_dim=d,
         n_splits=n_splits, scale=scale, theta=theta, n_seqs=n_seqs, ld_qkv=qkv.stride(0),
         cache_seq_stride=seq_stride, workspace=_ptr(workspace), workspace_bytes=workspace.numel())
+    args.ctx_cap = ctx_cap
     if prefetch is not None:
         args.prefetch = _ptr(prefetch)
         args.prefetch_bytes = min(prefetch.numel() * prefetch.element_size(), 48 << 20)

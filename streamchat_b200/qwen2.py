@@ -164,7 +164,7 @@ class Qwen2Engine:
         return ops.gemv(last, self.lm_head, out=self._logits[slot:slot + 1])
 
     # ---------------------------------------------------------------- decode
-    def _decode_step_launches(self, R: int = 1) -> None:
+    def _decode_step_launches(self, R: int = 1, ctx_cap: int = 0) -> None:
         """One cached decode step for the first R cache slots (5*layers + 2 launches): embedding
         gather (+ first RMSNorm), then per layer qkv GEMV -> fused RoPE/append/attention/combine ->
         o_proj GEMV (+residual, + post-attention RMSNorm by its last block) -> gate|up GEMV (SiLU-gate
@@ -179,7 +179,8 @@ class Qwen2Engine:
         eps = c.rms_norm_eps
         # KV splits: ~2 blocks per SM in ONE wave whatever the batch is (fewer partials to combine)
         G = Hq // Hkv
-        smem_min = -(-self.max_ctx * G * 4 // (96 * 1024))       # per-split score buffer must fit in shared memory
+        cap = ctx_cap if 0 < ctx_cap < self.max_ctx else self.max_ctx
+        smem_min = -(-cap * G * 4 // (48 * 1024))                # per-split score buffer: <= 48 KB per block
         splits = max(2, smem_min, min(self.decode_splits, 296 // (R * Hkv)))
         L0 = self.layers[0]
         ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
@@ -190,7 +191,7 @@ class Qwen2Engine:
             ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
                                        self.state[1, :R], Hq, scale, self._attn_ws, n_splits=splits,
-                                       out=self._attn[:R], prefetch=ly["o_w"])
+                                       out=self._attn[:R], prefetch=ly["o_w"], ctx_cap=cap)
             ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2,
                      post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
             if R > 8:
@@ -211,8 +212,16 @@ class Qwen2Engine:
     def launches_per_decode_step(self) -> int:
         return 1 + self.cfg.num_hidden_layers * 5 + 1
 
-    def _ensure_graph(self, R: int) -> "torch.cuda.CUDAGraph":
-        g = self._graphs.get(R)
+    def _ctx_bucket(self, need: int) -> int:
+        """Context capacity class of a decode graph (power of two, >= 2048, <= max_ctx)."""
+        b = 2048
+        while b < need and b < self.max_ctx:
+            b *= 2
+        return min(b, self.max_ctx)
+
+    def _ensure_graph(self, R: int, ctx_cap: int = 0) -> "torch.cuda.CUDAGraph":
+        ctx_cap = ctx_cap or self.max_ctx
+        g = self._graphs.get((R, ctx_cap))
         if g is not None:
             return g
         # warm-up on a side stream (loads modules, sets func attributes), then capture.  Both scribble on
@@ -223,15 +232,15 @@ class Qwen2Engine:
         with torch.cuda.stream(s):
             self.state[0].fill_(0)
             self.state[1].fill_(1)
-            self._decode_step_launches(R)
+            self._decode_step_launches(R, ctx_cap)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.state[0].fill_(0)
         self.state[1].fill_(1)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._decode_step_launches(R)
-        self._graphs[R] = g
+            self._decode_step_launches(R, ctx_cap)
+        self._graphs[(R, ctx_cap)] = g
         self.state.copy_(saved_state)
         self.next_id.copy_(saved_id)
         torch.cuda.synchronize(self.device)
@@ -253,10 +262,11 @@ class Qwen2Engine:
         if len(budgets) != n or min(budgets) < 1:
             raise ValueError("max_new_tokens must be a positive int or one per sequence")
         order = sorted(range(n), key=lambda i: -budgets[i])           # slot s holds caller's sequence order[s]
+        cap = self._ctx_bucket(max(int(x.shape[0]) + b for x, b in zip(inputs_embeds_list, budgets)))
         with torch.cuda.device(self.device):
             if use_graph:
                 for r in sorted({sum(1 for b in budgets if b > t) for t in [0] + budgets} - {0}):
-                    self._ensure_graph(r)                               # before prefill (see _ensure_graph)
+                    self._ensure_graph(r, cap)                          # before prefill (see _ensure_graph)
             self.reset()
             lens = []
             for s_, i in enumerate(order):
@@ -290,10 +300,10 @@ class Qwen2Engine:
                     break
                 Rn = sum(1 for b in slot_budget if b > step + 1)         # rows that need another token
                 if use_graph:
-                    self._graphs[Rn].replay()
+                    self._graphs[(Rn, cap)].replay()
                     self.graph_replays += 1
                 else:
-                    self._decode_step_launches(Rn)
+                    self._decode_step_launches(Rn, cap)
                 prof_steps += 1
                 prof_bytes += self.weight_bytes() + sum(self.kv_bytes_per_token(lens[s_] + step) for s_ in range(Rn))
             if ev0 is not None:

@@ -215,6 +215,14 @@ int scb_gather_rows_rmsnorm(const void* table, const int64_t* ids, int64_t n_ids
                             int64_t ld_out, const void* gamma, float eps, void* norm_out,
                             int64_t ld_norm, void* stream);
 
+/* Tail of a split-K decode layer (wide batches run o_proj / down_proj / qkv as S independent K-slices
+ * through scb_linear with fp32 partial outputs): out[r,n] = fp16(sum_s partial[s,r,n] + bias[n] +
+ * residual[r,n]) summed in split order, then optionally post_norm_out[r,:] = RMSNorm(out[r,:]) * gamma. */
+int scb_splitk_reduce(const float* partial, int64_t split_stride, int64_t ld_partial, int32_t n_splits,
+                      int64_t rows, int32_t n, const void* bias, const void* residual, int64_t ld_res,
+                      void* out, int64_t ld_out, const void* post_norm_gamma, void* post_norm_out,
+                      int64_t post_norm_ld, float post_norm_eps, void* stream);
+
 /* Greedy token choice: arg-max per row of logits (fp16 or fp32), lowest index wins ties —
  * torch.argmax over the fp16 lm_head output as HF generate does.  If counters != NULL the
  * n_counters device int32 values it points to are each incremented by one (position / length

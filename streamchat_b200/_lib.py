@@ -137,6 +137,7 @@ SYMBOLS = {
     "scb_rope_append": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _f, _vp, _vp, _vp, _i64, _vp]),
     "scb_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "scb_gather_rows_rmsnorm": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _f, _vp, _i64, _vp]),
+    "scb_splitk_reduce": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _f, _vp]),
     "scb_argmax_rows": (C.c_int, [_vp, _i32, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
 }
 

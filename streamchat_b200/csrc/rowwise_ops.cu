@@ -387,6 +387,61 @@ gather_rmsnorm_kernel(const __half* __restrict__ table, const long long* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// Split-K tail for the wide-batch decode layers: out[r,n] = fp16(sum_s partial[s,r,n] + bias[n] +
+// residual[r,n]) in split order (deterministic), optionally followed by the RMSNorm of the finished
+// row (the next layer's input norm).  One block per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, long long split_stride, long long ld_partial,
+                     int n_splits, int N, const __half* __restrict__ bias,
+                     const __half* __restrict__ residual, long long ld_res, __half* __restrict__ out,
+                     long long ld_out, const __half* __restrict__ pn_gamma, __half* __restrict__ pn_out,
+                     long long pn_ld, float pn_eps) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < (N >> 2); i += 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < n_splits; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + sp * split_stride + (long long)r * ld_partial + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float f[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (bias) {
+      const uint2 b = *reinterpret_cast<const uint2*>(bias + i * 4);
+      const float2 b0 = h2_to_f2(b.x), b1 = h2_to_f2(b.y);
+      f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+    }
+    if (residual) {
+      const uint2 q = *reinterpret_cast<const uint2*>(residual + (long long)r * ld_res + i * 4);
+      const float2 r0 = h2_to_f2(q.x), r1 = h2_to_f2(q.y);
+      f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+    }
+    uint2 o;
+    o.x = f2_to_h2(f[0], f[1]);
+    o.y = f2_to_h2(f[2], f[3]);
+    *reinterpret_cast<uint2*>(out + (long long)r * ld_out + i * 4) = o;
+    const float2 h0 = h2_to_f2(o.x), h1 = h2_to_f2(o.y);     // the norm sees the stored fp16 values
+    ss += h0.x * h0.x + h0.y * h0.y + h1.x * h1.x + h1.y * h1.y;
+  }
+  if (pn_out == nullptr) return;
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / (float)N + pn_eps);
+  __syncthreads();
+  for (int i = threadIdx.x; i < (N >> 2); i += 256) {
+    const uint2 q = *reinterpret_cast<const uint2*>(out + (long long)r * ld_out + i * 4);
+    const uint2 g = *reinterpret_cast<const uint2*>(pn_gamma + i * 4);
+    const float2 x0 = h2_to_f2(q.x), x1 = h2_to_f2(q.y), g0 = h2_to_f2(g.x), g1 = h2_to_f2(g.y);
+    uint2 o;
+    o.x = f2_to_h2(__half2float(__float2half_rn(x0.x * rstd)) * g0.x, __half2float(__float2half_rn(x0.y * rstd)) * g0.y);
+    o.y = f2_to_h2(__half2float(__float2half_rn(x1.x * rstd)) * g1.x, __half2float(__float2half_rn(x1.y * rstd)) * g1.y);
+    *reinterpret_cast<uint2*>(pn_out + (long long)r * pn_ld + i * 4) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Arg-max over rows of fp32 logits, lowest index wins ties (greedy decoding,
 // generation/utils.py greedy branch == torch.argmax).  One block per row.
 // ------------------------------------------------------------------------------------------
@@ -612,6 +667,28 @@ int scb_gather_rows_rmsnorm(const void* table, const int64_t* ids, int64_t n_ids
                              reinterpret_cast<const __half*>(gamma), eps,
                              reinterpret_cast<__half*>(norm_out), (long long)ld_norm));
   SCB_LAUNCH_OK("gather_rmsnorm_kernel");
+  return SCB_OK;
+}
+
+int scb_splitk_reduce(const float* partial, int64_t split_stride, int64_t ld_partial, int32_t n_splits,
+                      int64_t rows, int32_t n, const void* bias, const void* residual, int64_t ld_res,
+                      void* out, int64_t ld_out, const void* post_norm_gamma, void* post_norm_out,
+                      int64_t post_norm_ld, float post_norm_eps, void* stream) {
+  SCB_REQUIRE(partial && out && rows >= 1 && n >= 4 && n % 4 == 0 && n_splits >= 1, SCB_ERR_INVALID_ARG,
+              "scb_splitk_reduce: bad arguments");
+  SCB_REQUIRE(ld_partial % 4 == 0 && split_stride % 4 == 0 && ld_out % 4 == 0 && (!residual || ld_res % 4 == 0) &&
+                  (!post_norm_out || (post_norm_gamma && post_norm_ld % 4 == 0)),
+              SCB_ERR_INVALID_ARG, "scb_splitk_reduce: rows must be 8-byte aligned");
+  SCB_CUDA_OK(scb_launch_pdl(splitk_reduce_kernel, dim3((unsigned)rows), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), partial, (long long)split_stride,
+                             (long long)ld_partial, (int)n_splits, (int)n,
+                             reinterpret_cast<const __half*>(bias),
+                             reinterpret_cast<const __half*>(residual), (long long)ld_res,
+                             reinterpret_cast<__half*>(out), (long long)ld_out,
+                             reinterpret_cast<const __half*>(post_norm_gamma),
+                             reinterpret_cast<__half*>(post_norm_out), (long long)post_norm_ld,
+                             post_norm_eps));
+  SCB_LAUNCH_OK("splitk_reduce_kernel");
   return SCB_OK;
 }
 

@@ -338,6 +338,36 @@ def gather_rows_rmsnorm(table: torch.Tensor, ids: torch.Tensor, gamma: torch.Ten
           out.stride(0), _ptr(gamma), eps, _ptr(norm_out), norm_out.stride(0))
 
 
+def linear_splitk(a: torch.Tensor, w: torch.Tensor, n_splits: int, partial: torch.Tensor, out: torch.Tensor,
+                  bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                  post_norm: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> torch.Tensor:
+    """out = a @ w.T (+bias) (+residual) for few rows and a long K: the K range is cut into `n_splits`
+    slices that run as a batched tcgen05 GEMM (one CTA wave streams every weight byte once, fp32 partials
+    in `partial` [n_splits, rows, N]), then one reduce launch sums them in order and applies the epilogue
+    (and optionally the RMSNorm of the finished rows)."""
+    dev = _require_cuda(a, w, partial, out, bias, residual)
+    rows, k = a.shape
+    n = w.shape[0]
+    ks = k // n_splits
+    if ks * n_splits != k or ks % 8:
+        raise ValueError(f"k={k} cannot be cut into {n_splits} slices of a multiple of 8")
+    args = L.LinearArgs(a=_ptr(a), w=_ptr(w), bias=None, residual=None, out=_ptr(partial), m=rows, n=n, k=ks,
+                        lda=a.stride(0), ldw=w.stride(0), ldr=0, ldo=partial.stride(1), act=L.ACT_NONE,
+                        out_dtype=L.SCB_F32, batch=n_splits, stride_a=ks, stride_w=ks, stride_r=0,
+                        stride_o=partial.stride(0), alpha=1.0)
+    with torch.cuda.device(dev):
+        L.check(L.load().scb_linear(C.byref(args), _stream(dev)), "scb_linear")
+    pg = po = None
+    pld, pe = 0, 0.0
+    if post_norm is not None:
+        pg, po, pe = post_norm
+        pld = po.stride(0)
+    _call("scb_splitk_reduce", dev, _ptr(partial), partial.stride(0), partial.stride(1), n_splits, rows, n,
+          _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0),
+          _ptr(pg), _ptr(po), pld, pe)
+    return out
+
+
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
                 counter: Optional[torch.Tensor] = None) -> torch.Tensor:
     dev = _require_cuda(logits, out, counter)

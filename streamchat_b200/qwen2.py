@@ -89,6 +89,10 @@ class Qwen2Engine:
         self._x = torch.zeros((B, c.hidden_size), dtype=torch.float16, device=self.device)
         self._x2 = torch.zeros_like(self._x)
         self._nrm = torch.zeros_like(self._x)
+        # split-K partials of the wide-batch path: [splits <= 8, rows, widest N]
+        n_max = max(qkv_dim, c.hidden_size)
+        self._part = torch.zeros((8, B, n_max), dtype=torch.float32, device=self.device)
+        self._down_splits = next((s_ for s_ in (4, 8, 2, 1) if c.intermediate_size % (8 * s_) == 0), 1)
         self._qkv = torch.zeros((B, qkv_dim), dtype=torch.float16, device=self.device)
         self._attn = torch.zeros((B, c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
         self._gu = torch.zeros((B, c.intermediate_size), dtype=torch.float16, device=self.device)
@@ -185,23 +189,30 @@ class Qwen2Engine:
         L0 = self.layers[0]
         ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
         n_layers = len(self.layers)
+        wide = R > 8
         for i, ly in enumerate(self.layers):
             nxt_gamma = self.layers[i + 1]["ln1"] if i + 1 < n_layers else self.final_norm
             nxt_w = self.layers[i + 1]["qkv_w"] if i + 1 < n_layers else self.lm_head
-            ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
+            if wide:
+                # wide batches: the A-fragment reads of the streaming GEMV (R x K per 8 weight rows) outgrow
+                # L1, so every layer runs on the tcgen05 GEMM — split over K where N alone gives too few tiles
+                ops.linear_splitk(nrm, ly["qkv_w"], 4, self._part, self._qkv[:R], bias=ly["qkv_b"])
+            else:
+                ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
                                        self.state[1, :R], Hq, scale, self._attn_ws, n_splits=splits,
-                                       out=self._attn[:R], prefetch=ly["o_w"], ctx_cap=cap)
-            ops.gemv(self._attn[:R].view(R, Hq * hd), ly["o_w"], residual=x, out=x2,
-                     post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
-            if R > 8:
-                # wide batches: the A-fragment reads of the streaming GEMV (R x K per 8 weight rows) outgrow
-                # L1; the tcgen05 GEMM streams the same weights through TMA with the activations in smem
+                                       out=self._attn[:R], prefetch=None if wide else ly["o_w"], ctx_cap=cap)
+            attn2d = self._attn[:R].view(R, Hq * hd)
+            if wide:
+                ops.linear_splitk(attn2d, ly["o_w"], 4, self._part, x2, residual=x, post_norm=(ly["ln2"], nrm, eps))
                 ops.linear(nrm, ly["gu_w"], act=L.ACT_SILU_PAIR, out=self._gu[:R])
+                ops.linear_splitk(self._gu[:R], ly["down_w"], self._down_splits, self._part, x, residual=x2,
+                                  post_norm=(nxt_gamma, nrm, eps))
             else:
+                ops.gemv(attn2d, ly["o_w"], residual=x, out=x2, post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
                 ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])
-            ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x, post_norm=(nxt_gamma, nrm, eps),
-                     prefetch=nxt_w)
+                ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x, post_norm=(nxt_gamma, nrm, eps),
+                         prefetch=nxt_w)
         if R > 8:
             ops.linear(nrm, self.lm_head, out=self._logits[:R])
             ops.argmax_rows(self._logits[:R], out=self.next_id[:R], counter=self.state.view(-1))

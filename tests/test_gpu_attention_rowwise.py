@@ -367,3 +367,25 @@ def test_gemv_post_norm_prefetch_and_gather_norm(cuda):
     nrm = torch.zeros_like(x)
     ops.gather_rows_rmsnorm(table, ids, gamma, 1e-6, out=x, norm_out=nrm)
     assert torch.equal(x, table[ids]) and torch.equal(nrm, ops.rmsnorm(x, gamma, 1e-6))
+
+
+@pytest.mark.parametrize("rows,n,k,splits", [(13, 3584, 18944, 4), (9, 4608, 3584, 4), (16, 3584, 3584, 4), (3, 256, 512, 2)])
+def test_linear_splitk_matches_gemv(cuda, rows, n, k, splits):
+    """Wide decode batches: K-sliced tcgen05 GEMM + ordered reduce == the streaming GEMV path (same
+    fp16 inputs, fp32 accumulation) within fp16 output rounding, epilogues included."""
+    from streamchat_b200 import ops
+    torch.manual_seed(rows + n)
+    a = torch.randn(rows, k, device=cuda).half()
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()
+    res = torch.randn(rows, n, device=cuda).half()
+    bias = torch.randn(n, device=cuda).half()
+    gamma = (1 + 0.1 * torch.randn(n, device=cuda)).half()
+    part = torch.zeros(8, 16, max(n, 4608), device=cuda, dtype=torch.float32)
+    out = torch.zeros(rows, n, device=cuda, dtype=torch.float16)
+    nrm = torch.zeros_like(out)
+    ops.linear_splitk(a, w, splits, part, out, bias=bias, residual=res, post_norm=(gamma, nrm, 1e-6))
+    ref = (a.double() @ w.double().t() + bias.double() + res.double()).cpu()
+    assert ((out.double().cpu() - ref).abs() <= 2e-3 * (ref.abs() + 1)).all()
+    assert torch.equal(nrm, ops.rmsnorm(out, gamma, 1e-6))
+    ref_v = ops.gemv(a, w, bias=bias, residual=res)
+    assert (out.float() - ref_v.float()).abs().max().item() <= 2e-3 * (ref.abs().max().item() + 1)

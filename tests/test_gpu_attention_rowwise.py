@@ -386,6 +386,8 @@ def test_linear_splitk_matches_gemv(cuda, rows, n, k, splits):
     ops.linear_splitk(a, w, splits, part, out, bias=bias, residual=res, post_norm=(gamma, nrm, 1e-6))
     ref = (a.double() @ w.double().t() + bias.double() + res.double()).cpu()
     assert ((out.double().cpu() - ref).abs() <= 2e-3 * (ref.abs() + 1)).all()
-    assert torch.equal(nrm, ops.rmsnorm(out, gamma, 1e-6))
+    # same rounding points as the standalone norm; the sum of squares is ordered differently (1 fp16 ulp)
+    ref_n = ops.rmsnorm(out, gamma, 1e-6).float()
+    assert ((nrm.float() - ref_n).abs() <= 2e-3 * (ref_n.abs() + 1e-3)).all()
     ref_v = ops.gemv(a, w, bias=bias, residual=res)
     assert (out.float() - ref_v.float()).abs().max().item() <= 2e-3 * (ref.abs().max().item() + 1)

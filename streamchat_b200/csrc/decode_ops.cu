@@ -600,8 +600,8 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
                          long long next_w_bytes) {
   constexpr int HALF = HD / 2;
   extern __shared__ __align__(16) float dsm[];
-  float* q_s = dsm;                 // [G][HD] rotated q, pre-scaled by scale*log2(e)
-  float* s_s = dsm + G * HD;        // [G][per_max] scores -> probabilities
+  __half* q_h = reinterpret_cast<__half*>(dsm);   // [8][HD] rotated q (fp16, rows >= G zero): the mma B operand
+  float* s_s = dsm + 4 * HD;        // [G][per_max] scores (x scale*log2 e) -> exp2 values; per_max = 4 mod 16
   __shared__ float m_s[G], l_s[G];
   __shared__ float m_sp[G * 64], l_sp[G * 64];   // per-split statistics for the combine (n_splits <= 64)
   __shared__ float o_s[8][G][HD];   // per-warp partial outputs
@@ -641,9 +641,10 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
     const float x1 = __half2float(qp[i]), x2 = __half2float(qp[i + HALF]);
     const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
     const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
-    q_s[h * HD + i] = __half2float(__float2half_rn(a1 + b1)) * scale_log2;
-    q_s[h * HD + i + HALF] = __half2float(__float2half_rn(a2 + b2)) * scale_log2;
+    q_h[h * HD + i] = __float2half_rn(a1 + b1);
+    q_h[h * HD + i + HALF] = __float2half_rn(a2 + b2);
   }
+  for (int idx = G * HD + tid; idx < 8 * HD; idx += 256) q_h[idx] = __float2half_rn(0.f);   // unused mma columns
   // ---- the block that owns `pos` rotates and appends the new k, copies the new v
   if (pos >= begin && pos < end) {
     const __half* kp = qkv + (long long)(n_q + hk) * HD;
@@ -662,44 +663,41 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   __syncthreads();   // q_s ready; the appended row is visible to this block
 
-  // ---- phase 1: scores.  A pair of threads owns a position: thread j reads the 16-byte chunks
-  // j, j+2, j+4, ... of the K row, all of them in flight at once (128 positions per pass), partial
-  // dots meet with one shuffle.
+  // ---- phase 1: scores on the tensor pipe.  A warp owns 16 positions per tile: the K rows are the A
+  // operand of mma.m16n8k16 (M = positions, K = dims, N = the group's q heads), loaded straight from
+  // the cache as 16-byte pieces — the dot product does not care which dims share a k-slot, so thread
+  // (g,t) feeds dims [32c+8t, 32c+8t+8) of rows g / g+8 and the matching 16 bytes of q.  8 x 16 B in
+  // flight per thread.
   {
-    constexpr int CH = HD / 16;           // 16-byte chunks per thread
-    const int pr = tid >> 1, j = tid & 1;
-    const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD;
-    for (int p0 = 0; p0 < n_local; p0 += 128) {
-      const int pl = p0 + pr;
-      const bool ok = pl < n_local;
-      uint4 kv4[CH];
+    constexpr int NC = HD / 32;
+    const int g = lane >> 2, t = lane & 3;
+    uint4 qf[NC];
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        kv4[c] = ok ? *reinterpret_cast<const uint4*>(kb + (long long)pl * HD + (c * 2 + j) * 8)
-                    : make_uint4(0, 0, 0, 0);
-      float sc[G];
+    for (int c = 0; c < NC; ++c) qf[c] = *reinterpret_cast<const uint4*>(q_h + g * HD + c * 32 + t * 8);
+    const __half* kb = k_cache + ((long long)hk * max_pos + begin) * HD + t * 8;
+    for (int p0 = warp * 16; p0 < n_local; p0 += 128) {
+      const int r0 = p0 + g, r1 = r0 + 8;
+      const bool ok0 = r0 < n_local, ok1 = r1 < n_local;
+      uint4 k0[NC], k1[NC];
 #pragma unroll
-      for (int h = 0; h < G; ++h) sc[h] = 0.f;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        float kf[8];
-        unpack8(kv4[c], kf);
-        const int d0 = (c * 2 + j) * 8;
-#pragma unroll
-        for (int h = 0; h < G; ++h) {
-          const float4 qa = *reinterpret_cast<const float4*>(q_s + h * HD + d0);
-          const float4 qb = *reinterpret_cast<const float4*>(q_s + h * HD + d0 + 4);
-          sc[h] = fmaf(kf[0], qa.x, sc[h]); sc[h] = fmaf(kf[1], qa.y, sc[h]);
-          sc[h] = fmaf(kf[2], qa.z, sc[h]); sc[h] = fmaf(kf[3], qa.w, sc[h]);
-          sc[h] = fmaf(kf[4], qb.x, sc[h]); sc[h] = fmaf(kf[5], qb.y, sc[h]);
-          sc[h] = fmaf(kf[6], qb.z, sc[h]); sc[h] = fmaf(kf[7], qb.w, sc[h]);
-        }
+      for (int c = 0; c < NC; ++c) {
+        k0[c] = ok0 ? *reinterpret_cast<const uint4*>(kb + (long long)r0 * HD + c * 32) : make_uint4(0, 0, 0, 0);
+        k1[c] = ok1 ? *reinterpret_cast<const uint4*>(kb + (long long)r1 * HD + c * 32) : make_uint4(0, 0, 0, 0);
       }
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int h = 0; h < G; ++h) sc[h] += __shfl_xor_sync(0xffffffffu, sc[h], 1);
-      if (ok && j == 0) {
-#pragma unroll
-        for (int h = 0; h < G; ++h) s_s[h * per_max + pl] = sc[h];
+      for (int c = 0; c < NC; ++c) {
+        mma16816(d0, k0[c].x, k1[c].x, k0[c].y, k1[c].y, qf[c].x, qf[c].y);
+        mma16816(d1, k0[c].z, k1[c].z, k0[c].w, k1[c].w, qf[c].z, qf[c].w);
+      }
+      const int h0 = 2 * t;
+      if (h0 < G) {
+        if (ok0) s_s[h0 * per_max + r0] = (d0[0] + d1[0]) * scale_log2;
+        if (ok1) s_s[h0 * per_max + r1] = (d0[2] + d1[2]) * scale_log2;
+      }
+      if (h0 + 1 < G) {
+        if (ok0) s_s[(h0 + 1) * per_max + r0] = (d0[1] + d1[1]) * scale_log2;
+        if (ok1) s_s[(h0 + 1) * per_max + r1] = (d0[3] + d1[3]) * scale_log2;
       }
     }
   }
@@ -724,55 +722,70 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   __syncthreads();
 
-  // ---- phase 3: P·V.  thread = (dim group of 8, position group): 16-byte V loads, 4 in flight;
-  // position groups meet by one shuffle (lanes l, l^16) and a fixed-order sum over the warps.
+  // ---- phase 3: P·V on the tensor pipe, O^T = V^T · P^T: M = dims, K = positions, N = q heads.
+  // Thread (g,t) loads 16 bytes (dims 8g..8g+7) of positions 2t, 2t+1, 2t+8, 2t+9 of the tile; a byte
+  // permute of two such rows yields the (dim, position-pair) A registers — rows g / g+8 of m-tile j are
+  // dims 8g+2j / 8g+2j+1.  The probabilities are rounded to fp16 for the B operand (as the reference's
+  // fp16 softmax output is); accumulation is fp32.  8 x 16 B in flight per thread.
   {
-    constexpr int DG = HD / 8;            // 16 (HD=128) or 8 (HD=64) dim groups
-    constexpr int LPG = 32 / DG;          // position groups inside a warp: 2 or 4
-    constexpr int NPG = 8 * LPG;          // position groups per block
-    const int dg = lane % DG, pg = warp * LPG + lane / DG;
-    const __half* vb = v_cache + ((long long)hk * max_pos + begin) * HD + dg * 8;
-    float acc[G][8];
+    constexpr int NH = HD / 64;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[NH][4][4];
 #pragma unroll
-    for (int h = 0; h < G; ++h)
+    for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[h][e] = 0.f;
-    for (int p0 = pg; p0 < n_local; p0 += 4 * NPG) {
-      uint4 vv[4];
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int pl = p0 + u * NPG;
-        vv[u] = pl < n_local ? *reinterpret_cast<const uint4*>(vb + (long long)pl * HD)
-                             : make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 4; ++e) acc[hh][j][e] = 0.f;
+    const __half* vb = v_cache + ((long long)hk * max_pos + begin) * HD + g * 8;
+    const float* er = s_s + (g < G ? g : 0) * per_max;
+    for (int p0 = warp * 16; p0 < n_local; p0 += 128) {
+      const int pa = p0 + 2 * t, pb = pa + 8;
+      const bool oka0 = pa < n_local, oka1 = pa + 1 < n_local, okb0 = pb < n_local, okb1 = pb + 1 < n_local;
+      uint4 v[NH][4];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        const __half* vp = vb + hh * 64;
+        v[hh][0] = oka0 ? *reinterpret_cast<const uint4*>(vp + (long long)pa * HD) : make_uint4(0, 0, 0, 0);
+        v[hh][1] = oka1 ? *reinterpret_cast<const uint4*>(vp + (long long)(pa + 1) * HD) : make_uint4(0, 0, 0, 0);
+        v[hh][2] = okb0 ? *reinterpret_cast<const uint4*>(vp + (long long)pb * HD) : make_uint4(0, 0, 0, 0);
+        v[hh][3] = okb1 ? *reinterpret_cast<const uint4*>(vp + (long long)(pb + 1) * HD) : make_uint4(0, 0, 0, 0);
       }
+      float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+      if (g < G) {
+        if (oka0) ea = *reinterpret_cast<const float2*>(er + pa);
+        if (okb0) eb = *reinterpret_cast<const float2*>(er + pb);
+        if (!oka1) ea.y = 0.f;
+        if (!okb1) eb.y = 0.f;
+      }
+      const uint32_t b0 = f2_to_h2(ea.x, ea.y), b1 = f2_to_h2(eb.x, eb.y);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int pl = p0 + u * NPG;
-        if (pl < n_local) {
-          float vf[8];
-          unpack8(vv[u], vf);
+      for (int hh = 0; hh < NH; ++hh) {
+        const uint32_t w0[4] = {v[hh][0].x, v[hh][0].y, v[hh][0].z, v[hh][0].w};
+        const uint32_t w1[4] = {v[hh][1].x, v[hh][1].y, v[hh][1].z, v[hh][1].w};
+        const uint32_t w2[4] = {v[hh][2].x, v[hh][2].y, v[hh][2].z, v[hh][2].w};
+        const uint32_t w3[4] = {v[hh][3].x, v[hh][3].y, v[hh][3].z, v[hh][3].w};
 #pragma unroll
-          for (int h = 0; h < G; ++h) {
-            const float pr = s_s[h * per_max + pl];
+        for (int j = 0; j < 4; ++j)
+          mma16816(acc[hh][j], __byte_perm(w0[j], w1[j], 0x5410), __byte_perm(w0[j], w1[j], 0x7632),
+                   __byte_perm(w2[j], w3[j], 0x5410), __byte_perm(w2[j], w3[j], 0x7632), b0, b1);
+      }
+    }
+    const int h0 = 2 * t;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[h][e] = fmaf(pr, vf[e], acc[h][e]);
-          }
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d0 = hh * 64 + g * 8 + 2 * j;
+        if (h0 < G) {
+          o_s[warp][h0][d0] = acc[hh][j][0];
+          o_s[warp][h0][d0 + 1] = acc[hh][j][2];
+        }
+        if (h0 + 1 < G) {
+          o_s[warp][h0 + 1][d0] = acc[hh][j][1];
+          o_s[warp][h0 + 1][d0 + 1] = acc[hh][j][3];
         }
       }
-    }
-#pragma unroll
-    for (int h = 0; h < G; ++h)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if constexpr (LPG == 4) acc[h][e] += __shfl_xor_sync(0xffffffffu, acc[h][e], 8);
-        acc[h][e] += __shfl_xor_sync(0xffffffffu, acc[h][e], 16);
-      }
-    if (lane < DG) {
-#pragma unroll
-      for (int h = 0; h < G; ++h)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o_s[warp][h][dg * 8 + e] = acc[h][e];
-    }
   }
   __syncthreads();
   for (int idx = tid; idx < G * HD; idx += 256) {
@@ -1110,9 +1123,10 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
   // score-buffer sizing: the caller may bound the live context (ctx_cap <= max_pos) so that short
   // contexts do not pay shared memory (and occupancy) for the cache capacity
   const long long cap = (a->ctx_cap > 0 && a->ctx_cap < a->max_pos) ? a->ctx_cap : a->max_pos;
-  const int per_max = (int)((cap + a->n_splits - 1) / a->n_splits);
-  const int per_alloc = per_max > a->n_splits ? per_max : a->n_splits;   // the combine reuses the score buffer
-  const size_t smem = sizeof(float) * ((size_t)G * a->head_dim + (size_t)G * per_alloc);
+  const int per_need = (int)((cap + a->n_splits - 1) / a->n_splits);
+  const int per_min = per_need > a->n_splits ? per_need : a->n_splits;   // the combine reuses the score buffer
+  const int per_max = ((per_min + 11) / 16) * 16 + 4;   // row stride = 4 mod 16 floats: conflict-free mma stores
+  const size_t smem = sizeof(float) * ((size_t)4 * a->head_dim + (size_t)G * per_max);
   SCB_REQUIRE(smem <= 160 * 1024, SCB_ERR_UNSUPPORTED,
               "scb_decode_attention_fused: max_pos/n_splits too large for shared memory");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

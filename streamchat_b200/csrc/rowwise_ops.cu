@@ -327,6 +327,62 @@ __global__ void rope_append_kernel(__half* __restrict__ qkv, long long ld_qkv, i
   }
 }
 
+// Vector form for head_dim % 16 == 0 (the shapes on the path): the hd/2 angles of the row's position are
+// evaluated once per block, every thread then rotates 8 + 8 elements with 16-byte accesses.
+__global__ void __launch_bounds__(256)
+rope_append_vec_kernel(__half* __restrict__ qkv, long long ld_qkv, int n_q, int n_kv, int hd,
+                       const int* __restrict__ positions, int pos_base, float theta,
+                       const float* __restrict__ inv_freq_tab, __half* __restrict__ k_cache,
+                       __half* __restrict__ v_cache, long long max_pos) {
+  __shared__ float cs[128], sn[128];
+  const long long row = blockIdx.x;
+  const int pos = positions ? positions[row] : pos_base + (int)row;
+  __half* r = qkv + row * ld_qkv;
+  const int half = hd >> 1;
+  for (int i = threadIdx.x; i < half; i += 256) {
+    const float inv_freq = inv_freq_tab ? inv_freq_tab[i] : powf(theta, -(float)(2 * i) / (float)hd);
+    const float ang = (float)pos * inv_freq;
+    cs[i] = __half2float(__float2half_rn(cosf(ang)));
+    sn[i] = __half2float(__float2half_rn(sinf(ang)));
+  }
+  __syncthreads();
+  const int cpr = half >> 3;   // 16-byte chunks per half head
+  for (int idx = threadIdx.x; idx < (n_q + n_kv) * cpr; idx += 256) {
+    const int h = idx / cpr, c8 = (idx % cpr) * 8;
+    __half* p = r + (long long)h * hd + c8;
+    const uint4 lo = *reinterpret_cast<const uint4*>(p), hi = *reinterpret_cast<const uint4*>(p + half);
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x1 = h2_to_f2(lw[e]), x2 = h2_to_f2(hw[e]);
+      const float c0 = cs[c8 + 2 * e], c1 = cs[c8 + 2 * e + 1], s0 = sn[c8 + 2 * e], s1 = sn[c8 + 2 * e + 1];
+      // out1 = x1*cos + (-x2)*sin ; out2 = x2*cos + x1*sin, each product rounded to fp16
+      const float2 a1 = h2_to_f2(f2_to_h2(x1.x * c0, x1.y * c1)), b1 = h2_to_f2(f2_to_h2(-x2.x * s0, -x2.y * s1));
+      const float2 a2 = h2_to_f2(f2_to_h2(x2.x * c0, x2.y * c1)), b2 = h2_to_f2(f2_to_h2(x1.x * s0, x1.y * s1));
+      o1[e] = f2_to_h2(a1.x + b1.x, a1.y + b1.y);
+      o2[e] = f2_to_h2(a2.x + b2.x, a2.y + b2.y);
+    }
+    const uint4 v1 = make_uint4(o1[0], o1[1], o1[2], o1[3]), v2 = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+    *reinterpret_cast<uint4*>(p) = v1;
+    *reinterpret_cast<uint4*>(p + half) = v2;
+    if (h >= n_q && k_cache) {
+      __half* kc = k_cache + ((long long)(h - n_q) * max_pos + pos) * hd + c8;
+      *reinterpret_cast<uint4*>(kc) = v1;
+      *reinterpret_cast<uint4*>(kc + half) = v2;
+    }
+  }
+  if (v_cache) {
+    const __half* v = r + (long long)(n_q + n_kv) * hd;
+    const int vpr = hd >> 3;
+    for (int idx = threadIdx.x; idx < n_kv * vpr; idx += 256) {
+      const int h = idx / vpr, c8 = (idx % vpr) * 8;
+      *reinterpret_cast<uint4*>(v_cache + ((long long)h * max_pos + pos) * hd + c8) =
+          *reinterpret_cast<const uint4*>(v + (long long)h * hd + c8);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Embedding gather: out[r] = table[ids[r]]  (ids < 0 -> zeros)
 // ------------------------------------------------------------------------------------------
@@ -402,33 +458,95 @@ splitk_reduce_kernel(const float* __restrict__ partial, long long split_stride, 
   pdl_wait();
   const int r = blockIdx.x;
   float ss = 0.f;
-  for (int i = threadIdx.x; i < (N >> 2); i += 256) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sp = 0; sp < n_splits; ++sp) {
-      const float4 v = *reinterpret_cast<const float4*>(partial + sp * split_stride + (long long)r * ld_partial + i * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  constexpr int kC = 6;                    // rows up to 6144 wide stay in registers between the two passes
+  const bool in_regs = N <= 256 * 4 * kC;
+  uint2 keep[kC];
+  if (in_regs) {
+    float4 acc[kC];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < n_splits; ++sp) {      // splits are summed in index order (deterministic)
+      float4 v[kC];
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        const int i = threadIdx.x + c * 256;
+        v[c] = i < (N >> 2) ? __ldcg(reinterpret_cast<const float4*>(partial + sp * split_stride + (long long)r * ld_partial) + i)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        acc[c].x += v[c].x; acc[c].y += v[c].y; acc[c].z += v[c].z; acc[c].w += v[c].w;
+      }
     }
-    float f[4] = {acc.x, acc.y, acc.z, acc.w};
-    if (bias) {
-      const uint2 b = *reinterpret_cast<const uint2*>(bias + i * 4);
-      const float2 b0 = h2_to_f2(b.x), b1 = h2_to_f2(b.y);
-      f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const int i = threadIdx.x + c * 256;
+      keep[c] = make_uint2(0, 0);
+      if (i < (N >> 2)) {
+        float f[4] = {acc[c].x, acc[c].y, acc[c].z, acc[c].w};
+        if (bias) {
+          const uint2 b = *reinterpret_cast<const uint2*>(bias + i * 4);
+          const float2 b0 = h2_to_f2(b.x), b1 = h2_to_f2(b.y);
+          f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+        }
+        if (residual) {
+          const uint2 q = *reinterpret_cast<const uint2*>(residual + (long long)r * ld_res + i * 4);
+          const float2 r0 = h2_to_f2(q.x), r1 = h2_to_f2(q.y);
+          f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+        }
+        uint2 o;
+        o.x = f2_to_h2(f[0], f[1]);
+        o.y = f2_to_h2(f[2], f[3]);
+        *reinterpret_cast<uint2*>(out + (long long)r * ld_out + i * 4) = o;
+        keep[c] = o;
+        const float2 h0 = h2_to_f2(o.x), h1 = h2_to_f2(o.y);   // the norm sees the stored fp16 values
+        ss += h0.x * h0.x + h0.y * h0.y + h1.x * h1.x + h1.y * h1.y;
+      }
     }
-    if (residual) {
-      const uint2 q = *reinterpret_cast<const uint2*>(residual + (long long)r * ld_res + i * 4);
-      const float2 r0 = h2_to_f2(q.x), r1 = h2_to_f2(q.y);
-      f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+  } else {
+    for (int i = threadIdx.x; i < (N >> 2); i += 256) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < n_splits; ++sp) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + sp * split_stride + (long long)r * ld_partial + i * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      float f[4] = {acc.x, acc.y, acc.z, acc.w};
+      if (bias) {
+        const uint2 b = *reinterpret_cast<const uint2*>(bias + i * 4);
+        const float2 b0 = h2_to_f2(b.x), b1 = h2_to_f2(b.y);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b1.x; f[3] += b1.y;
+      }
+      if (residual) {
+        const uint2 q = *reinterpret_cast<const uint2*>(residual + (long long)r * ld_res + i * 4);
+        const float2 r0 = h2_to_f2(q.x), r1 = h2_to_f2(q.y);
+        f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+      }
+      uint2 o;
+      o.x = f2_to_h2(f[0], f[1]);
+      o.y = f2_to_h2(f[2], f[3]);
+      *reinterpret_cast<uint2*>(out + (long long)r * ld_out + i * 4) = o;
+      const float2 h0 = h2_to_f2(o.x), h1 = h2_to_f2(o.y);
+      ss += h0.x * h0.x + h0.y * h0.y + h1.x * h1.x + h1.y * h1.y;
     }
-    uint2 o;
-    o.x = f2_to_h2(f[0], f[1]);
-    o.y = f2_to_h2(f[2], f[3]);
-    *reinterpret_cast<uint2*>(out + (long long)r * ld_out + i * 4) = o;
-    const float2 h0 = h2_to_f2(o.x), h1 = h2_to_f2(o.y);     // the norm sees the stored fp16 values
-    ss += h0.x * h0.x + h0.y * h0.y + h1.x * h1.x + h1.y * h1.y;
   }
   if (pn_out == nullptr) return;
   ss = block_sum(ss, red);
   const float rstd = rsqrtf(ss / (float)N + pn_eps);
+  if (in_regs) {
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const int i = threadIdx.x + c * 256;
+      if (i < (N >> 2)) {
+        const uint2 g = *reinterpret_cast<const uint2*>(pn_gamma + i * 4);
+        const float2 x0 = h2_to_f2(keep[c].x), x1 = h2_to_f2(keep[c].y), g0 = h2_to_f2(g.x), g1 = h2_to_f2(g.y);
+        uint2 o;
+        o.x = f2_to_h2(__half2float(__float2half_rn(x0.x * rstd)) * g0.x, __half2float(__float2half_rn(x0.y * rstd)) * g0.y);
+        o.y = f2_to_h2(__half2float(__float2half_rn(x1.x * rstd)) * g1.x, __half2float(__float2half_rn(x1.y * rstd)) * g1.y);
+        *reinterpret_cast<uint2*>(pn_out + (long long)r * pn_ld + i * 4) = o;
+      }
+    }
+    return;
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < (N >> 2); i += 256) {
     const uint2 q = *reinterpret_cast<const uint2*>(out + (long long)r * ld_out + i * 4);
@@ -630,10 +748,16 @@ int scb_rope_append(void* qkv, int64_t ld_qkv, int64_t rows, int32_t n_q_heads, 
   SCB_REQUIRE(!k_cache || positions || pos_base + rows <= max_pos, SCB_ERR_INVALID_ARG,
               "scb_rope_append: positions exceed the cache (%lld + %lld > %lld)", (long long)pos_base,
               (long long)rows, (long long)max_pos);
-  rope_append_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__half*>(qkv), ld_qkv, n_q_heads, n_kv_heads, head_dim, positions, pos_base,
-      theta, inv_freq, reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), max_pos,
-      rows);
+  if (head_dim % 16 == 0 && head_dim <= 256 && ld_qkv % 8 == 0 && aligned16(qkv) &&
+      (!k_cache || (aligned16(k_cache) && aligned16(v_cache))))
+    rope_append_vec_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__half*>(qkv), ld_qkv, n_q_heads, n_kv_heads, head_dim, positions, pos_base,
+        theta, inv_freq, reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), max_pos);
+  else
+    rope_append_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__half*>(qkv), ld_qkv, n_q_heads, n_kv_heads, head_dim, positions, pos_base,
+        theta, inv_freq, reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), max_pos,
+        rows);
   SCB_LAUNCH_OK("rope_append_kernel");
   return SCB_OK;
 }

@@ -344,7 +344,7 @@ typedef struct scb_decode_attention_fused_args {
   int32_t n_q_heads, n_kv_heads, head_dim, n_splits;
   float scale;
   float theta;
-  int32_t n_seqs;            /* >= 1, n_seqs * n_kv_heads <= 64 */
+  int32_t n_seqs;            /* >= 1, n_seqs * n_kv_heads <= 256 */
   int32_t _pad;
   int64_t ld_qkv;            /* elements between the sequences' qkv rows */
   int64_t cache_seq_stride;  /* elements between the sequences' caches */

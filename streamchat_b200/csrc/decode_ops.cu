@@ -953,7 +953,15 @@ int scb_gemv(const scb_gemv_args* a, void* stream) {
       env_c = e ? atoi(e) : 0;
     }
     const int GW = (env_w == 8 || env_w == 16 || env_w == 32) ? env_w : kGWDefault;
-    const long long wave = (long long)sms * (32 / GW);     // 32 warps per SM
+    static int env_bps = -1;
+    if (env_bps < 0) {
+      const char* e = getenv("SCB_GEMV_BPS");
+      env_bps = e ? atoi(e) : 0;
+    }
+    // blocks per SM: fewer than the register file allows leaves room for the NEXT kernel's blocks, whose
+    // weight loads then start under programmatic dependent launch while this one is still streaming
+    const int bps = (env_bps >= 1 && env_bps <= 32 / GW) ? env_bps : 32 / GW;
+    const long long wave = (long long)sms * bps;
     // K chunks: fill whole waves (skinny layers), keep >= 2 batches of 8 tiles per warp
     // K chunking (C > 1) only pays when a layer has far fewer row groups than block slots; on the
     // Qwen2-7B shapes the ticket round trip costs more than it gains (profiles/r01_gemv_sweep.txt)
@@ -1092,8 +1100,8 @@ size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_he
                                                   int32_t n_kv_heads, int32_t head_dim,
                                                   int32_t n_splits) {
   if (n_seqs < 1 || n_q_heads < 1 || n_kv_heads < 1 || head_dim < 1 || n_splits < 1) return 0;
-  if (n_seqs * n_kv_heads > 64) return 0;  // tickets live in the first 256 bytes
-  return 256 + sizeof(float) * (size_t)n_seqs * n_q_heads * n_splits * (head_dim + 2);
+  if (n_seqs * n_kv_heads > 256) return 0;  // tickets live in the first 1024 bytes
+  return 1024 + sizeof(float) * (size_t)n_seqs * n_q_heads * n_splits * (head_dim + 2);
 }
 
 int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream) {
@@ -1109,15 +1117,15 @@ int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* s
               "scb_decode_attention_fused: group size %d unsupported (1,2,4,7,8)", G);
   SCB_REQUIRE(a->n_splits >= 1 && a->n_splits <= 64, SCB_ERR_INVALID_ARG,
               "scb_decode_attention_fused: n_splits out of range (1..64)");
-  SCB_REQUIRE(a->n_seqs >= 1 && a->n_seqs * a->n_kv_heads <= 64, SCB_ERR_INVALID_ARG,
-              "scb_decode_attention_fused: n_seqs=%d out of range (n_seqs * n_kv_heads <= 64)", a->n_seqs);
+  SCB_REQUIRE(a->n_seqs >= 1 && a->n_seqs * a->n_kv_heads <= 256, SCB_ERR_INVALID_ARG,
+              "scb_decode_attention_fused: n_seqs=%d out of range (n_seqs * n_kv_heads <= 256)", a->n_seqs);
   const size_t need = scb_decode_attention_fused_workspace_bytes(a->n_seqs, a->n_q_heads, a->n_kv_heads,
                                                                  a->head_dim, a->n_splits);
   SCB_REQUIRE(a->workspace_bytes >= need, SCB_ERR_WORKSPACE,
               "scb_decode_attention_fused: workspace %zu B < %zu B", a->workspace_bytes, need);
   char* ws = reinterpret_cast<char*>(a->workspace);
   unsigned* tickets = reinterpret_cast<unsigned*>(ws);   // zeroed by scb_decode_attention_fused_init
-  float* part_m = reinterpret_cast<float*>(ws + 256);
+  float* part_m = reinterpret_cast<float*>(ws + 1024);
   float* part_l = part_m + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   float* part_o = part_l + (size_t)a->n_seqs * a->n_q_heads * a->n_splits;
   // score-buffer sizing: the caller may bound the live context (ctx_cap <= max_pos) so that short

@@ -36,7 +36,7 @@ class LlavaQwenConfig:
     mm_use_im_patch_token: bool = False
     tokenizer_model_max_length: Optional[int] = None
     max_context: int = 16384
-    max_batch: int = 16           # memory captions / summaries decoded together, one weight pass per step
+    max_batch: int = 32           # memory captions / summaries decoded together, one weight pass per step
 
     @property
     def hidden_size(self) -> int:
@@ -166,7 +166,7 @@ class LlavaQwenForCausalLM:
         decode step streams the weights once for all of them."""
         out: List[Optional[torch.Tensor]] = [None] * len(requests)
         n_batches = -(-len(requests) // self.llm.max_batch)
-        B = -(-len(requests) // n_batches) if requests else 1          # even batches: 25 -> 13 + 12
+        B = -(-len(requests) // n_batches) if requests else 1          # even batches: 40 -> 20 + 20
         for i in range(0, len(requests), B):
             embeds, budgets = [], []
             for ids, img, max_new in requests[i:i + B]:

@@ -45,8 +45,8 @@ class Qwen2Engine:
         self.max_ctx = max_ctx
         self.decode_splits = decode_splits
         self.max_batch = max_batch
-        if max_batch < 1 or max_batch > 16:
-            raise ValueError('max_batch must be in 1..16 (rows of the decode GEMV)')
+        if max_batch < 1 or max_batch > 32:
+            raise ValueError('max_batch must be in 1..32 (sequences decoded in lock-step)')
         c = cfg
         if c.head_dim not in (64, 128):
             raise ValueError(f"head_dim {c.head_dim} unsupported (64 or 128)")
@@ -101,6 +101,7 @@ class Qwen2Engine:
                                                              c.num_key_value_heads, hd, decode_splits, n_seqs=B)
         self._graphs = {}
         self.graph_replays = 0
+        self.graph_launches = 0      # kernels launched through graph replays (launch_count() only sees eager calls)
         self.profile: Optional[list] = None   # bench.py: (start event, end event, steps, bytes) per decode loop
 
     # ---------------------------------------------------------------- weights / work accounting
@@ -220,8 +221,9 @@ class Qwen2Engine:
             ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R],
                      counters=self.state.view(-1))
 
-    def launches_per_decode_step(self) -> int:
-        return 1 + self.cfg.num_hidden_layers * 5 + 1
+    def launches_per_decode_step(self, R: int = 1) -> int:
+        # <= 8 rows: gather+norm, 5 per layer, lm_head with fused arg-max; wider: split-K GEMM + reduce pairs
+        return 1 + self.cfg.num_hidden_layers * (8 if R > 8 else 5) + (2 if R > 8 else 1)
 
     def _ctx_bucket(self, need: int) -> int:
         """Context capacity class of a decode graph (power of two, >= 2048, <= max_ctx)."""
@@ -280,10 +282,18 @@ class Qwen2Engine:
                     self._ensure_graph(r, cap)                          # before prefill (see _ensure_graph)
             self.reset()
             lens = []
+            pf0 = pf1 = None
+            if self.profile is not None:
+                pf0, pf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pf0.record()
             for s_, i in enumerate(order):
                 logits = self.prefill(inputs_embeds_list[i], slot=s_)
                 ops.argmax_rows(logits, out=self.next_id[s_:s_ + 1])
                 lens.append(self.ctx_lens[s_])
+            if pf0 is not None:
+                pf1.record()
+                self.profile.append({"kind": "prefill", "events": (pf0, pf1), "tokens": sum(lens), "rows": n,
+                                     "flops": sum(self.prefill_flops(t) for t in lens)})
             st = torch.zeros((2, self.max_batch), dtype=torch.int32)
             st[0, :n] = torch.tensor(lens, dtype=torch.int32)
             st[1, :n] = st[0, :n] + 1
@@ -313,13 +323,15 @@ class Qwen2Engine:
                 if use_graph:
                     self._graphs[(Rn, cap)].replay()
                     self.graph_replays += 1
+                    self.graph_launches += self.launches_per_decode_step(Rn)
                 else:
                     self._decode_step_launches(Rn, cap)
                 prof_steps += 1
                 prof_bytes += self.weight_bytes() + sum(self.kv_bytes_per_token(lens[s_] + step) for s_ in range(Rn))
             if ev0 is not None:
                 ev1.record()
-                self.profile.append({"events": (ev0, ev1), "steps": prof_steps, "rows": n, "bytes": prof_bytes})
+                self.profile.append({"kind": "decode", "events": (ev0, ev1), "steps": prof_steps, "rows": n,
+                                     "bytes": prof_bytes})
             rows = out[:n_steps].t().contiguous()
             host = rows.tolist() if eos else None
             results: List[Optional[torch.Tensor]] = [None] * n

@@ -154,3 +154,21 @@ def test_mixed_budget_requests_equal_sequential(cuda, golden_dir):
     assert torch.equal(bat[1], seq[0])
     for got, want in zip([bat[0], bat[2], bat[3]], seq[1:]):
         assert torch.equal(got, want)
+
+
+def test_wide_batch_generation_equals_sequential(cuda, golden_dir):
+    """More than 8 sequences in lock-step take the tcgen05 path (K-sliced GEMMs + ordered reduce, batched
+    decode attention over 20 caches): every row still gets the ids of its one-at-a-time run."""
+    g, W, model = _tiny(golden_dir, cuda)
+    torch.manual_seed(11)
+    ids = torch.from_numpy(g["prompt_ids"])
+    embs = [(torch.randn(5 + 3 * i, 256) * 0.5).half().to(cuda) for i in range(20)]
+    seq = [model.generate_with_image_embedding(ids, image_embeddings=[e], do_sample=False, max_new_tokens=8)
+           for e in embs]
+    budgets = [8] * 18 + [5, 3]
+    reqs = [(ids, [e], b) for e, b in zip(embs, budgets)]
+    bat = model.generate_requests(reqs, modalities=["video"])
+    assert len(bat) == 20
+    for a, b, n in zip(seq, bat, budgets):
+        assert b.shape == (1, n)
+        assert torch.equal(a[:, :n], b)

@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--caption-tokens", type=int, default=128)
     ap.add_argument("--answer-tokens", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--text-encoder", default="bert", choices=["bert", "hash"],
+                    help="retrieval text embedder: BERT-large-shaped encoder on the GPU, or synthetic hash vectors")
     return ap.parse_args()
 
 
@@ -147,7 +149,8 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
         embs = [M_embed(sess, node) for node in sess.long_memory_tree]
         packed = pack_memory_embeddings(embs, 16, 1024, device)
         index, owner, local = live_rows(gather_memory_embeddings(packed))
-        q = sess.embedding_model(sess.embedding_tokenizer, QUESTION)
+        from streamchat_b200 import memory as M
+        q = M.embed_text(sess.embedding_model, sess.embedding_tokenizer, QUESTION)
         scores, idx = ops.cosine_topk(index, q, k=1)
         sess.global_best = (scores, owner[idx[0, 0]], local[idx[0, 0]])
     with _stage("answer"):
@@ -184,14 +187,23 @@ def ours(args):
     tokenizer, model, _, _ = load_pretrained_model(args.model, None, "llava_qwen", device_map=str(device),
                                                    overwrite_config=None if tiny else {"max_context": 32768})
     S = model.config.vision.image_size
-    embedder = HashTextEmbedder(1024, device)
+    if args.text_encoder == "bert" and not tiny:
+        # retrieval text encoder on the GPU (BERT-large shape, random init); texts are tokenised
+        # by the word-hash stand-in tokenizer over the BERT vocabulary
+        from streamchat_b200.longva.model.builder import ByteTokenizer
+        from streamchat_b200.text_encoder import BertConfig, BertTextEncoder, random_bert_weights
+        bcfg = BertConfig()
+        embedder = BertTextEncoder(random_bert_weights(bcfg, device, seed=7), bcfg, device)
+        embed_tok = ByteTokenizer(bcfg.vocab_size)
+    else:
+        embedder, embed_tok = HashTextEmbedder(1024, device), None
     cfg = StreamConfig(answer_tokens=args.answer_tokens)
     import streamchat_b200.memory as M
     M.CAPTION_TOKENS = args.caption_tokens
 
     def factory():
         np.random.seed(1234)                 # forgetting-curve sampling uses the global numpy RNG (H1)
-        return StreamingSession(model, tokenizer, embedder, None, None, cfg)
+        return StreamingSession(model, tokenizer, embedder, embed_tok, None, cfg)
 
     g = torch.Generator(device=device).manual_seed(1000 + rank)
     frames_dev = torch.randn((n_frames, 3, S, S), generator=g, device=device, dtype=torch.float16)
@@ -262,12 +274,20 @@ def ours(args):
         breakdown["llm_decode_rows"] = {str(r): sum(p["steps"] for p in dec if p["rows"] == r) // args.steps
                                         for r in sorted({p["rows"] for p in dec})}
     roofline = None
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_decode_traffic.json")
+    if os.path.exists(tpath):      # DRAM bytes of one decode step (1 sequence, ctx 5800) from the ncu capture named there
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = {"bytes_per_decode_step": tj["dram_read_bytes"] + tj["dram_write_bytes"],
+                   "algorithmic_bytes_same_step": tj["algorithmic_bytes"], "rows": tj["rows"], "ctx": tj["ctx"],
+                   "source": "profiles/r01_decode_traffic.json"}
     if dec_steps:
         achieved = dec_bytes / (dec_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "decode step = one CUDA graph: gemv_mma_kernel x113 + decode_attn_fused_kernel x28 (<= 8 rows), "
                               "linear_tcgen05 split-K + reduce for wider batches; bytes = weights + live KV per step",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": None,
+                    "peak_source": peak_src, "traffic": traffic,
                     "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,
                     "share_of_step_time": dec_ms / (ms if ms else 1)}
 
@@ -280,6 +300,8 @@ def ours(args):
                                f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)"
                                if not tiny else f"tiny smoke stream: {n_frames} frames/rank",
                    "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_per_rank": n_frames,
+                   "text_encoder": ("BERT-large shape on the GPU (random init), node embeddings cached"
+                                    if (args.text_encoder == "bert" and not tiny) else "synthetic hash vectors"),
                    "sharding": "frames sharded by rank; one NCCL all-gather of memory embeddings" if world > 1 else "single rank",
                    "l2": "inputs larger than L2 (677 MB frames + 15 GB weights per step); no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

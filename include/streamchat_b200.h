@@ -186,6 +186,33 @@ int scb_vit_embed_layernorm(const void* patch_embeds, int64_t ld_patch, const vo
                             int32_t n_img, int32_t tokens_per_img, int32_t dim, void* out,
                             int64_t ld_out, void* stream);
 
+/* ---- frame ingest (a-V1): `process_images` utiles.py:71-87 = CLIPImageProcessor.preprocess on the
+ * BGR->RGB-swapped cv2 frame (inference_streaming_longva_v2.py:507-511).  Pillow's 8-bit bicubic resample is
+ * two passes of fixed-point convolutions (libImaging/Resample.c: 22 fractional bits, every pass rounded to
+ * uint8); bounds[o] = (first input index, tap count), coeffs[o][0..ksize) int32, both for the output range
+ * that survives the centre crop.
+ * Horizontal pass: src uint8 [n, rows, W, 3] (strides in bytes) -> dst uint8 [n, rows, out_w, 3]. */
+int scb_resample_h_u8(const uint8_t* src, int64_t n_img, int64_t img_stride, int64_t row_stride, int32_t rows,
+                      const int32_t* bounds, const int32_t* coeffs, int32_t ksize, int32_t out_w, uint8_t* dst,
+                      void* stream);
+
+/* Vertical pass (bounds/coeffs NULL: no resample, rows start at row_offset) + crop + value table + CHW store:
+ * out[n, c, y, x] = lut[c][ pixel(n, y, x + x_offset)[swap_rb ? 2-c : c] ], lut float [3,256] holding
+ * ((v * 1/255) - mean_c) / std_c; out fp16 or fp32 [n, 3, out_size, out_size]. */
+int scb_resample_v_normalize(const uint8_t* src, int64_t n_img, int64_t img_stride, int64_t row_stride,
+                             int32_t x_offset, const int32_t* bounds, const int32_t* coeffs, int32_t ksize,
+                             int32_t row_offset, int32_t out_size, const float* lut, int32_t swap_rb, void* out,
+                             int32_t out_dtype, void* stream);
+
+/* BertEmbeddings.forward of the retrieval text encoder (the reference embeds the query and every node text
+ * with `model(**ids).last_hidden_state[:, 0]`, utiles.py:704-708,723-726,757-760; HF modeling_bert.py
+ * BertEmbeddings): row r = LayerNorm(word[ids[r]] + token_type[0] + position[position_ids[r]]).
+ * ids / position_ids are device int64 arrays; tables fp16; out fp16 [n_tokens, dim]. */
+int scb_text_embed_layernorm(const int64_t* ids, const int64_t* position_ids, int64_t n_tokens,
+                             const void* word_embeddings, const void* position_embeddings,
+                             const void* token_type_row, const void* gamma, const void* beta, float eps,
+                             int32_t dim, void* out, int64_t ld_out, void* stream);
+
 /* SpatialPool average, stride 2 (longva/model/multimodal_resampler/spatial_pool.py:23-32):
  * in rows [n*img_stride_rows + tok_offset + y*grid + x] -> out rows [n*(grid/2)^2 + ...]. */
 int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows, int32_t tok_offset,

@@ -132,6 +132,10 @@ SYMBOLS = {
     "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
     "scb_rmsnorm": (C.c_int, [_vp, _i64, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
     "scb_vit_embed_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _f, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "scb_resample_h_u8": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "scb_resample_v_normalize": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp,
+                                           _i32, _vp]),
+    "scb_text_embed_layernorm": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _i32, _vp, _i64, _vp]),
     "scb_avgpool2x2_tokens": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "scb_silu_mul": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _vp]),
     "scb_rope_append": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _f, _vp, _vp, _vp, _i64, _vp]),

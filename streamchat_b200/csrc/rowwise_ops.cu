@@ -384,6 +384,68 @@ rope_append_vec_kernel(__half* __restrict__ qkv, long long ld_qkv, int n_q, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// BERT embeddings (modeling_bert.py BertEmbeddings.forward): row r = LayerNorm(word[ids[r]] +
+// position[pos[r]] + token_type[0]), sums and statistics in fp32.  One block per token.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNormThreads)
+text_embed_layernorm_kernel(const long long* __restrict__ ids, const long long* __restrict__ pos,
+                            const __half* __restrict__ word, const __half* __restrict__ pos_tab,
+                            const __half* __restrict__ type_row, const __half* __restrict__ gamma,
+                            const __half* __restrict__ beta, float eps, int D, __half* __restrict__ out,
+                            long long ld_out) {
+  __shared__ float red[kNormThreads / 32];
+  const long long row = blockIdx.x;
+  const __half* w = word + ids[row] * D;
+  const __half* pp = pos_tab + pos[row] * D;
+  const int nvec = D >> 3;
+  float v[kNormMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      float a[8], b[8], t[8];
+      unpack8(*reinterpret_cast<const uint4*>(w + i * 8), a);
+      unpack8(*reinterpret_cast<const uint4*>(pp + i * 8), b);
+      unpack8(*reinterpret_cast<const uint4*>(type_row + i * 8), t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[c][e] = a[e] + t[e] + b[e];   // BertEmbeddings order: (word + token_type) + position
+        s += v[c][e];
+      }
+    }
+  }
+  s = block_sum(s, red);
+  const float mean = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[c][e] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  q = block_sum(q, red);
+  const float rstd = rsqrtf(q / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c) {
+    const int i = c * kNormThreads + threadIdx.x;
+    if (i < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + i * 8), g);
+      unpack8(*reinterpret_cast<const uint4*>(beta + i * 8), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * g[e] + b[e];
+      *reinterpret_cast<uint4*>(out + row * ld_out + i * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Embedding gather: out[r] = table[ids[r]]  (ids < 0 -> zeros)
 // ------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const __half* __restrict__ table, const long long* __restrict__ ids,
@@ -704,6 +766,26 @@ int scb_vit_embed_layernorm(const void* patch_embeds, int64_t ld_patch, const vo
               "scb_vit_embed_layernorm: bad token geometry");
   return norm_common(2, patch_embeds, ld_patch, gamma, beta, eps, (int64_t)n_img * tokens_per_img, dim,
                      out, ld_out, cls_embedding, pos_embedding, tokens_per_img, stream);
+}
+
+int scb_text_embed_layernorm(const int64_t* ids, const int64_t* position_ids, int64_t n_tokens,
+                             const void* word_embeddings, const void* position_embeddings,
+                             const void* token_type_row, const void* gamma, const void* beta, float eps,
+                             int32_t dim, void* out, int64_t ld_out, void* stream) {
+  SCB_REQUIRE(ids && position_ids && word_embeddings && position_embeddings && token_type_row && gamma &&
+                  beta && out && n_tokens >= 1,
+              SCB_ERR_INVALID_ARG, "scb_text_embed_layernorm: NULL buffer / no tokens");
+  SCB_REQUIRE(dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks && ld_out % 8 == 0 &&
+                  aligned16(word_embeddings) && aligned16(position_embeddings) && aligned16(token_type_row) &&
+                  aligned16(gamma) && aligned16(beta) && aligned16(out),
+              SCB_ERR_INVALID_ARG, "scb_text_embed_layernorm: dim %d / alignment unsupported", dim);
+  text_embed_layernorm_kernel<<<(unsigned)n_tokens, kNormThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), reinterpret_cast<const long long*>(position_ids),
+      reinterpret_cast<const __half*>(word_embeddings), reinterpret_cast<const __half*>(position_embeddings),
+      reinterpret_cast<const __half*>(token_type_row), reinterpret_cast<const __half*>(gamma),
+      reinterpret_cast<const __half*>(beta), eps, (int)dim, reinterpret_cast<__half*>(out), (long long)ld_out);
+  SCB_LAUNCH_OK("text_embed_layernorm_kernel");
+  return SCB_OK;
 }
 
 int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows, int32_t tok_offset,

@@ -267,6 +267,11 @@ def _best_by_cosine(nodes: Sequence[MultimodalTreeNode], query_embedding: torch.
                     default):
     """Reference rule (utiles.py:719-742): best_sim starts at 0, strict '>' — first maximum wins,
     non-positive similarities never win.  One cosine_topk launch replaces the Python loop."""
+    missing = [n for n in nodes if n.text_embedding is None]
+    if len(missing) > 1 and hasattr(model, "encode_texts"):
+        # on-device encoder (text_encoder.BertTextEncoder): one packed forward for every uncached node text
+        for n, e in zip(missing, model.encode_texts(tokenizer, [n.text for n in missing])):
+            n.text_embedding = e
     index = torch.stack([_node_embedding(n, model, tokenizer) for n in nodes]).to(query_embedding.device)
     scores, idx = ops.cosine_topk(index, query_embedding, k=1)
     s, i = float(scores[0, 0]), int(idx[0, 0])

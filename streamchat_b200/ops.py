@@ -288,6 +288,20 @@ def vit_embed_layernorm(patch_embeds: torch.Tensor, cls: torch.Tensor, pos: torc
     return out
 
 
+def text_embed_layernorm(ids: torch.Tensor, position_ids: torch.Tensor, word: torch.Tensor, pos: torch.Tensor,
+                         token_type_row: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                         eps: float) -> torch.Tensor:
+    """BERT embeddings + LayerNorm for a packed token list: ids / position_ids int64 [n] -> [n, D] fp16."""
+    dev = _require_cuda(ids, position_ids, word, pos, token_type_row, gamma, beta)
+    if ids.dtype != torch.int64 or position_ids.dtype != torch.int64 or ids.shape != position_ids.shape:
+        raise ValueError("ids and position_ids must be int64 tensors of the same shape")
+    n, dim = ids.numel(), word.shape[1]
+    out = torch.empty((n, dim), dtype=torch.float16, device=dev)
+    _call("scb_text_embed_layernorm", dev, _ptr(ids), _ptr(position_ids), n, _ptr(word), _ptr(pos),
+          _ptr(token_type_row), _ptr(gamma), _ptr(beta), eps, dim, _ptr(out), out.stride(0))
+    return out
+
+
 def avgpool2x2_tokens(x: torch.Tensor, n_img: int, tokens_per_img: int, tok_offset: int, grid: int) -> torch.Tensor:
     """x [n_img*tokens_per_img, D] -> [n_img*(grid/2)^2, D]."""
     dev = _require_cuda(x)

@@ -125,6 +125,19 @@ def _stage(name):
     return _S()
 
 
+def workload_config(args, n_frames: int, tiny: bool, world: int) -> dict:
+    """The `config` object of the JSON line — shared by both arms so the driver compares like with like."""
+    return {"workload": f"stream: {n_frames} frames/rank 336x336 in segments of {args.segment}, chunk 40, "
+                        f"{args.caption_tokens}-token greedy caption per chunk, tree merge every 10 chunks "
+                        f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)"
+                        if not tiny else f"tiny smoke stream: {n_frames} frames/rank",
+            "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_per_rank": n_frames,
+            "text_encoder": ("BERT-large shape on the GPU (random init), node embeddings cached"
+                             if (args.text_encoder == "bert" and not tiny) else "synthetic hash vectors"),
+            "sharding": "frames sharded by rank; one NCCL all-gather of memory embeddings" if world > 1 else "single rank",
+            "l2": "inputs larger than L2 (677 MB frames + 15 GB weights per step); no explicit flush"}
+
+
 def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, device, e2e: bool):
     """One step.  Returns (answer ids tensor, h2d bytes, d2h bytes)."""
     import torch.distributed as dist
@@ -145,10 +158,10 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
     if world > 1:
         # the one exchange step (§8e): all-gather the per-rank memory embeddings (root-node text
         # embeddings) so every rank's retrieval sees the global index; top-k is computed redundantly
-        from streamchat_b200.distributed import gather_memory_embeddings, live_rows, pack_memory_embeddings
-        embs = [M_embed(sess, node) for node in sess.long_memory_tree]
-        packed = pack_memory_embeddings(embs, 16, 1024, device)
-        index, owner, local = live_rows(gather_memory_embeddings(packed))
+        from streamchat_b200.distributed import exchange_memory_index
+        with _stage("exchange"):
+            index, owner, local = exchange_memory_index(sess.long_memory_tree, sess.embedding_model,
+                                                        sess.embedding_tokenizer, device, max_rows=16)
         from streamchat_b200 import memory as M
         q = M.embed_text(sess.embedding_model, sess.embedding_tokenizer, QUESTION)
         scores, idx = ops.cosine_topk(index, q, k=1)
@@ -159,11 +172,6 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
         ids_host = ids.cpu()                                                  # device -> host read of the result
         d2h += ids_host.numel() * ids_host.element_size()
     return ids, h2d, d2h
-
-
-def M_embed(sess, node):
-    from streamchat_b200 import memory as M
-    return M._node_embedding(node, sess.embedding_model, sess.embedding_tokenizer)
 
 
 def ours(args):
@@ -295,15 +303,7 @@ def ours(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-        "config": {"workload": f"stream: {n_frames} frames/rank 336x336 in segments of {args.segment}, chunk 40, "
-                               f"{args.caption_tokens}-token greedy caption per chunk, tree merge every 10 chunks "
-                               f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)"
-                               if not tiny else f"tiny smoke stream: {n_frames} frames/rank",
-                   "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_per_rank": n_frames,
-                   "text_encoder": ("BERT-large shape on the GPU (random init), node embeddings cached"
-                                    if (args.text_encoder == "bert" and not tiny) else "synthetic hash vectors"),
-                   "sharding": "frames sharded by rank; one NCCL all-gather of memory embeddings" if world > 1 else "single rank",
-                   "l2": "inputs larger than L2 (677 MB frames + 15 GB weights per step); no explicit flush"},
+        "config": workload_config(args, n_frames, tiny, world),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "impl": "ours",
@@ -418,7 +418,7 @@ def reference(args):
         "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_frames / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"stream: {n_frames} frames (bounded CPU sample, extrapolated)", "model": args.model},
+        "config": workload_config(args, n_frames, tiny, 1),
         "cpu_baseline": best,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -50,3 +50,19 @@ def live_rows(gathered: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch
     world = dist.get_world_size() if dist.is_initialized() else 1
     per = gathered.shape[0] // world
     return gathered[rows, :dim].contiguous(), rows // per, rows % per
+
+
+def exchange_memory_index(tree, embedding_model, embedding_tokenizer, device, max_rows: int = 64, group=None):
+    """The ONE exchange step of the sharded stream (§8e): every rank embeds the root nodes of its own
+    memory tree (pending captions / summaries are generated first, in lock-step batches — never one
+    node at a time — and all texts go through one packed encoder forward), then a single all-gather
+    gives every rank the global index.  Returns (index [n_live, D] fp32, owner rank, local row)."""
+    from . import memory as M
+    nodes = list(tree or [])[:max_rows]
+    if nodes:
+        embs = M.node_embeddings(nodes, embedding_model, embedding_tokenizer)
+        dim = embs.shape[1]
+    else:
+        embs, dim = [], getattr(embedding_model, "dim", 1024)
+    packed = pack_memory_embeddings(list(embs), max_rows, dim, device)
+    return live_rows(gather_memory_embeddings(packed, group))

@@ -263,16 +263,23 @@ def _node_embedding(node, model, tokenizer) -> torch.Tensor:
     return node.text_embedding
 
 
+def node_embeddings(nodes: Sequence[MultimodalTreeNode], model, tokenizer) -> torch.Tensor:
+    """[len(nodes), D] text embeddings of `nodes`, cached on the nodes.  Pending texts are generated first
+    in lock-step batches (never one node at a time), then every uncached text goes through ONE packed
+    forward of the on-device encoder (text_encoder.BertTextEncoder.encode_texts)."""
+    resolve_pending(list(nodes))
+    missing = [n for n in nodes if n.text_embedding is None]
+    if len(missing) > 1 and hasattr(model, "encode_texts"):
+        for n, e in zip(missing, model.encode_texts(tokenizer, [n.text for n in missing])):
+            n.text_embedding = e
+    return torch.stack([_node_embedding(n, model, tokenizer) for n in nodes])
+
+
 def _best_by_cosine(nodes: Sequence[MultimodalTreeNode], query_embedding: torch.Tensor, model, tokenizer,
                     default):
     """Reference rule (utiles.py:719-742): best_sim starts at 0, strict '>' — first maximum wins,
     non-positive similarities never win.  One cosine_topk launch replaces the Python loop."""
-    missing = [n for n in nodes if n.text_embedding is None]
-    if len(missing) > 1 and hasattr(model, "encode_texts"):
-        # on-device encoder (text_encoder.BertTextEncoder): one packed forward for every uncached node text
-        for n, e in zip(missing, model.encode_texts(tokenizer, [n.text for n in missing])):
-            n.text_embedding = e
-    index = torch.stack([_node_embedding(n, model, tokenizer) for n in nodes]).to(query_embedding.device)
+    index = node_embeddings(nodes, model, tokenizer).to(query_embedding.device)
     scores, idx = ops.cosine_topk(index, query_embedding, k=1)
     s, i = float(scores[0, 0]), int(idx[0, 0])
     if VERBOSE:

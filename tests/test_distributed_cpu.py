@@ -41,6 +41,53 @@ def test_shard_and_gather_world2():
     assert own0 == [0, 0, 0, 1, 1, 1, 1] and loc0 == [0, 1, 2, 0, 1, 2, 3]
 
 
+def _exchange_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from streamchat_b200 import memory as M
+    from streamchat_b200.distributed import exchange_memory_index
+    from streamchat_b200.stream import HashTextEmbedder
+    emb = HashTextEmbedder(32, "cpu")
+    calls = []
+
+    class Summ:                       # records how the pending texts were generated (one batch, not per node)
+        device = torch.device("cpu")
+
+        def generate_requests(self, reqs, modalities=None):
+            calls.append(len(reqs))
+            return [torch.tensor([[rank, i]]) for i in range(len(reqs))]
+
+    class Tok:
+        def batch_decode(self, ids, skip_special_tokens=True):
+            return ["rank%d text%d" % tuple(ids[0].tolist())]
+
+    nodes = []
+    for i in range(2 + rank):
+        n = M.MultimodalTreeNode(torch.zeros(1, 4, 8), None)
+        n._pending = {"kind": "caption", "summarizer": Summ(), "tokenizer": Tok(), "input_ids": torch.zeros(1, 3),
+                      "features": torch.zeros(4, 8), "max_new": 4}
+        nodes.append(n)
+    index, owner, local = exchange_memory_index(nodes, emb, None, "cpu", max_rows=4)
+    expect = torch.stack([emb(None, f"rank{r} text{i}") for r in range(world) for i in range(2 + r)])
+    ret[rank] = (calls, torch.equal(index, expect), owner.tolist(), local.tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_memory_index_world2():
+    """Pending texts are generated in ONE lock-step batch per rank before the all-gather, and every rank ends
+    up with the same global index in rank order."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret[0][0] == [2] and ret[1][0] == [3]
+    assert ret[0][1] and ret[1][1]
+    assert ret[0][2] == ret[1][2] == [0, 0, 1, 1, 1]
+    assert ret[0][3] == ret[1][3] == [0, 1, 0, 1, 2]
+
+
 def test_shard_range_properties():
     from streamchat_b200.distributed import shard_range
     for n in (0, 1, 7, 1000, 1001):

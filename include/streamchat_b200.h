@@ -388,6 +388,69 @@ size_t scb_decode_attention_fused_workspace_bytes(int32_t n_seqs, int32_t n_q_he
                                                   int32_t n_splits);
 int scb_decode_attention_fused(const scb_decode_attention_fused_args* a, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * scb_qwen2_decoder_* — ONE persistent kernel per cached decode step (1..4 sequences in
+ * lock-step).  Replaces the whole per-token body of Qwen2ForCausalLM.generate reached from
+ * longva/model/language_model/llava_qwen.py:155 (transformers modeling_qwen2.py:269-311 per
+ * layer, :474-475 lm_head on the last position, greedy arg-max of generation/utils.py): token
+ * embedding gather, per layer RMSNorm -> qkv (+bias) -> RoPE + KV append + attention over the
+ * cache -> o_proj (+residual) -> RMSNorm -> gate|up (SiLU gate) -> down (+residual), final
+ * RMSNorm, lm_head, arg-max (lowest index wins), position/length bookkeeping.
+ *
+ * One CTA per SM stays resident for the step.  A producer warp streams every weight matrix
+ * through a shared-memory ring with TMA (16 rows x 512 k tiles, 128-byte swizzle) and runs ahead
+ * of the layer dependencies — weights depend on nothing — so HBM keeps streaming across the
+ * grid-wide barriers that separate the stages; eight consumer warps feed the tiles to
+ * mma.sync.m16n8k16 (weights = A operand, activations = B operand from shared memory) and own the
+ * attention stage.  HBM-bound: algorithmic bytes per step = all weights + the live KV cache.
+ *
+ * The handle owns device memory allocated at creation (tensor maps, per-layer pointer table,
+ * a few MB of workspace); weights and caches stay caller-owned and must outlive the handle.
+ * Weight layouts: PyTorch Linear [n, k] fp16, k contiguous, k % 64 == 0, n % 16 == 0;
+ * gu_w is the row-interleaved gate|up matrix [2*inter, hidden] (row 2i = gate_i, 2i+1 = up_i).
+ * ------------------------------------------------------------------------- */
+typedef struct scb_qwen2_decoder_desc {
+  int32_t n_layers, hidden, n_q_heads, n_kv_heads, head_dim, inter, vocab;
+  int32_t max_seqs;          /* cache slots: k/v caches are [max_seqs, n_kv_heads, max_ctx, head_dim] */
+  int64_t max_ctx;
+  float rms_eps, rope_theta;
+  const float* inv_freq;     /* device [head_dim/2] fp32 or NULL -> theta^(-2i/hd) */
+  const void* embed;         /* device [vocab, hidden] fp16 */
+  const void* final_norm;    /* device [hidden] fp16 */
+  const void* lm_head;       /* device [vocab, hidden] fp16 */
+  /* HOST arrays of n_layers device pointers */
+  const void* const* qkv_w;  /* [ (n_q+2*n_kv)*hd, hidden ] */
+  const void* const* qkv_b;  /* [ (n_q+2*n_kv)*hd ] or NULL entries */
+  const void* const* o_w;    /* [ hidden, n_q*hd ] */
+  const void* const* gu_w;   /* [ 2*inter, hidden ] interleaved */
+  const void* const* down_w; /* [ hidden, inter ] */
+  const void* const* ln1;    /* [hidden] input RMSNorm weight */
+  const void* const* ln2;    /* [hidden] post-attention RMSNorm weight */
+  void* const* k_cache;
+  void* const* v_cache;
+} scb_qwen2_decoder_desc;
+
+typedef struct scb_qwen2_decode_step_args {
+  void* decoder;             /* handle from scb_qwen2_decoder_create */
+  int32_t rows;              /* 1..scb_qwen2_decoder_max_rows(): sequences decoding in lock-step (cache slots 0..rows-1) */
+  int32_t n_counters;
+  int64_t* next_id;          /* device [rows] in: token to feed, out: greedy next token */
+  const int32_t* kv_len;     /* device [rows]: context length INCLUDING the token being decoded */
+  int32_t* counters;         /* optional device ints incremented by one at the end of the step */
+  void* logits;              /* device [rows, ld_logits] fp16, written */
+  int64_t ld_logits;
+  int64_t ctx_cap;           /* upper bound of every kv_len (0 = max_ctx): sizes the score buffer */
+} scb_qwen2_decode_step_args;
+
+int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle);
+int scb_qwen2_decoder_destroy(void* handle);
+int scb_qwen2_decoder_max_rows(void);
+int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream);
+/* Debug aid: per-CTA clock64 stamps of the last step, 16 per layer (layer start, then after every
+ * prologue / stage / grid barrier).  The first call arms the recording and returns 0; later calls
+ * copy [n_sm][n_layers][16] int64 into host_out (capacity in elements) and return the count; -1 on error. */
+long long scb_qwen2_decoder_profile(void* decoder, long long* host_out, long long capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,26 @@ class DecodeAttentionFusedArgs(C.Structure):
     ]
 
 
+class Qwen2DecoderDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("hidden", C.c_int32), ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32),
+        ("head_dim", C.c_int32), ("inter", C.c_int32), ("vocab", C.c_int32), ("max_seqs", C.c_int32),
+        ("max_ctx", C.c_int64), ("rms_eps", C.c_float), ("rope_theta", C.c_float),
+        ("inv_freq", C.c_void_p), ("embed", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p),
+        ("qkv_w", C.POINTER(C.c_void_p)), ("qkv_b", C.POINTER(C.c_void_p)), ("o_w", C.POINTER(C.c_void_p)),
+        ("gu_w", C.POINTER(C.c_void_p)), ("down_w", C.POINTER(C.c_void_p)), ("ln1", C.POINTER(C.c_void_p)),
+        ("ln2", C.POINTER(C.c_void_p)), ("k_cache", C.POINTER(C.c_void_p)), ("v_cache", C.POINTER(C.c_void_p)),
+    ]
+
+
+class Qwen2DecodeStepArgs(C.Structure):
+    _fields_ = [
+        ("decoder", C.c_void_p), ("rows", C.c_int32), ("n_counters", C.c_int32),
+        ("next_id", C.c_void_p), ("kv_len", C.c_void_p), ("counters", C.c_void_p),
+        ("logits", C.c_void_p), ("ld_logits", C.c_int64), ("ctx_cap", C.c_int64),
+    ]
+
+
 PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
 
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -128,6 +148,11 @@ SYMBOLS = {
     "scb_decode_attention": (C.c_int, [C.POINTER(DecodeAttentionArgs), C.c_void_p]),
     "scb_decode_attention_fused_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i32]),
     "scb_decode_attention_fused": (C.c_int, [C.POINTER(DecodeAttentionFusedArgs), C.c_void_p]),
+    "scb_qwen2_decoder_create": (C.c_int, [C.POINTER(Qwen2DecoderDesc), C.POINTER(C.c_void_p)]),
+    "scb_qwen2_decoder_destroy": (C.c_int, [C.c_void_p]),
+    "scb_qwen2_decoder_max_rows": (C.c_int, []),
+    "scb_qwen2_decode_step": (C.c_int, [C.POINTER(Qwen2DecodeStepArgs), C.c_void_p]),
+    "scb_qwen2_decoder_profile": (C.c_longlong, [C.c_void_p, C.POINTER(C.c_longlong), C.c_longlong]),
     "scb_im2col_patch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp]),
     "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),
     "scb_rmsnorm": (C.c_int, [_vp, _i64, _vp, _f, _i64, _i32, _vp, _i64, _vp]),

@@ -1,0 +1,1233 @@
+// decode_mega.cu — one persistent kernel per cached decode step (scb_qwen2_decode_step).
+//
+// Replaces the per-token body of Qwen2ForCausalLM.generate reached from
+// longva/model/language_model/llava_qwen.py:155 (transformers modeling_qwen2.py:269-311 per layer,
+// :474-475 lm_head, greedy arg-max) for 1..4 sequences decoding in lock-step.  The step is
+// HBM-bound: every weight byte and the live KV cache are read once (14.4 GB at LongVA-7B shapes),
+// so the design goal is an HBM stream that never stops:
+//
+//   * one CTA per SM stays resident for the whole step (cooperative launch, 288 threads);
+//   * warp 8 is the producer: it walks the step's weight matrices in execution order and streams
+//     this CTA's share as 16-row x 512-k tiles (16 KB) into a shared-memory ring with TMA
+//     (3-D tensor map (64 k, row, k-block), 128-byte swizzle).  Weights depend on nothing, so the
+//     producer runs ahead of the layer dependencies and HBM keeps streaming while the consumers
+//     sit in a grid barrier or in the attention stage;
+//   * warps 0-7 are the consumers: warp w owns k-block w (64 k) of every tile and feeds it to
+//     mma.sync.m16n8k16 (weights = A operand read with conflict-free 16-byte shared loads thanks to a
+//     row permutation, activations = B operand from a shared-memory copy of the layer input); the
+//     k-reduction across warps happens once per 16-row tile in a fixed order (deterministic);
+//   * the stages of a layer (qkv | attention partials | attention combine | o_proj | gate|up | down)
+//     are separated by grid barriers (one atomic + one flag, consumers only).  Skinny matrices
+//     (o_proj, down_proj: 224 row tiles for 148 SMs) are cut along K so that every SM streams the
+//     same number of bytes; the two partial sums of a tile are added in a fixed order by the next
+//     stage's prologue, which also applies residual + RMSNorm (HF rounding points reproduced).
+//
+// Algorithmic bytes per step = sum of weight bytes + 2 * n_layers * n_kv * ctx * head_dim * 2 per row.
+#include "scb_common.cuh"
+#include <math.h>
+#include <mutex>
+#include <new>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int kCWarps = 8;                 // consumer warps
+constexpr int kCThreads = kCWarps * 32;    // 256
+constexpr int kMegaThreads = kCThreads + 32;
+constexpr int kUnitRows = 16;
+constexpr int kUnitK = 512;
+constexpr int kUnitBytes = kUnitRows * kUnitK * 2;   // 16 KB
+constexpr int kRMax = 4;
+constexpr int kMaxStages = 12;
+constexpr int kMaxSplits = 64;
+constexpr int kProfStamps = 16;
+
+struct MegaLayer {          // device-resident, one per layer
+  const __half* w[4];       // qkv, o, gate|up, down (for the L2 prefetch; the data path uses the tensor maps)
+  const __half* qkv_b;
+  const __half* ln1;
+  const __half* ln2;
+  __half* k_cache;
+  __half* v_cache;
+};
+
+struct StageShape {         // one weight matrix
+  int n_tiles;              // ceil(n / 16)
+  int chunks;               // ceil(k / 512)
+  int split;                // 1: units are (tile, chunk) pairs cut anywhere; 0: whole tiles per CTA
+  int n, k;
+};
+
+struct MegaParams {
+  const CUtensorMap* maps;  // [4 * n_layers + 1]: qkv, o, gu, down per layer, then lm_head
+  const MegaLayer* layers;
+  StageShape shp[5];        // qkv, o, gu, down, lm_head
+  int n_layers, H, n_q, n_kv, I, V, qkv_dim;
+  float eps, theta, scale_log2;
+  const float* inv_freq;
+  const __half* embed;
+  const __half* final_norm;
+  const __half* lm_head;
+  long long max_ctx, cache_seq_stride;
+  // per step
+  int R, per_max, n_splits, n_stage, act_ld;
+  long long* next_id;
+  const int* kv_len;
+  int* counters;
+  int n_counters;
+  __half* logits;
+  long long ld_logits;
+  // workspace (handle-owned)
+  __half *x_buf, *x2_buf, *qkv_buf, *attn_buf, *gu_buf;
+  float *part_o, *part_d;               // [2][kRMax][H]
+  float *att_m, *att_l, *att_o;         // [kRMax][n_q][n_splits] (+ [HD])
+  float* cand_val;                      // [grid][kRMax]
+  int* cand_idx;
+  unsigned* bar_flag;
+  unsigned long long* bar_count;
+  long long* prof;                      // optional [grid][n_layers][kProfStamps] clock64 stamps (debug)
+};
+
+SCB_DEVICE void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// fp16 value written by another CTA before the last grid barrier: read through L2
+SCB_DEVICE float ldcg_h(const __half* p) { return __half2float(__ldcg(p)); }
+
+// barrier among the 256 consumer threads only (the producer warp never joins)
+SCB_DEVICE void cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+SCB_DEVICE unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SCB_DEVICE void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid barrier for the consumer threads of every CTA.  count is monotonic (never reset): barrier number g
+// completes when count == g * gridDim.x; flag publishes the last completed g.  The grid size is fixed per
+// handle, so count == flag * gridDim.x holds between launches.  Release / acquire ride on the atomic and the
+// polling load (bar.sync makes them cumulative over the CTA's threads); data written before a barrier by
+// other CTAs is always read with ld.global.cg, so no L1 invalidation (gpu-scope fence) is needed.
+// (A per-CTA flag array polled by every CTA was measured 2.5x slower: 148 x 148 acquire loads per round.)
+SCB_DEVICE void grid_sync(const MegaParams& p, unsigned& gen) {
+  cbar();
+  if (threadIdx.x == 0) {
+    gen += 1;
+    unsigned long long old;
+    asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(p.bar_count) : "memory");
+    if (old + 1ull == (unsigned long long)gen * gridDim.x) {
+      st_release_u32(p.bar_flag, gen);
+    } else {
+      while ((int)(ld_acquire_u32(p.bar_flag) - gen) < 0) {
+      }
+    }
+  }
+  cbar();
+}
+
+struct Ring {
+  uint8_t* buf;
+  uint64_t* full;
+  uint64_t* empty;
+  int n_stage;
+  int flat;        // units of this CTA's flattened sequence consumed by earlier stages (slot = index % n_stage)
+};
+
+// this CTA's unit range of a stage
+SCB_DEVICE void unit_range(const StageShape& s, long long& u0, long long& u1) {
+  const long long G = gridDim.x, c = blockIdx.x;
+  if (s.split) {
+    const long long U = (long long)s.n_tiles * s.chunks;
+    u0 = c * U / G;
+    u1 = (c + 1) * U / G;
+  } else {
+    u0 = (c * s.n_tiles / G) * s.chunks;
+    u1 = ((c + 1) * s.n_tiles / G) * s.chunks;
+  }
+}
+
+SCB_DEVICE float block_sum_256(float v, float* red8) {   // consumers only; red8: 8 floats of scratch
+  v = warp_sum(v);
+  cbar();
+  if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5] = v;
+  cbar();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kCWarps; ++w) t += red8[w];
+  return t;
+}
+
+
+enum { ST_QKV = 0, ST_O = 1, ST_GU = 2, ST_DOWN = 3, ST_LM = 4 };
+
+// ------------------------------------------------------------------------------------------
+// One weight stage for the consumers: out-tile sums of act (shared, [R][act_ld] fp16) against this
+// CTA's units, flushed per 16-row tile.
+// ------------------------------------------------------------------------------------------
+struct LmBest {
+  float v;
+  int i;
+};
+
+SCB_DEVICE uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// A warp owns WHOLE units (unit f of the CTA's flattened sequence belongs to warp f mod 8): the
+// per-unit overhead (barrier wait, slot release, index math) is paid once per 16 KB instead of once per
+// 2 KB, which keeps the consumers off the issue-bound regime (the first version spent ~500 issue cycles per
+// unit and capped the stream at ~24 B/clk/SM).  The warps' partial tile sums meet in shared memory once
+// per tile, in warp order.
+template <int KIND>
+SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLayer* ly, Ring& ring,
+                          const __half* act, float* red, int& red_buf, LmBest& best) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int rho = (g >> 1) | ((g & 1) << 2);   // weight row (mod 8) fed to mma row g: keeps the 16-byte
+                                               // reads of a quarter-warp on 8 distinct swizzled chunks
+  long long u0l, u1l;
+  unit_range(s, u0l, u1l);
+  const int u0 = (int)u0l, u1 = (int)u1l;
+  const int R = p.R;
+  const uint32_t ring_s = smem_u32(ring.buf);
+  const uint32_t offa0 = (uint32_t)(rho * 128 + ((t ^ rho) << 4));          // k-step parity 0
+  const uint32_t offa1 = (uint32_t)(rho * 128 + (((4 + t) ^ rho) << 4));    // k-step parity 1
+  const uint32_t act_s = smem_u32(act) + (uint32_t)((g * p.act_ld + t * 8) * 2);
+  const bool b_live = g < R;
+  const int f0 = ring.flat;   // flattened index of unit u0
+  const int chunks = s.chunks;
+  int tile = u0 / chunks;
+  for (int ua = u0; ua < u1; ++tile) {
+    const int ub = min(u1, (tile + 1) * chunks);
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+    // A unit belongs to the warp given by its RING SLOT (slot & 7), so consecutive uses of a slot have the
+    // same owner: a warp never waits on a slot whose previous phase it has not consumed itself (an mbarrier
+    // parity wait is only sound one phase ahead).
+    int slot = (f0 + ua - u0) % ring.n_stage;
+    uint32_t parity = (uint32_t)((f0 + ua - u0) / ring.n_stage) & 1u;
+    for (int u = ua; u < ub; ++u, ++slot) {
+      if (slot == ring.n_stage) {
+        slot = 0;
+        parity ^= 1u;
+      }
+      if ((slot & 7) != warp) continue;
+      const int kbase = (u - tile * chunks) * kUnitK;
+      mbar_wait(&ring.full[slot], parity);
+      const uint32_t base = ring_s + (uint32_t)slot * kUnitBytes;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t off = (uint32_t)((j >> 1) * 2048) + ((j & 1) ? offa1 : offa0);
+        const uint4 a0 = lds128(base + off);
+        const uint4 a1 = lds128(base + off + 1024);
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        const int k = kbase + 32 * j;
+        if (b_live && k + t * 8 < s.k) b = lds128(act_s + (uint32_t)(k * 2));
+        mma16816(d0, a0.x, a1.x, a0.y, a1.y, b.x, b.y);
+        mma16816(d1, a0.z, a1.z, a0.w, a1.w, b.z, b.w);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ring.empty[slot]);
+    }
+    {
+      // ---- flush the tile: fixed-order sum over the 8 warps' partial sums
+      float* r = red + red_buf * (kCWarps * kUnitRows * kRMax);
+      if (t < 2) {
+        float* q = r + (warp * kUnitRows + rho) * kRMax + 2 * t;
+        q[0] = d0[0] + d1[0];
+        q[1] = d0[1] + d1[1];
+        q[8 * kRMax] = d0[2] + d1[2];
+        q[8 * kRMax + 1] = d0[3] + d1[3];
+      }
+      cbar();
+      red_buf ^= 1;
+      const bool has_first = tile * chunks >= u0;
+      const bool has_last = (tile + 1) * chunks <= u1;
+      if (KIND == ST_GU) {
+        // rows (2i, 2i+1) = (gate_i, up_i): out = fp16(silu(fp16 gate)) * fp16 up  (modeling_qwen2.py:41-48)
+        if (tid < 8 * kRMax) {
+          const int i = tid >> 2, n = tid & 3;
+          const int o = tile * 8 + i;
+          if (n < R && 2 * o + 1 < s.n) {
+            float sg = 0.f, su = 0.f;
+#pragma unroll
+            for (int w = 0; w < kCWarps; ++w) {
+              sg += r[(w * kUnitRows + 2 * i) * kRMax + n];
+              su += r[(w * kUnitRows + 2 * i + 1) * kRMax + n];
+            }
+            const float gt = __half2float(__float2half_rn(sg));
+            const float up = __half2float(__float2half_rn(su));
+            const float sl = __half2float(__float2half_rn(__fdividef(gt, 1.f + __expf(-gt))));
+            p.gu_buf[(size_t)n * p.I + o] = __float2half_rn(sl * up);
+          }
+        }
+      } else if (tid < kUnitRows * kRMax) {
+        const int row = tid >> 2, n = tid & 3;
+        const int o = tile * kUnitRows + row;
+        if (n < R && o < s.n) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kCWarps; ++w) v += r[(w * kUnitRows + row) * kRMax + n];
+          if (KIND == ST_QKV) {
+            if (ly->qkv_b) v += __half2float(ly->qkv_b[o]);
+            p.qkv_buf[(size_t)n * p.qkv_dim + o] = __float2half_rn(v);
+          } else if (KIND == ST_O || KIND == ST_DOWN) {
+            float* part = (KIND == ST_O) ? p.part_o : p.part_d;
+            const size_t slot_stride = (size_t)kRMax * p.H;
+            const size_t idx = (size_t)n * p.H + o;
+            if (has_first) {
+              part[idx] = v;
+              if (has_last) part[slot_stride + idx] = 0.f;
+            } else {
+              part[slot_stride + idx] = v;
+            }
+          } else {  // ST_LM
+            const __half hv = __float2half_rn(v);
+            p.logits[(size_t)n * p.ld_logits + o] = hv;
+            const float fv = __half2float(hv);   // the arg-max sees the stored (rounded) logits
+            if (fv > best.v || (fv == best.v && o < best.i)) {
+              best.v = fv;
+              best.i = o;
+            }
+          }
+        }
+      }
+    }
+    ua = ub;
+  }
+  ring.flat += u1 - u0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Prologues: build the stage's input rows in shared memory (act [R][act_ld] fp16).
+// ------------------------------------------------------------------------------------------
+// Pull this CTA's split of every live sequence's K and V rows of one layer into L2 ahead of the
+// attention stage (the addresses depend only on the context lengths).
+SCB_DEVICE void prefetch_kv_l2(const MegaParams& p, const MegaLayer* ly, int hk, int split, int head_dim) {
+  if (split >= p.n_splits) return;
+  for (int n = 0; n < p.R; ++n) {
+    const int kv_len = p.kv_len[n];
+    const int per = (kv_len + p.n_splits - 1) / p.n_splits;
+    const int begin = split * per, end = min(kv_len, begin + per);
+    if (end <= begin) continue;
+    const size_t off = (size_t)n * p.cache_seq_stride + ((size_t)hk * p.max_ctx + begin) * head_dim;
+    const long long bytes = (long long)(end - begin) * head_dim * 2;
+    const char* kp = reinterpret_cast<const char*>(ly->k_cache + off);
+    const char* vp = reinterpret_cast<const char*>(ly->v_cache + off);
+    for (long long o = (long long)threadIdx.x * 128; o < bytes; o += (long long)kCThreads * 128) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + o));
+    }
+  }
+}
+
+// x = fp16(res + p0 + p1) (or the embedding rows), optional copy-out by CTA 0, then
+// act = fp16(fp16(x * rstd) * gamma)  — RMSNorm in HF's order (modeling_qwen2.py:249-263).
+// Work items are (row, 8-element chunk) pairs spread over the 256 threads, four per thread per batch with
+// every global load of the batch issued before its first use (one L2 round trip per batch whatever R is),
+// and ONE block reduction for all rows' sums of squares.
+SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red, const __half* res,
+                              const float* part, const __half* embed_rows, __half* x_out,
+                              const __half* gamma, const MegaLayer* kv_layer = nullptr, int hk = 0, int split = 0,
+                              int head_dim = 0) {
+  constexpr int CHB = 4;                        // items per thread per batch
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, n_chunks = H >> 3, n_items = p.R * n_chunks;
+  const size_t slot_stride = (size_t)kRMax * H;
+  float ss[kRMax];
+#pragma unroll
+  for (int r = 0; r < kRMax; ++r) ss[r] = 0.f;
+  for (int i0 = 0; i0 < n_items; i0 += kCThreads * CHB) {
+    uint4 rr[CHB];
+    float4 q0[CHB][2], q1[CHB][2];
+#pragma unroll
+    for (int j = 0; j < CHB; ++j) {
+      const int i = min(i0 + j * kCThreads + tid, n_items - 1);   // clamped: loads stay unconditional (registers)
+      const int n = i / n_chunks, c = i - n * n_chunks;
+      if (embed_rows) {
+        rr[j] = *reinterpret_cast<const uint4*>(embed_rows + (size_t)p.next_id[n] * H + c * 8);
+        q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        rr[j] = __ldcg(reinterpret_cast<const uint4*>(res + (size_t)n * H + c * 8));
+        const float4* s0 = reinterpret_cast<const float4*>(part + (size_t)n * H + c * 8);
+        const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
+        q0[j][0] = __ldcg(s0); q0[j][1] = __ldcg(s0 + 1);
+        q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
+      }
+    }
+    // the attention stage's K / V rows start their trip to L2 behind this batch's loads
+    if (kv_layer && i0 == 0) prefetch_kv_l2(p, kv_layer, hk, split, head_dim);
+#pragma unroll
+    for (int j = 0; j < CHB; ++j) {
+      const int i = i0 + j * kCThreads + tid;
+      if (i < n_items) {
+        const int n = i / n_chunks, c = i - n * n_chunks;
+        float x[8];
+        const float2 r0 = h2_to_f2(rr[j].x), r1 = h2_to_f2(rr[j].y), r2 = h2_to_f2(rr[j].z), r3 = h2_to_f2(rr[j].w);
+        x[0] = r0.x; x[1] = r0.y; x[2] = r1.x; x[3] = r1.y; x[4] = r2.x; x[5] = r2.y; x[6] = r3.x; x[7] = r3.y;
+        if (!embed_rows) {
+          const float a0[8] = {q0[j][0].x, q0[j][0].y, q0[j][0].z, q0[j][0].w, q0[j][1].x, q0[j][1].y, q0[j][1].z, q0[j][1].w};
+          const float a1[8] = {q1[j][0].x, q1[j][0].y, q1[j][0].z, q1[j][0].w, q1[j][1].x, q1[j][1].y, q1[j][1].z, q1[j][1].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = __half2float(__float2half_rn((a0[e] + a1[e]) + x[e]));
+        }
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sq = fmaf(x[e], x[e], sq);
+#pragma unroll
+        for (int r = 0; r < kRMax; ++r) ss[r] += (r == n) ? sq : 0.f;
+        uint4 o;
+        o.x = f2_to_h2(x[0], x[1]); o.y = f2_to_h2(x[2], x[3]); o.z = f2_to_h2(x[4], x[5]); o.w = f2_to_h2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld + c * 8) = o;
+        if (x_out && blockIdx.x == 0) *reinterpret_cast<uint4*>(x_out + (size_t)n * H + c * 8) = o;
+      }
+    }
+  }
+  // gamma for this thread's first pass-2 items travels while the block reduces
+  constexpr int GP = 4;
+  uint4 gpre[GP];
+#pragma unroll
+  for (int j = 0; j < GP; ++j) {
+    const int i = min(tid + j * kCThreads, n_items - 1);
+    gpre[j] = *reinterpret_cast<const uint4*>(gamma + (i % n_chunks) * 8);
+  }
+  // one reduction for all rows (red: [kRMax][8 warps])
+#pragma unroll
+  for (int r = 0; r < kRMax; ++r) ss[r] = warp_sum(ss[r]);
+  cbar();
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < kRMax; ++r) red[r * kCWarps + warp] = ss[r];
+  }
+  cbar();
+  float rstd[kRMax];
+#pragma unroll
+  for (int r = 0; r < kRMax; ++r) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) tot += red[r * kCWarps + w];
+    rstd[r] = rsqrtf(tot / (float)H + p.eps);
+  }
+  auto pass2 = [&](int i, const uint4& g4) {
+    const int n = i / n_chunks, c = i - n * n_chunks;
+    __half* a = act + (size_t)n * p.act_ld + c * 8;
+    const uint4 xv = *reinterpret_cast<const uint4*>(a);
+    float rs = rstd[0];
+#pragma unroll
+    for (int r = 1; r < kRMax; ++r) rs = (r == n) ? rstd[r] : rs;
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 xf = h2_to_f2(xs[e]), gf = h2_to_f2(gs[e]);
+      o[e] = f2_to_h2(__half2float(__float2half_rn(xf.x * rs)) * gf.x, __half2float(__float2half_rn(xf.y * rs)) * gf.y);
+    }
+    *reinterpret_cast<uint4*>(a) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+#pragma unroll
+  for (int j = 0; j < GP; ++j) {
+    const int i = tid + j * kCThreads;
+    if (i < n_items) pass2(i, gpre[j]);
+  }
+  for (int i = tid + GP * kCThreads; i < n_items; i += kCThreads)
+    pass2(i, *reinterpret_cast<const uint4*>(gamma + (i % n_chunks) * 8));
+  cbar();
+}
+
+// act <- src rows ([R][len] fp16 in global, written by other CTAs before the last grid barrier);
+// five independent 16-byte L2 loads in flight per thread, rows flattened.
+SCB_DEVICE void prologue_copy(const MegaParams& p, __half* act, const __half* src, int len) {
+  constexpr int U = 5;
+  const int tid = threadIdx.x, n16 = len >> 3, n_items = p.R * n16;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  for (int i0 = 0; i0 < n_items; i0 += kCThreads * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = __ldcg(s4 + min(i0 + u * kCThreads + tid, n_items - 1));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kCThreads + tid;
+      if (i < n_items) {
+        const int n = i / n16, j = i - n * n16;
+        *reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld + j * 8) = v[u];
+      }
+    }
+  }
+  cbar();
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention stage 1: this CTA = (kv head, split).  RoPE of the new q / k (same fp16 rounding points
+// as rope_append), KV append by the split that owns the new position, split-KV attention of the
+// group's q heads on mma.sync (as decode_attn_fused_kernel), partial (m, l, o) to the workspace.
+// ------------------------------------------------------------------------------------------
+template <int HD, int G>
+SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint8_t* scratch, int hk, int split,
+                                  int seq) {
+  constexpr int HALF = HD / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_max = p.per_max, n_splits = p.n_splits;
+  __half* q_h = reinterpret_cast<__half*>(scratch);                    // [8][HD] fp16
+  float* cs_s = reinterpret_cast<float*>(scratch + 8 * HD * 2);          // [HALF]
+  float* sn_s = cs_s + HALF;                                             // [HALF]
+  float* m_s = sn_s + HALF;                                              // [8]
+  float* l_s = m_s + 8;                                                  // [8]
+  float* o_s = l_s + 8;                                                  // [8 warps][G][HD]
+  float* s_s = o_s + 8 * G * HD;                                         // [G][per_max]
+  const __half* qkv = p.qkv_buf + (size_t)seq * p.qkv_dim;
+  __half* k_cache = ly->k_cache + (size_t)seq * p.cache_seq_stride;
+  __half* v_cache = ly->v_cache + (size_t)seq * p.cache_seq_stride;
+  const long long max_pos = p.max_ctx;
+  const int kv_len = p.kv_len[seq];
+  const int pos = kv_len - 1;
+  const int per = (kv_len + n_splits - 1) / n_splits;
+  const int begin = split * per, end = min(kv_len, begin + per);
+  const int n_local = min(per_max, max(0, end - begin));
+
+  if (tid < HALF) {
+    const float f = p.inv_freq ? p.inv_freq[tid] : powf(p.theta, -(float)(2 * tid) / (float)HD);
+    const float ang = (float)pos * f;
+    cs_s[tid] = __half2float(__float2half_rn(cosf(ang)));
+    sn_s[tid] = __half2float(__float2half_rn(sinf(ang)));
+  }
+  cbar();
+  for (int idx = tid; idx < G * HALF; idx += kCThreads) {
+    const int h = idx / HALF, i = idx % HALF;
+    const float c = cs_s[i], sn = sn_s[i];
+    const __half* qp = qkv + (size_t)(hk * G + h) * HD;
+    const float x1 = ldcg_h(qp + i), x2 = ldcg_h(qp + i + HALF);
+    const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
+    const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
+    q_h[h * HD + i] = __float2half_rn(a1 + b1);
+    q_h[h * HD + i + HALF] = __float2half_rn(a2 + b2);
+  }
+  for (int idx = G * HD + tid; idx < 8 * HD; idx += kCThreads) q_h[idx] = __float2half_rn(0.f);
+  if (pos >= begin && pos < end) {
+    const __half* kp = qkv + (size_t)(p.n_q + hk) * HD;
+    const __half* vp = qkv + (size_t)(p.n_q + p.n_kv + hk) * HD;
+    __half* kc = k_cache + ((size_t)hk * max_pos + pos) * HD;
+    __half* vc = v_cache + ((size_t)hk * max_pos + pos) * HD;
+    for (int i = tid; i < HALF; i += kCThreads) {
+      const float c = cs_s[i], sn = sn_s[i];
+      const float x1 = ldcg_h(kp + i), x2 = ldcg_h(kp + i + HALF);
+      const float a1 = __half2float(__float2half_rn(x1 * c)), b1 = __half2float(__float2half_rn(-x2 * sn));
+      const float a2 = __half2float(__float2half_rn(x2 * c)), b2 = __half2float(__float2half_rn(x1 * sn));
+      kc[i] = __float2half_rn(a1 + b1);
+      kc[i + HALF] = __float2half_rn(a2 + b2);
+    }
+    for (int i = tid; i < HD; i += kCThreads)
+      vc[i] = __ldcg(vp + i);
+  }
+  cbar();   // q_h ready; the appended row is visible to this CTA (block-scope ordering)
+
+  // ---- scores: K rows are the A operand (M = positions, K = dims, N = the group's q heads)
+  {
+    constexpr int NC = HD / 32;
+    const int g = lane >> 2, t = lane & 3;
+    uint4 qf[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) qf[c] = *reinterpret_cast<const uint4*>(q_h + g * HD + c * 32 + t * 8);
+    const __half* kb = k_cache + ((size_t)hk * max_pos + begin) * HD + t * 8;
+    // two 128-position sweeps per iteration: all 16-byte loads of both are in flight before the first mma
+    for (int p0 = warp * 16; p0 < n_local; p0 += 256) {
+      uint4 k0[2][NC], k1[2][NC];
+      bool ok0[2], ok1[2];
+#pragma unroll
+      for (int sw = 0; sw < 2; ++sw) {
+        const int r0 = p0 + sw * 128 + g, r1 = r0 + 8;
+        ok0[sw] = r0 < n_local;
+        ok1[sw] = r1 < n_local;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          k0[sw][c] = ok0[sw] ? *reinterpret_cast<const uint4*>(kb + (size_t)r0 * HD + c * 32) : make_uint4(0, 0, 0, 0);
+          k1[sw][c] = ok1[sw] ? *reinterpret_cast<const uint4*>(kb + (size_t)r1 * HD + c * 32) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int sw = 0; sw < 2; ++sw) {
+        const int r0 = p0 + sw * 128 + g, r1 = r0 + 8;
+        float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          mma16816(d0, k0[sw][c].x, k1[sw][c].x, k0[sw][c].y, k1[sw][c].y, qf[c].x, qf[c].y);
+          mma16816(d1, k0[sw][c].z, k1[sw][c].z, k0[sw][c].w, k1[sw][c].w, qf[c].z, qf[c].w);
+        }
+        const int h0 = 2 * t;
+        if (h0 < G) {
+          if (ok0[sw]) s_s[h0 * per_max + r0] = (d0[0] + d1[0]) * p.scale_log2;
+          if (ok1[sw]) s_s[h0 * per_max + r1] = (d0[2] + d1[2]) * p.scale_log2;
+        }
+        if (h0 + 1 < G) {
+          if (ok0[sw]) s_s[(h0 + 1) * per_max + r0] = (d0[1] + d1[1]) * p.scale_log2;
+          if (ok1[sw]) s_s[(h0 + 1) * per_max + r1] = (d0[3] + d1[3]) * p.scale_log2;
+        }
+      }
+    }
+  }
+  cbar();
+  // ---- per-head softmax statistics (warp h)
+  if (warp < G) {
+    float mx = -INFINITY;
+    for (int pl = lane; pl < n_local; pl += 32) mx = fmaxf(mx, s_s[warp * per_max + pl]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int pl = lane; pl < n_local; pl += 32) {
+      const float e = exp2f(s_s[warp * per_max + pl] - mx);
+      s_s[warp * per_max + pl] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      m_s[warp] = mx;
+      l_s[warp] = sum;
+    }
+  }
+  cbar();
+  // ---- O^T = V^T · P^T: M = dims, K = positions, N = q heads (probabilities rounded to fp16)
+  {
+    constexpr int NH = HD / 64;
+    const int g = lane >> 2, t = lane & 3;
+    float acc[NH][4][4];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[hh][j][e] = 0.f;
+    const __half* vb = v_cache + ((size_t)hk * max_pos + begin) * HD + g * 8;
+    const float* er = s_s + (g < G ? g : 0) * per_max;
+    for (int p0 = warp * 16; p0 < n_local; p0 += 256) {
+      uint4 v[2][NH][4];
+#pragma unroll
+      for (int sw = 0; sw < 2; ++sw) {
+        const int pa = p0 + sw * 128 + 2 * t, pb = pa + 8;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          const __half* vp = vb + hh * 64;
+          v[sw][hh][0] = pa < n_local ? *reinterpret_cast<const uint4*>(vp + (size_t)pa * HD) : make_uint4(0, 0, 0, 0);
+          v[sw][hh][1] = pa + 1 < n_local ? *reinterpret_cast<const uint4*>(vp + (size_t)(pa + 1) * HD) : make_uint4(0, 0, 0, 0);
+          v[sw][hh][2] = pb < n_local ? *reinterpret_cast<const uint4*>(vp + (size_t)pb * HD) : make_uint4(0, 0, 0, 0);
+          v[sw][hh][3] = pb + 1 < n_local ? *reinterpret_cast<const uint4*>(vp + (size_t)(pb + 1) * HD) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int sw = 0; sw < 2; ++sw) {
+        const int pa = p0 + sw * 128 + 2 * t, pb = pa + 8;
+        const bool oka0 = pa < n_local, oka1 = pa + 1 < n_local, okb0 = pb < n_local, okb1 = pb + 1 < n_local;
+        float2 ea = make_float2(0.f, 0.f), eb = make_float2(0.f, 0.f);
+        if (g < G) {
+          if (oka0) ea = *reinterpret_cast<const float2*>(er + pa);
+          if (okb0) eb = *reinterpret_cast<const float2*>(er + pb);
+          if (!oka1) ea.y = 0.f;
+          if (!okb1) eb.y = 0.f;
+        }
+        const uint32_t b0 = f2_to_h2(ea.x, ea.y), b1 = f2_to_h2(eb.x, eb.y);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          const uint32_t w0[4] = {v[sw][hh][0].x, v[sw][hh][0].y, v[sw][hh][0].z, v[sw][hh][0].w};
+          const uint32_t w1[4] = {v[sw][hh][1].x, v[sw][hh][1].y, v[sw][hh][1].z, v[sw][hh][1].w};
+          const uint32_t w2[4] = {v[sw][hh][2].x, v[sw][hh][2].y, v[sw][hh][2].z, v[sw][hh][2].w};
+          const uint32_t w3[4] = {v[sw][hh][3].x, v[sw][hh][3].y, v[sw][hh][3].z, v[sw][hh][3].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma16816(acc[hh][j], __byte_perm(w0[j], w1[j], 0x5410), __byte_perm(w0[j], w1[j], 0x7632),
+                     __byte_perm(w2[j], w3[j], 0x5410), __byte_perm(w2[j], w3[j], 0x7632), b0, b1);
+        }
+      }
+    }
+    const int h0 = 2 * t;
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d0 = hh * 64 + g * 8 + 2 * j;
+        if (h0 < G) {
+          o_s[(warp * G + h0) * HD + d0] = acc[hh][j][0];
+          o_s[(warp * G + h0) * HD + d0 + 1] = acc[hh][j][2];
+        }
+        if (h0 + 1 < G) {
+          o_s[(warp * G + h0 + 1) * HD + d0] = acc[hh][j][1];
+          o_s[(warp * G + h0 + 1) * HD + d0 + 1] = acc[hh][j][3];
+        }
+      }
+  }
+  cbar();
+  for (int idx = tid; idx < G * HD; idx += kCThreads) {
+    const int h = idx / HD, d = idx % HD;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += o_s[(w * G + h) * HD + d];
+    const size_t pi = ((size_t)seq * p.n_q + hk * G + h) * n_splits + split;
+    p.att_o[pi * HD + d] = v;
+    if (d == 0) {
+      p.att_m[pi] = m_s[h];
+      p.att_l[pi] = l_s[h];
+    }
+  }
+  cbar();   // scratch reuse by the next sequence
+}
+
+// Attention stage 2: task = (sequence, q head, 32-dim slice): merge the splits' partials in split order.
+// 256 threads = 32 dims x 8 split groups; a thread's <= 8 partial loads are issued before the split
+// weights exist (they do not depend on them), so a task costs one L2 round trip.
+template <int HD>
+SCB_DEVICE void attention_combine(const MegaParams& p, uint8_t* scratch, int task) {
+  constexpr int QS = HD / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_splits = p.n_splits;
+  float* w_s = reinterpret_cast<float*>(scratch);    // [kMaxSplits]
+  float* inv_l = w_s + kMaxSplits;                   // [1]
+  float* acc_s = inv_l + 8;                          // [8][32]
+  const int head_task = task / QS, d = (task - head_task * QS) * 32 + lane;   // head_task = seq * n_q + head
+  const size_t base = (size_t)head_task * n_splits;
+  const float* po = p.att_o + base * HD + d;
+  float ov[kMaxSplits / kCWarps];
+#pragma unroll
+  for (int j = 0; j < kMaxSplits / kCWarps; ++j) {
+    const int sp = warp + j * kCWarps;
+    ov[j] = sp < n_splits ? __ldcg(po + (size_t)sp * HD) : 0.f;
+  }
+  if (warp == 0) {
+    float mm = -INFINITY;
+    float pm[kMaxSplits / 32], pl[kMaxSplits / 32];
+#pragma unroll
+    for (int j = 0; j < kMaxSplits / 32; ++j) {
+      const int sp = lane + j * 32;
+      pm[j] = sp < n_splits ? __ldcg(p.att_m + base + sp) : -INFINITY;
+      pl[j] = sp < n_splits ? __ldcg(p.att_l + base + sp) : 0.f;
+      mm = fmaxf(mm, pm[j]);
+    }
+    mm = warp_max(mm);
+    float ll = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxSplits / 32; ++j) {
+      const int sp = lane + j * 32;
+      const float scl = (pm[j] == -INFINITY) ? 0.f : exp2f(pm[j] - mm);
+      if (sp < n_splits) w_s[sp] = scl;
+      ll = fmaf(pl[j], scl, ll);
+    }
+    ll = warp_sum(ll);
+    if (lane == 0) inv_l[0] = ll > 0.f ? 1.f / ll : 0.f;
+  }
+  cbar();
+  {
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxSplits / kCWarps; ++j) {
+      const int sp = warp + j * kCWarps;
+      if (sp < n_splits) o = fmaf(ov[j], w_s[sp], o);
+    }
+    acc_s[warp * 32 + lane] = o;
+  }
+  cbar();
+  if (warp == 0) {
+    float o = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < kCWarps; ++gq) o += acc_s[gq * 32 + lane];
+    p.attn_buf[(size_t)head_task * HD + d] = __float2half_rn(o * inv_l[0]);   // [seq][n_q][HD]
+  }
+  cbar();
+}
+
+// ------------------------------------------------------------------------------------------
+template <int HD, int G>
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __grid_constant__ MegaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* ring_buf = smem;
+  uint8_t* scratch = ring_buf + (size_t)p.n_stage * kUnitBytes;            // act rows / attention scratch
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages];
+  __shared__ float red[2 * kCWarps * kUnitRows * kRMax];
+  __shared__ float red8[kRMax * kCWarps];
+  __shared__ float lm_v[kUnitRows * kRMax];
+  __shared__ int lm_i[kUnitRows * kRMax];
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stage; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);      // released by the one warp that owns the unit
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kCWarps) {
+    // ===================== producer: every weight tile of the step, in execution order =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      const int n_mats = 4 * p.n_layers + 1;
+      for (int m = 0; m < n_mats; ++m) {
+        const StageShape& s = p.shp[m == n_mats - 1 ? ST_LM : (m & 3)];
+        const CUtensorMap* map = p.maps + m;
+        long long u0, u1;
+        unit_range(s, u0, u1);
+        int tile = (int)(u0 / s.chunks), kc = (int)(u0 - (long long)tile * s.chunks);
+        for (long long u = u0; u < u1; ++u, ++kc) {
+          if (kc == s.chunks) {
+            kc = 0;
+            ++tile;
+          }
+          mbar_wait(&empty[slot], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[slot], kUnitBytes);
+          tma_load_3d(ring_buf + (size_t)slot * kUnitBytes, map, &full[slot], 0, tile * kUnitRows, kc * 8);
+          if (++slot == p.n_stage) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  Ring ring{ring_buf, full, empty, p.n_stage, 0};
+  __half* act = reinterpret_cast<__half*>(scratch);
+  unsigned gen = 0;
+  if (tid == 0) gen = ld_acquire_u32(p.bar_flag);   // only thread 0 uses it
+  int red_buf = 0;
+  LmBest best{-INFINITY, 0x7fffffff};
+  const int cta = blockIdx.x;
+  const int hk = cta % p.n_kv, split = cta / p.n_kv;
+
+  long long* prof = (p.prof && tid == 0) ? p.prof + (size_t)cta * p.n_layers * kProfStamps : nullptr;
+#define SCB_STAMP(i) do { if (prof) prof[l * kProfStamps + (i)] = clock64(); } while (0)
+  for (int l = 0; l < p.n_layers; ++l) {
+    const MegaLayer* ly = p.layers + l;
+    SCB_STAMP(0);
+    // ---- qkv: x = embedding rows (layer 0) or x2 + down partials; act = RMSNorm(x) * ln1
+    prologue_norm(p, act, red8, p.x2_buf, p.part_d, l == 0 ? p.embed : nullptr, p.x_buf, ly->ln1, ly, hk, split, HD);
+    SCB_STAMP(1);
+    run_stage<ST_QKV>(p, p.shp[ST_QKV], ly, ring, act, red, red_buf, best);
+    SCB_STAMP(2);
+    grid_sync(p, gen);
+    SCB_STAMP(3);
+    // ---- attention partials
+    if (split < p.n_splits)
+      for (int n = 0; n < p.R; ++n) attention_partial<HD, G>(p, ly, scratch, hk, split, n);
+    SCB_STAMP(4);
+    grid_sync(p, gen);
+    SCB_STAMP(5);
+    for (int task = cta; task < p.R * p.n_q * (HD / 32); task += gridDim.x) attention_combine<HD>(p, scratch, task);
+    SCB_STAMP(6);
+    grid_sync(p, gen);
+    SCB_STAMP(7);
+    // ---- o_proj
+    prologue_copy(p, act, p.attn_buf, p.n_q * HD);
+    SCB_STAMP(8);
+    run_stage<ST_O>(p, p.shp[ST_O], ly, ring, act, red, red_buf, best);
+    SCB_STAMP(9);
+    grid_sync(p, gen);
+    SCB_STAMP(10);
+    // ---- gate|up: x2 = x + o partials; act = RMSNorm(x2) * ln2
+    prologue_norm(p, act, red8, p.x_buf, p.part_o, nullptr, p.x2_buf, ly->ln2);
+    SCB_STAMP(11);
+    run_stage<ST_GU>(p, p.shp[ST_GU], ly, ring, act, red, red_buf, best);
+    SCB_STAMP(12);
+    grid_sync(p, gen);
+    SCB_STAMP(13);
+    // ---- down
+    prologue_copy(p, act, p.gu_buf, p.I);
+    SCB_STAMP(14);
+    run_stage<ST_DOWN>(p, p.shp[ST_DOWN], ly, ring, act, red, red_buf, best);
+    SCB_STAMP(15);
+    grid_sync(p, gen);
+  }
+#undef SCB_STAMP
+  // ---- final norm + lm_head + arg-max
+  prologue_norm(p, act, red8, p.x2_buf, p.part_d, nullptr, nullptr, p.final_norm);
+  run_stage<ST_LM>(p, p.shp[ST_LM], nullptr, ring, act, red, red_buf, best);
+  if (tid < kUnitRows * kRMax) {
+    lm_v[tid] = best.v;
+    lm_i[tid] = best.i;
+  }
+  cbar();
+  if (tid < p.R) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int row = 0; row < kUnitRows; ++row) {
+      const float v = lm_v[row * kRMax + tid];
+      const int i = lm_i[row * kRMax + tid];
+      if (v > bv || (v == bv && i < bi)) {
+        bv = v;
+        bi = i;
+      }
+    }
+    p.cand_val[(size_t)cta * kRMax + tid] = bv;
+    p.cand_idx[(size_t)cta * kRMax + tid] = bi;
+  }
+  grid_sync(p, gen);
+  if (cta == 0) {
+    if (warp < p.R) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < (int)gridDim.x; c += 32) {
+        const float v = __ldcg(p.cand_val + (size_t)c * kRMax + warp);
+        const int i = __ldcg(p.cand_idx + (size_t)c * kRMax + warp);
+        if (v > bv || (v == bv && i < bi)) {
+          bv = v;
+          bi = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) p.next_id[warp] = (bi == 0x7fffffff) ? 0 : (long long)bi;
+    }
+    if (tid == 0)
+      for (int cc = 0; cc < p.n_counters; ++cc) p.counters[cc] += 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn mega_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// W [n, k] fp16, k contiguous -> (64 k, row, k-block) view; box (64, 16, 8) lands in shared memory as
+// [8 k-blocks][16 rows][128 B] with the 128-byte swizzle keyed on the row; OOB rows / k-blocks read zero.
+int make_weight_map(CUtensorMap* out, const void* w, long long n, long long k) {
+  EncodeTiledFn fn = mega_encode_fn();
+  SCB_REQUIRE(fn != nullptr, SCB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {64, (cuuint64_t)n, (cuuint64_t)(k / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)k * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)kUnitRows, 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCB_REQUIRE(r == CUDA_SUCCESS, SCB_ERR_CUDA, "cuTensorMapEncodeTiled(weight %lld x %lld) failed (%d)", n, k,
+              (int)r);
+  return SCB_OK;
+}
+
+struct MegaHandle {
+  uint32_t magic;
+  MegaParams base;
+  int grid;
+  int head_dim, group;
+  void* dev_maps;
+  void* dev_layers;
+  void* dev_ws;
+  void* dev_prof;
+  int smem_limit;
+};
+constexpr uint32_t kMagic = 0x51323244u;
+
+typedef void (*MegaKernel)(const MegaParams);
+MegaKernel pick_kernel(int hd, int g) {
+#define SCB_MK(HD, GG) \
+  if (hd == HD && g == GG) return decode_mega_kernel<HD, GG>;
+  SCB_MK(128, 1) SCB_MK(128, 2) SCB_MK(128, 4) SCB_MK(128, 7) SCB_MK(128, 8)
+  SCB_MK(64, 1) SCB_MK(64, 2) SCB_MK(64, 4) SCB_MK(64, 7) SCB_MK(64, 8)
+#undef SCB_MK
+  return nullptr;
+}
+
+StageShape make_shape(long long n, long long k, int grid, bool may_split) {
+  StageShape s;
+  s.n = (int)n;
+  s.k = (int)k;
+  s.n_tiles = (int)((n + kUnitRows - 1) / kUnitRows);
+  s.chunks = (int)((k + kUnitK - 1) / kUnitK);
+  const long long U = (long long)s.n_tiles * s.chunks;
+  // cutting tiles along K is only sound while a tile spans at most two CTAs (two partial slots)
+  s.split = (may_split && U / grid >= s.chunks) ? 1 : 0;
+  return s;
+}
+
+size_t attn_scratch_bytes(int hd, int g, int per_max) {
+  return (size_t)8 * hd * 2 + sizeof(float) * ((size_t)hd + 16 + (size_t)8 * g * hd + (size_t)g * per_max);
+}
+
+}  // namespace
+
+extern "C" {
+
+int scb_qwen2_decoder_max_rows(void) { return kRMax; }
+
+int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle) {
+  SCB_REQUIRE(d != nullptr && out_handle != nullptr, SCB_ERR_INVALID_ARG, "scb_qwen2_decoder_create: NULL argument");
+  *out_handle = nullptr;
+  SCB_REQUIRE(d->n_layers >= 1 && d->hidden >= 64 && d->n_q_heads >= 1 && d->n_kv_heads >= 1 && d->inter >= 64 &&
+                  d->vocab >= 16 && d->max_seqs >= 1 && d->max_ctx >= 1,
+              SCB_ERR_INVALID_ARG, "scb_qwen2_decoder_create: bad dimensions");
+  SCB_REQUIRE(d->n_q_heads % d->n_kv_heads == 0, SCB_ERR_INVALID_ARG, "scb_qwen2_decoder_create: n_q %% n_kv != 0");
+  const int G = d->n_q_heads / d->n_kv_heads;
+  MegaKernel kern = pick_kernel(d->head_dim, G);
+  SCB_REQUIRE(kern != nullptr, SCB_ERR_UNSUPPORTED,
+              "scb_qwen2_decoder_create: head_dim=%d group=%d unsupported (64|128 x 1,2,4,7,8)", d->head_dim, G);
+  const long long qkv_dim = (long long)(d->n_q_heads + 2 * d->n_kv_heads) * d->head_dim;
+  const long long attn_dim = (long long)d->n_q_heads * d->head_dim;
+  SCB_REQUIRE(d->hidden % 64 == 0 && d->inter % 64 == 0 && attn_dim % 64 == 0, SCB_ERR_UNSUPPORTED,
+              "scb_qwen2_decoder_create: hidden / inter / n_q*head_dim must be multiples of 64");
+  SCB_REQUIRE(d->hidden % 16 == 0 && qkv_dim % 16 == 0 && d->vocab % 16 == 0 && d->inter % 8 == 0,
+              SCB_ERR_UNSUPPORTED, "scb_qwen2_decoder_create: output widths must be multiples of 16");
+  SCB_REQUIRE(d->embed && d->final_norm && d->lm_head && d->qkv_w && d->o_w && d->gu_w && d->down_w && d->ln1 &&
+                  d->ln2 && d->k_cache && d->v_cache,
+              SCB_ERR_INVALID_ARG, "scb_qwen2_decoder_create: NULL pointer table");
+
+  int dev = 0;
+  SCB_CUDA_OK(cudaGetDevice(&dev));
+  int coop = 0, smem_optin = 0;
+  SCB_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  SCB_REQUIRE(coop != 0, SCB_ERR_UNSUPPORTED, "scb_qwen2_decoder_create: device lacks cooperative launch");
+  SCB_CUDA_OK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int grid = scb_num_sms();
+
+  MegaHandle* h = new (std::nothrow) MegaHandle();
+  SCB_REQUIRE(h != nullptr, SCB_ERR_CUDA, "scb_qwen2_decoder_create: out of host memory");
+  h->magic = kMagic;
+  h->grid = grid;
+  h->head_dim = d->head_dim;
+  h->group = G;
+  h->smem_limit = smem_optin;
+  h->dev_maps = h->dev_layers = h->dev_ws = h->dev_prof = nullptr;
+  MegaParams& p = h->base;
+  memset(&p, 0, sizeof(p));
+  p.n_layers = d->n_layers; p.H = d->hidden; p.n_q = d->n_q_heads; p.n_kv = d->n_kv_heads;
+  p.I = d->inter; p.V = d->vocab; p.qkv_dim = (int)qkv_dim;
+  p.eps = d->rms_eps; p.theta = d->rope_theta;
+  p.scale_log2 = (1.f / sqrtf((float)d->head_dim)) * 1.4426950408889634f;
+  p.inv_freq = d->inv_freq;
+  p.embed = reinterpret_cast<const __half*>(d->embed);
+  p.final_norm = reinterpret_cast<const __half*>(d->final_norm);
+  p.lm_head = reinterpret_cast<const __half*>(d->lm_head);
+  p.max_ctx = d->max_ctx;
+  p.cache_seq_stride = (long long)d->n_kv_heads * d->max_ctx * d->head_dim;
+  p.shp[ST_QKV] = make_shape(qkv_dim, d->hidden, grid, false);
+  p.shp[ST_O] = make_shape(d->hidden, attn_dim, grid, true);
+  p.shp[ST_GU] = make_shape(2ll * d->inter, d->hidden, grid, false);
+  p.shp[ST_DOWN] = make_shape(d->hidden, d->inter, grid, true);
+  p.shp[ST_LM] = make_shape(d->vocab, d->hidden, grid, false);
+  int ns = grid / d->n_kv_heads;
+  if (ns > kMaxSplits) ns = kMaxSplits;
+  if (ns < 1) {
+    delete h;
+    SCB_REQUIRE(false, SCB_ERR_UNSUPPORTED, "scb_qwen2_decoder_create: more kv heads than SMs");
+  }
+  p.n_splits = ns;
+
+  // ---- tensor maps + layer table
+  const int n_mats = 4 * d->n_layers + 1;
+  CUtensorMap* maps = new (std::nothrow) CUtensorMap[n_mats];
+  MegaLayer* layers = new (std::nothrow) MegaLayer[d->n_layers];
+  int rc = (maps && layers) ? SCB_OK : SCB_ERR_CUDA;
+  for (int l = 0; rc == SCB_OK && l < d->n_layers; ++l) {
+    if (!d->qkv_w[l] || !d->o_w[l] || !d->gu_w[l] || !d->down_w[l] || !d->ln1[l] || !d->ln2[l] || !d->k_cache[l] ||
+        !d->v_cache[l]) {
+      scb_set_error("scb_qwen2_decoder_create: NULL pointer for layer %d", l);
+      rc = SCB_ERR_INVALID_ARG;
+      break;
+    }
+    rc = make_weight_map(&maps[4 * l + 0], d->qkv_w[l], qkv_dim, d->hidden);
+    if (rc == SCB_OK) rc = make_weight_map(&maps[4 * l + 1], d->o_w[l], d->hidden, attn_dim);
+    if (rc == SCB_OK) rc = make_weight_map(&maps[4 * l + 2], d->gu_w[l], 2ll * d->inter, d->hidden);
+    if (rc == SCB_OK) rc = make_weight_map(&maps[4 * l + 3], d->down_w[l], d->hidden, d->inter);
+    layers[l].w[0] = reinterpret_cast<const __half*>(d->qkv_w[l]);
+    layers[l].w[1] = reinterpret_cast<const __half*>(d->o_w[l]);
+    layers[l].w[2] = reinterpret_cast<const __half*>(d->gu_w[l]);
+    layers[l].w[3] = reinterpret_cast<const __half*>(d->down_w[l]);
+    layers[l].qkv_b = reinterpret_cast<const __half*>(d->qkv_b ? d->qkv_b[l] : nullptr);
+    layers[l].ln1 = reinterpret_cast<const __half*>(d->ln1[l]);
+    layers[l].ln2 = reinterpret_cast<const __half*>(d->ln2[l]);
+    layers[l].k_cache = reinterpret_cast<__half*>(d->k_cache[l]);
+    layers[l].v_cache = reinterpret_cast<__half*>(d->v_cache[l]);
+  }
+  if (rc == SCB_OK) rc = make_weight_map(&maps[n_mats - 1], d->lm_head, d->vocab, d->hidden);
+
+  // ---- workspace
+  const size_t H = d->hidden, I = d->inter;
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+    const size_t o = off;
+    off = scb_align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_bar = take(256);
+  const size_t o_cnt = take(256);
+  const size_t o_x = take(kRMax * H * 2), o_x2 = take(kRMax * H * 2);
+  const size_t o_qkv = take(kRMax * (size_t)qkv_dim * 2), o_attn = take(kRMax * (size_t)attn_dim * 2);
+  const size_t o_gu = take(kRMax * I * 2);
+  const size_t o_po = take(2 * kRMax * H * 4), o_pd = take(2 * kRMax * H * 4);
+  const size_t n_part = (size_t)kRMax * d->n_q_heads * ns;
+  const size_t o_am = take(n_part * 4), o_al = take(n_part * 4), o_ao = take(n_part * d->head_dim * 4);
+  const size_t o_cv = take((size_t)grid * kRMax * 4), o_ci = take((size_t)grid * kRMax * 4);
+  auto fail = [&](int code) {
+    if (h->dev_maps) cudaFree(h->dev_maps);
+    if (h->dev_layers) cudaFree(h->dev_layers);
+    if (h->dev_ws) cudaFree(h->dev_ws);
+    delete[] maps;
+    delete[] layers;
+    delete h;
+    return code;
+  };
+  if (rc != SCB_OK) return fail(rc);
+  if (cudaMalloc(&h->dev_maps, sizeof(CUtensorMap) * n_mats) != cudaSuccess ||
+      cudaMalloc(&h->dev_layers, sizeof(MegaLayer) * d->n_layers) != cudaSuccess ||
+      cudaMalloc(&h->dev_ws, off) != cudaSuccess) {
+    scb_set_error("scb_qwen2_decoder_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(SCB_ERR_CUDA);
+  }
+  if (cudaMemcpy(h->dev_maps, maps, sizeof(CUtensorMap) * n_mats, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->dev_layers, layers, sizeof(MegaLayer) * d->n_layers, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemset(h->dev_ws, 0, off) != cudaSuccess) {
+    scb_set_error("scb_qwen2_decoder_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(SCB_ERR_CUDA);
+  }
+  delete[] maps;
+  delete[] layers;
+  char* ws = reinterpret_cast<char*>(h->dev_ws);
+  p.maps = reinterpret_cast<const CUtensorMap*>(h->dev_maps);
+  p.layers = reinterpret_cast<const MegaLayer*>(h->dev_layers);
+  p.bar_flag = reinterpret_cast<unsigned*>(ws + o_bar);
+  p.bar_count = reinterpret_cast<unsigned long long*>(ws + o_cnt);
+  p.x_buf = reinterpret_cast<__half*>(ws + o_x);
+  p.x2_buf = reinterpret_cast<__half*>(ws + o_x2);
+  p.qkv_buf = reinterpret_cast<__half*>(ws + o_qkv);
+  p.attn_buf = reinterpret_cast<__half*>(ws + o_attn);
+  p.gu_buf = reinterpret_cast<__half*>(ws + o_gu);
+  p.part_o = reinterpret_cast<float*>(ws + o_po);
+  p.part_d = reinterpret_cast<float*>(ws + o_pd);
+  p.att_m = reinterpret_cast<float*>(ws + o_am);
+  p.att_l = reinterpret_cast<float*>(ws + o_al);
+  p.att_o = reinterpret_cast<float*>(ws + o_ao);
+  p.cand_val = reinterpret_cast<float*>(ws + o_cv);
+  p.cand_idx = reinterpret_cast<int*>(ws + o_ci);
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 8 * 1024) !=
+      cudaSuccess) {
+    scb_set_error("scb_qwen2_decoder_create: cannot opt in to %d B of shared memory", smem_optin - 8 * 1024);
+    return fail(SCB_ERR_CUDA);
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMegaThreads, smem_optin - 8 * 1024) !=
+          cudaSuccess ||
+      per_sm < 1) {
+    scb_set_error("scb_qwen2_decoder_create: kernel does not fit one CTA per SM");
+    return fail(SCB_ERR_UNSUPPORTED);
+  }
+  *out_handle = h;
+  return SCB_OK;
+}
+
+int scb_qwen2_decoder_destroy(void* handle) {
+  MegaHandle* h = reinterpret_cast<MegaHandle*>(handle);
+  SCB_REQUIRE(h != nullptr && h->magic == kMagic, SCB_ERR_INVALID_ARG, "scb_qwen2_decoder_destroy: bad handle");
+  h->magic = 0;
+  cudaFree(h->dev_maps);
+  cudaFree(h->dev_layers);
+  cudaFree(h->dev_ws);
+  if (h->dev_prof) cudaFree(h->dev_prof);
+  delete h;
+  return SCB_OK;
+}
+
+// Debug: per-CTA clock64 stamps of the LAST step (16 per layer: layer start, then after each prologue /
+// stage / grid barrier).  First call arms the recording (returns 0 stamps); later calls copy
+// [grid][n_layers][16] int64 to `host_out` (capacity in elements) and return the element count.
+long long scb_qwen2_decoder_profile(void* handle, long long* host_out, long long capacity) {
+  MegaHandle* h = reinterpret_cast<MegaHandle*>(handle);
+  if (h == nullptr || h->magic != kMagic) return -1;
+  const long long n = (long long)h->grid * h->base.n_layers * kProfStamps;
+  if (!h->dev_prof) {
+    if (cudaMalloc(&h->dev_prof, n * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(h->dev_prof, 0, n * sizeof(long long));
+    h->base.prof = reinterpret_cast<long long*>(h->dev_prof);
+    return 0;
+  }
+  if (host_out == nullptr || capacity < n) return -1;
+  if (cudaMemcpy(host_out, h->dev_prof, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
+}
+
+int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: args is NULL");
+  MegaHandle* h = reinterpret_cast<MegaHandle*>(a->decoder);
+  SCB_REQUIRE(h != nullptr && h->magic == kMagic, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: bad decoder handle");
+  SCB_REQUIRE(a->rows >= 1 && a->rows <= kRMax, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: rows=%d not in 1..%d",
+              a->rows, kRMax);
+  SCB_REQUIRE(a->next_id && a->kv_len && a->logits, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: NULL buffer");
+  SCB_REQUIRE(a->ld_logits >= h->base.V, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: ld_logits < vocab");
+  SCB_REQUIRE(a->n_counters == 0 || a->counters, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: counters is NULL");
+  MegaParams p = h->base;
+  p.R = a->rows;
+  p.next_id = reinterpret_cast<long long*>(a->next_id);
+  p.kv_len = a->kv_len;
+  p.counters = a->counters;
+  p.n_counters = a->n_counters;
+  p.logits = reinterpret_cast<__half*>(a->logits);
+  p.ld_logits = a->ld_logits;
+  const long long cap = (a->ctx_cap > 0 && a->ctx_cap < p.max_ctx) ? a->ctx_cap : p.max_ctx;
+  const int per_need = (int)((cap + p.n_splits - 1) / p.n_splits);
+  p.per_max = ((per_need + 11) / 16) * 16 + 4;   // row stride = 4 mod 16 floats: conflict-free score stores
+  // shared-memory budget: ring stages + max(activation rows, attention scratch)
+  int kmax = p.H;
+  if (p.I > kmax) kmax = p.I;
+  if (p.n_q * h->head_dim > kmax) kmax = p.n_q * h->head_dim;
+  p.act_ld = kmax + 8;
+  size_t scratch = (size_t)p.R * p.act_ld * 2;
+  const size_t attn_b = attn_scratch_bytes(h->head_dim, h->group, p.per_max);
+  if (attn_b > scratch) scratch = attn_b;
+  const size_t comb = sizeof(float) * (kMaxSplits + 8 + (size_t)kCThreads);
+  if (comb > scratch) scratch = comb;
+  scratch = scb_align_up(scratch, 1024);
+  const long long budget = (long long)h->smem_limit - 8 * 1024 - 1024 - (long long)scratch;
+  int n_stage = (int)(budget / kUnitBytes);
+  if (n_stage > kMaxStages) n_stage = kMaxStages;
+  SCB_REQUIRE(n_stage >= 2, SCB_ERR_UNSUPPORTED,
+              "scb_qwen2_decode_step: rows=%d x k=%d (+ctx_cap %lld) leaves no shared memory for the weight ring",
+              a->rows, kmax, cap);
+  p.n_stage = n_stage;
+  const size_t smem = 1024 + (size_t)n_stage * kUnitBytes + scratch;
+  MegaKernel kern = pick_kernel(h->head_dim, h->group);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(h->grid);
+  cfg.blockDim = dim3(kMegaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  SCB_LAUNCH_OK("decode_mega_kernel");
+  return SCB_OK;
+}
+
+}  // extern "C"

@@ -493,3 +493,68 @@ def decode_attention_fused_workspace(dev, n_q: int, n_kv: int, head_dim: int, n_
     if n == 0:
         raise ValueError("invalid decode_attention_fused configuration")
     return torch.zeros(n, dtype=torch.uint8, device=dev)
+
+
+# ------------------------------------------------------------------------------------------
+class Qwen2Decoder:
+    """Handle of the persistent decode-step kernel (scb_qwen2_decoder_*): one launch per cached decode
+    step for 1..max_rows sequences.  Holds references to every tensor whose pointer the handle keeps."""
+
+    def __init__(self, *, embed: torch.Tensor, final_norm: torch.Tensor, lm_head: torch.Tensor, layers: list,
+                 k_cache: list, v_cache: list, n_q: int, n_kv: int, head_dim: int, inter: int, eps: float,
+                 theta: float, inv_freq: Optional[torch.Tensor], max_ctx: int):
+        dev = _require_cuda(embed, final_norm, lm_head)
+        n = len(layers)
+        self._keep = (embed, final_norm, lm_head, layers, k_cache, v_cache, inv_freq)
+
+        def table(ts):
+            arr = (C.c_void_p * n)()
+            for i, t in enumerate(ts):
+                if t is not None:
+                    if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float16):
+                        raise L.ScbError("Qwen2Decoder: weights / caches must be contiguous fp16 CUDA tensors")
+                    arr[i] = t.data_ptr()
+            return arr
+
+        self._tables = [table([ly.get(k) for ly in layers]) for k in ("qkv_w", "qkv_b", "o_w", "gu_w", "down_w", "ln1", "ln2")]
+        self._tables += [table(k_cache), table(v_cache)]
+        d = L.Qwen2DecoderDesc()
+        d.n_layers, d.hidden, d.n_q_heads, d.n_kv_heads = n, embed.shape[1], n_q, n_kv
+        d.head_dim, d.inter, d.vocab, d.max_seqs = head_dim, inter, lm_head.shape[0], k_cache[0].shape[0]
+        d.max_ctx, d.rms_eps, d.rope_theta = max_ctx, eps, theta
+        d.inv_freq = _ptr(inv_freq)
+        d.embed, d.final_norm, d.lm_head = embed.data_ptr(), final_norm.data_ptr(), lm_head.data_ptr()
+        (d.qkv_w, d.qkv_b, d.o_w, d.gu_w, d.down_w, d.ln1, d.ln2, d.k_cache, d.v_cache) = [
+            C.cast(t, C.POINTER(C.c_void_p)) for t in self._tables]
+        self.device = dev
+        self.vocab = lm_head.shape[0]
+        self.max_rows = int(L.load().scb_qwen2_decoder_max_rows())
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            L.check(L.load().scb_qwen2_decoder_create(C.byref(d), C.byref(h)), "scb_qwen2_decoder_create")
+        self._h = h
+
+    def step(self, rows: int, next_id: torch.Tensor, kv_len: torch.Tensor, logits: torch.Tensor,
+             counters: Optional[torch.Tensor] = None, ctx_cap: int = 0) -> None:
+        """One decode step for cache slots 0..rows-1: consumes next_id[:rows] (int64), writes the greedy
+        next tokens back into it, fp16 logits into logits[:rows], and adds 1 to every int32 of `counters`."""
+        _require_cuda(next_id, kv_len, logits, counters)
+        if next_id.dtype != torch.int64 or kv_len.dtype != torch.int32 or logits.dtype != torch.float16:
+            raise TypeError("Qwen2Decoder.step: next_id int64, kv_len int32, logits fp16")
+        a = L.Qwen2DecodeStepArgs()
+        a.decoder, a.rows = self._h, rows
+        a.next_id, a.kv_len, a.logits, a.ld_logits = next_id.data_ptr(), kv_len.data_ptr(), logits.data_ptr(), logits.stride(0)
+        a.counters, a.n_counters = _ptr(counters), (counters.numel() if counters is not None else 0)
+        a.ctx_cap = ctx_cap
+        L.check(L.load().scb_qwen2_decode_step(C.byref(a), _stream(self.device)), "scb_qwen2_decode_step")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            L.load().scb_qwen2_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -12,6 +12,8 @@ gate|up [2I, H], down [H, I], all fp16 row-major (K contiguous); KV cache per la
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -45,6 +47,7 @@ class Qwen2Engine:
         self.max_ctx = max_ctx
         self.decode_splits = decode_splits
         self.max_batch = max_batch
+        self.mega_rows = int(os.environ.get("SCB_DECODE_MEGA_ROWS", "4"))   # widest batch the persistent kernel takes
         if max_batch < 1 or max_batch > 32:
             raise ValueError('max_batch must be in 1..32 (sequences decoded in lock-step)')
         c = cfg
@@ -99,6 +102,19 @@ class Qwen2Engine:
         self._logits = torch.zeros((B, c.vocab_size), dtype=torch.float16, device=self.device)
         self._attn_ws = ops.decode_attention_fused_workspace(self.device, c.num_attention_heads,
                                                              c.num_key_value_heads, hd, decode_splits, n_seqs=B)
+        # persistent decode-step kernel (one launch per step) for narrow lock-step batches; shapes it does not
+        # cover (and SCB_DECODE_MEGA=0) keep the per-layer kernel chain below — both are CUDA paths
+        self._mega = None
+        self.mega_unsupported: Optional[str] = None
+        if os.environ.get("SCB_DECODE_MEGA", "1") != "0":
+            try:
+                self._mega = ops.Qwen2Decoder(
+                    embed=self.embed, final_norm=self.final_norm, lm_head=self.lm_head, layers=self.layers,
+                    k_cache=self.k_cache, v_cache=self.v_cache, n_q=c.num_attention_heads,
+                    n_kv=c.num_key_value_heads, head_dim=hd, inter=c.intermediate_size, eps=c.rms_norm_eps,
+                    theta=c.rope_theta, inv_freq=self.inv_freq, max_ctx=max_ctx)
+            except L.ScbError as e:
+                self.mega_unsupported = str(e)
         self._graphs = {}
         self.graph_replays = 0
         self.graph_launches = 0      # kernels launched through graph replays (launch_count() only sees eager calls)
@@ -179,6 +195,10 @@ class Qwen2Engine:
         [position, kv_len] state.  Rows are independent: a sequence decodes to the same ids whatever R is."""
         c = self.cfg
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
+        if self._use_mega(R):
+            cap = ctx_cap if 0 < ctx_cap < self.max_ctx else self.max_ctx
+            self._mega.step(R, self.next_id, self.state[1], self._logits, counters=self.state.view(-1), ctx_cap=cap)
+            return
         scale = hd ** -0.5
         x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
         eps = c.rms_norm_eps
@@ -221,7 +241,12 @@ class Qwen2Engine:
             ops.gemv(nrm, self.lm_head, out=self._logits[:R], argmax_out=self.next_id[:R],
                      counters=self.state.view(-1))
 
+    def _use_mega(self, R: int) -> bool:
+        return self._mega is not None and R <= min(self._mega.max_rows, self.mega_rows)
+
     def launches_per_decode_step(self, R: int = 1) -> int:
+        if self._use_mega(R):
+            return 1
         # <= 8 rows: gather+norm, 5 per layer, lm_head with fused arg-max; wider: split-K GEMM + reduce pairs
         return 1 + self.cfg.num_hidden_layers * (8 if R > 8 else 5) + (2 if R > 8 else 1)
 

@@ -29,10 +29,10 @@ for R in Rs:
         eng.generate_batch([x] * R, steps + 1, use_graph=use_graph)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        p = eng.profile[0]
+        p = [q for q in eng.profile if q.get("kind", "decode") == "decode"][0]
         n = p["steps"] if use_graph else steps
         ms = p["events"][0].elapsed_time(p["events"][1])
         by = eng.weight_bytes() + R * eng.kv_bytes_per_token(ctx + steps // 2)
         print(f"R={R} graph={use_graph} ctx={ctx}: {ms / steps:.3f} ms/step  {by / (ms / steps * 1e-3) / 1e9:.0f} GB/s "
-              f"(weights {eng.weight_bytes() / 1e9:.2f} GB)  wall incl. prefill {wall:.2f}s PDL={os.environ.get('SCB_PDL', '1')}")
+              f"(weights {eng.weight_bytes() / 1e9:.2f} GB)  wall incl. prefill {wall:.2f}s PDL={os.environ.get('SCB_PDL', '1')} mega={eng._use_mega(R)}")
         eng.profile = None

@@ -333,133 +333,106 @@ SCB_DEVICE void prefetch_kv_l2(const MegaParams& p, const MegaLayer* ly, int hk,
 
 // x = fp16(res + p0 + p1) (or the embedding rows), optional copy-out by CTA 0, then
 // act = fp16(fp16(x * rstd) * gamma)  — RMSNorm in HF's order (modeling_qwen2.py:249-263).
-// Work items are (row, 8-element chunk) pairs spread over the 256 threads, four per thread per batch with
-// every global load of the batch issued before its first use (one L2 round trip per batch whatever R is),
-// and ONE block reduction for all rows' sums of squares.
-SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red, const __half* res,
+// A thread owns 8-element chunks; every global load of a pass is issued before the first use
+// (one L2 round trip per pass instead of one per element group).
+SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, const __half* res,
                               const float* part, const __half* embed_rows, __half* x_out,
                               const __half* gamma, const MegaLayer* kv_layer = nullptr, int hk = 0, int split = 0,
                               int head_dim = 0) {
-  constexpr int CHB = 4;                        // items per thread per batch
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int H = p.H, n_chunks = H >> 3, n_items = p.R * n_chunks;
+  constexpr int CH = 2;                         // chunks per thread per pass
+  const int tid = threadIdx.x;
+  const int H = p.H, n_chunks = H >> 3;
   const size_t slot_stride = (size_t)kRMax * H;
-  float ss[kRMax];
+  for (int n = 0; n < p.R; ++n) {
+    __half* a = act + (size_t)n * p.act_ld;
+    float ss = 0.f;
+    const __half* er = embed_rows ? embed_rows + (size_t)p.next_id[n] * H : nullptr;
+    for (int c0 = 0; c0 < n_chunks; c0 += kCThreads * CH) {
+      uint4 rr[CH];
+      float4 q0[CH][2], q1[CH][2];
 #pragma unroll
-  for (int r = 0; r < kRMax; ++r) ss[r] = 0.f;
-  for (int i0 = 0; i0 < n_items; i0 += kCThreads * CHB) {
-    uint4 rr[CHB];
-    float4 q0[CHB][2], q1[CHB][2];
-#pragma unroll
-    for (int j = 0; j < CHB; ++j) {
-      const int i = min(i0 + j * kCThreads + tid, n_items - 1);   // clamped: loads stay unconditional (registers)
-      const int n = i / n_chunks, c = i - n * n_chunks;
-      if (embed_rows) {
-        rr[j] = *reinterpret_cast<const uint4*>(embed_rows + (size_t)p.next_id[n] * H + c * 8);
-        q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        rr[j] = __ldcg(reinterpret_cast<const uint4*>(res + (size_t)n * H + c * 8));
-        const float4* s0 = reinterpret_cast<const float4*>(part + (size_t)n * H + c * 8);
-        const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
-        q0[j][0] = __ldcg(s0); q0[j][1] = __ldcg(s0 + 1);
-        q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
-      }
-    }
-    // the attention stage's K / V rows start their trip to L2 behind this batch's loads
-    if (kv_layer && i0 == 0) prefetch_kv_l2(p, kv_layer, hk, split, head_dim);
-#pragma unroll
-    for (int j = 0; j < CHB; ++j) {
-      const int i = i0 + j * kCThreads + tid;
-      if (i < n_items) {
-        const int n = i / n_chunks, c = i - n * n_chunks;
-        float x[8];
-        const float2 r0 = h2_to_f2(rr[j].x), r1 = h2_to_f2(rr[j].y), r2 = h2_to_f2(rr[j].z), r3 = h2_to_f2(rr[j].w);
-        x[0] = r0.x; x[1] = r0.y; x[2] = r1.x; x[3] = r1.y; x[4] = r2.x; x[5] = r2.y; x[6] = r3.x; x[7] = r3.y;
-        if (!embed_rows) {
-          const float a0[8] = {q0[j][0].x, q0[j][0].y, q0[j][0].z, q0[j][0].w, q0[j][1].x, q0[j][1].y, q0[j][1].z, q0[j][1].w};
-          const float a1[8] = {q1[j][0].x, q1[j][0].y, q1[j][0].z, q1[j][0].w, q1[j][1].x, q1[j][1].y, q1[j][1].z, q1[j][1].w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = __half2float(__float2half_rn((a0[e] + a1[e]) + x[e]));
+      for (int j = 0; j < CH; ++j) {
+        const int c = min(c0 + j * kCThreads + tid, n_chunks - 1);   // clamped: loads stay unconditional (registers)
+        if (er) {
+          rr[j] = *reinterpret_cast<const uint4*>(er + c * 8);
+          q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          rr[j] = __ldcg(reinterpret_cast<const uint4*>(res + (size_t)n * H + c * 8));
+          const float4* s0 = reinterpret_cast<const float4*>(part + (size_t)n * H + c * 8);
+          const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
+          q0[j][0] = __ldcg(s0); q0[j][1] = __ldcg(s0 + 1);
+          q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
         }
-        float sq = 0.f;
+      }
+      // the attention stage's K / V rows start their trip to L2 behind this batch's loads
+      if (kv_layer && n == 0 && c0 == 0) prefetch_kv_l2(p, kv_layer, hk, split, head_dim);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sq = fmaf(x[e], x[e], sq);
+      for (int j = 0; j < CH; ++j) {
+        const int c = c0 + j * kCThreads + tid;
+        if (c < n_chunks) {
+          float x[8];
+          const float2 r0 = h2_to_f2(rr[j].x), r1 = h2_to_f2(rr[j].y), r2 = h2_to_f2(rr[j].z), r3 = h2_to_f2(rr[j].w);
+          x[0] = r0.x; x[1] = r0.y; x[2] = r1.x; x[3] = r1.y; x[4] = r2.x; x[5] = r2.y; x[6] = r3.x; x[7] = r3.y;
+          if (!er) {
+            const float a0[8] = {q0[j][0].x, q0[j][0].y, q0[j][0].z, q0[j][0].w, q0[j][1].x, q0[j][1].y, q0[j][1].z, q0[j][1].w};
+            const float a1[8] = {q1[j][0].x, q1[j][0].y, q1[j][0].z, q1[j][0].w, q1[j][1].x, q1[j][1].y, q1[j][1].z, q1[j][1].w};
 #pragma unroll
-        for (int r = 0; r < kRMax; ++r) ss[r] += (r == n) ? sq : 0.f;
-        uint4 o;
-        o.x = f2_to_h2(x[0], x[1]); o.y = f2_to_h2(x[2], x[3]); o.z = f2_to_h2(x[4], x[5]); o.w = f2_to_h2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld + c * 8) = o;
-        if (x_out && blockIdx.x == 0) *reinterpret_cast<uint4*>(x_out + (size_t)n * H + c * 8) = o;
+            for (int e = 0; e < 8; ++e) x[e] = __half2float(__float2half_rn((a0[e] + a1[e]) + x[e]));
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+          uint4 o;
+          o.x = f2_to_h2(x[0], x[1]); o.y = f2_to_h2(x[2], x[3]); o.z = f2_to_h2(x[4], x[5]); o.w = f2_to_h2(x[6], x[7]);
+          *reinterpret_cast<uint4*>(a + c * 8) = o;
+          if (x_out && blockIdx.x == 0) *reinterpret_cast<uint4*>(x_out + (size_t)n * H + c * 8) = o;
+        }
+      }
+    }
+    // gamma travels while the block reduces
+    uint4 gm[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) gm[j] = *reinterpret_cast<const uint4*>(gamma + min(j * kCThreads + tid, n_chunks - 1) * 8);
+    const float tot = block_sum_256(ss, red8);
+    const float rstd = rsqrtf(tot / (float)H + p.eps);
+    for (int c0 = 0; c0 < n_chunks; c0 += kCThreads * CH) {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int c = c0 + j * kCThreads + tid;
+        if (c < n_chunks) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(a + c * 8);   // own writes
+          const uint4 g4 = (c0 == 0) ? gm[j] : *reinterpret_cast<const uint4*>(gamma + c * 8);
+          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xf = h2_to_f2(xs[e]), gf = h2_to_f2(gs[e]);
+            o[e] = f2_to_h2(__half2float(__float2half_rn(xf.x * rstd)) * gf.x,
+                            __half2float(__float2half_rn(xf.y * rstd)) * gf.y);
+          }
+          *reinterpret_cast<uint4*>(a + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
   }
-  // gamma for this thread's first pass-2 items travels while the block reduces
-  constexpr int GP = 4;
-  uint4 gpre[GP];
-#pragma unroll
-  for (int j = 0; j < GP; ++j) {
-    const int i = min(tid + j * kCThreads, n_items - 1);
-    gpre[j] = *reinterpret_cast<const uint4*>(gamma + (i % n_chunks) * 8);
-  }
-  // one reduction for all rows (red: [kRMax][8 warps])
-#pragma unroll
-  for (int r = 0; r < kRMax; ++r) ss[r] = warp_sum(ss[r]);
-  cbar();
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < kRMax; ++r) red[r * kCWarps + warp] = ss[r];
-  }
-  cbar();
-  float rstd[kRMax];
-#pragma unroll
-  for (int r = 0; r < kRMax; ++r) {
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < kCWarps; ++w) tot += red[r * kCWarps + w];
-    rstd[r] = rsqrtf(tot / (float)H + p.eps);
-  }
-  auto pass2 = [&](int i, const uint4& g4) {
-    const int n = i / n_chunks, c = i - n * n_chunks;
-    __half* a = act + (size_t)n * p.act_ld + c * 8;
-    const uint4 xv = *reinterpret_cast<const uint4*>(a);
-    float rs = rstd[0];
-#pragma unroll
-    for (int r = 1; r < kRMax; ++r) rs = (r == n) ? rstd[r] : rs;
-    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 xf = h2_to_f2(xs[e]), gf = h2_to_f2(gs[e]);
-      o[e] = f2_to_h2(__half2float(__float2half_rn(xf.x * rs)) * gf.x, __half2float(__float2half_rn(xf.y * rs)) * gf.y);
-    }
-    *reinterpret_cast<uint4*>(a) = make_uint4(o[0], o[1], o[2], o[3]);
-  };
-#pragma unroll
-  for (int j = 0; j < GP; ++j) {
-    const int i = tid + j * kCThreads;
-    if (i < n_items) pass2(i, gpre[j]);
-  }
-  for (int i = tid + GP * kCThreads; i < n_items; i += kCThreads)
-    pass2(i, *reinterpret_cast<const uint4*>(gamma + (i % n_chunks) * 8));
   cbar();
 }
 
 // act <- src rows ([R][len] fp16 in global, written by other CTAs before the last grid barrier);
-// five independent 16-byte L2 loads in flight per thread, rows flattened.
+// five independent 16-byte L2 loads in flight per thread.
 SCB_DEVICE void prologue_copy(const MegaParams& p, __half* act, const __half* src, int len) {
   constexpr int U = 5;
-  const int tid = threadIdx.x, n16 = len >> 3, n_items = p.R * n16;
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
-  for (int i0 = 0; i0 < n_items; i0 += kCThreads * U) {
-    uint4 v[U];
+  const int tid = threadIdx.x, n16 = len >> 3;
+  for (int n = 0; n < p.R; ++n) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)n * len);
+    uint4* d4 = reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld);
+    for (int i0 = 0; i0 < n16; i0 += kCThreads * U) {
+      uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = __ldcg(s4 + min(i0 + u * kCThreads + tid, n_items - 1));
+      for (int u = 0; u < U; ++u) v[u] = __ldcg(s4 + min(i0 + u * kCThreads + tid, n16 - 1));
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kCThreads + tid;
-      if (i < n_items) {
-        const int n = i / n16, j = i - n * n16;
-        *reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld + j * 8) = v[u];
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kCThreads + tid;
+        if (i < n16) d4[i] = v[u];
       }
     }
   }

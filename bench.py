@@ -283,17 +283,18 @@ def ours(args):
                                         for r in sorted({p["rows"] for p in dec})}
     roofline = None
     traffic = None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_decode_traffic.json")
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_decode_mega_traffic.json")
     if os.path.exists(tpath):      # DRAM bytes of one decode step (1 sequence, ctx 5800) from the ncu capture named there
         with open(tpath) as f:
             tj = json.load(f)
         traffic = {"bytes_per_decode_step": tj["dram_read_bytes"] + tj["dram_write_bytes"],
                    "algorithmic_bytes_same_step": tj["algorithmic_bytes"], "rows": tj["rows"], "ctx": tj["ctx"],
-                   "source": "profiles/r01_decode_traffic.json"}
+                   "source": "profiles/r01_decode_mega_traffic.json"}
     if dec_steps:
         achieved = dec_bytes / (dec_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "decode step = one CUDA graph: gemv_mma_kernel x113 + decode_attn_fused_kernel x28 (<= 8 rows), "
-                              "linear_tcgen05 split-K + reduce for wider batches; bytes = weights + live KV per step",
+        roofline = {"bound": "hbm", "kernel": "decode step: decode_mega_kernel (ONE persistent launch per step, <= 4 rows: TMA weight ring + "
+                              "mma.sync consumers + grid barriers); linear_tcgen05 split-K + reduce + decode_attn_fused for wider "
+                              "batches; bytes = weights + live KV per step",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "traffic": traffic,
                     "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,

@@ -19,6 +19,7 @@
 #include "scb_common.cuh"
 #include <math.h>
 #include <mutex>
+#include <stdlib.h>
 #include <unordered_map>
 
 namespace {
@@ -65,24 +66,33 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
 };
 
-template <int D, int kBKV>
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+// NSB = number of S buffers in TMEM.  2: S_{j+1} is computed while the softmax works on S_j (one CTA per SM,
+// D = 128).  1: S + O fit 256 columns and the tiles 112 KB, so TWO CTAs share an SM and fill each other's
+// softmax / MMA gaps with 8 softmax warps per SM instead of 4 (D = 64: the CLIP tower, where the 4-warp
+// softmax of a lone CTA left the tensor pipe idle 85 % of the time).
+template <int D, int kBKV, int NSB, int KS>
 struct ACfg {
   static constexpr int kSub = D / 64;                  // 64-column sub-tiles per row
   static constexpr int kQBytes = kBQ * D * 2;
   static constexpr int kKBytes = kBKV * D * 2;
   static constexpr int kPBytes = kBQ * kBKV * 2;
-  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 192;
-  // S is double-buffered: S_{j+1} is computed while the softmax works on S_j.
-  //   S0: [0,128)  S1: [128,256)  O_j: [256,256+D)   -> 512 columns, one CTA per SM
-  static constexpr int kTmemCols = 512;
+  static constexpr int kThreads = (2 + 4 * KS) * 32;   // TMA warp, MMA warp, 4*KS softmax warps
+  static constexpr int kXBytes = KS == 2 ? 3 * 2 * kBQ * 4 : 0;   // max (x2 parities) / sum exchange between the halves of a row
+  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 192 + kXBytes;
+  //   S buffers: [sb*kBKV, (sb+1)*kBKV)   O_j: [NSB*kBKV, NSB*kBKV + D)
+  static constexpr int kOCol = NSB * kBKV;
+  static constexpr int kTmemCols = pow2_cols(NSB * kBKV + D);
+  static constexpr int kMinBlocks = (kTmemCols <= 256 && 2 * (kSmemBytes + 1024) <= 228 * 1024) ? 2 : 1;
 };
 
-template <int D, int kBKV>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <int D, int kBKV, int NSB, int KS>
+__global__ void __launch_bounds__((ACfg<D, kBKV, NSB, KS>::kThreads), (ACfg<D, kBKV, NSB, KS>::kMinBlocks))
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
                          const __grid_constant__ CUtensorMap map_k,
                          const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
-  using C = ACfg<D, kBKV>;
+  using C = ACfg<D, kBKV, NSB, KS>;
   // 128-byte swizzle atoms need 1024-byte aligned tiles; there is no static shared memory in this
   // kernel, so the dynamic window starts aligned (checked below — two CTAs per SM leave no slack).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -103,9 +113,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
   uint64_t* o_full = bars + 14;
   uint64_t* o_empty = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* xch = reinterpret_cast<float*>(sp + C::kPBytes + 192);   // [3][2][kBQ] (KS == 2 only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBQ;
+  // causal: the tiles with the most key blocks are scheduled first (no long tail of late heavy CTAs)
+  const int q0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * kBQ;
   const int h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.n_q_heads / p.n_kv_heads);
   const int causal_off = p.kv_len - p.q_len;
@@ -128,11 +140,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
     }
     for (int sb = 0; sb < 2; ++sb) {
       mbar_init(&s_full[sb], 1);
-      mbar_init(&s_empty[sb], 4);
+      mbar_init(&s_empty[sb], 4 * KS);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 4 * KS);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 4 * KS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -143,8 +155,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;          // + 128 * (j & 1)
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_s = tmem_base;          // + kBKV * (j % NSB)
+  const uint32_t tmem_o = tmem_base + (uint32_t)C::kOCol;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -173,9 +185,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       constexpr uint32_t idesc_s = umma_idesc_f16(kBQ, kBKV, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_f16(kBQ, D, 0, 1);  // B = V is MN-major
       auto issue_s = [&](int j) {
-        const int st = j % kKVStages, sb = j & 1;
+        const int st = j % kKVStages, sb = j % NSB;
         mbar_wait(&k_full[st], (uint32_t)(j / kKVStages) & 1u);
-        if (j >= 2) mbar_wait(&s_empty[sb], (uint32_t)((j >> 1) - 1) & 1u);   // softmax done with S_{j-2}
+        if (j >= NSB) mbar_wait(&s_empty[sb], (uint32_t)((j / NSB) - 1) & 1u);   // softmax done with S_{j-NSB}
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -184,19 +196,17 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
           const uint64_t db =
               umma_desc_k_sw128(smem_u32(sk + st * C::kKBytes + (kk / 4) * (kBKV * 128))) +
               (uint64_t)((kk % 4) * 2);
-          umma_f16_ss(tmem_s + (uint32_t)(sb * 128), da, db, idesc_s, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_s + (uint32_t)(sb * kBKV), da, db, idesc_s, kk != 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[sb]);
       };
       mbar_wait(q_full, 0);
-      issue_s(0);
-      if (n_blocks > 1) issue_s(1);
+      for (int j = 0; j < NSB && j < n_blocks; ++j) issue_s(j);
       for (int j = 0; j < n_blocks; ++j) {
         const int st = j % kKVStages;
         mbar_wait(&v_full[st], (uint32_t)(j / kKVStages) & 1u);
-        mbar_wait(p_full, (uint32_t)j & 1u);
-        if (j > 0) mbar_wait(o_empty, (uint32_t)(j - 1) & 1u);
+        mbar_wait(p_full, (uint32_t)j & 1u);     // P_j written (and O rescaled if the maximum jumped)
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kBKV / 16; ++kk) {
@@ -204,126 +214,121 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
               umma_desc_k_sw128(smem_u32(sp + (kk / 4) * (kBQ * 128))) + (uint64_t)((kk % 4) * 2);
           const uint64_t db = umma_desc_mn_sw128(smem_u32(sv + st * C::kKBytes + kk * 2048),
                                                  (uint32_t)(kBKV * 128));
-          umma_f16_ss(tmem_o, da, db, idesc_o, kk != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);   // O accumulates over the blocks
         }
         umma_commit(&v_empty[st]);
         umma_commit(o_full);
-        if (j + 2 < n_blocks) issue_s(j + 2);   // keeps the tensor pipe busy under the next softmax
+        if (j + NSB < n_blocks) issue_s(j + NSB);   // keeps the tensor pipe busy under the next softmax
       }
     }
   } else {
-    // ===================== softmax + output (warps 2..5) =====================
-    const int quad = warp & 3;
+    // ===================== softmax + output (warps 2 .. 2+4*KS) =====================
+    // KS threads share a query row: thread (r, half) owns kBKV/KS score columns and D/KS output dims, so
+    // the per-block softmax work of a row is split over two warps of the same TMEM lane quadrant (KS = 2:
+    // 8 softmax warps per CTA, two per scheduler — the lone warp per scheduler of KS = 1 could not hide its
+    // own tcgen05.ld / MUFU latencies).  The halves exchange the block maximum (and the row sum at the end).
+    constexpr int CW = kBKV / KS, DH = D / KS;
+    const int quad = warp & 3;             // TMEM lane quadrant a warp may access = warp id mod 4
+    const int half = (warp - 2) >> 2;      // 0 .. KS-1
     const int r = quad * 32 + lane;        // row inside the query tile == TMEM lane
     const int qpos = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+    const uint32_t tmem_o_own = tmem_o + lane_addr + (uint32_t)(half * DH);
+    // TMEM reads are the scarce resource of this kernel (64 B/clk/SM: reading S twice and O once per block
+    // cost ~3000 of the ~4000 cycles a block took).  So: the S row is read ONCE into registers, and O stays
+    // in TMEM as the accumulator of the P·V MMAs — it is only touched when the running maximum moved by more
+    // than 2^8 (lazy rescale: P is computed against a slightly stale maximum, exact after the final 1/l).
+    float m_ref = -INFINITY, l_run = 0.f;
     const int key_limit = p.causal ? min(p.kv_len - 1, qpos + causal_off) : p.kv_len - 1;
 
-    // O_{j-1} = P_{j-1}·V_{j-1} is folded into the register accumulator AFTER pass 1 of block j, so
-    // the P·V MMA runs under that pass instead of stalling the softmax warps.
-    auto fold_o = [&](int jj) {
-      mbar_wait(o_full, (uint32_t)jj & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] += __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
-    };
-
     for (int j = 0; j < n_blocks; ++j) {
-      const int sb = j & 1;
-      const uint32_t tmem_sj = tmem_s + (uint32_t)(sb * 128);
-      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
+      const int sb = j % NSB;
+      const uint32_t tmem_sj = tmem_s + (uint32_t)(sb * kBKV) + lane_addr + (uint32_t)(half * CW);
+      mbar_wait(&s_full[sb], (uint32_t)(j / NSB) & 1u);
       tc_fence_after();
-      const int key0 = j * kBKV;
-      // Interior blocks (every key visible to every row of the warp) take a mask-free path: the
-      // softmax warps are instruction-bound, so per-element compares are not free.
-      const bool full_blk = __all_sync(0xffffffffu, key0 + kBKV - 1 <= key_limit);
-      // ---- pass 1: row maximum of this block
+      const int key0 = j * kBKV + half * CW;
+      uint32_t sv[CW];
+#pragma unroll
+      for (int c0 = 0; c0 < CW; c0 += 32) tmem_ld_32x32b_x32(tmem_sj + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&sv[c0]));
+      tmem_ld_wait();
+      // interior blocks (every key visible to every row of the warp) skip the mask
+      if (!__all_sync(0xffffffffu, key0 + CW - 1 <= key_limit)) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i)
+          if (key0 + i > key_limit) sv[i] = 0xff800000u;   // -inf
+      }
       float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kBKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_sj + lane_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (full_blk) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            m_blk = fmaxf(m_blk, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-        } else {
+      for (int i = 0; i < CW; i += 2) m_blk = fmaxf(m_blk, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+      if (KS == 2) {
+        // the two halves of a row agree on the block maximum (double-buffered by block parity)
+        float* mx = xch + (j & 1) * (2 * kBQ);
+        mx[half * kBQ + r] = m_blk;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        m_blk = fmaxf(m_blk, mx[(half ^ 1) * kBQ + r]);
+      }
+      const float m_new = fmaxf(m_ref, m_blk);
+      // rescale O (and l) only when the maximum moved by more than 2^8; identical decision in both halves
+      const bool need = (m_new - m_ref) * p.scale_log2 > 8.f;   // also true for m_ref == -inf < m_new
+      bool o_seen = false;     // has this thread observed the completion of P·V_{j-1} in this block?
+      if (j == 0) {
+        m_ref = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        o_seen = true;
+        const float alpha = need ? exp2f((m_ref - m_new) * p.scale_log2) : 1.f;   // m_ref == -inf -> 0 (O row is 0)
+        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);        // P·V_{j-1} has landed in O
+        tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + c0 + i <= key_limit) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_o_own + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x32(tmem_o_own + (uint32_t)c0, v);
         }
+        tmem_st_wait();
+        l_run *= alpha;
+        if (need) m_ref = m_new;
       }
-      const float m_new = fmaxf(m_run, m_blk);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f((m_run - m_use) * p.scale_log2);  // m_run == -inf -> 0
-      const float mb = m_use * p.scale_log2;
-      if (j > 0) fold_o(j - 1);          // also guarantees P·V_{j-1} has finished reading the P tile
-      if (__any_sync(0xffffffffu, alpha != 1.f)) {   // the running max rarely moves after the first blocks
+      // P·V_{j-1} must have finished READING the P tile before block j overwrites it (this also observes every
+      // phase of o_full in order — an mbarrier parity wait is only sound one phase behind)
+      if (j > 0 && !o_seen) mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+      const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
+      // ---- P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
+      unsigned long long sc2, mb2, l2 = 0ull;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(p.scale_log2));
+      asm("mov.b64 %0, {%1, %1};" : "=l"(mb2) : "f"(-mb));
 #pragma unroll
-        for (int i = 0; i < D; ++i) o_acc[i] *= alpha;
-      }
-      // ---- pass 2: P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
-      float l_blk = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < kBKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_sj + lane_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
+      for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t packed[16];
-        if (full_blk) {
-          // packed fp32x2 FMA for the scale/shift (half the FMA-pipe instructions), MUFU ex2
-          unsigned long long sc2, mb2, l2 = 0ull;
-          asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(p.scale_log2));
-          asm("mov.b64 %0, {%1, %1};" : "=l"(mb2) : "f"(-mb));
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            unsigned long long x2, e2;
-            asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(v[i]), "r"(v[i + 1]));
-            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(x2), "l"(sc2), "l"(mb2));
-            float x0, x1;
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(p0), "f"(p1));
-            asm("add.f32x2 %0, %0, %1;" : "+l"(l2) : "l"(e2));
-            packed[i >> 1] = f2_to_h2(p0, p1);
-          }
-          float la, lb;
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(la), "=f"(lb) : "l"(l2));
-          l_blk += la + lb;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = 0.f, p1 = 0.f;
-            if (key0 + c0 + i <= key_limit) p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mb));
-            if (key0 + c0 + i + 1 <= key_limit)
-              p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mb));
-            l_blk += p0 + p1;
-            packed[i >> 1] = f2_to_h2(p0, p1);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          unsigned long long x2, e2;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "r"(sv[c0 + i]), "r"(sv[c0 + i + 1]));
+          asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(x2), "l"(sc2), "l"(mb2));
+          float x0, x1;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);   // exp2(-inf) = 0 for masked keys
+          asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(p0), "f"(p1));
+          asm("add.f32x2 %0, %0, %1;" : "+l"(l2) : "l"(e2));
+          packed[i >> 1] = f2_to_h2(p0, p1);
         }
-        uint8_t* tile = sp + (c0 / 64) * (kBQ * 128) + r * 128;
+        const int cc = half * CW + c0;     // column inside the kBKV-wide P tile
+        uint8_t* tile = sp + (cc / 64) * (kBQ * 128) + r * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c0 % 64) / 8 + q) ^ (r & 7);
+          const int chunk = ((cc % 64) / 8 + q) ^ (r & 7);
           *reinterpret_cast<uint4*>(tile + chunk * 16) =
               make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
         }
       }
-      // S_j fully consumed -> the issuer may overwrite this buffer with S_{j+2}; P_j is ready
+      {
+        float la, lb;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(la), "=f"(lb) : "l"(l2));
+        l_run += la + lb;
+      }
+      // S_j fully consumed -> the issuer may overwrite this buffer with S_{j+NSB}; P_j (and a rescaled O) ready
       tc_fence_before();
       fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor core
       __syncwarp();
@@ -331,25 +336,44 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         mbar_arrive(&s_empty[sb]);
         mbar_arrive(p_full);
       }
-      l_run = l_run * alpha + l_blk;
-      m_run = m_new;
     }
-    if (n_blocks > 0) fold_o(n_blocks - 1);
-
-    if (qpos < p.q_len) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __half* op = p.out + (long long)b * p.o_stride_b + (long long)qpos * p.o_stride_t +
-                   (long long)h * p.o_stride_h;
+    if (KS == 2) {
+      // row sum = sum of the halves' partial sums (both against the same reference maximum)
+      float* ls = xch + 2 * (2 * kBQ);
+      ls[half * kBQ + r] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      l_run += ls[(half ^ 1) * kBQ + r];
+    }
+    if (n_blocks > 0) {
+      mbar_wait(o_full, (uint32_t)(n_blocks - 1) & 1u);
+      tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __half* op = p.out + (long long)b * p.o_stride_b + (long long)qpos * p.o_stride_t +
+                 (long long)h * p.o_stride_h + half * DH;
 #pragma unroll
-      for (int c = 0; c < D; c += 8) {
-        uint4 o;
-        o.x = f2_to_h2(o_acc[c] * inv, o_acc[c + 1] * inv);
-        o.y = f2_to_h2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-        o.z = f2_to_h2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
-        o.w = f2_to_h2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
-        *reinterpret_cast<uint4*>(op + c) = o;
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t v[32];
+      if (n_blocks > 0) {
+        tmem_ld_32x32b_x32(tmem_o_own + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (qpos < p.q_len) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 o;
+          o.x = f2_to_h2(__uint_as_float(v[c]) * inv, __uint_as_float(v[c + 1]) * inv);
+          o.y = f2_to_h2(__uint_as_float(v[c + 2]) * inv, __uint_as_float(v[c + 3]) * inv);
+          o.z = f2_to_h2(__uint_as_float(v[c + 4]) * inv, __uint_as_float(v[c + 5]) * inv);
+          o.w = f2_to_h2(__uint_as_float(v[c + 6]) * inv, __uint_as_float(v[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c0 + c) = o;
+        }
       }
     }
+    tc_fence_before();
   }
 
   tc_fence_before();
@@ -401,9 +425,9 @@ int make_map4(CUtensorMap* out, const void* ptr, int d, long long len, int heads
   return SCB_OK;
 }
 
-template <int D, int kBKV>
+template <int D, int kBKV, int NSB, int KS>
 int launch_attn(const scb_attention_args* a, cudaStream_t st) {
-  using C = ACfg<D, kBKV>;
+  using C = ACfg<D, kBKV, NSB, KS>;
   CUtensorMap mq, mk, mv;
   int rc = make_map4(&mq, a->q, D, a->q_len, a->n_q_heads, a->batch, a->q_stride_t, a->q_stride_h,
                      a->q_stride_b, kBQ);
@@ -421,7 +445,7 @@ int launch_attn(const scb_attention_args* a, cudaStream_t st) {
   p.n_q_heads = a->n_q_heads; p.n_kv_heads = a->n_kv_heads;
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  auto kern = attention_tcgen05_kernel<D, kBKV>;
+  auto kern = attention_tcgen05_kernel<D, kBKV, NSB, KS>;
   static bool attr_set = false;
   if (!attr_set) {
     SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,7 +453,7 @@ int launch_attn(const scb_attention_args* a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((unsigned)((a->q_len + kBQ - 1) / kBQ), (unsigned)a->n_q_heads, (unsigned)a->batch);
-  kern<<<grid, kAttnThreads, C::kSmemBytes, st>>>(mq, mk, mv, p);
+  kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(mq, mk, mv, p);
   SCB_LAUNCH_OK("attention_tcgen05_kernel");
   return SCB_OK;
 }
@@ -457,6 +481,15 @@ extern "C" int scb_attention(const scb_attention_args* a, void* stream) {
   SCB_REQUIRE(((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v | (uintptr_t)a->out) % 16 == 0,
               SCB_ERR_INVALID_ARG, "scb_attention: buffers must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->head_dim == 64) return launch_attn<64, 128>(a, st);
-  return launch_attn<128, 128>(a, st);
+  // variants: 0 = 128-key blocks, one thread per row; 1 = 128-key blocks, two threads per row (8 softmax
+  // warps); 2 = 64-key blocks, one thread per row, TWO CTAs per SM (256 TMEM columns, 112 KB each): the two
+  // CTAs drift apart, so one reads S from TMEM (64 B/clk/SM) while the other one is in its exp2 phase.
+  static const int v64 = [] { const char* e = getenv("SCB_ATTN64"); return e ? atoi(e) : 2; }();
+  static const int v128 = [] { const char* e = getenv("SCB_ATTN128"); return e ? atoi(e) : 2; }();
+  if (a->head_dim == 64) {
+    if (v64 == 2) return launch_attn<64, 64, 2, 1>(a, st);
+    return v64 == 1 ? launch_attn<64, 128, 2, 2>(a, st) : launch_attn<64, 128, 2, 1>(a, st);
+  }
+  if (v128 == 2) return launch_attn<128, 64, 2, 1>(a, st);
+  return v128 == 1 ? launch_attn<128, 128, 2, 2>(a, st) : launch_attn<128, 128, 2, 1>(a, st);
 }

@@ -85,6 +85,18 @@ def bench_kmeans():
     print(json.dumps({"kernel": "kmeans_assign_only", "ms": med * 1e3, "gbs": by / med / 1e9}))
 
 
+def bench_attn():
+    import math
+    for name, B, T, Hq, Hkv, D, causal in [("qwen2_prefill", 1, 5824, 28, 4, 128, True), ("clip_vit", 64, 577, 16, 16, 64, False)]:
+        q = torch.randn(B, T, Hq, D, device=dev).half()
+        k = torch.randn(B, T, Hkv, D, device=dev).half()
+        v = torch.randn(B, T, Hkv, D, device=dev).half()
+        med, best = timeit(lambda: ops.attention(q, k, v, 1.0 / math.sqrt(D), causal), iters=10, flush=False)
+        fl = 4.0 * B * Hq * T * T * D * (0.5 if causal else 1.0)
+        print(json.dumps({"kernel": "attention", "shape": name, "us": med * 1e6, "tflops": fl / med / 1e12,
+                          "variant": os.environ.get("SCB_ATTN128" if D == 128 else "SCB_ATTN64", "default")}))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["linear", "topk", "kmeans"]
     for w in which:

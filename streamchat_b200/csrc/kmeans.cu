@@ -14,8 +14,8 @@
 //                    4 points x K accumulators in registers and does the (x-c)^2 sums with
 //                    packed fp32x2 FADD2/FFMA2.  Partials are reduced in a fixed order
 //                    (deterministic labels; no float atomics).
-//   assign_final   : per (b): sum slices in order, sqrt, first-min argmin, weighted counts,
-//                    counting sort of the points by label.
+//   assign_labels  : warp per (b, point): sum slices in order, sqrt, first-min argmin.
+//   assign_sort    : per (b): weighted counts, counting sort of the points by label.
 //   update_partial : grid (column chunks, B).  Thread owns a vector column, walks the sorted
 //                    member list cluster by cluster (single accumulator set), writes the new
 //                    centroid and a partial of |c_old - c_new|^2.
@@ -348,49 +348,227 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
 }
 
 // ------------------------------------------------------------------------------------------
-// assign_final: one block per batch entry.
+// assign_dot_mma — the assign pass for LARGE fp16 problems that only need labels (the memory-tree merge:
+// 400 frames x 516 096 dims).  The packed-fp32 (x-c)^2 kernel above is instruction-bound (~440 warp
+// instructions per 2 KB of points: 2.6 TB/s); argmin_k |x-c_k|^2 == argmin_k (|c_k|^2 - 2 x.c_k), and the
+// dot products are a k-reduction the tensor pipe does as a side job: mma.sync.m16n8k16 with 16 POINTS x 16
+// dims straight from HBM as the A operand (fp16 as stored — no conversion, no staging) and the centroids
+// as the B operand.  Centroids are fp32 means, so each one enters as TWO fp16 terms (hi = fp16(c),
+// lo = fp16(c - hi)): the fp16 products are exact in the fp32 accumulator and the pair carries 22 bits
+// of the centroid, i.e. the dot products are as accurate as the fp32 FMA chain.  ~24 warp instructions
+// per 2 KB.  Not used when the caller wants distances (cancellation near a point's own centroid) or the
+// eps-shifted torch distance: those keep the exact kernel.
+//   partial[b][tile*4 + quarter][n][k] = sum over the quarter's columns of x[n][d] * c[b][k][d]
+//   cnorm_partial[b][tile][k]          = sum over the tile's columns of c[b][k][d]^2
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-kmeans_assign_final(const float* __restrict__ partial, const float* __restrict__ weights,
-                    int n_points, int n_clusters, int n_slices, int* __restrict__ labels,
-                    float* __restrict__ out_dist, float* __restrict__ wsum,
-                    int* __restrict__ order, int* __restrict__ starts) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  __shared__ int cnt[kMaxClusters + 1];
-  // one warp per point: lanes stride over the partial slices (fixed order -> deterministic sums)
+constexpr int kDotTileCols = 2048;
+constexpr int kDotThreads = 256;   // (512-column tiles / 128-thread blocks were measured slower: 119 vs 113 us)
+constexpr int kDotRowBytes = kDotTileCols * 2 + 64;      // +64 B: clusters g and g+1 land on different banks
+constexpr int kDotSmem = 2 * 8 * kDotRowBytes;           // hi and lo tiles, 8 cluster rows each
+
+SCB_DEVICE void mma16816_km(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                            uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kDotThreads, 2)
+kmeans_assign_dot_mma(const __half* __restrict__ x, const float* __restrict__ cent, int n_points,
+                      int n_clusters, long long dim, float* __restrict__ partial,
+                      float* __restrict__ cnorm_partial) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t* c_hi = dsm;
+  uint8_t* c_lo = dsm + 8 * kDotRowBytes;
+  __shared__ float cn_red[kDotThreads / 32][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.y, n_tiles = gridDim.x;
+  const long long col0 = (long long)tile * kDotTileCols;
+  const int ncols = (int)min((long long)kDotTileCols, dim - col0);
+  const float* cb = cent + (long long)b * n_clusters * dim + col0;
+
+  // ---- stage the centroid tile as fp16 (hi, lo) pairs; rows >= n_clusters and columns >= ncols are zero
   {
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int n = warp; n < n_points; n += kThreads / 32) {
-      float best = INFINITY;
-      int bi = 0;
-      for (int k = 0; k < n_clusters; ++k) {
-        float s = 0.f;
-        for (int sl = lane; sl < n_slices; sl += 32)
-          s += partial[(((long long)b * n_slices + sl) * n_points + n) * n_clusters + k];
-        s = warp_sum(s);
-        const float d = sqrtf(s);
-        if (k == 0 || d < best) {  // first minimum wins (torch.argmin; NaN-free inputs assumed)
-          best = d;
-          bi = k;
-        }
-      }
-      if (lane == 0) {
-        labels[(long long)b * n_points + n] = bi;
-        if (out_dist) out_dist[(long long)b * n_points + n] = best;
-      }
+    float cn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cn[k] = 0.f;
+    for (int i = tid; i < 8 * (kDotTileCols / 4); i += kDotThreads) {
+      const int k = i / (kDotTileCols / 4), c = (i - k * (kDotTileCols / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < n_clusters && c < ncols) v = *reinterpret_cast<const float4*>(cb + (long long)k * dim + c);   // ncols % 8 == 0
+      const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+      const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+      const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+      uint2 hv, lv;
+      hv.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      hv.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+      lv.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      lv.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+      *reinterpret_cast<uint2*>(c_hi + k * kDotRowBytes + c * 2) = hv;
+      *reinterpret_cast<uint2*>(c_lo + k * kDotRowBytes + c * 2) = lv;
+      const float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) cn[kk] += (kk == k) ? sq : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = warp_sum(cn[k]);
+      if (lane == 0) cn_red[warp][k] = v;
     }
   }
-  if (order == nullptr) return;
   __syncthreads();
-  // Stable counting sort by label (serial over points per cluster owner: N is small) and
-  // weight sums in ascending point order (deterministic).
+  if (tid < n_clusters) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDotThreads / 32; ++w) v += cn_red[w][tid];
+    cnorm_partial[((long long)b * n_tiles + tile) * n_clusters + tid] = v;
+  }
+
+  // ---- work items = (group of 16 points, quarter of the tile's columns), handed to the warps round-robin
+  const int g = lane >> 2, t = lane & 3;
+  const int n_groups = (n_points + 15) >> 4;
+  const uint32_t hi_s = smem_u32(c_hi) + (uint32_t)(g * kDotRowBytes + t * 16);
+  const uint32_t lo_s = smem_u32(c_lo) + (uint32_t)(g * kDotRowBytes + t * 16);
+  constexpr int QCOLS = kDotTileCols / 4, QSTEPS = QCOLS / 32;
+  for (int item = warp; item < n_groups * 4; item += kDotThreads / 32) {
+    const int grp = item >> 2, q = item & 3;
+    const int r0 = min(grp * 16 + g, n_points - 1), r1 = min(grp * 16 + g + 8, n_points - 1);   // clamped rows are discarded
+    const __half* p0 = x + (long long)r0 * dim + col0 + q * QCOLS + t * 8;
+    const __half* p1 = x + (long long)r1 * dim + col0 + q * QCOLS + t * 8;
+    const int lim = ncols - q * QCOLS - t * 8;     // columns left from this thread's first element
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s0 = 0; s0 < QSTEPS; s0 += 4) {
+      uint4 a0[4], a1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {          // 8 x 16 B in flight per thread
+        const bool ok = (s0 + u) * 32 < lim;
+        a0[u] = ok ? ld_stream_u4(p0 + (s0 + u) * 32) : make_uint4(0, 0, 0, 0);
+        a1[u] = ok ? ld_stream_u4(p1 + (s0 + u) * 32) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t off = (uint32_t)((q * QCOLS + (s0 + u) * 32) * 2);
+        uint4 bh, bl;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(bh.x), "=r"(bh.y), "=r"(bh.z), "=r"(bh.w) : "r"(hi_s + off));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(bl.x), "=r"(bl.y), "=r"(bl.z), "=r"(bl.w) : "r"(lo_s + off));
+        mma16816_km(d0, a0[u].x, a1[u].x, a0[u].y, a1[u].y, bh.x, bh.y);
+        mma16816_km(d1, a0[u].z, a1[u].z, a0[u].w, a1[u].w, bh.z, bh.w);
+        mma16816_km(d0, a0[u].x, a1[u].x, a0[u].y, a1[u].y, bl.x, bl.y);
+        mma16816_km(d1, a0[u].z, a1[u].z, a0[u].w, a1[u].w, bl.z, bl.w);
+      }
+    }
+    // D[m][n]: thread (g,t) holds points g / g+8, clusters 2t / 2t+1
+    float* pp = partial + (((long long)b * n_tiles + tile) * 4 + q) * (long long)n_points * n_clusters;
+    const int n0 = grp * 16 + g, n1 = n0 + 8, k0 = 2 * t;
+    if (n0 < n_points) {
+      if (k0 < n_clusters) pp[(long long)n0 * n_clusters + k0] = d0[0] + d1[0];
+      if (k0 + 1 < n_clusters) pp[(long long)n0 * n_clusters + k0 + 1] = d0[1] + d1[1];
+    }
+    if (n1 < n_points) {
+      if (k0 < n_clusters) pp[(long long)n1 * n_clusters + k0] = d0[2] + d1[2];
+      if (k0 + 1 < n_clusters) pp[(long long)n1 * n_clusters + k0 + 1] = d0[3] + d1[3];
+    }
+  }
+}
+
+// labels from the dot products: argmin_k (|c_k|^2 - 2 x.c_k), first minimum wins
+__global__ void __launch_bounds__(kThreads)
+kmeans_assign_labels_dot(const float* __restrict__ partial, const float* __restrict__ cnorm_partial,
+                         int n_points, int n_clusters, int n_slices, int n_tiles, int* __restrict__ labels) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * (kThreads / 32) + warp;
+  if (n >= n_points) return;
+  const float* pp = partial + ((long long)b * n_slices * n_points + n) * n_clusters;
+  const long long slice_stride = (long long)n_points * n_clusters;
+  float best = INFINITY;
+  int bi = 0;
+  for (int k = 0; k < n_clusters; ++k) {
+    float s = 0.f, cn = 0.f;
+    // 32 independent loads in flight per lane (one L2 round trip per 1024 slices), summed in slice order
+    for (int s0 = 0; s0 < n_slices; s0 += 1024) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int sl = s0 + j * 32 + lane;
+        v[j] = sl < n_slices ? pp[(long long)sl * slice_stride + k] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += v[j];
+    }
+    for (int tl = lane; tl < n_tiles; tl += 32) cn += cnorm_partial[((long long)b * n_tiles + tl) * n_clusters + k];
+    s = warp_sum(s);
+    cn = warp_sum(cn);
+    const float score = cn - 2.f * s;
+    if (k == 0 || score < best) {
+      best = score;
+      bi = k;
+    }
+  }
+  if (lane == 0) labels[(long long)b * n_points + n] = bi;
+}
+
+// ------------------------------------------------------------------------------------------
+// assign_final: two small kernels.
+//   assign_labels : one WARP per (batch entry, point), 8 points per block: the K x n_slices partial sums of
+//                   a point are summed in slice order with every load of a cluster in flight at once.
+//                   (The first version ran all points of a batch entry through ONE block, a serial chain
+//                   of ~250 dependent L2 round trips: 320 us of the 617 us Lloyd iteration at 400 x 516 096.)
+//   assign_sort   : one block per batch entry: stable counting sort of the points by label + weight sums
+//                   from a shared-memory copy of the labels.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+kmeans_assign_labels(const float* __restrict__ partial, int n_points, int n_clusters, int n_slices,
+                     int* __restrict__ labels, float* __restrict__ out_dist) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * (kThreads / 32) + warp;
+  if (n >= n_points) return;
+  const float* pp = partial + ((long long)b * n_slices * n_points + n) * n_clusters;
+  const long long slice_stride = (long long)n_points * n_clusters;
+  float best = INFINITY;
+  int bi = 0;
+  for (int k = 0; k < n_clusters; ++k) {
+    // lanes stride over the slices; fixed order per lane, then the xor tree -> deterministic sums
+    float s = 0.f;
+    int sl = lane;
+    for (; sl + 96 < n_slices; sl += 128) {
+      const float a0 = pp[(long long)sl * slice_stride + k], a1 = pp[(long long)(sl + 32) * slice_stride + k];
+      const float a2 = pp[(long long)(sl + 64) * slice_stride + k], a3 = pp[(long long)(sl + 96) * slice_stride + k];
+      s += a0; s += a1; s += a2; s += a3;
+    }
+    for (; sl < n_slices; sl += 32) s += pp[(long long)sl * slice_stride + k];
+    s = warp_sum(s);
+    const float d = sqrtf(s);
+    if (k == 0 || d < best) {  // first minimum wins (torch.argmin; NaN-free inputs assumed)
+      best = d;
+      bi = k;
+    }
+  }
+  if (lane == 0) {
+    labels[(long long)b * n_points + n] = bi;
+    if (out_dist) out_dist[(long long)b * n_points + n] = best;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+kmeans_assign_sort(const int* __restrict__ labels, const float* __restrict__ weights, int n_points,
+                   int n_clusters, float* __restrict__ wsum, int* __restrict__ order,
+                   int* __restrict__ starts) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  extern __shared__ int lab_s[];            // [n_points]
+  __shared__ int cnt[kMaxClusters + 1];
+  for (int i = tid; i < n_points; i += kThreads) lab_s[i] = labels[(long long)b * n_points + i];
   if (tid <= n_clusters) cnt[tid] = 0;
   __syncthreads();
+  // stable counting sort (serial over points per cluster owner: N is small) and weight sums in
+  // ascending point order (deterministic)
   if (tid < n_clusters) {
     int c = 0;
     float ws = 0.f;
     for (int n = 0; n < n_points; ++n)
-      if (labels[(long long)b * n_points + n] == tid) {
+      if (lab_s[n] == tid) {
         ++c;
         ws += weights ? weights[n] : 1.f;
       }
@@ -406,15 +584,15 @@ kmeans_assign_final(const float* __restrict__ partial, const float* __restrict__
   if (tid < n_clusters) {
     int pos = cnt[tid];
     for (int n = 0; n < n_points; ++n)
-      if (labels[(long long)b * n_points + n] == tid) order[(long long)b * n_points + pos++] = n;
+      if (lab_s[n] == tid) order[(long long)b * n_points + pos++] = n;
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // update_partial
 // ------------------------------------------------------------------------------------------
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(kThreads)
+template <typename T, bool kVec, int TH>
+__global__ void __launch_bounds__(TH)
 kmeans_update_partial(const T* __restrict__ x, const float* __restrict__ weights,
                       const float* __restrict__ cent, const int* __restrict__ order,
                       const int* __restrict__ starts, const float* __restrict__ wsum, int n_points,
@@ -426,12 +604,12 @@ kmeans_update_partial(const T* __restrict__ x, const float* __restrict__ weights
   const int n_chunks = gridDim.x;
   extern __shared__ int sm_order[];  // [n_points] member list of this batch entry
   __shared__ int sm_starts[kMaxClusters + 1];
-  __shared__ float red[kThreads / 32];
-  for (int i = tid; i < n_points; i += kThreads) sm_order[i] = order[(long long)b * n_points + i];
+  __shared__ float red[TH / 32];
+  for (int i = tid; i < n_points; i += TH) sm_order[i] = order[(long long)b * n_points + i];
   if (tid <= n_clusters) sm_starts[tid] = starts[(long long)b * (n_clusters + 1) + tid];
   __syncthreads();
 
-  const long long col = ((long long)blockIdx.x * kThreads + tid) * E;
+  const long long col = ((long long)blockIdx.x * TH + tid) * E;
   const bool active = col < dim;
   for (int k = 0; k < n_clusters; ++k) {
     float acc[E];
@@ -508,7 +686,7 @@ kmeans_update_partial(const T* __restrict__ x, const float* __restrict__ weights
     if (tid == 0) {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) v += red[w];
+      for (int w = 0; w < TH / 32; ++w) v += red[w];
       shift_partial[((long long)b * n_clusters + k) * n_chunks + blockIdx.x] = v;
     }
     __syncthreads();
@@ -533,7 +711,8 @@ struct Plan {
   int n_slices;                   // partial-sum slices summed by assign_final
   int kt_async = 8;
   int n_chunks;                   // update: column chunks
-  size_t partial_off, order_off, starts_off, shiftp_off, total;
+  int dot_tiles;                  // assign_dot_mma: column tiles of 2048 (0 = path not applicable)
+  size_t partial_off, order_off, starts_off, shiftp_off, cnorm_off, total;
 };
 
 Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esize, bool aligned) {
@@ -565,15 +744,23 @@ Plan make_plan(int n_points, int n_clusters, int n_batch, long long dim, int esi
   p.points_per_split = groups_per_split * kPG;
   p.n_splits = (n_points + p.points_per_split - 1) / p.points_per_split;
   p.n_chunks = (int)passes;
+  // tensor-pipe dot-product assign: fp16 points, 16-byte rows, <= 8 clusters, big enough to matter
+  p.dot_tiles = (esize == 2 && p.vec && n_clusters <= 8 && dim % 8 == 0 && (long long)n_points * dim >= (1ll << 24))
+                    ? (int)((dim + kDotTileCols - 1) / kDotTileCols) : 0;
   size_t off = 0;
   p.partial_off = off;
-  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * p.n_slices * n_points * n_clusters, 256);
+  size_t n_part = (size_t)n_batch * p.n_slices * n_points * n_clusters;
+  const size_t n_part_dot = (size_t)n_batch * p.dot_tiles * 4 * n_points * n_clusters;
+  if (n_part_dot > n_part) n_part = n_part_dot;
+  off = scb_align_up(off + sizeof(float) * n_part, 256);
   p.order_off = off;
   off = scb_align_up(off + sizeof(int) * (size_t)n_batch * n_points, 256);
   p.starts_off = off;
   off = scb_align_up(off + sizeof(int) * (size_t)n_batch * (n_clusters + 1), 256);
   p.shiftp_off = off;
-  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * n_clusters * p.n_chunks, 256);
+  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * n_clusters * p.n_chunks * (kThreads / 64), 256);
+  p.cnorm_off = off;
+  off = scb_align_up(off + sizeof(float) * (size_t)n_batch * (p.dot_tiles + 1) * n_clusters, 256);
   p.total = off;
   return p;
 }
@@ -595,6 +782,23 @@ int run(const scb_kmeans_step_args* a, cudaStream_t st) {
   float* shiftp = reinterpret_cast<float*>(ws + p.shiftp_off);
   const T* x = reinterpret_cast<const T*>(a->points);
 
+  const bool use_dot = p.dot_tiles > 0 && a->dist_eps == 0.f && a->out_dist == nullptr && sizeof(T) == 2 &&
+                       a->n_batch <= 65535;
+  if (use_dot) {
+    float* cnorm_p = reinterpret_cast<float*>(ws + p.cnorm_off);
+    static bool attr = false;
+    if (!attr) {
+      SCB_CUDA_OK(cudaFuncSetAttribute(kmeans_assign_dot_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDotSmem));
+      attr = true;
+    }
+    kmeans_assign_dot_mma<<<dim3(p.dot_tiles, a->n_batch), kDotThreads, kDotSmem, st>>>(
+        reinterpret_cast<const __half*>(a->points), a->centroids, a->n_points, a->n_clusters, a->dim, partial, cnorm_p);
+    SCB_LAUNCH_OK("kmeans_assign_dot_mma");
+    dim3 gl((a->n_points + kThreads / 32 - 1) / (kThreads / 32), a->n_batch);
+    kmeans_assign_labels_dot<<<gl, kThreads, 0, st>>>(partial, cnorm_p, a->n_points, a->n_clusters, p.dot_tiles * 4,
+                                                      p.dot_tiles, a->out_labels);
+    SCB_LAUNCH_OK("kmeans_assign_labels_dot");
+  } else {
   dim3 g1(p.n_tiles, p.n_splits, a->n_batch);
   const bool eps = a->dist_eps != 0.f;
 #define SCB_KM_ASSIGN(VEC, EPS)                                                                    \
@@ -628,24 +832,36 @@ int run(const scb_kmeans_step_args* a, cudaStream_t st) {
 #undef SCB_KM_ASYNC
   SCB_LAUNCH_OK("kmeans_assign_partial");
 
-  kmeans_assign_final<<<a->n_batch, kThreads, 0, st>>>(
-      partial, a->weights, a->n_points, a->n_clusters, p.n_slices, a->out_labels, a->out_dist,
-      a->do_update ? a->out_wsum : nullptr, a->do_update ? order : nullptr, starts);
-  SCB_LAUNCH_OK("kmeans_assign_final");
+  dim3 gl((a->n_points + kThreads / 32 - 1) / (kThreads / 32), a->n_batch);
+  kmeans_assign_labels<<<gl, kThreads, 0, st>>>(partial, a->n_points, a->n_clusters, p.n_slices, a->out_labels,
+                                                a->out_dist);
+  SCB_LAUNCH_OK("kmeans_assign_labels");
+  }
   if (!a->do_update) return SCB_OK;
+  kmeans_assign_sort<<<a->n_batch, kThreads, sizeof(int) * (size_t)a->n_points, st>>>(
+      a->out_labels, a->weights, a->n_points, a->n_clusters, a->out_wsum, order, starts);
+  SCB_LAUNCH_OK("kmeans_assign_sort");
 
-  dim3 g2(p.n_chunks, a->n_batch);
+  // (64-thread blocks — ~1000 blocks, all resident — were measured slower than 256-thread ones: 153 vs 122 us)
+  const bool small_blocks = false;
+  const int upd_threads = small_blocks ? 64 : kThreads;
+  const int upd_chunks = small_blocks ? p.n_chunks * (kThreads / 64) : p.n_chunks;
+  dim3 g2(upd_chunks, a->n_batch);
   size_t smem = sizeof(int) * (size_t)a->n_points;
-  if (p.vec)
-    kmeans_update_partial<T, true><<<g2, kThreads, smem, st>>>(
+  if (small_blocks)
+    kmeans_update_partial<T, true, 64><<<g2, upd_threads, smem, st>>>(
+        x, a->weights, a->centroids, order, starts, a->out_wsum, a->n_points, a->n_clusters, a->dim,
+        a->out_centroids, shiftp);
+  else if (p.vec)
+    kmeans_update_partial<T, true, kThreads><<<g2, kThreads, smem, st>>>(
         x, a->weights, a->centroids, order, starts, a->out_wsum, a->n_points, a->n_clusters, a->dim,
         a->out_centroids, shiftp);
   else
-    kmeans_update_partial<T, false><<<g2, kThreads, smem, st>>>(
+    kmeans_update_partial<T, false, kThreads><<<g2, kThreads, smem, st>>>(
         x, a->weights, a->centroids, order, starts, a->out_wsum, a->n_points, a->n_clusters, a->dim,
         a->out_centroids, shiftp);
   SCB_LAUNCH_OK("kmeans_update_partial");
-  kmeans_update_final<<<a->n_batch * a->n_clusters, 32, 0, st>>>(shiftp, p.n_chunks, a->out_shift);
+  kmeans_update_final<<<a->n_batch * a->n_clusters, 32, 0, st>>>(shiftp, upd_chunks, a->out_shift);
   SCB_LAUNCH_OK("kmeans_update_final");
   return SCB_OK;
 }

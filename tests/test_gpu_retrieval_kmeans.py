@@ -150,3 +150,27 @@ def test_kmeans_merge_size_properties(cuda):
     r2 = ops.kmeans_step(x, r["centroids"], None, do_update=True)
     assert torch.equal(r2["labels"][0].long(), planted)
     assert float(r2["shift"].sum()) < 1e-2
+
+
+def test_kmeans_dot_assign_matches_exact_assign(cuda):
+    """Large fp16 problems that only need labels take the tensor-pipe dot-product assign
+    (argmin_k |c_k|^2 - 2 x.c_k, centroids as fp16 hi+lo pairs); asking for distances forces the exact
+    (x-c)^2 kernel.  Same labels, same updated centroids — on clustered AND on structureless points
+    (ragged sizes: 70 points = 4.4 groups of 16, dim not a multiple of the 2048-column tile)."""
+    from streamchat_b200 import ops
+    torch.manual_seed(7)
+    n, d, k = 70, 262144 + 1032, 5
+    for clustered in (True, False):
+        x = torch.randn(n, d, device=cuda)
+        if clustered:
+            centers = torch.randn(k, d, device=cuda) * 2
+            x = x * 0.5 + centers[torch.randint(0, k, (n,), device=cuda)]
+        x = x.half()
+        cent = x[:k].float().unsqueeze(0).contiguous()
+        for _ in range(3):
+            fast = ops.kmeans_step(x, cent, None, do_update=True, want_dist=False)
+            exact = ops.kmeans_step(x, cent, None, do_update=True, want_dist=True)
+            assert torch.equal(fast["labels"], exact["labels"])
+            assert torch.equal(fast["centroids"], exact["centroids"])
+            cent = exact["centroids"]
+            cent[exact["wsum"] == 0] = x[0].float()       # keep empty clusters alive (host repair rule, not under test)

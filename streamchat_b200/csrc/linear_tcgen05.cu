@@ -18,6 +18,7 @@
 #include "scb_common.cuh"
 #include <math.h>
 #include <mutex>
+#include <stdlib.h>
 #include <unordered_map>
 
 namespace {
@@ -47,6 +48,7 @@ struct EpiParams {
   int out_f32;
   int batch;
   int res_vec, out_vec;  // 16-byte vector access is legal for residual / out rows
+  int gm;                // rasterisation: M tiles per group (tm fastest inside a group, then tn, then the next group)
   float alpha;
 };
 
@@ -61,6 +63,20 @@ SCB_DEVICE float apply_act(float v, int act) {
     default:
       return v;
   }
+}
+
+// Tile order.  Consecutive tile indices run over the M tiles of a GROUP of gm M-tiles first, then over N,
+// then to the next group: the ~148 tiles in flight share gm A row-panels and ~148/gm W panels through L2.
+// gm = tiles_m (one group) streams W once and re-reads A per N tile — right when A fits L2 (prefill
+// gate|up); a small gm reads A once and re-reads W per group — right when A is the big operand (down_proj,
+// CLIP fc2 at 64 frames: the A re-reads of the one-group order made those HBM-bound at ~5 TB/s).
+SCB_DEVICE void tile_coords(int r, int tiles_m, int tiles_n, int gm, int& tm, int& tn) {
+  const int per_group = gm * tiles_n;
+  const int grp = r / per_group, rem = r - grp * per_group;
+  const int m0 = grp * gm;
+  const int gsize = min(gm, tiles_m - m0);
+  tn = rem / gsize;
+  tm = m0 + rem - tn * gsize;
 }
 
 template <int BN>
@@ -118,7 +134,8 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int b = (int)(t / tiles_per_batch);
         const int r = (int)(t - (long long)b * tiles_per_batch);
-        const int tm = r % tiles_m, tn = r / tiles_m;
+        int tm, tn;
+        tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
@@ -175,7 +192,8 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int b = (int)(t / tiles_per_batch);
       const int r = (int)(t - (long long)b * tiles_per_batch);
-      const int tm = r % tiles_m, tn = r / tiles_m;
+      int tm, tn;
+      tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const long long row = (long long)tm * BM + quad * 32 + lane;
@@ -417,6 +435,16 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   ep.out_f32 = a->out_dtype == SCB_F32;
   ep.batch = a->batch;
   ep.alpha = a->alpha;
+  {
+    // A panel bytes decide the order (see tile_coords): one group while A stays L2-resident, groups of 8 otherwise
+    static const int force_gm = [] { const char* e = getenv("SCB_LINEAR_GM"); return e ? atoi(e) : 0; }();   // tuning aid
+    const long long tiles_m = (a->m + BM - 1) / BM;
+    const long long a_bytes = (long long)a->m * a->k * 2;
+    int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : 8;
+    if (force_gm > 0) gm = force_gm;
+    if (gm > tiles_m) gm = (int)tiles_m;
+    ep.gm = gm < 1 ? 1 : gm;
+  }
   const int ov = ep.out_f32 ? 4 : 8;
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
@@ -468,6 +496,9 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // Narrow problems keep more CTAs busy with 128-wide tiles; wide ones amortise A with 256.
   const long long tiles256 = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256) * a->batch;
+  static const int force_bn = [] { const char* e = getenv("SCB_LINEAR_BN"); return e ? atoi(e) : 0; }();   // tuning aid
+  if (force_bn == 128) return launch<128>(a, st);
+  if (force_bn == 256 && a->n > 128) return launch<256>(a, st);
   if (a->n <= 128 || tiles256 < scb_num_sms()) return launch<128>(a, st);
   return launch<256>(a, st);
 }

@@ -301,6 +301,8 @@ class Qwen2Engine:
             raise ValueError("max_new_tokens must be a positive int or one per sequence")
         order = sorted(range(n), key=lambda i: -budgets[i])           # slot s holds caller's sequence order[s]
         cap = self._ctx_bucket(max(int(x.shape[0]) + b for x, b in zip(inputs_embeds_list, budgets)))
+        if os.environ.get("SCB_NO_GRAPH") == "1":      # profiling aid: every kernel as its own launch (ncu launch lists)
+            use_graph = False
         with torch.cuda.device(self.device):
             if use_graph:
                 for r in sorted({sum(1 for b in budgets if b > t) for t in [0] + budgets} - {0}):

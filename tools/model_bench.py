@@ -51,3 +51,20 @@ if tokens:
     ms = timed(pf, 1 if once else 3)
     fl = eng.prefill_flops(tokens)
     print(f"prefill {tokens} tokens: {ms:.2f} ms  {fl / ms / 1e9:.0f} TFLOP/s")
+
+if tokens and "--graph" in sys.argv:
+    # same prefill captured in a CUDA graph: what do the host-side launch gaps cost?
+    eng.reset()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng.reset(); eng.prefill(x)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    eng.reset()
+    with torch.cuda.graph(g):
+        eng.prefill(x)
+    eng.reset()
+    ms = timed(lambda: g.replay(), 3)
+    print(f"prefill {tokens} tokens, CUDA graph replay: {ms:.2f} ms  {eng.prefill_flops(tokens) / ms / 1e9:.0f} TFLOP/s")

@@ -27,11 +27,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 192;
 
-template <int BN>
+template <int BN, bool CG2 = false>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  // CG2 (CTA pair, cta_group::2 MMA): a CTA stages only ITS half of the W tile -> 32 KB per stage, 6 stages
+  static constexpr int kStages = CG2 ? 6 : ((BN == 256) ? 4 : 6);
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (CG2 ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -79,11 +80,79 @@ SCB_DEVICE void tile_coords(int r, int tiles_m, int tiles_n, int gm, int& tm, in
   tm = m0 + rem - tn * gsize;
 }
 
-template <int BN>
+// ---- CTA-pair variant (CG2): the two CTAs of a cluster compute ONE 256 x BN tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256): each CTA stages its own 128 rows of A and its own HALF of the W
+// tile, the leader CTA (rank 0) issues the MMAs, which read A from both CTAs' shared memory and each half of
+// W once — per CTA and k-block 32 KB land in shared memory and 8 KB are read per MMA instead of 48 / 12, which
+// is what the single-CTA tile is bound by (128 B/clk of shared-memory bandwidth against 96 B/clk of operand
+// reads + 96 B/clk of TMA writes).  Accumulator rows stay with their CTA (128 TMEM lanes each), so the
+// epilogue is unchanged.  Cross-CTA signalling: TMA completions of both CTAs count on the LEADER's full
+// barrier, tcgen05.commit multicasts slot releases / accumulator-ready to both CTAs, the peer's epilogue
+// warps arrive on the leader's accumulator-empty barrier through the cluster address space.
+SCB_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SCB_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+SCB_DEVICE uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+SCB_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of a CTA pair member: data into THIS CTA's shared memory, bytes counted on `bar_cluster_addr`
+// (a shared::cluster address — the leader's barrier)
+SCB_DEVICE void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0,
+                                int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "r"(c2)
+      : "memory");
+}
+SCB_DEVICE void umma_f16_ss_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+SCB_DEVICE void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+SCB_DEVICE void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+SCB_DEVICE void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+SCB_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int BN, bool MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_w, const EpiParams ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MC>;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned tile bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -98,11 +167,17 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (int)((ep.m + BM - 1) / BM);
+  const int tiles_m_real = (int)((ep.m + BM - 1) / BM);
+  // MC: the schedule runs over PAIRS of M tiles (one per CTA of the cluster); a missing second tile of an odd
+  // count reads zero rows and stores nothing
+  const int tiles_m = MC ? (tiles_m_real + 1) / 2 : tiles_m_real;
   const int tiles_n = (int)((ep.n + BN - 1) / BN);
   const long long tiles_per_batch = (long long)tiles_m * tiles_n;
   const long long n_tiles = tiles_per_batch * ep.batch;
   const int k_blocks = (int)((ep.k + BK - 1) / BK);
+  const int crank = MC ? (int)cluster_ctarank() : 0;
+  const long long t_first = MC ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long t_step = MC ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -113,16 +188,22 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[s], MC ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (MC) {
+      tmem_alloc_cg2(tmem_slot, C::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,16 +212,25 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (long long t = t_first; t < n_tiles; t += t_step) {
         const int b = (int)(t / tiles_per_batch);
         const int r = (int)(t - (long long)b * tiles_per_batch);
         int tm, tn;
         tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
+        if (MC) tm = 2 * tm + crank;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-          tma_load_3d(smem_a + stage * C::kABytes, &map_a, &full[stage], kb * BK, tm * BM, b);
-          tma_load_3d(smem_b + stage * C::kBBytes, &map_w, &full[stage], kb * BK, tn * BN, b);
+          if (MC) {
+            // both CTAs' bytes count on the leader's barrier (armed by the leader for the pair)
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            tma_load_3d_cg2(smem_a + stage * C::kABytes, &map_a, lbar, kb * BK, tm * BM, b);
+            tma_load_3d_cg2(smem_b + stage * C::kBBytes, &map_w, lbar, kb * BK, tn * BN + crank * (BN / 2), b);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+            tma_load_3d(smem_a + stage * C::kABytes, &map_a, &full[stage], kb * BK, tm * BM, b);
+            tma_load_3d(smem_b + stage * C::kBBytes, &map_w, &full[stage], kb * BK, tn * BN, b);
+          }
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -150,13 +240,13 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    if (lane == 0 && (!MC || crank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_f16(MC ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (long long t = t_first; t < n_tiles; t += t_step) {
         mbar_wait(&tempty[as], aphase ^ 1);  // epilogue drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -168,16 +258,20 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the >>4 address field
-            umma_f16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                        (kb | kk) != 0 ? 1u : 0u);
+            if (MC)
+              umma_f16_ss_cg2(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            else
+              umma_f16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (MC) umma_commit_cg2(&empty[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
+          else umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        if (MC) umma_commit_cg2(&tfull[as], (uint16_t)3);   // accumulator complete -> both CTAs' epilogues
+        else umma_commit(&tfull[as]);  // accumulator complete -> epilogue
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -189,11 +283,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int as = 0;
     uint32_t aphase = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    for (long long t = t_first; t < n_tiles; t += t_step) {
       const int b = (int)(t / tiles_per_batch);
       const int r = (int)(t - (long long)b * tiles_per_batch);
       int tm, tn;
       tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
+      if (MC) tm = 2 * tm + crank;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const long long row = (long long)tm * BM + quad * 32 + lane;
@@ -323,7 +418,10 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       // all TMEM reads of this warp are complete (wait::ld above): release the stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (MC && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));   // the leader's MMA warp waits
+        else mbar_arrive(&tempty[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -333,10 +431,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / read it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (MC) tmem_dealloc_cg2(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -416,13 +516,13 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long k, lon
   return SCB_OK;
 }
 
-template <int BN>
+template <int BN, bool MC>
 int launch(const scb_linear_args* a, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MC>;
   CUtensorMap ma, mw;
   int rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->stride_a, a->batch, BM);
   if (rc != SCB_OK) return rc;
-  rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, BN);
+  rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, MC ? BN / 2 : BN);
   if (rc != SCB_OK) return rc;
   EpiParams ep;
   ep.bias = reinterpret_cast<const __half*>(a->bias);
@@ -438,9 +538,9 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   {
     // A panel bytes decide the order (see tile_coords): one group while A stays L2-resident, groups of 8 otherwise
     static const int force_gm = [] { const char* e = getenv("SCB_LINEAR_GM"); return e ? atoi(e) : 0; }();   // tuning aid
-    const long long tiles_m = (a->m + BM - 1) / BM;
+    const long long tiles_m = MC ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
     const long long a_bytes = (long long)a->m * a->k * 2;
-    int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : 8;
+    int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : (MC ? 4 : 8);
     if (force_gm > 0) gm = force_gm;
     if (gm > tiles_m) gm = (int)tiles_m;
     ep.gm = gm < 1 ? 1 : gm;
@@ -449,16 +549,34 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
   static bool attr_set = false;  // per template instantiation
-  auto kern = linear_tcgen05_kernel<BN>;
+  auto kern = linear_tcgen05_kernel<BN, MC>;
   if (!attr_set) {
     SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     attr_set = true;
   }
-  const long long tiles = ((a->m + BM - 1) / BM) * ((a->n + BN - 1) / BN) * a->batch;
+  const long long tm_sched = MC ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
+  const long long tiles = tm_sched * ((a->n + BN - 1) / BN) * a->batch;
   const int sms = scb_num_sms();
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  kern<<<grid, kGemmThreads, C::kSmemBytes, st>>>(ma, mw, ep);
+  if (MC) {
+    const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mw, ep));
+  } else {
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    kern<<<grid, kGemmThreads, C::kSmemBytes, st>>>(ma, mw, ep);
+  }
   SCB_LAUNCH_OK("linear_tcgen05_kernel");
   return SCB_OK;
 }
@@ -497,8 +615,10 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
   // Narrow problems keep more CTAs busy with 128-wide tiles; wide ones amortise A with 256.
   const long long tiles256 = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256) * a->batch;
   static const int force_bn = [] { const char* e = getenv("SCB_LINEAR_BN"); return e ? atoi(e) : 0; }();   // tuning aid
-  if (force_bn == 128) return launch<128>(a, st);
-  if (force_bn == 256 && a->n > 128) return launch<256>(a, st);
-  if (a->n <= 128 || tiles256 < scb_num_sms()) return launch<128>(a, st);
-  return launch<256>(a, st);
+  static const int use_mc = [] { const char* e = getenv("SCB_LINEAR_PAIR"); return e ? atoi(e) : 1; }();   // 0: single-CTA tiles only
+  if (force_bn == 128) return launch<128, false>(a, st);
+  if (a->n <= 128 || (tiles256 < scb_num_sms() && force_bn != 256)) return launch<128, false>(a, st);
+  // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two M tiles to pair up
+  if (use_mc && a->m > BM) return launch<256, true>(a, st);
+  return launch<256, false>(a, st);
 }

@@ -358,7 +358,8 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
 // of the centroid, i.e. the dot products are as accurate as the fp32 FMA chain.  ~24 warp instructions
 // per 2 KB.  Not used when the caller wants distances (cancellation near a point's own centroid) or the
 // eps-shifted torch distance: those keep the exact kernel.
-//   partial[b][tile*4 + quarter][n][k] = sum over the quarter's columns of x[n][d] * c[b][k][d]
+//   partial[b][n][k][tile*4 + quarter] = sum over the quarter's columns of x[n][d] * c[b][k][d]
+//                                        (slice index contiguous: the label kernel reads whole lines)
 //   cnorm_partial[b][tile][k]          = sum over the tile's columns of c[b][k][d]^2
 // ------------------------------------------------------------------------------------------
 constexpr int kDotTileCols = 2048;
@@ -461,15 +462,16 @@ kmeans_assign_dot_mma(const __half* __restrict__ x, const float* __restrict__ ce
       }
     }
     // D[m][n]: thread (g,t) holds points g / g+8, clusters 2t / 2t+1
-    float* pp = partial + (((long long)b * n_tiles + tile) * 4 + q) * (long long)n_points * n_clusters;
+    const long long n_slices = (long long)n_tiles * 4;
+    float* pp = partial + (long long)b * n_points * n_clusters * n_slices + (tile * 4 + q);
     const int n0 = grp * 16 + g, n1 = n0 + 8, k0 = 2 * t;
     if (n0 < n_points) {
-      if (k0 < n_clusters) pp[(long long)n0 * n_clusters + k0] = d0[0] + d1[0];
-      if (k0 + 1 < n_clusters) pp[(long long)n0 * n_clusters + k0 + 1] = d0[1] + d1[1];
+      if (k0 < n_clusters) pp[((long long)n0 * n_clusters + k0) * n_slices] = d0[0] + d1[0];
+      if (k0 + 1 < n_clusters) pp[((long long)n0 * n_clusters + k0 + 1) * n_slices] = d0[1] + d1[1];
     }
     if (n1 < n_points) {
-      if (k0 < n_clusters) pp[(long long)n1 * n_clusters + k0] = d0[2] + d1[2];
-      if (k0 + 1 < n_clusters) pp[(long long)n1 * n_clusters + k0 + 1] = d0[3] + d1[3];
+      if (k0 < n_clusters) pp[((long long)n1 * n_clusters + k0) * n_slices] = d0[2] + d1[2];
+      if (k0 + 1 < n_clusters) pp[((long long)n1 * n_clusters + k0 + 1) * n_slices] = d0[3] + d1[3];
     }
   }
 }
@@ -481,19 +483,19 @@ kmeans_assign_labels_dot(const float* __restrict__ partial, const float* __restr
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * (kThreads / 32) + warp;
   if (n >= n_points) return;
-  const float* pp = partial + ((long long)b * n_slices * n_points + n) * n_clusters;
-  const long long slice_stride = (long long)n_points * n_clusters;
+  const float* pp = partial + ((long long)b * n_points + n) * n_clusters * (long long)n_slices;
   float best = INFINITY;
   int bi = 0;
   for (int k = 0; k < n_clusters; ++k) {
+    const float* pk = pp + (long long)k * n_slices;
     float s = 0.f, cn = 0.f;
-    // 32 independent loads in flight per lane (one L2 round trip per 1024 slices), summed in slice order
+    // 32 independent coalesced loads in flight per lane (one round trip per 1024 slices), fixed order
     for (int s0 = 0; s0 < n_slices; s0 += 1024) {
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int sl = s0 + j * 32 + lane;
-        v[j] = sl < n_slices ? pp[(long long)sl * slice_stride + k] : 0.f;
+        v[j] = sl < n_slices ? pk[sl] : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) s += v[j];
@@ -562,15 +564,60 @@ kmeans_assign_sort(const int* __restrict__ labels, const float* __restrict__ wei
   for (int i = tid; i < n_points; i += kThreads) lab_s[i] = labels[(long long)b * n_points + i];
   if (tid <= n_clusters) cnt[tid] = 0;
   __syncthreads();
-  // stable counting sort (serial over points per cluster owner: N is small) and weight sums in
-  // ascending point order (deterministic)
+  if (weights == nullptr) {
+    // Unweighted (every caller on the hot path): warp w owns the contiguous point range [w*per, (w+1)*per);
+    // ballots count / place the members of each cluster in ascending point order (stable), counts are exact
+    // integers so wsum is bit-identical to the serial sum.
+    __shared__ int wcnt[kThreads / 32][kMaxClusters];
+    const int lane = tid & 31, warp = tid >> 5;
+    const int per = (((n_points + kThreads / 32 - 1) / (kThreads / 32)) + 31) & ~31;
+    const int n0 = warp * per, n1 = min(n_points, n0 + per);
+    for (int k = lane; k < n_clusters; k += 32) wcnt[warp][k] = 0;
+    __syncwarp();
+    for (int c0 = n0; c0 < n1; c0 += 32) {
+      const int lab = (c0 + lane < n1) ? lab_s[c0 + lane] : -1;
+      for (int k = 0; k < n_clusters; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, lab == k);
+        if (lane == 0 && m) wcnt[warp][k] += __popc(m);
+      }
+    }
+    __syncthreads();
+    if (tid < n_clusters) {
+      int c = 0;
+      for (int w = 0; w < kThreads / 32; ++w) {
+        const int v = wcnt[w][tid];
+        wcnt[w][tid] = c;              // exclusive prefix over the warps: this warp's first slot inside cluster tid
+        c += v;
+      }
+      cnt[tid + 1] = c;
+      wsum[(long long)b * n_clusters + tid] = (float)c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < n_clusters; ++k) cnt[k + 1] += cnt[k];
+      for (int k = 0; k <= n_clusters; ++k) starts[(long long)b * (n_clusters + 1) + k] = cnt[k];
+    }
+    __syncthreads();
+    for (int c0 = n0; c0 < n1; c0 += 32) {
+      const int lab = (c0 + lane < n1) ? lab_s[c0 + lane] : -1;
+      for (int k = 0; k < n_clusters; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, lab == k);
+        if (lab == k) order[(long long)b * n_points + cnt[k] + wcnt[warp][k] + __popc(m & ((1u << lane) - 1u))] = c0 + lane;
+        __syncwarp();
+        if (lane == 0 && m) wcnt[warp][k] += __popc(m);
+        __syncwarp();
+      }
+    }
+    return;
+  }
+  // weighted: serial per cluster owner, weight sums in ascending point order (deterministic)
   if (tid < n_clusters) {
     int c = 0;
     float ws = 0.f;
     for (int n = 0; n < n_points; ++n)
       if (lab_s[n] == tid) {
         ++c;
-        ws += weights ? weights[n] : 1.f;
+        ws += weights[n];
       }
     cnt[tid + 1] = c;
     wsum[(long long)b * n_clusters + tid] = ws;

@@ -155,7 +155,7 @@ class LocalMemoryRetrieval:
             return None, loaded
         if not vs_path:
             vs_path = f"memory_index_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}"
-        emb = self.embeddings([d.page_content for d in docs]).to(self.device, torch.float32).contiguous()
+        emb = self._embed_cached([d.page_content for d in docs])
         prev = self._stores.get(vs_path) if os.path.isdir(vs_path) else None
         if prev is not None:                                                # FAISS.load_local + add_documents (:238-241)
             docs = prev.docs + docs
@@ -164,8 +164,44 @@ class LocalMemoryRetrieval:
         os.makedirs(vs_path, exist_ok=True)                                 # keeps the driver's exists()/rmtree logic valid
         return vs_path, loaded
 
-    def load_memory_index(self, vs_path):
+    # ---- O(new turns) per question instead of O(history) -------------------------------------
+    # The reference re-embeds the whole dialogue history and rewrites the FAISS directory on every question
+    # (memory_utils.py:76-83).  Same results here with (1) an embedding cache keyed by the turn text, so only
+    # turns not seen before go through the encoder, and (2) an explicit snapshot of the device-resident index
+    # (one file, written when the caller asks) instead of a per-question rewrite.
+    _embed_cache: Dict[str, torch.Tensor] = {}
+    embed_calls: int = 0       # texts actually sent to the encoder (tests / accounting)
+
+    def _embed_cached(self, texts: Sequence[str]) -> torch.Tensor:
+        cache = self._embed_cache
+        new = [t for t in dict.fromkeys(texts) if t not in cache]
+        if new:
+            rows = self.embeddings(new).to(self.device, torch.float32)
+            self.embed_calls += len(new)
+            for t, r in zip(new, rows):
+                cache[t] = r
+        return torch.stack([cache[t] for t in texts]).contiguous()
+
+    def save_snapshot(self, vs_path: str) -> str:
+        """Write the index held for `vs_path` (documents + fp32 embeddings) to `<vs_path>/index.pt`."""
         store = self._stores[vs_path]
+        os.makedirs(vs_path, exist_ok=True)
+        path = os.path.join(vs_path, "index.pt")
+        torch.save({"docs": [(d.page_content, d.metadata) for d in store.docs],
+                    "embeddings": store.embeddings.detach().cpu(), "chunk_size": store.chunk_size}, path)
+        return path
+
+    def load_memory_index(self, vs_path):
+        store = self._stores.get(vs_path)
+        if store is None:                                                   # new process: resume from the snapshot
+            path = os.path.join(vs_path, "index.pt")
+            if not os.path.exists(path):
+                raise KeyError(f"no memory index for {vs_path!r} (neither in this process nor snapshotted)")
+            blob = torch.load(path, map_location="cpu")
+            docs = [Document(t, dict(m)) for t, m in blob["docs"]]
+            store = MemoryIndex(docs, blob["embeddings"].to(self.device, torch.float32).contiguous(), self.embeddings,
+                                blob.get("chunk_size", self.chunk_size))
+            self._stores[vs_path] = store
         store.chunk_size = self.chunk_size
         return store
 

@@ -110,3 +110,44 @@ def test_dropin_import_paths():
         sys.path.remove(os.path.join(root, "dropin"))
         for m in [k for k in sys.modules if k.split(".")[0] in ("longva", "utiles", "torch_kmeans", "memory_bank")]:
             del sys.modules[m]
+
+
+def test_embedding_cache_and_snapshot_cpu(tmp_path):
+    """§8f-4: a second build of the index embeds only the turns it has not seen, and the index can be
+    snapshotted and reloaded in a fresh retrieval object (no search here: that needs the GPU)."""
+    import json
+
+    from streamchat_b200.memory_bank import LocalMemoryRetrieval
+    seen = []
+
+    def embed_fn(texts):
+        seen.append(list(texts))
+        return torch.from_numpy(_embed_np(list(texts)))
+
+    def write(n_turns):
+        mem = {"alice": {"name": "alice", "history": {"2024-05-01": [{"query": f"q{i}", "response": f"a{i}"} for i in range(n_turns)]}}}
+        p = tmp_path / "mem.json"
+        p.write_text(json.dumps(mem))
+        return str(p)
+
+    qa = LocalMemoryRetrieval()
+    qa._stores, qa._embed_cache = {}, {}
+    qa.init_cfg("minilm-l6", "cpu", 1, "en", embed_fn=embed_fn)
+    qa.device = torch.device("cpu")
+    vs = str(tmp_path / "vs")
+    qa.init_memory_vector_store(write(3), vs, "alice")
+    n_first = sum(len(t) for t in seen)
+    import shutil
+    shutil.rmtree(vs)                                   # the driver deletes the directory before every rebuild
+    qa.init_memory_vector_store(write(5), vs, "alice")
+    n_second = sum(len(t) for t in seen) - n_first
+    store = qa.load_memory_index(vs)
+    assert n_second == len(store.docs) - n_first > 0    # only the new turns went through the encoder
+    path = qa.save_snapshot(vs)
+    qb = LocalMemoryRetrieval()
+    qb._stores = {}
+    qb.init_cfg("minilm-l6", "cpu", 1, "en", embed_fn=embed_fn)
+    qb.device = torch.device("cpu")
+    again = qb.load_memory_index(vs)
+    assert [d.page_content for d in again.docs] == [d.page_content for d in store.docs]
+    assert torch.equal(again.embeddings, store.embeddings) and os.path.exists(path)

@@ -197,8 +197,17 @@ class Qwen2Engine:
         hd, Hq, Hkv = c.head_dim, c.num_attention_heads, c.num_key_value_heads
         if self._use_mega(R):
             cap = ctx_cap if 0 < ctx_cap < self.max_ctx else self.max_ctx
-            self._mega.step(R, self.next_id, self.state[1], self._logits, counters=self.state.view(-1), ctx_cap=cap)
-            return
+            try:
+                self._mega.step(R, self.next_id, self.state[1], self._logits, counters=self.state.view(-1), ctx_cap=cap)
+                return
+            except L.ScbError as e:
+                # e.g. a cooperative launch refused because the device is partitioned / shared, or a (rows, context)
+                # combination whose activations leave no room for the weight ring: the per-layer chain (also CUDA)
+                # takes over.  Launch errors surface before anything ran, so the step is simply redone there.
+                if torch.cuda.is_current_stream_capturing():
+                    raise
+                self.mega_unsupported = str(e)
+                self.mega_rows = R - 1
         scale = hd ** -0.5
         x, x2, nrm = self._x[:R], self._x2[:R], self._nrm[:R]
         eps = c.rms_norm_eps

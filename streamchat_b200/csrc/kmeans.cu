@@ -355,7 +355,7 @@ kmeans_assign_partial_async(const T* __restrict__ x, const float* __restrict__ c
 // dims straight from HBM as the A operand (fp16 as stored — no conversion, no staging) and the centroids
 // as the B operand.  Centroids are fp32 means, so each one enters as TWO fp16 terms (hi = fp16(c),
 // lo = fp16(c - hi)): the fp16 products are exact in the fp32 accumulator and the pair carries 22 bits
-// of the centroid, i.e. the dot products are as accurate as the fp32 FMA chain.  ~24 warp instructions
+// of the centroid (absolute floor 2^-25 from fp16 subnormals), i.e. the dot products are as accurate as the fp32 FMA chain.  ~24 warp instructions
 // per 2 KB.  Not used when the caller wants distances (cancellation near a point's own centroid) or the
 // eps-shifted torch distance: those keep the exact kernel.
 //   partial[b][n][k][tile*4 + quarter] = sum over the quarter's columns of x[n][d] * c[b][k][d]

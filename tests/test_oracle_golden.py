@@ -65,3 +65,28 @@ def test_cos_topk_oracle_properties():
     assert oret.running_argmax_top1([-0.5, -0.1]) is None
     assert oret.running_argmax_top1([0.2, 0.7, 0.7]) == 1
     assert oret.running_argmax_top1([-1.0], default=0) == 0
+
+
+def test_dot_assign_formulation_matches_exact_assign_cpu():
+    """The large-merge assign kernel ranks clusters by |c|^2 - 2 x.c with every fp32 centroid entering as two
+    fp16 terms (hi = fp16(c), lo = fp16(c - hi)).  On CPU, in float64: (a) the hi+lo pair reproduces the
+    centroid to ~2^-22 relative (absolute floor 2^-25: fp16 subnormals), (b) the ranking equals the arg-min of sum (x-c)^2 on clustered and on
+    structureless fp16 points, including means of several points (not fp16-representable)."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n, d, k = 96, 4096, 5
+    for clustered in (True, False):
+        x = rng.standard_normal((n, d))
+        if clustered:
+            x = 0.5 * x + 2.0 * rng.standard_normal((k, d))[rng.integers(0, k, n)]
+        x = x.astype(np.float16)
+        lab0 = rng.integers(0, k, n)
+        c = np.stack([x[lab0 == j].astype(np.float32).mean(0) for j in range(k)]).astype(np.float32)
+        hi = c.astype(np.float16)
+        lo = (c - hi.astype(np.float32)).astype(np.float16)
+        rec = hi.astype(np.float64) + lo.astype(np.float64)
+        assert np.all(np.abs(rec - c) <= np.maximum(2.0 ** -21 * np.abs(c), 2.0 ** -24))   # 22 bits, fp16-subnormal floor
+        xd = x.astype(np.float64)
+        exact = ((xd[:, None, :] - c.astype(np.float64)[None]) ** 2).sum(-1)
+        score = (rec ** 2).sum(-1)[None, :] - 2.0 * xd @ rec.T
+        assert np.array_equal(exact.argmin(1), score.argmin(1))

@@ -296,7 +296,9 @@ def ours(args):
                               "mma.sync consumers + grid barriers); linear_tcgen05 split-K + reduce + decode_attn_fused for wider "
                               "batches; bytes = weights + live KV per step",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "peak_source": peak_src, "traffic": traffic,
+                    "peak_source": peak_src,
+                    # DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed ncu capture
+                    "traffic": traffic["bytes_per_decode_step"] if traffic else None, "traffic_detail": traffic,
                     "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,
                     "share_of_step_time": dec_ms / (ms if ms else 1)}
 

@@ -148,11 +148,11 @@ SCB_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN, bool MC>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_w, const EpiParams ep) {
-  using C = Cfg<BN, MC>;
+  using C = Cfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned tile bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -168,16 +168,16 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m_real = (int)((ep.m + BM - 1) / BM);
-  // MC: the schedule runs over PAIRS of M tiles (one per CTA of the cluster); a missing second tile of an odd
+  // PAIR: the schedule runs over PAIRS of M tiles (one per CTA of the cluster); a missing second tile of an odd
   // count reads zero rows and stores nothing
-  const int tiles_m = MC ? (tiles_m_real + 1) / 2 : tiles_m_real;
+  const int tiles_m = PAIR ? (tiles_m_real + 1) / 2 : tiles_m_real;
   const int tiles_n = (int)((ep.n + BN - 1) / BN);
   const long long tiles_per_batch = (long long)tiles_m * tiles_n;
   const long long n_tiles = tiles_per_batch * ep.batch;
   const int k_blocks = (int)((ep.k + BK - 1) / BK);
-  const int crank = MC ? (int)cluster_ctarank() : 0;
-  const long long t_first = MC ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
-  const long long t_step = MC ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const long long t_first = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long t_step = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -188,12 +188,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], MC ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (MC) {
+    if (PAIR) {
       tmem_alloc_cg2(tmem_slot, C::kTmemCols);
       tmem_relinquish_cg2();
     } else {
@@ -203,7 +203,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -217,10 +217,10 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         const int r = (int)(t - (long long)b * tiles_per_batch);
         int tm, tn;
         tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
-        if (MC) tm = 2 * tm + crank;
+        if (PAIR) tm = 2 * tm + crank;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (MC) {
+          if (PAIR) {
             // both CTAs' bytes count on the leader's barrier (armed by the leader for the pair)
             if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
             const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
@@ -240,8 +240,8 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && (!MC || crank == 0)) {
-      constexpr uint32_t idesc = umma_idesc_f16(MC ? 2 * BM : BM, BN);
+    if (lane == 0 && (!PAIR || crank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -258,19 +258,19 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in the >>4 address field
-            if (MC)
+            if (PAIR)
               umma_f16_ss_cg2(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
             else
               umma_f16_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          if (MC) umma_commit_cg2(&empty[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
+          if (PAIR) umma_commit_cg2(&empty[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
           else umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (MC) umma_commit_cg2(&tfull[as], (uint16_t)3);   // accumulator complete -> both CTAs' epilogues
+        if (PAIR) umma_commit_cg2(&tfull[as], (uint16_t)3);   // accumulator complete -> both CTAs' epilogues
         else umma_commit(&tfull[as]);  // accumulator complete -> epilogue
         if (++as == 2) {
           as = 0;
@@ -288,7 +288,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const int r = (int)(t - (long long)b * tiles_per_batch);
       int tm, tn;
       tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
-      if (MC) tm = 2 * tm + crank;
+      if (PAIR) tm = 2 * tm + crank;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const long long row = (long long)tm * BM + quad * 32 + lane;
@@ -419,7 +419,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (MC && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));   // the leader's MMA warp waits
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));   // the leader's MMA warp waits
         else mbar_arrive(&tempty[as]);
       }
       if (++as == 2) {
@@ -431,11 +431,11 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / read it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    if (MC) tmem_dealloc_cg2(tmem_base, C::kTmemCols);
+    if (PAIR) tmem_dealloc_cg2(tmem_base, C::kTmemCols);
     else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
@@ -516,13 +516,13 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long k, lon
   return SCB_OK;
 }
 
-template <int BN, bool MC>
+template <int BN, bool PAIR>
 int launch(const scb_linear_args* a, cudaStream_t st) {
-  using C = Cfg<BN, MC>;
+  using C = Cfg<BN, PAIR>;
   CUtensorMap ma, mw;
   int rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->stride_a, a->batch, BM);
   if (rc != SCB_OK) return rc;
-  rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, MC ? BN / 2 : BN);
+  rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, PAIR ? BN / 2 : BN);
   if (rc != SCB_OK) return rc;
   EpiParams ep;
   ep.bias = reinterpret_cast<const __half*>(a->bias);
@@ -538,9 +538,9 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   {
     // A panel bytes decide the order (see tile_coords): one group while A stays L2-resident, groups of 8 otherwise
     static const int force_gm = [] { const char* e = getenv("SCB_LINEAR_GM"); return e ? atoi(e) : 0; }();   // tuning aid
-    const long long tiles_m = MC ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
+    const long long tiles_m = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
     const long long a_bytes = (long long)a->m * a->k * 2;
-    int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : (MC ? 4 : 8);
+    int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : (PAIR ? 4 : 8);
     if (force_gm > 0) gm = force_gm;
     if (gm > tiles_m) gm = (int)tiles_m;
     ep.gm = gm < 1 ? 1 : gm;
@@ -549,16 +549,16 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
   static bool attr_set = false;  // per template instantiation
-  auto kern = linear_tcgen05_kernel<BN, MC>;
+  auto kern = linear_tcgen05_kernel<BN, PAIR>;
   if (!attr_set) {
     SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     attr_set = true;
   }
-  const long long tm_sched = MC ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
+  const long long tm_sched = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
   const long long tiles = tm_sched * ((a->n + BN - 1) / BN) * a->batch;
   const int sms = scb_num_sms();
-  if (MC) {
+  if (PAIR) {
     const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
@@ -615,10 +615,10 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
   // Narrow problems keep more CTAs busy with 128-wide tiles; wide ones amortise A with 256.
   const long long tiles256 = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256) * a->batch;
   static const int force_bn = [] { const char* e = getenv("SCB_LINEAR_BN"); return e ? atoi(e) : 0; }();   // tuning aid
-  static const int use_mc = [] { const char* e = getenv("SCB_LINEAR_PAIR"); return e ? atoi(e) : 1; }();   // 0: single-CTA tiles only
+  static const int use_pair = [] { const char* e = getenv("SCB_LINEAR_PAIR"); return e ? atoi(e) : 1; }();   // 0: single-CTA tiles only
   if (force_bn == 128) return launch<128, false>(a, st);
   if (a->n <= 128 || (tiles256 < scb_num_sms() && force_bn != 256)) return launch<128, false>(a, st);
   // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two M tiles to pair up
-  if (use_mc && a->m > BM) return launch<256, true>(a, st);
+  if (use_pair && a->m > BM) return launch<256, true>(a, st);
   return launch<256, false>(a, st);
 }

@@ -249,10 +249,11 @@ def ours(args):
 
     for _ in range(max(args.warmup, 0)):
         run_stream(factory, frames_dev, host_frames, args.segment, world, rank, device, False)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None     # one nvidia-smi poller per job (rank 0's GPU), not one per rank
+    if sampler:
+        sampler.start()
     ms, _, _, launches, prof = timed(False, args.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     breakdown = {}
     for name, a0, a1 in STAGE_EVENTS:
         breakdown[name] = breakdown.get(name, 0.0) + a0.elapsed_time(a1) / args.steps

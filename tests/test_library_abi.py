@@ -61,3 +61,37 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, f"product modules import the oracle: {bad}"
+
+
+def test_ctypes_structs_match_header_layout(tmp_path):
+    """Every argument struct of the header, compiled by gcc, has the size and the field offsets of its ctypes
+    mirror in streamchat_b200/_lib.py (a renamed or re-ordered field fails to compile or to compare)."""
+    import subprocess
+
+    from streamchat_b200 import _lib
+    pairs = {
+        "scb_cosine_topk_args": _lib.CosineTopkArgs, "scb_kmeans_step_args": _lib.KmeansStepArgs,
+        "scb_linear_args": _lib.LinearArgs, "scb_attention_args": _lib.AttentionArgs, "scb_gemv_args": _lib.GemvArgs,
+        "scb_decode_attention_args": _lib.DecodeAttentionArgs,
+        "scb_decode_attention_fused_args": _lib.DecodeAttentionFusedArgs,
+        "scb_qwen2_decoder_desc": _lib.Qwen2DecoderDesc, "scb_qwen2_decode_step_args": _lib.Qwen2DecodeStepArgs,
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "streamchat_b200.h")}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True, capture_output=True)
+    got = {}
+    for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines():
+        s, f, v = ln.split()
+        got[(s, f)] = int(v)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)

@@ -446,6 +446,16 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
 int scb_qwen2_decoder_destroy(void* handle);
 int scb_qwen2_decoder_max_rows(void);
 int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream);
+/* Long-context prefill of ONE sequence as a single native call over the decoder handle: appends n_tokens
+ * rows of inputs_embeds ([n_tokens, hidden] fp16) to cache slot `slot` at position pos0 (per layer RMSNorm ->
+ * qkv -> RoPE + KV append -> fused causal attention over the cache -> o_proj -> RMSNorm -> gate|up -> down) and
+ * writes the fp16 lm_head row of the LAST position to logits_row [vocab]  (modeling_qwen2.py:269-311, :474-475
+ * reached from llava_qwen.py:155).  Same kernels, order and rounding points as the per-launch path
+ * (scb_rmsnorm / scb_linear / scb_rope_append / scb_attention / scb_gemv).  The first
+ * scb_gemv_workspace_bytes(1) bytes of the workspace must be zero before the first call (they are left zero). */
+size_t scb_qwen2_prefill_workspace_bytes(void* decoder, int64_t n_tokens);
+int scb_qwen2_prefill(void* decoder, const void* inputs_embeds, int64_t n_tokens, int32_t slot, int64_t pos0,
+                      void* logits_row, void* workspace, size_t workspace_bytes, void* stream);
 /* Debug aid: per-CTA clock64 stamps of the last step, 16 per layer (layer start, then after every
  * prologue / stage / grid barrier).  The first call arms the recording and returns 0; later calls
  * copy [n_sm][n_layers][16] int64 into host_out (capacity in elements) and return the count; -1 on error. */

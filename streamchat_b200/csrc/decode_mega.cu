@@ -28,6 +28,7 @@
 #include <mutex>
 #include <new>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -919,6 +920,8 @@ struct MegaHandle {
   void* dev_ws;
   void* dev_prof;
   int smem_limit;
+  MegaLayer* host_layers;   // host copy of the per-layer pointer table (scb_qwen2_prefill)
+  int hidden, inter, vocab, n_q, n_kv, qkv_dim, max_seqs;
 };
 constexpr uint32_t kMagic = 0x51323244u;
 
@@ -991,6 +994,9 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
   h->group = G;
   h->smem_limit = smem_optin;
   h->dev_maps = h->dev_layers = h->dev_ws = h->dev_prof = nullptr;
+  h->host_layers = nullptr;
+  h->hidden = d->hidden; h->inter = d->inter; h->vocab = d->vocab; h->n_q = d->n_q_heads; h->n_kv = d->n_kv_heads;
+  h->qkv_dim = (int)qkv_dim; h->max_seqs = d->max_seqs;
   MegaParams& p = h->base;
   memset(&p, 0, sizeof(p));
   p.n_layers = d->n_layers; p.H = d->hidden; p.n_q = d->n_q_heads; p.n_kv = d->n_kv_heads;
@@ -1066,7 +1072,7 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
     if (h->dev_layers) cudaFree(h->dev_layers);
     if (h->dev_ws) cudaFree(h->dev_ws);
     delete[] maps;
-    delete[] layers;
+    delete[] layers;          // == h->host_layers once the handle has taken it over
     delete h;
     return code;
   };
@@ -1084,7 +1090,8 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
     return fail(SCB_ERR_CUDA);
   }
   delete[] maps;
-  delete[] layers;
+  maps = nullptr;             // fail() below must not free these twice
+  h->host_layers = layers;
   char* ws = reinterpret_cast<char*>(h->dev_ws);
   p.maps = reinterpret_cast<const CUtensorMap*>(h->dev_maps);
   p.layers = reinterpret_cast<const MegaLayer*>(h->dev_layers);
@@ -1126,6 +1133,7 @@ int scb_qwen2_decoder_destroy(void* handle) {
   cudaFree(h->dev_layers);
   cudaFree(h->dev_ws);
   if (h->dev_prof) cudaFree(h->dev_prof);
+  delete[] h->host_layers;
   delete h;
   return SCB_OK;
 }
@@ -1201,6 +1209,111 @@ int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream) {
   SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   SCB_LAUNCH_OK("decode_mega_kernel");
   return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scb_qwen2_prefill — the long-context prefill of one sequence as ONE native call over the decoder
+// handle: per layer RMSNorm -> qkv GEMM (+bias) -> RoPE + KV append -> fused causal attention over the
+// cache -> o_proj GEMM (+residual) -> RMSNorm -> gate|up GEMM (SiLU gate) -> down GEMM (+residual), then
+// final RMSNorm and lm_head on the LAST position only (modeling_qwen2.py:269-311, :474-475 reached from
+// longva/model/language_model/llava_qwen.py:155).  Same kernels, same order and the same rounding points
+// as the per-launch path of qwen2.Qwen2Engine.prefill; only the launch loop moves out of Python.
+// ------------------------------------------------------------------------------------------
+size_t scb_qwen2_prefill_workspace_bytes(void* handle, int64_t n_tokens) {
+  MegaHandle* h = reinterpret_cast<MegaHandle*>(handle);
+  if (h == nullptr || h->magic != kMagic || n_tokens < 1) return 0;
+  const size_t T = (size_t)n_tokens;
+  size_t off = scb_align_up(scb_gemv_workspace_bytes(1), 256);
+  off += 3 * scb_align_up(T * h->hidden * 2, 256);                       // x ping-pong + normalised rows
+  off += scb_align_up(T * (size_t)h->qkv_dim * 2, 256);
+  off += scb_align_up(T * (size_t)h->n_q * h->head_dim * 2, 256);
+  off += scb_align_up(T * (size_t)h->inter * 2, 256);
+  return off;
+}
+
+int scb_qwen2_prefill(void* handle, const void* inputs_embeds, int64_t n_tokens, int32_t slot, int64_t pos0,
+                      void* logits_row, void* workspace, size_t workspace_bytes, void* stream) {
+  MegaHandle* h = reinterpret_cast<MegaHandle*>(handle);
+  SCB_REQUIRE(h != nullptr && h->magic == kMagic, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: bad decoder handle");
+  SCB_REQUIRE(inputs_embeds && logits_row && workspace, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: NULL buffer");
+  SCB_REQUIRE(n_tokens >= 1 && slot >= 0 && slot < h->max_seqs && pos0 >= 0 && pos0 + n_tokens <= h->base.max_ctx,
+              SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: tokens=%lld slot=%d pos0=%lld out of range (max_ctx %lld)",
+              (long long)n_tokens, slot, (long long)pos0, h->base.max_ctx);
+  const size_t need = scb_qwen2_prefill_workspace_bytes(handle, n_tokens);
+  SCB_REQUIRE(workspace_bytes >= need, SCB_ERR_WORKSPACE, "scb_qwen2_prefill: workspace %zu B < required %zu B",
+              workspace_bytes, need);
+  const MegaParams& p = h->base;
+  const size_t T = (size_t)n_tokens;
+  const int H = h->hidden, I = h->inter, hd = h->head_dim, QKV = h->qkv_dim, A = h->n_q * hd;
+  char* ws = reinterpret_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* q = ws + off;
+    off += scb_align_up(bytes, 256);
+    return q;
+  };
+  char* gemv_ws = take(scb_gemv_workspace_bytes(1));     // zero before the first call (ticket), left zero
+  __half* xa = reinterpret_cast<__half*>(take(T * H * 2));
+  __half* xb = reinterpret_cast<__half*>(take(T * H * 2));
+  __half* y = reinterpret_cast<__half*>(take(T * H * 2));
+  __half* qkv = reinterpret_cast<__half*>(take(T * (size_t)QKV * 2));
+  __half* ctx = reinterpret_cast<__half*>(take(T * (size_t)A * 2));
+  __half* gu = reinterpret_cast<__half*>(take(T * (size_t)I * 2));
+  auto linear = [&](const void* a, int64_t k, const void* w, int64_t n, const void* bias, const void* res, void* out,
+                    int act) {
+    scb_linear_args la;
+    memset(&la, 0, sizeof(la));
+    la.a = a; la.w = w; la.bias = bias; la.residual = res; la.out = out;
+    la.m = n_tokens; la.n = n; la.k = k;
+    la.lda = k; la.ldw = k; la.ldr = n; la.ldo = act == SCB_ACT_SILU_PAIR ? n / 2 : n;
+    la.act = act; la.out_dtype = SCB_F16; la.batch = 1; la.alpha = 1.f;
+    return scb_linear(&la, stream);
+  };
+  const __half* x = reinterpret_cast<const __half*>(inputs_embeds);
+  __half* xn = xa;          // output of the current layer's o_proj (x2), then of down (the next x)
+  const float scale = 1.f / sqrtf((float)hd);
+  int rc = SCB_OK;
+  for (int l = 0; l < p.n_layers && rc == SCB_OK; ++l) {
+    const MegaLayer& ly = h->host_layers[l];
+    __half* kc = ly.k_cache + (size_t)slot * p.cache_seq_stride;
+    __half* vc = ly.v_cache + (size_t)slot * p.cache_seq_stride;
+    rc = scb_rmsnorm(x, H, ly.ln1, p.eps, n_tokens, H, y, H, stream);
+    if (rc == SCB_OK) rc = linear(y, H, ly.w[0], QKV, ly.qkv_b, nullptr, qkv, SCB_ACT_NONE);
+    if (rc == SCB_OK)
+      rc = scb_rope_append(qkv, QKV, n_tokens, h->n_q, h->n_kv, hd, nullptr, (int32_t)pos0, p.theta, p.inv_freq, kc, vc,
+                           p.max_ctx, stream);
+    if (rc == SCB_OK) {
+      scb_attention_args aa;
+      memset(&aa, 0, sizeof(aa));
+      aa.q = qkv; aa.k = kc; aa.v = vc; aa.out = ctx;
+      aa.batch = 1; aa.n_q_heads = h->n_q; aa.n_kv_heads = h->n_kv; aa.head_dim = hd;
+      aa.q_len = n_tokens; aa.kv_len = pos0 + n_tokens;
+      aa.q_stride_t = QKV; aa.q_stride_h = hd;
+      aa.k_stride_t = hd; aa.k_stride_h = p.max_ctx * hd;
+      aa.v_stride_t = hd; aa.v_stride_h = p.max_ctx * hd;
+      aa.o_stride_t = A; aa.o_stride_h = hd;
+      aa.scale = scale; aa.causal = 1;
+      rc = scb_attention(&aa, stream);
+    }
+    __half* x2 = (x == xa) ? xb : xa;                       // never the buffer x lives in
+    if (rc == SCB_OK) rc = linear(ctx, A, ly.w[1], H, nullptr, x, x2, SCB_ACT_NONE);
+    if (rc == SCB_OK) rc = scb_rmsnorm(x2, H, ly.ln2, p.eps, n_tokens, H, y, H, stream);
+    if (rc == SCB_OK) rc = linear(y, H, ly.w[2], 2ll * I, nullptr, nullptr, gu, SCB_ACT_SILU_PAIR);
+    xn = (x2 == xa) ? xb : xa;
+    if (rc == SCB_OK) rc = linear(gu, I, ly.w[3], H, nullptr, x2, xn, SCB_ACT_NONE);
+    x = xn;
+  }
+  if (rc != SCB_OK) return rc;
+  // final norm + lm_head on the last position only
+  rc = scb_rmsnorm(x + (T - 1) * H, H, p.final_norm, p.eps, 1, H, y, H, stream);
+  if (rc != SCB_OK) return rc;
+  scb_gemv_args ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.a = y; ga.w = p.lm_head; ga.out = logits_row;
+  ga.n = h->vocab; ga.k = H; ga.lda = H; ga.ldw = H; ga.ldo = h->vocab;
+  ga.rows = 1; ga.prologue = SCB_PRO_NONE; ga.out_dtype = SCB_F16;
+  ga.workspace = gemv_ws; ga.workspace_bytes = scb_gemv_workspace_bytes(1);
+  return scb_gemv(&ga, stream);
 }
 
 }  // extern "C"

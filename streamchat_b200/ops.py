@@ -548,6 +548,21 @@ class Qwen2Decoder:
         a.ctx_cap = ctx_cap
         L.check(L.load().scb_qwen2_decode_step(C.byref(a), _stream(self.device)), "scb_qwen2_decode_step")
 
+    def prefill(self, inputs_embeds: torch.Tensor, slot: int, pos0: int, logits_row: torch.Tensor) -> None:
+        """scb_qwen2_prefill: the whole prefill of one sequence as one native call (see the header)."""
+        _require_cuda(inputs_embeds, logits_row)
+        if inputs_embeds.dtype != torch.float16 or not inputs_embeds.is_contiguous() or logits_row.dtype != torch.float16:
+            raise TypeError("Qwen2Decoder.prefill: contiguous fp16 inputs_embeds, fp16 logits row")
+        lib = L.load()
+        T = inputs_embeds.shape[0]
+        need = int(lib.scb_qwen2_prefill_workspace_bytes(self._h, T))
+        ws = getattr(self, "_prefill_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)     # zero: the lm_head GEMV's ticket
+            self._prefill_ws = ws
+        L.check(lib.scb_qwen2_prefill(self._h, inputs_embeds.data_ptr(), T, slot, pos0, logits_row.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _stream(self.device)), "scb_qwen2_prefill")
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             L.load().scb_qwen2_decoder_destroy(self._h)

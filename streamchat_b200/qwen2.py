@@ -164,6 +164,11 @@ class Qwen2Engine:
         pos0 = self.ctx_lens[slot]
         if pos0 + T > self.max_ctx:
             raise ValueError(f"context {pos0 + T} exceeds max_ctx {self.max_ctx}")
+        if self._mega is not None and os.environ.get("SCB_NATIVE_PREFILL") == "1":
+            # opt-in: the same launches issued by ONE native call (scb_qwen2_prefill) instead of from Python
+            self._mega.prefill(x, slot, pos0, self._logits[slot])
+            self.ctx_lens[slot] = pos0 + T
+            return self._logits[slot:slot + 1]
         scale = hd ** -0.5
         for i, ly in enumerate(self.layers):
             kc, vc = self.k_cache[i][slot], self.v_cache[i][slot]

@@ -40,6 +40,12 @@ def test_version_and_error_string():
     assert lib.scb_cosine_topk_workspace_bytes(10000, 1, 8) > 0
     assert lib.scb_cosine_topk_workspace_bytes(10000, 1, 64) == 0
     assert lib.scb_kmeans_step_workspace_bytes(400, 5, 1, 516096) > 0
+    # handle-based entry points reject a NULL / foreign handle before touching CUDA
+    assert lib.scb_qwen2_prefill_workspace_bytes(None, 16) == 0
+    assert lib.scb_qwen2_prefill(None, None, 16, 0, 0, None, None, 0, None) == -1
+    assert b"handle" in lib.scb_last_error()
+    assert lib.scb_qwen2_decoder_destroy(None) == -1
+    assert lib.scb_qwen2_decoder_max_rows() >= 1
 
 
 def test_product_path_has_no_cpu_fallback():

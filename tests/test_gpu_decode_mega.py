@@ -101,3 +101,27 @@ def test_mega_abi_errors(cuda):
     bad = L.Qwen2DecodeStepArgs()
     assert L.load().scb_qwen2_decode_step(bad, None) != 0                       # NULL handle
     assert b"handle" in L.load().scb_last_error()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SCB_TEST_NATIVE_PREFILL") != "1",
+                    reason="scb_qwen2_prefill was written after round 1's GPU budget was spent: run with "
+                           "SCB_TEST_NATIVE_PREFILL=1 to validate it before making it the default")
+def test_native_prefill_equals_per_launch_prefill(cuda, monkeypatch):
+    """One native call (scb_qwen2_prefill) issues exactly the launches of Qwen2Engine.prefill: logits of the last
+    position and the KV cache rows must be bit-identical, including a chunked continuation (pos0 > 0)."""
+    from streamchat_b200.qwen2 import Qwen2Config
+    cfg = Qwen2Config(hidden_size=512, intermediate_size=1024, num_hidden_layers=3, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=1008)
+    _, a, b = _engine_pair(cuda, cfg, seed=9, std=0.05, max_batch=2)
+    torch.manual_seed(4)
+    x1 = (torch.randn(150, 512) * 0.5).half().to(cuda)
+    x2 = (torch.randn(37, 512) * 0.5).half().to(cuda)
+    monkeypatch.setenv("SCB_NATIVE_PREFILL", "1")
+    la1 = a.prefill(x1, slot=1).clone()
+    la2 = a.prefill(x2, slot=1).clone()
+    monkeypatch.delenv("SCB_NATIVE_PREFILL")
+    lb1 = b.prefill(x1, slot=1).clone()
+    lb2 = b.prefill(x2, slot=1).clone()
+    assert torch.equal(la1, lb1) and torch.equal(la2, lb2)
+    for ka, kb, va, vb in zip(a.k_cache, b.k_cache, a.v_cache, b.v_cache):
+        assert torch.equal(ka[1, :, :187], kb[1, :, :187]) and torch.equal(va[1, :, :187], vb[1, :, :187])

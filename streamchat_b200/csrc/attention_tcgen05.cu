@@ -446,12 +446,7 @@ int launch_attn(const scb_attention_args* a, cudaStream_t st) {
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   auto kern = attention_tcgen05_kernel<D, kBKV, NSB, KS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::kSmemBytes));
-    attr_set = true;
-  }
+  SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   dim3 grid((unsigned)((a->q_len + kBQ - 1) / kBQ), (unsigned)a->n_q_heads, (unsigned)a->batch);
   kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(mq, mk, mv, p);
   SCB_LAUNCH_OK("attention_tcgen05_kernel");

@@ -317,7 +317,7 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
 SCB_DEVICE void prefetch_kv_l2(const MegaParams& p, const MegaLayer* ly, int hk, int split, int head_dim) {
   if (split >= p.n_splits) return;
   for (int n = 0; n < p.R; ++n) {
-    const int kv_len = p.kv_len[n];
+    const int kv_len = max(1, min(p.kv_len[n], (int)p.max_ctx));   // same clamp as attention_partial
     const int per = (kv_len + p.n_splits - 1) / p.n_splits;
     const int begin = split * per, end = min(kv_len, begin + per);
     if (end <= begin) continue;
@@ -462,7 +462,11 @@ SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint
   __half* k_cache = ly->k_cache + (size_t)seq * p.cache_seq_stride;
   __half* v_cache = ly->v_cache + (size_t)seq * p.cache_seq_stride;
   const long long max_pos = p.max_ctx;
-  const int kv_len = p.kv_len[seq];
+  // the host validates lengths (Qwen2Engine raises before a step could run past the cache); this guard keeps a
+  // bad length from ever writing outside the slot: the length is clamped and the append skipped
+  const int kv_raw = p.kv_len[seq];
+  const bool kv_ok = kv_raw >= 1 && kv_raw <= max_pos;
+  const int kv_len = max(1, min(kv_raw, (int)max_pos));
   const int pos = kv_len - 1;
   const int per = (kv_len + n_splits - 1) / n_splits;
   const int begin = split * per, end = min(kv_len, begin + per);
@@ -486,7 +490,7 @@ SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint
     q_h[h * HD + i + HALF] = __float2half_rn(a2 + b2);
   }
   for (int idx = G * HD + tid; idx < 8 * HD; idx += kCThreads) q_h[idx] = __float2half_rn(0.f);
-  if (pos >= begin && pos < end) {
+  if (kv_ok && pos >= begin && pos < end) {
     const __half* kp = qkv + (size_t)(p.n_q + hk) * HD;
     const __half* vp = qkv + (size_t)(p.n_q + p.n_kv + hk) * HD;
     __half* kc = k_cache + ((size_t)hk * max_pos + pos) * HD;

@@ -619,7 +619,11 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   part_l += (long long)seq * n_q * n_splits;
   part_o += (long long)seq * n_q * n_splits * HD;
   tickets += seq * n_kv;
-  const int kv_len = len_dev[seq];
+  // the host validates lengths; this guard keeps a bad one from writing outside the cache slot (length
+  // clamped, append skipped)
+  const int kv_raw = len_dev[seq];
+  const bool kv_ok = kv_raw >= 1 && kv_raw <= max_pos;
+  const int kv_len = max(1, min(kv_raw, (int)max_pos));
   const int pos = kv_len - 1;       // position of the token being decoded
   const int per = (kv_len + n_splits - 1) / n_splits;
   const int begin = split * per, end = min(kv_len, begin + per);
@@ -646,7 +650,7 @@ decode_attn_fused_kernel(const __half* __restrict__ qkv, const float* __restrict
   }
   for (int idx = G * HD + tid; idx < 8 * HD; idx += 256) q_h[idx] = __float2half_rn(0.f);   // unused mma columns
   // ---- the block that owns `pos` rotates and appends the new k, copies the new v
-  if (pos >= begin && pos < end) {
+  if (kv_ok && pos >= begin && pos < end) {
     const __half* kp = qkv + (long long)(n_q + hk) * HD;
     const __half* vp = qkv + (long long)(n_q + n_kv + hk) * HD;
     __half* kc = k_cache + ((long long)hk * max_pos + pos) * HD;

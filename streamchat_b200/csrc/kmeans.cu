@@ -833,11 +833,7 @@ int run(const scb_kmeans_step_args* a, cudaStream_t st) {
                        a->n_batch <= 65535;
   if (use_dot) {
     float* cnorm_p = reinterpret_cast<float*>(ws + p.cnorm_off);
-    static bool attr = false;
-    if (!attr) {
-      SCB_CUDA_OK(cudaFuncSetAttribute(kmeans_assign_dot_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDotSmem));
-      attr = true;
-    }
+    SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kmeans_assign_dot_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kDotSmem);
     kmeans_assign_dot_mma<<<dim3(p.dot_tiles, a->n_batch), kDotThreads, kDotSmem, st>>>(
         reinterpret_cast<const __half*>(a->points), a->centroids, a->n_points, a->n_clusters, a->dim, partial, cnorm_p);
     SCB_LAUNCH_OK("kmeans_assign_dot_mma");

@@ -548,13 +548,8 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   const int ov = ep.out_f32 ? 4 : 8;
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
-  static bool attr_set = false;  // per template instantiation
   auto kern = linear_tcgen05_kernel<BN, PAIR>;
-  if (!attr_set) {
-    SCB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::kSmemBytes));
-    attr_set = true;
-  }
+  SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);  // per instantiation
   const long long tm_sched = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
   const long long tiles = tm_sched * ((a->n + BN - 1) / BN) * a->batch;
   const int sms = scb_num_sms();

@@ -49,6 +49,26 @@ bool scb_pdl_enabled();  // programmatic dependent launch for the decode chain (
 
 static inline size_t scb_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Function attributes (opt-in shared memory) are per DEVICE: `mask` holds one bit per device ordinal that
+// already has the attribute.  Returns true when the caller still has to set it on the current device; two
+// threads racing on the same device both set it, which is harmless.  Ordinals >= 64 always set it.
+static inline bool scb_attr_needed(std::atomic<uint64_t>& mask, uint64_t* bit_out) {
+  int dev = 0;
+  *bit_out = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  *bit_out = 1ull << dev;
+  return (mask.load(std::memory_order_acquire) & *bit_out) == 0;
+}
+#define SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, attr, value)                         \
+  do {                                                                               \
+    static std::atomic<uint64_t> _mask{0};                                           \
+    uint64_t _bit;                                                                   \
+    if (scb_attr_needed(_mask, &_bit)) {                                             \
+      SCB_CUDA_OK(cudaFuncSetAttribute(kern, attr, value));                          \
+      _mask.fetch_or(_bit, std::memory_order_release);                               \
+    }                                                                                \
+  } while (0)
+
 // ----------------------------------------------------------------------------------------
 // device: small utilities
 // ----------------------------------------------------------------------------------------

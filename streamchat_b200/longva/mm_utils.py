@@ -28,3 +28,26 @@ def tokenizer_image_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX
 def get_model_name_from_path(model_path: str) -> str:
     parts = model_path.strip("/").split("/")
     return parts[-2] + "_" + parts[-1] if parts[-1].startswith("checkpoint-") else parts[-1]
+
+
+def process_images(images, image_processor, model_cfg):
+    """longva/mm_utils.py:314-338 for the aspect modes LongVA checkpoints use: no `image_aspect_ratio` (the
+    processor is applied to the whole list) and "pad" (expand to a mean-coloured square first).  The high-res /
+    any-res tilings belong to other model families and are not on the path."""
+    mode = getattr(model_cfg, "image_aspect_ratio", None)
+    if mode is None:
+        return image_processor(images, return_tensors="pt")["pixel_values"]
+    if mode == "pad":
+        from PIL import Image
+        fill = tuple(int(x * 255) for x in image_processor.image_mean)
+        out = []
+        for im in images:
+            w, h = im.size
+            if w != h:
+                side = max(w, h)
+                sq = Image.new(im.mode, (side, side), fill)
+                sq.paste(im, ((side - w) // 2, (side - h) // 2))
+                im = sq
+            out.append(image_processor.preprocess(im, return_tensors="pt")["pixel_values"][0])
+        return torch.stack(out, dim=0) if all(x.shape == out[0].shape for x in out) else out
+    raise NotImplementedError(f"image_aspect_ratio={mode!r} is not used by LongVA (longva/mm_utils.py:317-328)")

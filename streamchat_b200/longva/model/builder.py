@@ -155,7 +155,16 @@ def _config_from_hf(path: str) -> LlavaQwenConfig:
                                   num_attention_heads=vc["num_attention_heads"], image_size=vc["image_size"],
                                   patch_size=vc["patch_size"], layer_norm_eps=vc.get("layer_norm_eps", 1e-5),
                                   select_layer=c.get("mm_vision_select_layer", -2))
-    return LlavaQwenConfig(llm=llm, vision=vision, mm_projector_type=c.get("mm_projector_type", "mlp2x_gelu"),
+    # stop ids: generation_config.json wins over config.json, as in HF generate() (the reference reaches it through
+    # super().generate(), llava_qwen.py:155; for LongVA-7B-DPO this is <|im_end|> / <|endoftext|>)
+    eos, pad = c.get("eos_token_id"), c.get("pad_token_id")
+    gpath = os.path.join(path, "generation_config.json")
+    if os.path.exists(gpath):
+        gc = json.load(open(gpath))
+        eos = gc.get("eos_token_id", eos)
+        pad = gc.get("pad_token_id", pad)
+    return LlavaQwenConfig(llm=llm, vision=vision, eos_token_id=eos, pad_token_id=pad,
+                           mm_projector_type=c.get("mm_projector_type", "mlp2x_gelu"),
                            mm_resampler_type=c.get("mm_resampler_type", "spatial_pool"),
                            mm_spatial_pool_mode=c.get("mm_spatial_pool_mode", "average"),
                            mm_spatial_pool_stride=c.get("mm_spatial_pool_stride", 2),

@@ -13,7 +13,7 @@ language model in streamchat_b200.qwen2.Qwen2Engine (hand-written CUDA behind th
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Union
 
 import torch
 
@@ -35,8 +35,13 @@ class LlavaQwenConfig:
     mm_use_im_start_end: bool = False
     mm_use_im_patch_token: bool = False
     tokenizer_model_max_length: Optional[int] = None
-    max_context: int = 16384
+    max_context: int = 32768      # KV-cache slot length: an answer prompt carries 13-18 K tokens (short memory + 3 x 5 760-token nodes)
     max_batch: int = 32           # memory captions / summaries decoded together, one weight pass per step
+    # generation stops at these ids (generation_config.json / config.json of the checkpoint, read by
+    # load_pretrained_model) — what HF generate() does by default under the reference's super().generate(),
+    # llava_qwen.py:155.  None (random-init synthetic models): every generation runs its full budget.
+    eos_token_id: Optional[Union[int, List[int]]] = None
+    pad_token_id: Optional[int] = None
 
     @property
     def hidden_size(self) -> int:
@@ -155,15 +160,17 @@ class LlavaQwenForCausalLM:
         return self.llm.generate(inputs_embeds[0], max_new_tokens=int(kwargs.pop("max_new_tokens", 20)),
                                  do_sample=do_sample, temperature=temperature,
                                  top_k=kwargs.pop("top_k", 50), top_p=kwargs.pop("top_p", None),
-                                 eos_token_id=kwargs.pop("eos_token_id", None))
+                                 eos_token_id=kwargs.pop("eos_token_id", self.config.eos_token_id))
 
     @torch.no_grad()
-    def generate_requests(self, requests, modalities: Optional[List[str]] = ["image"], eos_token_id=None):
+    def generate_requests(self, requests, modalities: Optional[List[str]] = ["image"], eos_token_id="config"):
         """Greedy generation for several independent requests `(input_ids, image_embeddings | None,
         max_new_tokens)` — e.g. the per-chunk captions of one memory update (utiles.py:539-559) plus a
         pending text summary (utiles.py:594-605).  Each request yields exactly the ids the
         one-at-a-time `generate_with_image_embedding` call yields; they are decoded in lock-step so every
         decode step streams the weights once for all of them."""
+        if isinstance(eos_token_id, str):      # "config": the checkpoint's own stop ids (HF generate's default)
+            eos_token_id = self.config.eos_token_id
         out: List[Optional[torch.Tensor]] = [None] * len(requests)
         n_batches = -(-len(requests) // self.llm.max_batch)
         B = -(-len(requests) // n_batches) if requests else 1          # even batches: 40 -> 20 + 20
@@ -182,6 +189,6 @@ class LlavaQwenForCausalLM:
 
     def generate_with_image_embedding_batch(self, inputs: torch.Tensor, image_embeddings_list: List[torch.Tensor],
                                             modalities: Optional[List[str]] = ["image"], max_new_tokens: int = 20,
-                                            eos_token_id=None) -> List[torch.Tensor]:
+                                            eos_token_id="config") -> List[torch.Tensor]:
         return self.generate_requests([(inputs, [e], max_new_tokens) for e in image_embeddings_list],
                                       modalities, eos_token_id)

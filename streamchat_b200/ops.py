@@ -546,7 +546,8 @@ class Qwen2Decoder:
         a.next_id, a.kv_len, a.logits, a.ld_logits = next_id.data_ptr(), kv_len.data_ptr(), logits.data_ptr(), logits.stride(0)
         a.counters, a.n_counters = _ptr(counters), (counters.numel() if counters is not None else 0)
         a.ctx_cap = ctx_cap
-        L.check(L.load().scb_qwen2_decode_step(C.byref(a), _stream(self.device)), "scb_qwen2_decode_step")
+        with torch.cuda.device(self.device):
+            L.check(L.load().scb_qwen2_decode_step(C.byref(a), _stream(self.device)), "scb_qwen2_decode_step")
 
     def prefill(self, inputs_embeds: torch.Tensor, slot: int, pos0: int, logits_row: torch.Tensor) -> None:
         """scb_qwen2_prefill: the whole prefill of one sequence as one native call (see the header)."""
@@ -560,8 +561,9 @@ class Qwen2Decoder:
         if ws is None or ws.numel() < need:
             ws = torch.zeros(need, dtype=torch.uint8, device=self.device)     # zero: the lm_head GEMV's ticket
             self._prefill_ws = ws
-        L.check(lib.scb_qwen2_prefill(self._h, inputs_embeds.data_ptr(), T, slot, pos0, logits_row.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), _stream(self.device)), "scb_qwen2_prefill")
+        with torch.cuda.device(self.device):
+            L.check(lib.scb_qwen2_prefill(self._h, inputs_embeds.data_ptr(), T, slot, pos0, logits_row.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _stream(self.device)), "scb_qwen2_prefill")
 
     def close(self) -> None:
         if getattr(self, "_h", None):

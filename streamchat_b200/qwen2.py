@@ -58,7 +58,8 @@ class Qwen2Engine:
             return weights[name].to(device=self.device, dtype=torch.float16).contiguous()
 
         self.embed = w("model.embed_tokens.weight")
-        self.lm_head = w("lm_head.weight")
+        # checkpoints saved with tie_word_embeddings carry no lm_head.weight: the head IS the embedding table
+        self.lm_head = w("lm_head.weight") if "lm_head.weight" in weights else self.embed
         self.final_norm = w("model.norm.weight")
         self.layers = []
         for i in range(c.num_hidden_layers):
@@ -264,6 +265,16 @@ class Qwen2Engine:
         # <= 8 rows: gather+norm, 5 per layer, lm_head with fused arg-max; wider: split-K GEMM + reduce pairs
         return 1 + self.cfg.num_hidden_layers * (8 if R > 8 else 5) + (2 if R > 8 else 1)
 
+    def _check_context(self, prompt_lens, budgets) -> None:
+        """A generation of `b` new tokens after a prompt of T tokens appends KV rows up to position T + b - 2 and
+        attends over T + b - 1 of them: that has to fit the cache slot.  HF's DynamicCache grows without bound; here
+        the slot is fixed (`max_context` of the model config), so the call fails BEFORE anything is launched rather
+        than writing past the slot."""
+        for T, b in zip(prompt_lens, budgets):
+            if T + b - 1 > self.max_ctx:
+                raise ValueError(f"prompt of {T} tokens + {b} new tokens needs a context of {T + b - 1} > max_ctx "
+                                 f"{self.max_ctx}: raise LlavaQwenConfig.max_context (overwrite_config) or shorten the request")
+
     def _ctx_bucket(self, need: int) -> int:
         """Context capacity class of a decode graph (power of two, >= 2048, <= max_ctx)."""
         b = 2048
@@ -313,6 +324,7 @@ class Qwen2Engine:
         budgets = [int(max_new_tokens)] * n if isinstance(max_new_tokens, int) else [int(b) for b in max_new_tokens]
         if len(budgets) != n or min(budgets) < 1:
             raise ValueError("max_new_tokens must be a positive int or one per sequence")
+        self._check_context([int(x.shape[0]) for x in inputs_embeds_list], budgets)
         order = sorted(range(n), key=lambda i: -budgets[i])           # slot s holds caller's sequence order[s]
         cap = self._ctx_bucket(max(int(x.shape[0]) + b for x, b in zip(inputs_embeds_list, budgets)))
         if os.environ.get("SCB_NO_GRAPH") == "1":      # profiling aid: every kernel as its own launch (ncu launch lists)
@@ -396,6 +408,7 @@ class Qwen2Engine:
         if (not do_sample) or temperature == 0:
             return self.generate_batch([inputs_embeds], max_new_tokens, eos_token_id, use_graph)[0]
         # sampling path: same kernels, token drawn by torch.multinomial as HF does (hazard H2)
+        self._check_context([int(inputs_embeds.shape[0])], [int(max_new_tokens)])
         with torch.cuda.device(self.device):
             self.reset()
             logits = self.prefill(inputs_embeds, slot=0)

@@ -138,16 +138,31 @@ def random_weights(cfg: LlavaQwenConfig, device, seed: int = 0, std: float = 0.0
     return W
 
 
+def _tower_dir(model_path: str, c: dict) -> Optional[str]:
+    """Directory of the CLIP tower named by `mm_vision_tower`: absolute, or relative to the checkpoint (a hub id
+    such as "openai/clip-vit-large-patch14-336" resolves to neither and means: ViT-L/14-336 defaults, tower
+    weights inside the main checkpoint — LongVA-7B was trained with the tower unfrozen)."""
+    vt = c.get("mm_vision_tower")
+    if not vt:
+        return None
+    for cand in (vt, os.path.join(model_path, vt)):
+        if os.path.exists(os.path.join(cand, "config.json")):
+            return cand
+    return None
+
+
 def _config_from_hf(path: str) -> LlavaQwenConfig:
     c = json.load(open(os.path.join(path, "config.json")))
+    # transformers >= 5 stores theta under rope_parameters; 4.x (the reference's pin) at the top level
+    theta = c.get("rope_theta", (c.get("rope_parameters") or {}).get("rope_theta", 1e6))
     llm = Qwen2Config(hidden_size=c["hidden_size"], intermediate_size=c["intermediate_size"],
                       num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
                       num_key_value_heads=c.get("num_key_value_heads", c["num_attention_heads"]),
-                      vocab_size=c["vocab_size"], rope_theta=float(c.get("rope_theta", 1e6)),
+                      vocab_size=c["vocab_size"], rope_theta=float(theta),
                       rms_norm_eps=float(c.get("rms_norm_eps", 1e-6)))
     vision = ClipVisionConfig(select_layer=c.get("mm_vision_select_layer", -2))
-    vt = c.get("mm_vision_tower")
-    if vt and os.path.exists(os.path.join(vt, "config.json")):
+    vt = _tower_dir(path, c)
+    if vt:
         vc = json.load(open(os.path.join(vt, "config.json")))
         vc = vc.get("vision_config", vc)
         vision = ClipVisionConfig(hidden_size=vc["hidden_size"], intermediate_size=vc["intermediate_size"],
@@ -169,21 +184,55 @@ def _config_from_hf(path: str) -> LlavaQwenConfig:
                            mm_spatial_pool_mode=c.get("mm_spatial_pool_mode", "average"),
                            mm_spatial_pool_stride=c.get("mm_spatial_pool_stride", 2),
                            mm_use_im_start_end=c.get("mm_use_im_start_end", False),
-                           mm_use_im_patch_token=c.get("mm_use_im_patch_token", False),
+                           # the reference reads this flag with a default of True (builder.py:261)
+                           mm_use_im_patch_token=c.get("mm_use_im_patch_token", True),
                            tokenizer_model_max_length=c.get("tokenizer_model_max_length"))
 
 
 def _load_safetensors(path: str) -> Dict[str, torch.Tensor]:
+    """Every tensor of the checkpoint's *.safetensors shards (model.safetensors or the files an index names)."""
     from safetensors import safe_open
     W: Dict[str, torch.Tensor] = {}
-    for fn in sorted(os.listdir(path)):
-        if fn.endswith(".safetensors"):
-            with safe_open(os.path.join(path, fn), framework="pt", device="cpu") as f:
-                for k in f.keys():
-                    W[k] = f.get_tensor(k)
+    idx = os.path.join(path, "model.safetensors.index.json")
+    if os.path.exists(idx):
+        files = sorted(set(json.load(open(idx))["weight_map"].values()))
+    else:
+        files = sorted(fn for fn in os.listdir(path) if fn.endswith(".safetensors"))
+    for fn in files:
+        with safe_open(os.path.join(path, fn), framework="pt", device="cpu") as f:
+            for k in f.keys():
+                W[k] = f.get_tensor(k)
     if not W:
         raise FileNotFoundError(f"no *.safetensors under {path}")
     return W
+
+
+def resize_token_embeddings(weights: Dict[str, torch.Tensor], llm: Qwen2Config, n_tokens: int) -> None:
+    """`model.resize_token_embeddings(len(tokenizer))` of the reference loader (builder.py:266), applied to the weight
+    dict in place.  Fewer tokens than rows: both tables are CUT to len(tokenizer) rows, exactly as HF does (the
+    logits the reference arg-maxes over have len(tokenizer) entries).  More tokens than rows: rows are appended
+    holding the mean of the existing rows (HF draws them at random: they belong to tokens no prompt on the path
+    contains unless the caller types the literal <im_patch> / <im_start> markers).  The decode kernels stream the
+    lm_head in 16-row tiles, so a cut table is padded back to a multiple of 16 with copies of row 0 — a copy can
+    never win the lowest-index-wins arg-max over the original; `logit_vocab` records the true width."""
+    emb = weights["model.embed_tokens.weight"]
+    head = weights.get("lm_head.weight", emb)
+    rows = emb.shape[0]
+    if n_tokens == rows:
+        return
+    if n_tokens > rows:
+        grow = n_tokens - rows
+        emb = torch.cat([emb, emb.float().mean(0, keepdim=True).to(emb.dtype).expand(grow, -1)], 0)
+        head = torch.cat([head, head.float().mean(0, keepdim=True).to(head.dtype).expand(grow, -1)], 0)
+    else:
+        emb, head = emb[:n_tokens], head[:n_tokens]
+    pad = (-n_tokens) % 16
+    if pad:
+        head = torch.cat([head, head[:1].expand(pad, -1)], 0)
+    weights["model.embed_tokens.weight"] = emb.contiguous()
+    weights["lm_head.weight"] = head.contiguous()
+    llm.vocab_size = head.shape[0]
+    llm.logit_vocab = n_tokens
 
 
 def _device_from_map(device_map, device) -> torch.device:
@@ -209,16 +258,33 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
         tokenizer = ByteTokenizer(cfg.llm.vocab_size)
         image_processor = SyntheticImageProcessor(cfg.vision.image_size)
     else:
+        from transformers import AutoTokenizer, CLIPImageProcessor
+        from ..constants import DEFAULT_IM_END_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IMAGE_PATCH_TOKEN
         cfg = _config_from_hf(model_path)
         weights = _load_safetensors(model_path)
-        from transformers import AutoTokenizer, CLIPImageProcessor
+        hf_cfg = json.load(open(os.path.join(model_path, "config.json")))
+        vt = _tower_dir(model_path, hf_cfg)
+        if not any(k.startswith(VT) for k in weights):
+            # frozen-tower checkpoints keep the CLIP weights in the tower's own directory (clip_encoder.py:40-41)
+            if vt is None:
+                raise FileNotFoundError(f"{model_path} holds no vision-tower weights and mm_vision_tower="
+                                        f"{hf_cfg.get('mm_vision_tower')!r} is not a local directory")
+            for k, v in _load_safetensors(vt).items():
+                weights["model.vision_tower.vision_tower." + k] = v
         tokenizer = AutoTokenizer.from_pretrained(model_path)
-        vt = json.load(open(os.path.join(model_path, "config.json"))).get("mm_vision_tower", model_path)
-        image_processor = CLIPImageProcessor.from_pretrained(vt)
+        # builder.py:258-266: marker tokens are added, then the embedding tables follow len(tokenizer)
+        if cfg.mm_use_im_patch_token:
+            tokenizer.add_tokens([DEFAULT_IMAGE_PATCH_TOKEN], special_tokens=True)
+        if cfg.mm_use_im_start_end:
+            tokenizer.add_tokens([DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN], special_tokens=True)
+        resize_token_embeddings(weights, cfg.llm, len(tokenizer))
+        image_processor = CLIPImageProcessor.from_pretrained(vt if vt else hf_cfg.get("mm_vision_tower", model_path))
     if overwrite_config:
         for k, v in overwrite_config.items():
             setattr(cfg, k, v)
     model = LlavaQwenForCausalLM(cfg, weights, dev)
     del weights
+    # builder.py:277-284 reports the checkpoint's max_sequence_length / max_position_embeddings; what bounds a
+    # generation HERE is the KV-cache slot, so that is what callers get
     context_len = getattr(cfg, "max_context", 2048)
     return tokenizer, model, image_processor, context_len

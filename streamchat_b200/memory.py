@@ -32,6 +32,10 @@ RESET = "\033[0m"
 VERBOSE = False  # the reference prints the whole tree on every update (utiles.py:491-504)
 CAPTION_TOKENS = 128   # max_new_tokens of the per-chunk caption (utiles.py:555)
 SUMMARY_TOKENS = 256   # max_new_tokens of the merge summary (utiles.py:604)
+# The reference samples captions / summaries at T=0.1 (utiles.py:551-552,600-601).  The driver calls
+# fast_building_memory_tree_summarize_token positionally (inference_streaming_longva_v2.py:351), so the greedy
+# override of parity runs (hazard H2) is a module switch as well as a keyword.
+CAPTION_DO_SAMPLE = True
 
 
 class MultimodalTreeNode:
@@ -171,7 +175,7 @@ def make_summary_prompt(caption_list, tokenizer, conv_templates):
 
 def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_clusters, interval, summarizer,
                                               input_ids, tokenizer, chunked_feature_list, existing_tree=None,
-                                              *, caption_do_sample=True, kmeans_init_indices=None,
+                                              *, caption_do_sample=None, kmeans_init_indices=None,
                                               conv_templates=None, lazy_text=True):
     """One memory-tree update: caption every new chunk, append depth-0 nodes, perform at most one
     merge (k-means over the merged nodes' frames + text summary).  Same positional signature as
@@ -181,6 +185,8 @@ def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_cl
     if conv_templates is None:
         from .longva.conversation import conv_templates as _ct
         conv_templates = _ct
+    if caption_do_sample is None:
+        caption_do_sample = CAPTION_DO_SAMPLE
     flat_chunks = []
     for chunk_feature in chunked_feature_list:
         dimension = chunk_feature[0].shape[-1]

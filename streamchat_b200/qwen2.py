@@ -33,6 +33,7 @@ class Qwen2Config:
     vocab_size: int = 152064
     rope_theta: float = 1000000.0
     rms_norm_eps: float = 1e-6
+    logit_vocab: Optional[int] = None   # true logit width when the lm_head was padded to a 16-row multiple (builder.resize_token_embeddings)
 
     @property
     def head_dim(self) -> int:
@@ -165,8 +166,10 @@ class Qwen2Engine:
         pos0 = self.ctx_lens[slot]
         if pos0 + T > self.max_ctx:
             raise ValueError(f"context {pos0 + T} exceeds max_ctx {self.max_ctx}")
-        if self._mega is not None and os.environ.get("SCB_NATIVE_PREFILL") == "1":
-            # opt-in: the same launches issued by ONE native call (scb_qwen2_prefill) instead of from Python
+        if self._mega is not None and os.environ.get("SCB_NATIVE_PREFILL", "1") != "0":
+            # ONE native call (scb_qwen2_prefill) issues the whole launch sequence below from C++ over the decoder
+            # handle's pointer tables and a reused workspace (no per-op tensor allocations); SCB_NATIVE_PREFILL=0
+            # keeps the per-launch Python loop (same kernels, bit-identical results — tests/test_gpu_fullwidth.py)
             self._mega.prefill(x, slot, pos0, self._logits[slot])
             self.ctx_lens[slot] = pos0 + T
             return self._logits[slot:slot + 1]
@@ -420,14 +423,15 @@ class Qwen2Engine:
             if eos_token_id is not None:
                 eos = set(eos_token_id) if isinstance(eos_token_id, (list, tuple, set)) else {int(eos_token_id)}
             toks = []
-            self.next_id[:1].copy_(self._sample(logits, temperature, top_k, top_p))
+            lv = self.cfg.logit_vocab or self.cfg.vocab_size
+            self.next_id[:1].copy_(self._sample(logits[:, :lv], temperature, top_k, top_p))
             for step in range(max_new_tokens):
                 t = int(self.next_id[0])
                 toks.append(t)
                 if t in eos or step == max_new_tokens - 1:
                     break
                 self._decode_step_launches(1)            # advances state, overwrites next_id with the arg-max
-                self.next_id[:1].copy_(self._sample(self._logits[:1], temperature, top_k, top_p))
+                self.next_id[:1].copy_(self._sample(self._logits[:1, :lv], temperature, top_k, top_p))
             self.ctx_lens[0] = T + len(toks) - 1
             return torch.tensor([toks], dtype=torch.int64, device=self.device)
 

@@ -25,3 +25,5 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))   # tests/parity.py, tests/fakes.py

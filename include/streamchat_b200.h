@@ -461,6 +461,61 @@ int scb_qwen2_prefill(void* decoder, const void* inputs_embeds, int64_t n_tokens
  * copy [n_sm][n_layers][16] int64 into host_out (capacity in elements) and return the count; -1 on error. */
 long long scb_qwen2_decoder_profile(void* decoder, long long* host_out, long long capacity);
 
+/* ------------------------------------------------------------------------- *
+ * scb_vit_encode — `model.encode_images(images)` as ONE native call.
+ * Replaces: LlavaMetaForCausalLM.encode_images longva/model/llava_arch.py:179-184 =
+ *   CLIPVisionTower.forward / feature_select  longva/model/multimodal_encoder/clip_encoder.py:46-79
+ *   (HF CLIPVisionModel, hidden_states[select_layer] without the CLS token), mm_projector mlp2x_gelu
+ *   longva/model/multimodal_projector/builder.py:41-48 and SpatialPool (2x2 average)
+ *   longva/model/multimodal_resampler/spatial_pool.py:23-32.
+ * The handle holds host copies of the weight pointer tables (weights stay caller-owned device
+ * memory, fp16, PyTorch Linear layout; qkv_w / qkv_b are the q|k|v projections concatenated along
+ * the output dim; patch_w is the Conv2d kernel flattened to [hidden, kpad], columns beyond
+ * channels*patch^2 zero).  One call enqueues the whole pass for n_frames frames into the
+ * caller's workspace: no allocation, no synchronisation, CUDA-graph capturable.
+ * n_layers = the layers that feed hidden_states[select_layer] (23 of 24 for ViT-L/14, select -2).
+ * ------------------------------------------------------------------------- */
+typedef struct scb_vit_encoder_desc {
+  int32_t n_layers, hidden, n_heads, inter;
+  int32_t image_size, patch, channels, kpad;
+  int32_t out_dim;           /* projector / LLM width */
+  float ln_eps;
+  const void* patch_w;       /* [hidden, kpad] */
+  const void* cls;           /* [hidden] */
+  const void* pos;           /* [tokens, hidden] */
+  const void* pre_g;         /* pre_layrnorm weight / bias [hidden] */
+  const void* pre_b;
+  const void* proj1_w;       /* [out_dim, hidden] + bias */
+  const void* proj1_b;
+  const void* proj2_w;       /* [out_dim, out_dim] + bias */
+  const void* proj2_b;
+  /* HOST arrays of n_layers device pointers */
+  const void* const* ln1_g;
+  const void* const* ln1_b;
+  const void* const* qkv_w;  /* [3*hidden, hidden] */
+  const void* const* qkv_b;  /* [3*hidden] */
+  const void* const* out_w;  /* [hidden, hidden] */
+  const void* const* out_b;
+  const void* const* ln2_g;
+  const void* const* ln2_b;
+  const void* const* fc1_w;  /* [inter, hidden] */
+  const void* const* fc1_b;
+  const void* const* fc2_w;  /* [hidden, inter] */
+  const void* const* fc2_b;
+} scb_vit_encoder_desc;
+
+int scb_vit_encoder_create(const scb_vit_encoder_desc* d, void** out_handle);
+int scb_vit_encoder_destroy(void* handle);
+size_t scb_vit_encode_workspace_bytes(void* handle, int32_t n_frames);
+/* pixels [n_frames, channels, S, S] fp16 (CLIP-normalised) -> out [n_frames, (S/patch/2)^2, out_dim] fp16.
+ * tower_out (optional, may be NULL): hidden_states[select_layer] [n_frames * tokens, hidden] fp16, CLS rows included. */
+int scb_vit_encode(void* handle, const void* pixels, int32_t n_frames, void* out, void* tower_out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* scb_kmeans_assign_update — the name SURVEY.md §8(b) lists for the Lloyd assign + update step: identical to
+ * scb_kmeans_step (same argument struct, same workspace query). */
+int scb_kmeans_assign_update(const scb_kmeans_step_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,17 @@ class Qwen2DecodeStepArgs(C.Structure):
     ]
 
 
+class VitEncoderDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("hidden", C.c_int32), ("n_heads", C.c_int32), ("inter", C.c_int32),
+        ("image_size", C.c_int32), ("patch", C.c_int32), ("channels", C.c_int32), ("kpad", C.c_int32),
+        ("out_dim", C.c_int32), ("ln_eps", C.c_float),
+        ("patch_w", C.c_void_p), ("cls", C.c_void_p), ("pos", C.c_void_p), ("pre_g", C.c_void_p), ("pre_b", C.c_void_p),
+        ("proj1_w", C.c_void_p), ("proj1_b", C.c_void_p), ("proj2_w", C.c_void_p), ("proj2_b", C.c_void_p),
+    ] + [(n, C.POINTER(C.c_void_p)) for n in ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_g", "ln2_b",
+                                              "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
 PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
 
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -140,6 +151,12 @@ SYMBOLS = {
     "scb_cosine_topk": (C.c_int, [C.POINTER(CosineTopkArgs), C.c_void_p]),
     "scb_kmeans_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "scb_kmeans_step": (C.c_int, [C.POINTER(KmeansStepArgs), C.c_void_p]),
+    "scb_kmeans_assign_update": (C.c_int, [C.POINTER(KmeansStepArgs), C.c_void_p]),
+    "scb_vit_encoder_create": (C.c_int, [C.POINTER(VitEncoderDesc), C.POINTER(C.c_void_p)]),
+    "scb_vit_encoder_destroy": (C.c_int, [C.c_void_p]),
+    "scb_vit_encode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "scb_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                 C.c_void_p]),
     "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "scb_attention": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "scb_gemv": (C.c_int, [C.POINTER(GemvArgs), C.c_void_p]),

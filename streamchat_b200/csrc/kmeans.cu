@@ -946,4 +946,7 @@ int scb_kmeans_step(const scb_kmeans_step_args* a, void* stream) {
   return run<__half>(a, st);
 }
 
+// the name SURVEY.md §8(b) lists for this op
+int scb_kmeans_assign_update(const scb_kmeans_step_args* a, void* stream) { return scb_kmeans_step(a, stream); }
+
 }  // extern "C"

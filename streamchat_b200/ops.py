@@ -575,3 +575,76 @@ class Qwen2Decoder:
             self.close()
         except Exception:
             pass
+
+
+class VitEncoder:
+    """Handle of the native `encode_images` entry point (scb_vit_encoder_* / scb_vit_encode): the whole CLIP tower ->
+    projector -> 2x2 pool pass as one C call into a reused workspace.  Holds references to every weight tensor."""
+
+    LAYER_KEYS = ("ln1_g", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_g", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+
+    def __init__(self, *, layers: list, patch_w: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, pre_g: torch.Tensor,
+                 pre_b: torch.Tensor, proj1_w: torch.Tensor, proj1_b: torch.Tensor, proj2_w: torch.Tensor,
+                 proj2_b: torch.Tensor, n_heads: int, image_size: int, patch: int, channels: int, ln_eps: float):
+        dev = _require_cuda(patch_w, cls, pos, proj1_w, proj2_w)
+        n = len(layers)
+        self._keep = (layers, patch_w, cls, pos, pre_g, pre_b, proj1_w, proj1_b, proj2_w, proj2_b)
+
+        def ok(t):
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float16):
+                raise L.ScbError("VitEncoder: weights must be contiguous fp16 CUDA tensors")
+            return t.data_ptr()
+
+        self._tables = []
+        for key in self.LAYER_KEYS:
+            arr = (C.c_void_p * max(n, 1))()
+            for i, ly in enumerate(layers):
+                arr[i] = ok(ly[key])
+            self._tables.append(arr)
+        d = L.VitEncoderDesc()
+        d.n_layers, d.hidden, d.n_heads = n, patch_w.shape[0], n_heads
+        d.inter = layers[0]["fc1_w"].shape[0] if n else 8
+        d.image_size, d.patch, d.channels, d.kpad = image_size, patch, channels, patch_w.shape[1]
+        d.out_dim, d.ln_eps = proj2_w.shape[0], ln_eps
+        d.patch_w, d.cls, d.pos, d.pre_g, d.pre_b = ok(patch_w), ok(cls), ok(pos), ok(pre_g), ok(pre_b)
+        d.proj1_w, d.proj1_b, d.proj2_w, d.proj2_b = ok(proj1_w), ok(proj1_b), ok(proj2_w), ok(proj2_b)
+        for key, arr in zip(self.LAYER_KEYS, self._tables):
+            setattr(d, key, C.cast(arr, C.POINTER(C.c_void_p)))
+        self.device = dev
+        self.tokens = (image_size // patch) ** 2 + 1
+        self.pooled = (image_size // patch // 2) ** 2
+        self.hidden, self.out_dim = patch_w.shape[0], proj2_w.shape[0]
+        self._ws: Optional[torch.Tensor] = None
+        h = C.c_void_p()
+        L.check(L.load().scb_vit_encoder_create(C.byref(d), C.byref(h)), "scb_vit_encoder_create")
+        self._h = h
+
+    def encode(self, pixels: torch.Tensor, want_tower: bool = False):
+        """pixels [n, C, S, S] fp16 contiguous -> features [n, pooled, out_dim] fp16 (and the tower's hidden state
+        [n * tokens, hidden] when asked)."""
+        _require_cuda(pixels)
+        if pixels.dtype != torch.float16 or not pixels.is_contiguous() or pixels.dim() != 4:
+            raise TypeError("VitEncoder.encode: contiguous fp16 [n, C, S, S] pixels")
+        lib = L.load()
+        n = pixels.shape[0]
+        need = int(lib.scb_vit_encode_workspace_bytes(self._h, n))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None                           # release before growing
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty((n, self.pooled, self.out_dim), dtype=torch.float16, device=self.device)
+        tower = torch.empty((n * self.tokens, self.hidden), dtype=torch.float16, device=self.device) if want_tower else None
+        with torch.cuda.device(self.device):
+            L.check(lib.scb_vit_encode(self._h, pixels.data_ptr(), n, out.data_ptr(), _ptr(tower), self._ws.data_ptr(),
+                                       self._ws.numel(), _stream(self.device)), "scb_vit_encode")
+        return (out, tower) if want_tower else out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            L.load().scb_vit_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -16,6 +16,7 @@ the 2x2 mean is taken before Linear-2 (it commutes with Linear-2 exactly in real
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -99,6 +100,12 @@ class VisionEncoder:
         self.proj1_w, self.proj1_b = w("model.mm_projector.0.weight"), w("model.mm_projector.0.bias")
         self.proj2_w, self.proj2_b = w("model.mm_projector.2.weight"), w("model.mm_projector.2.bias")
         self.out_dim = self.proj2_w.shape[0]
+        # native entry point: the whole pass below as ONE C call (scb_vit_encode) over the same kernels
+        self._native = ops.VitEncoder(
+            layers=self.layers, patch_w=self.patch_w, cls=self.cls, pos=self.pos, pre_g=self.pre_g, pre_b=self.pre_b,
+            proj1_w=self.proj1_w, proj1_b=self.proj1_b, proj2_w=self.proj2_w, proj2_b=self.proj2_b,
+            n_heads=cfg.num_attention_heads, image_size=cfg.image_size, patch=cfg.patch_size,
+            channels=cfg.num_channels, ln_eps=cfg.layer_norm_eps)
 
     # FLOPs of the formulation executed, per frame (for bench.py's roofline)
     def flops_per_frame(self) -> float:
@@ -134,6 +141,10 @@ class VisionEncoder:
     def _encode_pass(self, pixels: torch.Tensor) -> torch.Tensor:
         c = self.cfg
         n = pixels.shape[0]
+        if os.environ.get("SCB_NATIVE_VIT", "1") != "0":
+            # one native call issues the launch sequence below from C++ into a reused workspace (no per-op output
+            # allocations); SCB_NATIVE_VIT=0 keeps the per-launch Python loop (same kernels, bit-identical results)
+            return self._native.encode(pixels.contiguous())
         x = self.tower(pixels)
         y = ops.linear(x, self.proj1_w, bias=self.proj1_b, act=L.ACT_GELU_ERF)      # CLS rows ride along
         y = ops.avgpool2x2_tokens(y, n, c.tokens, 1, c.grid)                         # drops CLS, 2x2 mean

@@ -46,6 +46,11 @@ def test_version_and_error_string():
     assert b"handle" in lib.scb_last_error()
     assert lib.scb_qwen2_decoder_destroy(None) == -1
     assert lib.scb_qwen2_decoder_max_rows() >= 1
+    assert lib.scb_vit_encode_workspace_bytes(None, 4) == 0
+    assert lib.scb_vit_encode(None, None, 4, None, None, None, 0, None) == -1
+    assert b"handle" in lib.scb_last_error()
+    assert lib.scb_vit_encoder_destroy(None) == -1
+    assert lib.scb_kmeans_assign_update(None, None) == -1          # SURVEY §8(b)'s name for scb_kmeans_step
 
 
 def test_product_path_has_no_cpu_fallback():
@@ -81,6 +86,7 @@ def test_ctypes_structs_match_header_layout(tmp_path):
         "scb_decode_attention_args": _lib.DecodeAttentionArgs,
         "scb_decode_attention_fused_args": _lib.DecodeAttentionFusedArgs,
         "scb_qwen2_decoder_desc": _lib.Qwen2DecoderDesc, "scb_qwen2_decode_step_args": _lib.Qwen2DecodeStepArgs,
+        "scb_vit_encoder_desc": _lib.VitEncoderDesc,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "streamchat_b200.h")}"',
              'int main(void) {']

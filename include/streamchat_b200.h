@@ -512,6 +512,38 @@ size_t scb_vit_encode_workspace_bytes(void* handle, int32_t n_frames);
 int scb_vit_encode(void* handle, const void* pixels, int32_t n_frames, void* out, void* tower_out, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * scb_allgather_embed — the ONE exchange step of the frame-sharded stream: every rank's
+ * memory embeddings (pooled frame features = depth-0 node centroids, [chunks_per_rank * 40*144, H] fp16) gathered
+ * IN PLACE into the buffer the consumers read (k-means merges, the answer's visual context, cosine top-k) by a
+ * push over NVLink / NVSwitch peer memory.  No reference counterpart: the reference runs two replicas serially
+ * (inference_streaming_longva_v2.py:697,700,879).
+ *
+ * Buffers: every rank allocates its gather buffer with scb_peer_alloc(scb_allgather_embed_buffer_bytes(...)) —
+ * cudaMalloc memory laid out as [world][slice_bytes] followed by a 256-byte flag block, zero-initialised — sends
+ * the 64-byte IPC handle to its peers over any control plane (torch.distributed in this repo) and maps theirs with
+ * scb_peer_open.  Rank r writes its own contribution at offset r*slice_bytes of ITS buffer, then every rank calls
+ * scb_allgather_embed once with the same, strictly increasing epoch: a copy kernel stores the rank's slice into
+ * every peer's buffer, publishes the epoch in the peers' flag blocks (system-scope release) and waits until every
+ * peer's epoch arrived in its own; when the kernel has finished on the caller's stream the whole buffer is valid.
+ * The caller separates two gathers by any inter-rank synchronisation that proves the consumers of the first are
+ * done (in this repo: the collective that ends the answer stage).
+ * ------------------------------------------------------------------------- */
+typedef struct scb_allgather_embed_args {
+  void* const* peer_bufs;    /* HOST array [world]: every rank's buffer as mapped in THIS process (own at [rank]) */
+  int32_t rank, world;       /* world <= 16 */
+  int64_t slice_bytes;       /* bytes per rank, multiple of 16 */
+  uint32_t epoch;            /* >= 1, strictly increasing over the calls on one set of buffers */
+  int32_t _pad;
+} scb_allgather_embed_args;
+
+size_t scb_allgather_embed_buffer_bytes(int64_t slice_bytes, int32_t world);
+int scb_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes */);
+int scb_peer_free(void* dev_ptr);
+int scb_peer_open(const void* ipc_handle /* 64 bytes */, void** mapped_ptr);
+int scb_peer_close(void* mapped_ptr);
+int scb_allgather_embed(const scb_allgather_embed_args* a, void* stream);
+
 /* scb_kmeans_assign_update — the name SURVEY.md §8(b) lists for the Lloyd assign + update step: identical to
  * scb_kmeans_step (same argument struct, same workspace query). */
 int scb_kmeans_assign_update(const scb_kmeans_step_args* a, void* stream);

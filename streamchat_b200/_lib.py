@@ -138,6 +138,11 @@ class VitEncoderDesc(C.Structure):
                                               "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class AllgatherEmbedArgs(C.Structure):
+    _fields_ = [("peer_bufs", C.POINTER(C.c_void_p)), ("rank", C.c_int32), ("world", C.c_int32),
+                ("slice_bytes", C.c_int64), ("epoch", C.c_uint32), ("_pad", C.c_int32)]
+
+
 PRO_NONE, PRO_RMSNORM, PRO_SILU_MUL = 0, 1, 2
 
 _vp, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -157,6 +162,12 @@ SYMBOLS = {
     "scb_vit_encode_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
     "scb_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                  C.c_void_p]),
+    "scb_allgather_embed_buffer_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "scb_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "scb_peer_free": (C.c_int, [C.c_void_p]),
+    "scb_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "scb_peer_close": (C.c_int, [C.c_void_p]),
+    "scb_allgather_embed": (C.c_int, [C.POINTER(AllgatherEmbedArgs), C.c_void_p]),
     "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
     "scb_attention": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "scb_gemv": (C.c_int, [C.POINTER(GemvArgs), C.c_void_p]),

@@ -112,6 +112,42 @@ def resolve_pending(nodes) -> int:
     return done
 
 
+def texts_read_by_search(all_nodes) -> list:
+    """The nodes whose `.text` a tree search may read (utiles.py:709-764): every depth-0 root and everything BELOW a
+    deeper root — never the deeper roots' own summaries, which therefore may stay pending across a question."""
+    out = []
+    for n in all_nodes:
+        if n.depth == 0:
+            out.append(n)
+        else:
+            out.extend(n.children)
+    return out
+
+
+def _all_nodes(nodes) -> list:
+    out = []
+    for n in nodes:
+        out.append(n)
+        out.extend(_all_nodes(n.children))
+    return out
+
+
+def ready_summaries(nodes) -> list:
+    """Pending merge summaries (anywhere under `nodes`) whose children's texts all exist: they can be generated now,
+    e.g. in the same lock-step batch as an answer (stream.StreamingSession.answer)."""
+    todo: list = []
+    _collect_pending(nodes, todo)
+    todo = list({id(n): n for n in todo}.values())
+    return [n for n in todo if n._pending["kind"] == "summary" and all(c._pending is None for c in n._pending["children"])]
+
+
+def summary_request(node):
+    """`(input_ids, None, max_new_tokens)` of a ready pending summary (utiles.py:506-523,594-605)."""
+    r = node._pending
+    ids = make_summary_prompt([c._text for c in r["children"]], r["tokenizer"], r["conv_templates"])
+    return ids, None, r["max_new"]
+
+
 def calculate_forgetting_probabilities(length, tau=10):
     t = np.arange(length)
     R_t = np.exp(-t / tau)
@@ -176,24 +212,30 @@ def make_summary_prompt(caption_list, tokenizer, conv_templates):
 def fast_building_memory_tree_summarize_token(k_means_chunk_feature_list, num_clusters, interval, summarizer,
                                               input_ids, tokenizer, chunked_feature_list, existing_tree=None,
                                               *, caption_do_sample=None, kmeans_init_indices=None,
-                                              conv_templates=None, lazy_text=True):
+                                              conv_templates=None, lazy_text=True, chunk_nodes=None):
     """One memory-tree update: caption every new chunk, append depth-0 nodes, perform at most one
     merge (k-means over the merged nodes' frames + text summary).  Same positional signature as
     utiles.py:489; keyword-only extras inject determinism.  With a greedy captioner that offers
     `generate_requests` (the sm_100a engine) and `lazy_text`, captions and summaries are deferred and
-    generated in lock-step batches by `resolve_pending` — identical ids, far fewer weight passes."""
+    generated in lock-step batches by `resolve_pending` — identical ids, far fewer weight passes.
+    `chunk_nodes`: depth-0 nodes built elsewhere for these chunks (the frame-sharded stream captions a chunk on the
+    rank that owns it and gathers the result, distributed.ShardedStreamingSession) — used instead of captioning."""
     if conv_templates is None:
         from .longva.conversation import conv_templates as _ct
         conv_templates = _ct
     if caption_do_sample is None:
         caption_do_sample = CAPTION_DO_SAMPLE
     flat_chunks = []
-    for chunk_feature in chunked_feature_list:
+    for chunk_feature in (chunked_feature_list if chunk_nodes is None else []):
         dimension = chunk_feature[0].shape[-1]
         flat_chunks.append(torch.cat(chunk_feature, dim=0).reshape(-1, dimension).to(summarizer.device))
     lazy = (not caption_do_sample) and hasattr(summarizer, "generate_requests") and lazy_text
     nodes = []
-    if lazy:
+    if chunk_nodes is not None:
+        if len(chunk_nodes) != len(k_means_chunk_feature_list):
+            raise ValueError("chunk_nodes must hold one depth-0 node per chunk")
+        nodes = list(chunk_nodes)
+    elif lazy:
         # greedy captions are recipes until somebody needs the text (see MultimodalTreeNode)
         for t, feats in zip(k_means_chunk_feature_list, flat_chunks):
             n = MultimodalTreeNode(t, None, depth=0)
@@ -299,7 +341,7 @@ def fast_search_tree_multi_modal_with_embedding(all_nodes, query, image_embeddin
     path_features: List[torch.Tensor] = []
     path_text: List[str] = []
     redundant_nodes = []
-    resolve_pending(all_nodes)          # every node text the walk may read, in batched generations
+    resolve_pending(texts_read_by_search(all_nodes))   # every text the walk may read, in batched generations
     query_embedding = embed_text(model, tokenizer, query)
     for node in all_nodes:
         current_node = node

@@ -648,3 +648,89 @@ class VitEncoder:
             self.close()
         except Exception:
             pass
+
+
+class _RawCudaBuffer:
+    """`__cuda_array_interface__` view of library-allocated device memory (lets torch wrap it without a copy)."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerGather:
+    """Gather buffer of the frame-sharded stream, shared over NVLink peer memory (scb_peer_* / scb_allgather_embed).
+
+    `buffer` is a torch view [world, *slice_shape] of library-allocated memory: rank r fills buffer[r]; `allgather()`
+    pushes it into every peer's buffer and returns (asynchronously, on the current stream) with every slice valid.
+    The 64-byte IPC handles travel over `torch.distributed` (control plane).  Construction is a collective: every
+    rank of `group` must call it; it raises on every rank if ANY rank cannot map its peers (the caller then lets NCCL
+    move the bytes)."""
+
+    def __init__(self, shape, dtype: torch.dtype, rank: int, world: int, device, group=None):
+        import torch.distributed as dist
+        if shape[0] != world:
+            raise ValueError("PeerGather: shape[0] must be the world size")
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        lib = L.load()
+        elem = torch.empty((), dtype=dtype).element_size()
+        n = 1
+        for d in shape[1:]:
+            n *= int(d)
+        self.slice_bytes = n * elem
+        total = int(lib.scb_allgather_embed_buffer_bytes(self.slice_bytes, world))
+        if total == 0:
+            raise L.ScbError(f"PeerGather: slice of {self.slice_bytes} B x {world} ranks is not a valid configuration")
+        self._ptr = C.c_void_p()
+        self._mapped = {}
+        handle = (C.c_ubyte * 64)()
+        ok, err = 1, ""
+        with torch.cuda.device(self.device):
+            try:
+                L.check(lib.scb_peer_alloc(total, C.byref(self._ptr), handle), "scb_peer_alloc")
+            except L.ScbError as e:
+                ok, err = 0, str(e)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
+            if ok and all(h is not None for h in handles):
+                for r, h in enumerate(handles):
+                    if r == rank:
+                        continue
+                    p = C.c_void_p()
+                    rc = lib.scb_peer_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p))
+                    if rc != 0:
+                        ok, err = 0, lib.scb_last_error().decode("utf-8", "replace")
+                        break
+                    self._mapped[r] = p
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.close()
+                raise L.ScbError(f"PeerGather: peer memory unavailable on some rank ({err or 'a peer failed'})")
+        self._total = total
+        raw = torch.as_tensor(_RawCudaBuffer(self._ptr.value, self.slice_bytes * world, self), device=self.device)
+        self.buffer = raw.view(dtype).view(*shape)
+        self._table = (C.c_void_p * world)()
+        for r in range(world):
+            self._table[r] = self._ptr.value if r == rank else self._mapped[r].value
+        self.epoch = 0
+
+    def allgather(self) -> None:
+        self.epoch += 1
+        a = L.AllgatherEmbedArgs(peer_bufs=C.cast(self._table, C.POINTER(C.c_void_p)), rank=self.rank, world=self.world,
+                                 slice_bytes=self.slice_bytes, epoch=self.epoch)
+        with torch.cuda.device(self.device):
+            L.check(L.load().scb_allgather_embed(C.byref(a), _stream(self.device)), "scb_allgather_embed")
+
+    def close(self) -> None:
+        lib = L.load()
+        with torch.cuda.device(self.device):
+            for p in self._mapped.values():
+                lib.scb_peer_close(p)
+            self._mapped = {}
+            if self._ptr:
+                torch.cuda.synchronize(self.device)
+                lib.scb_peer_free(self._ptr)
+                self._ptr = C.c_void_p()

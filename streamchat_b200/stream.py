@@ -95,7 +95,9 @@ class StreamingSession:
         return list(torch.split(feats, 1))
 
     # ---- [B] ---------------------------------------------------------------------------------
-    def update_memory(self, buffer_cache: List[torch.Tensor], kmeans_init_indices=None):
+    def update_memory(self, buffer_cache: List[torch.Tensor], kmeans_init_indices=None, chunk_nodes=None):
+        """`chunk_nodes`: depth-0 nodes captioned elsewhere (one per chunk of `buffer_cache`) — the frame-sharded
+        stream builds them on the owning rank and gathers them (distributed.ShardedStreamingSession)."""
         c = self.cfg
         short_window = c.short_window
         if len(buffer_cache) > short_window:                                   # :319-324
@@ -107,12 +109,16 @@ class StreamingSession:
         probs = M.calculate_forgetting_probabilities(short_window, tau=c.tau)
         self.short_memory_buffer = M.select_data_without_replacement(wait_fifo, probs, remember)
         chunks = [buffer_cache[i:i + c.chunk_size] for i in range(0, len(buffer_cache), c.chunk_size)]
-        kmeans_chunks = [weighted_kmeans_feature(torch.cat(ch), c.num_clusters)[0] if len(ch) > c.chunk_size
-                         else torch.cat(ch) for ch in chunks]                  # :347 (guard never true, F4)
+        if chunk_nodes is not None:
+            kmeans_chunks = [n.centroids for n in chunk_nodes]                 # already stacked on the owning rank
+        else:
+            kmeans_chunks = [weighted_kmeans_feature(torch.cat(ch), c.num_clusters)[0] if len(ch) > c.chunk_size
+                             else torch.cat(ch) for ch in chunks]              # :347 (guard never true, F4)
         self.long_memory_tree = M.fast_building_memory_tree_summarize_token(
             kmeans_chunks, c.num_clusters, c.interval, self.summarizer, self._caption_ids, self.tokenizer,
             chunks, self.long_memory_tree, caption_do_sample=c.caption_do_sample,
-            kmeans_init_indices=kmeans_init_indices, conv_templates=conv_templates, lazy_text=c.lazy_text)
+            kmeans_init_indices=kmeans_init_indices, conv_templates=conv_templates, lazy_text=c.lazy_text,
+            chunk_nodes=chunk_nodes)
         assert len(self.short_memory_buffer) > 0, "No memory ?"
         return self.long_memory_tree, self.short_memory_buffer
 
@@ -159,9 +165,24 @@ class StreamingSession:
     def answer(self, question: str, history_prompt: Optional[str] = None):
         input_ids, image_embeddings = self.build_question_inputs(question, history_prompt)
         t = self.cfg.temperature
-        output_ids = self.model.generate_with_image_embedding(
-            input_ids, image_embeddings=[image_embeddings], modalities=["video"],
-            do_sample=True if t > 0 else False, temperature=t, top_p=None, num_beams=1,
-            max_new_tokens=self.cfg.answer_tokens, use_cache=False)
+        # Merge summaries of the tree's roots are never read by a search (memory.texts_read_by_search), so with lazy
+        # texts they are still pending here; they are independent of the answer and decode in the SAME lock-step
+        # batch — one weight pass per step for the answer and the summaries instead of two generation loops
+        # (ids are those of the separate calls: rows of a batch are independent).
+        ready = []
+        if t == 0 and self.cfg.lazy_text and self.long_memory_tree is not None and self.summarizer is self.model \
+                and hasattr(self.model, "generate_requests"):
+            ready = M.ready_summaries(self.long_memory_tree)
+        if ready:
+            reqs = [(input_ids, [image_embeddings], self.cfg.answer_tokens)] + [M.summary_request(n) for n in ready]
+            outs = self.model.generate_requests(reqs, modalities=["video"])
+            output_ids = outs[0]
+            for n, ids in zip(ready, outs[1:]):
+                n.set_text(self.tokenizer.batch_decode(ids, skip_special_tokens=True)[0].strip())
+        else:
+            output_ids = self.model.generate_with_image_embedding(
+                input_ids, image_embeddings=[image_embeddings], modalities=["video"],
+                do_sample=True if t > 0 else False, temperature=t, top_p=None, num_beams=1,
+                max_new_tokens=self.cfg.answer_tokens, use_cache=False)
         text = self.tokenizer.batch_decode(output_ids, skip_special_tokens=True)[0].strip()
         return text, output_ids

@@ -3,17 +3,20 @@
 decode) on N B200s, plus the reference's CPU path timed beside it.
 
     python bench.py --gpus 1 --steps 3 --warmup 3                 # our arm (CUDA, sm_100a)
-    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0 # CPU oracle port on host cores
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0 # the reference's own code on the host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
 
-One step = one pass of the hot path over one synthetic stream per rank (BASELINE.json configs[4]
-shape): `--frames` 336x336 frames in segments of `--segment`; per segment [A] CLIP-ViT encode,
-[B] memory update (forgetting-curve short memory, 40-frame chunks each captioned with a 128-token
-greedy LongVA generation, tree merge = k-means over 400 frames + 256-token text summary); then
-(N>1) one NCCL all-gather of the per-rank memory embeddings, [C] cosine top-k tree search and a
-256-token answer.  Random-init LongVA-7B-shaped weights, synthetic frames (no datasets/checkpoints
-exist here).  Prints ONE JSON line (rank 0).
+One step = one pass of the hot path over ONE synthetic stream (BASELINE.json configs[4]): `--frames` (1000)
+336x336 frames arriving in segments of `--segment` (200); per segment [A] CLIP-ViT encode, [B] memory update
+(forgetting-curve short memory, 40-frame chunks each captioned with a 128-token greedy LongVA generation, tree merge
+= k-means over 400 frames + 256-token text summary); then [C] cosine top-k tree search and a 256-token answer.
+N > 1 shards THAT stream (strong scaling, north_star): chunk c -> rank c mod N encodes and captions it, ONE
+all-gather of the chunk features (node centroids, 1.03 GB) + caption ids over NVLink, memory updates replayed on the
+gathered memory, answer on rank 0 while the other ranks generate the merge summaries; `--scaling weak` runs the
+round-1 formulation (one independent 1000-frame stream per rank) and is also reported as the secondary key `weak`.
+Random-init LongVA-7B-shaped weights, synthetic frames (no datasets/checkpoints exist here).  Prints ONE JSON line
+(rank 0).
 """
 from __future__ import annotations
 
@@ -49,6 +52,10 @@ def parse_args():
     ap.add_argument("--caption-tokens", type=int, default=128)
     ap.add_argument("--answer-tokens", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: shard ONE stream over the ranks (strong, default) or one stream per rank (weak)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1, strong: skip the secondary weak-scaling measurement")
+    ap.add_argument("--no-peer", action="store_true", help="N > 1: move the gather with NCCL instead of scb_allgather_embed")
     ap.add_argument("--text-encoder", default="bert", choices=["bert", "hash"],
                     help="retrieval text embedder: BERT-large-shaped encoder on the GPU, or synthetic hash vectors")
     return ap.parse_args()
@@ -127,21 +134,30 @@ def _stage(name):
 
 def workload_config(args, n_frames: int, tiny: bool, world: int) -> dict:
     """The `config` object of the JSON line — shared by both arms so the driver compares like with like."""
-    return {"workload": f"stream: {n_frames} frames/rank 336x336 in segments of {args.segment}, chunk 40, "
-                        f"{args.caption_tokens}-token greedy caption per chunk, tree merge every 10 chunks "
-                        f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)"
-                        if not tiny else f"tiny smoke stream: {n_frames} frames/rank",
-            "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_per_rank": n_frames,
+    strong = world == 1 or args.scaling == "strong"
+    if world == 1:
+        sharding = "single rank"
+    elif strong:
+        sharding = (f"ONE stream over {world} ranks: chunk c (40 frames) -> rank c mod {world} (encode + caption), one in-place "
+                    "all-gather of chunk features + caption ids over NVLink, memory updates replayed on every rank, answer on "
+                    "rank 0 while ranks 1.. generate the merge summaries")
+    else:
+        sharding = f"{world} independent streams, one per rank (weak scaling)"
+    total = n_frames if strong else n_frames * world
+    return {"workload": (f"stream: {total} frames 336x336 in segments of {args.segment}, chunk 40, "
+                         f"{args.caption_tokens}-token greedy caption per chunk, tree merge every 10 chunks "
+                         f"(k-means 400->5 + 256-token summary), 1 question ({args.answer_tokens} tokens)")
+                        if not tiny else f"tiny smoke stream: {total} frames",
+            "model": args.model, "weights": "random-init normal(0,0.02) fp16", "frames_total": total,
+            "frames_per_rank": n_frames if not strong else None,
             "text_encoder": ("BERT-large shape on the GPU (random init), node embeddings cached"
                              if (args.text_encoder == "bert" and not tiny) else "synthetic hash vectors"),
-            "sharding": "frames sharded by rank; one NCCL all-gather of memory embeddings" if world > 1 else "single rank",
+            "sharding": sharding,
             "l2": "inputs larger than L2 (677 MB frames + 15 GB weights per step); no explicit flush"}
 
 
-def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, device, e2e: bool):
-    """One step.  Returns (answer ids tensor, h2d bytes, d2h bytes)."""
-    import torch.distributed as dist
-    from streamchat_b200 import ops
+def run_stream(session_factory, frames_dev, host_frames, segment, device, e2e: bool):
+    """One step on one rank: the whole stream through a StreamingSession.  Returns (answer ids, h2d bytes, d2h bytes)."""
     sess = session_factory()
     n = frames_dev.shape[0] if frames_dev is not None else host_frames.shape[0]
     h2d = d2h = 0
@@ -155,17 +171,6 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
             feats = sess.ingest(seg)
         with _stage("memory_update"):
             sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
-    if world > 1:
-        # the one exchange step (§8e): all-gather the per-rank memory embeddings (root-node text
-        # embeddings) so every rank's retrieval sees the global index; top-k is computed redundantly
-        from streamchat_b200.distributed import exchange_memory_index
-        with _stage("exchange"):
-            index, owner, local = exchange_memory_index(sess.long_memory_tree, sess.embedding_model,
-                                                        sess.embedding_tokenizer, device, max_rows=16)
-        from streamchat_b200 import memory as M
-        q = M.embed_text(sess.embedding_model, sess.embedding_tokenizer, QUESTION)
-        scores, idx = ops.cosine_topk(index, q, k=1)
-        sess.global_best = (scores, owner[idx[0, 0]], local[idx[0, 0]])
     with _stage("answer"):
         text, ids = sess.answer(QUESTION)
     if e2e:
@@ -174,9 +179,42 @@ def run_stream(session_factory, frames_dev, host_frames, segment, world, rank, d
     return ids, h2d, d2h
 
 
+def run_stream_sharded(session_factory, gather_buffer, my_frames_dev, my_frames_host, seg_slices, n_frames, segment,
+                       world, rank, device, e2e: bool):
+    """One step of the frame-sharded stream (distributed.ShardedStreamingSession): this rank ingests only the frames of
+    the chunks it owns (`seg_slices[i]` = its rows for segment i)."""
+    from streamchat_b200.distributed import ShardedStreamingSession
+    sess = session_factory()
+    sh = ShardedStreamingSession(sess, rank, world, n_frames, kmeans_init_indices=list(range(sess.cfg.num_clusters)),
+                                 gather_buffer=gather_buffer)
+    h2d = d2h = 0
+    for i, first in enumerate(range(0, n_frames, segment)):
+        a, b = seg_slices[i]
+        if b > a and e2e:
+            seg = my_frames_host[a:b].to(device, non_blocking=True)
+            h2d += seg.numel() * seg.element_size()
+        else:
+            seg = my_frames_dev[a:b] if b > a else None
+        with _stage("encode"):
+            sh.ingest_segment(first, min(segment, n_frames - first), seg)
+    with _stage("captions"):
+        sh.caption_my_chunks()
+    with _stage("exchange"):
+        sh.allgather_embed()
+    with _stage("memory_update"):
+        sh.replay_updates()
+    with _stage("answer"):
+        text, ids = sh.answer(QUESTION)
+    if e2e and rank == 0:
+        ids_host = ids.cpu()
+        d2h += ids_host.numel() * ids_host.element_size()
+    return ids, h2d, d2h, sh.exchanged_bytes
+
+
 def ours(args):
     import torch.distributed as dist
     from streamchat_b200 import _lib
+    from streamchat_b200.distributed import make_gather_buffer, owned_chunks
     from streamchat_b200.longva.model.builder import load_pretrained_model
     from streamchat_b200.stream import HashTextEmbedder, StreamConfig, StreamingSession
 
@@ -192,8 +230,8 @@ def ours(args):
 
     tiny = args.model.endswith("tiny")
     n_frames = args.frames or (160 if tiny else 1000)
-    tokenizer, model, _, _ = load_pretrained_model(args.model, None, "llava_qwen", device_map=str(device),
-                                                   overwrite_config=None if tiny else {"max_context": 32768})
+    strong = world > 1 and args.scaling == "strong"
+    tokenizer, model, _, _ = load_pretrained_model(args.model, None, "llava_qwen", device_map=str(device))
     S = model.config.vision.image_size
     if args.text_encoder == "bert" and not tiny:
         # retrieval text encoder on the GPU (BERT-large shape, random init); texts are tokenised
@@ -213,8 +251,24 @@ def ours(args):
         np.random.seed(1234)                 # forgetting-curve sampling uses the global numpy RNG (H1)
         return StreamingSession(model, tokenizer, embedder, embed_tok, None, cfg)
 
-    g = torch.Generator(device=device).manual_seed(1000 + rank)
+    # the synthetic stream: strong scaling shards ONE stream (same seed on every rank, each rank keeps the frames of
+    # its chunks); weak scaling / one GPU gives every rank its own stream
+    chunk = cfg.chunk_size
+    g = torch.Generator(device=device).manual_seed(1000 + (0 if strong else rank))
     frames_dev = torch.randn((n_frames, 3, S, S), generator=g, device=device, dtype=torch.float16)
+    seg_slices, gather_buffer = [], None
+    if strong:
+        keep, off = [], 0
+        for first in range(0, n_frames, args.segment):
+            nseg = min(args.segment, n_frames - first)
+            mine = owned_chunks(first // chunk, math.ceil(nseg / chunk), rank, world)
+            idx = [f for c in mine for f in range(c * chunk, min((c + 1) * chunk, first + nseg))]
+            keep += idx
+            seg_slices.append((off, off + len(idx)))
+            off += len(idx)
+        frames_dev = frames_dev[torch.tensor(keep, dtype=torch.long, device=device)].contiguous() if keep \
+            else frames_dev[:0].contiguous()
+        gather_buffer = make_gather_buffer(model, chunk, n_frames, rank, world, peer=not args.no_peer)
     host_frames = torch.empty(frames_dev.shape, dtype=torch.float16, pin_memory=True)
     host_frames.copy_(frames_dev)
     torch.cuda.synchronize()
@@ -224,7 +278,14 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e: bool, steps: int):
+    def one_step(e2e: bool, sharded: bool):
+        if sharded:
+            return run_stream_sharded(factory, gather_buffer, frames_dev, host_frames, seg_slices, n_frames, args.segment,
+                                      world, rank, device, e2e)
+        ids, a, b = run_stream(factory, None if e2e else frames_dev, host_frames, args.segment, device, e2e)
+        return ids, a, b, 0
+
+    def timed(e2e: bool, steps: int, sharded: bool):
         model.llm.profile = []
         STAGE_EVENTS.clear()
         barrier()
@@ -232,39 +293,59 @@ def ours(args):
         l0 = _lib.launch_count()
         r0 = model.llm.graph_launches
         e0.record()
-        h2d = d2h = 0
+        h2d = d2h = xb = 0
         for _ in range(steps):
-            _, a, b = run_stream(factory, None if e2e else frames_dev, host_frames, args.segment, world, rank,
-                                 device, e2e)
-            h2d, d2h = a, b
+            _, h2d, d2h, xb = one_step(e2e, sharded)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
+            t = torch.tensor([ms, float(h2d), float(d2h)], device=device, dtype=torch.float64)
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, h2d, d2h = float(mx[0]), int(t[1]), int(t[2])          # time: max over ranks; bytes: all ranks
         launches = (_lib.launch_count() - l0) + (model.llm.graph_launches - r0)
-        return ms, h2d, d2h, launches, list(model.llm.profile)
+        return ms, h2d, d2h, launches, list(model.llm.profile), xb
 
     for _ in range(max(args.warmup, 0)):
-        run_stream(factory, frames_dev, host_frames, args.segment, world, rank, device, False)
+        one_step(False, strong)
     sampler = ClockSampler(local) if rank == 0 else None     # one nvidia-smi poller per job (rank 0's GPU), not one per rank
     if sampler:
         sampler.start()
-    ms, _, _, launches, prof = timed(False, args.steps)
+    ms, _, _, launches, prof, xbytes = timed(False, args.steps, strong)
     clocks = sampler.stop() if sampler else None
     breakdown = {}
     for name, a0, a1 in STAGE_EVENTS:
         breakdown[name] = breakdown.get(name, 0.0) + a0.elapsed_time(a1) / args.steps
-    ms_e2e, h2d, d2h, _, _ = timed(True, args.steps)
+    ms_e2e, h2d, d2h, _, _, _ = timed(True, args.steps, strong)
 
-    total_frames = n_frames * world * args.steps
+    streams = 1 if (strong or world == 1) else world
+    total_frames = n_frames * streams * args.steps
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel family: the weight-streaming GEMVs of the decode step,
-    # timed live (CUDA events on the launching stream around every decode loop of the timed region)
+    weak = None
+    if strong and not args.no_weak:
+        # secondary: the round-1 formulation (one independent stream per rank, no data-path collective)
+        g2 = torch.Generator(device=device).manual_seed(1000 + rank)
+        frames_dev = None
+        frames_w = torch.randn((n_frames, 3, S, S), generator=g2, device=device, dtype=torch.float16)
+        run_stream(factory, frames_w, None, args.segment, device, False)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        run_stream(factory, frames_w, None, args.segment, device, False)
+        w1.record()
+        barrier()
+        t = torch.tensor([w0.elapsed_time(w1)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        weak = {"value": n_frames * world / (float(t) * 1e-3), "unit": "frames/s", "scaling": "weak",
+                "frames_per_rank": n_frames, "steps": 1, "ms_per_step": float(t),
+                "note": "one independent stream per rank (the round-1 bench formulation), device-resident frames"}
+
+    # roofline of the dominant kernel family: the weight-streaming decode step,
+    # timed live (CUDA events on the launching stream around every decode loop of the timed region, rank 0)
     peak, peak_src = load_peaks()
     for p in prof:
         p["ms"] = p["events"][0].elapsed_time(p["events"][1])
@@ -282,6 +363,12 @@ def ours(args):
         breakdown["llm_decode"] = dec_ms / args.steps
         breakdown["llm_decode_rows"] = {str(r): sum(p["steps"] for p in dec if p["rows"] == r) // args.steps
                                         for r in sorted({p["rows"] for p in dec})}
+    if world > 1:
+        breakdown["note"] = "stage times and decode profile are rank 0's; ms_per_step is the max over ranks"
+        if strong:
+            breakdown["exchange_bytes_received_per_rank"] = xbytes
+            breakdown["gather"] = "scb_allgather_embed (NVLink peer memory)" if not isinstance(gather_buffer, torch.Tensor) \
+                else "NCCL all_gather_into_tensor (in place)"
     roofline = None
     traffic = None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_decode_mega_traffic.json")
@@ -305,7 +392,8 @@ def ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (strong or world == 1) else "weak",
         "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
         "config": workload_config(args, n_frames, tiny, world),
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -313,18 +401,77 @@ def ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "impl": "ours",
         "breakdown_ms_per_step": breakdown,
     }
+    if weak is not None:
+        line["weak"] = weak
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(n_frames, args, tiny)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(n_frames: int, args, tiny: bool, budget_s: float = 25.0):
-    """The oracle port (oracle/longva_model.py) timed on the host cores on a bounded sample of the
-    same workload, extrapolated linearly in frames / layers / tokens."""
+_REF_MODEL = {}
+
+
+def cpu_baseline(n_frames: int, args, tiny: bool):
+    """The reference's CPU path on a bounded sample of the same workload.  With the reference staged under oracle/_ref
+    (oracle/stage_ref.py; done by build() wherever /root/reference exists) this is the REFERENCE'S OWN code —
+    LlavaQwenForCausalLM.encode_images / generate_with_image_embedding over HF transformers and
+    utiles.weighted_kmeans_feature — at the LongVA-7B widths with a reduced layer count, extrapolated to the full depth
+    with per-layer timings (kind "reference"); otherwise the oracle port (kind "port")."""
+    from oracle import ref_runner as R
+    if tiny or not R.available():
+        return cpu_baseline_port(n_frames, args, tiny)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Lv, Ll = 2, 2
+    if "m" not in _REF_MODEL:
+        t0 = time.perf_counter()
+        _REF_MODEL["m"] = R.build_reference_model(Lv, Ll)
+        _REF_MODEL["build_s"] = time.perf_counter() - t0
+    model = _REF_MODEL["m"]
+    chunk_tokens, n_text = 40 * 144, 56
+    enc = R.time_encode_images(model, 4)
+    gen = R.time_generate(model, chunk_tokens, n_text, 8)
+    km = R.time_weighted_kmeans(100, 144, 3584)
+    # ---- extrapolation to the full depth: t = (time outside the layers) + L_full x (time per layer)
+    t_frame = (enc["seconds"] - enc["layer_seconds"]) / enc["frames"] + R.VIT_LAYERS_FULL * enc["layer_seconds"] / (Lv * enc["frames"])
+    pre_over, pre_layer = gen["prefill_seconds"] - gen["prefill_layer_seconds"], gen["prefill_layer_seconds"] / Ll
+    dec_over = (gen["decode_seconds"] - gen["decode_layer_seconds"]) / gen["decode_steps"]
+    dec_layer = gen["decode_layer_seconds"] / (Ll * gen["decode_steps"])
+    t_prefill_chunk = pre_over + R.LLM_LAYERS_FULL * pre_layer                 # 5 816-token caption prompt
+    t_token = dec_over + R.LLM_LAYERS_FULL * dec_layer
+    n_chunks = math.ceil(n_frames / 40)
+    n_merges = n_chunks // 10
+    t_caption = t_prefill_chunk + (args.caption_tokens - 1) * t_token
+    answer_tokens_in = 5 * 144 + (n_merges + min(1, n_chunks % 10)) * chunk_tokens + 120   # short memory + retrieved nodes
+    t_answer = t_prefill_chunk * answer_tokens_in / gen["prefill_tokens"] + (args.answer_tokens - 1) * t_token
+    t_summary = t_prefill_chunk * 1400 / gen["prefill_tokens"] + 255 * t_token          # ~1 400-token text prompt
+    t_kmeans = n_merges * km["seconds"] * 400 / km["frames"]
+    total = n_frames * t_frame + n_chunks * t_caption + n_merges * t_summary + t_answer + t_kmeans
+    return {"value": n_frames / total, "unit": "frames/s", "cores": cores, "kind": "reference",
+            "sample": (f"the reference's own LlavaQwenForCausalLM (oracle/_ref, HF transformers) fp32 on {cores} threads at the "
+                       f"LongVA-7B widths with {Lv} of 24 CLIP and {Ll} of 28 Qwen2 layers: encode_images on {enc['frames']} frames "
+                       f"({enc['seconds']:.2f}s, {enc['layer_seconds']:.2f}s in layers), generate_with_image_embedding with one full "
+                       f"{gen['prefill_tokens']}-token caption prompt ({gen['prefill_seconds']:.2f}s prefill, {gen['prefill_layer_seconds']:.2f}s in "
+                       f"layers) + {gen['decode_steps']} cached decode steps ({gen['decode_seconds']:.2f}s, {gen['decode_layer_seconds']:.2f}s in layers), "
+                       f"utiles.weighted_kmeans_feature on 100x144x3584 ({km['seconds']:.2f}s); extrapolated to full depth as "
+                       f"outside-layer time + L_full x per-layer time, then to {n_frames} frames, {n_chunks} captions x "
+                       f"({gen['prefill_tokens']} prefill + {args.caption_tokens} decode tokens), {n_merges} merges (k-means over 400 "
+                       f"frames + 256-token summary) and one {args.answer_tokens}-token answer over ~{answer_tokens_in} prompt tokens "
+                       f"(prefill scaled linearly in tokens: attention's quadratic term ignored, favours the CPU)"),
+            "raw": {"encode": enc, "generate": gen, "kmeans": km, "model_build_seconds": _REF_MODEL["build_s"]},
+            "per_unit_seconds": {"frame_encode": t_frame, "caption": t_caption, "decode_token": t_token, "summary": t_summary,
+                                 "answer": t_answer, "kmeans_merges": t_kmeans},
+            "extrapolated_seconds_per_stream": total}
+
+
+def cpu_baseline_port(n_frames: int, args, tiny: bool):
+    """Fallback when oracle/_ref is not staged: the oracle port (oracle/longva_model.py) timed on the host cores on a
+    bounded sample of the same workload, extrapolated linearly in frames / layers / tokens."""
     from oracle import longva_model as om
     from streamchat_b200.longva.model.builder import SYNTHETIC
     cores = os.cpu_count() or 1
@@ -404,25 +551,28 @@ def cpu_baseline(n_frames: int, args, tiny: bool, budget_s: float = 25.0):
 
 
 def reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure
-    Python over HF transformers and /root/reference does not exist on the GPU box, so the timed
-    code is the oracle port (kind "port"), which tests/ pin against the reference's own outputs."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (the staged
+    reference under oracle/_ref when present, else the oracle port), each step one bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     tiny = args.model.endswith("tiny")
     n_frames = args.frames or (160 if tiny else 1000)
     vals = []
     for _ in range(max(args.warmup, 0) + max(args.steps, 1)):
         vals.append(cpu_baseline(n_frames, args, tiny))
-    best = vals[-1]
-    v = float(np.median([x["value"] for x in vals[max(args.warmup, 0):]]))
+    timed = vals[max(args.warmup, 0):]
+    best = dict(timed[-1])
+    v = float(np.median([x["value"] for x in timed]))
     best["value"] = v
+    best["values_per_step"] = [x["value"] for x in timed]
     print(json.dumps({
         "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * n_frames / v, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * n_frames / v, "higher_is_better": True,
+        "scaling": "strong" if args.scaling == "strong" or world == 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, n_frames, tiny, 1),
+        "config": workload_config(args, n_frames, tiny, world),
         "cpu_baseline": best,
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 

@@ -156,11 +156,17 @@ class ShardedStreamingSession:
         return self._feats[r, j, : k * self._P].view(k, self._P, self._H)
 
     # ---- the exchange ------------------------------------------------------------------------
-    @torch.no_grad()
     def finalize(self) -> None:
+        """My captions -> the ONE all-gather -> replay of the memory updates."""
+        self.caption_my_chunks()
+        self.allgather_embed()
+        self.replay_updates()
+
+    @torch.no_grad()
+    def caption_my_chunks(self) -> None:
+        """Captions of the chunks this rank owns, decoded in lock-step (utiles.py:539-559; greedy: hazard H2)."""
         from . import memory as M
         s = self.s
-        # 1. captions of my chunks, decoded in lock-step (utiles.py:539-559; greedy: parity runs, hazard H2)
         mine = [c for c in range(self.n_chunks) if c % self.world == self.rank and self.frames_in_chunk[c] > 0]
         if mine:
             reqs = [(s._caption_ids, [self.chunk_features(c).reshape(-1, self._H)], M.CAPTION_TOKENS) for c in mine]
@@ -168,9 +174,13 @@ class ShardedStreamingSession:
             for c, ids in zip(mine, outs):
                 r, j = self.slot(c)
                 self._ids[r, j, : ids.shape[1]].copy_(ids[0])
-        # 2. the ONE all-gather: pooled frame features (node centroids) + caption ids, in place
-        self.allgather_embed()
-        # 3. replay the memory updates on the gathered memory (every rank, redundantly)
+
+    @torch.no_grad()
+    def replay_updates(self) -> None:
+        """The reference's per-segment memory updates (inference_streaming_longva_v2.py:267-378) on the gathered
+        memory — every rank, redundantly: short-memory draw, depth-0 nodes with their captions, merges."""
+        from . import memory as M
+        s = self.s
         for first, n in self.segments:
             c0, nc = first // self.chunk, math.ceil(n / self.chunk)
             buffer_cache: List[torch.Tensor] = []

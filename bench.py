@@ -422,9 +422,15 @@ def cpu_baseline(n_frames: int, args, tiny: bool):
     LlavaQwenForCausalLM.encode_images / generate_with_image_embedding over HF transformers and
     utiles.weighted_kmeans_feature — at the LongVA-7B widths with a reduced layer count, extrapolated to the full depth
     with per-layer timings (kind "reference"); otherwise the oracle port (kind "port")."""
+    import contextlib
     from oracle import ref_runner as R
     if tiny or not R.available():
         return cpu_baseline_port(n_frames, args, tiny)
+    with contextlib.redirect_stdout(sys.stderr):      # the reference prints while importing / loading: stdout carries ONE JSON line
+        return _cpu_baseline_reference(n_frames, args, R)
+
+
+def _cpu_baseline_reference(n_frames: int, args, R):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Lv, Ll = 2, 2

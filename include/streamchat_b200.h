@@ -213,6 +213,14 @@ int scb_text_embed_layernorm(const int64_t* ids, const int64_t* position_ids, in
                              const void* token_type_row, const void* gamma, const void* beta, float eps,
                              int32_t dim, void* out, int64_t ld_out, void* stream);
 
+/* Sentence-embedding tail of the dialogue-memory encoder (memory_bank/memory_retrieval/local_doc_qa.py:185-194:
+ * langchain HuggingFaceEmbeddings = sentence-transformers all-MiniLM-L6-v2 = BertModel -> Pooling(mean over the
+ * attention mask) -> Normalize(p=2)).  hidden: packed last_hidden_state rows fp16; text t owns rows
+ * [offsets[t], offsets[t+1]) (device int32 [n_texts + 1]); out[t] = mean of its rows (fp32 sums, divided by
+ * max(count, 1e-9)), then divided by max(|.|_2, 1e-12) when normalize != 0.  out fp32 [n_texts, ld_out]. */
+int scb_mean_pool_normalize(const void* hidden, int64_t ld_hidden, const int32_t* offsets, int32_t n_texts,
+                            int32_t dim, float* out, int64_t ld_out, int32_t normalize, void* stream);
+
 /* SpatialPool average, stride 2 (longva/model/multimodal_resampler/spatial_pool.py:23-32):
  * in rows [n*img_stride_rows + tok_offset + y*grid + x] -> out rows [n*(grid/2)^2 + ...]. */
 int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows, int32_t tok_offset,

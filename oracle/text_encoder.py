@@ -65,3 +65,13 @@ def bert_last_hidden_state(W, ids, n_heads, eps=1e-12):
 def cls_embedding(W, ids, n_heads, eps=1e-12):
     """utiles.py:688-690 pooling(strategy='cls'): outputs[:, 0]."""
     return bert_last_hidden_state(W, ids, n_heads, eps)[0]
+
+
+def sentence_embedding(W, ids, n_heads, eps=1e-12, normalize=True):
+    """langchain HuggingFaceEmbeddings / sentence-transformers all-MiniLM-L6-v2 (local_doc_qa.py:185-194): BertModel ->
+    Pooling(mean over the attention mask: one unpadded text, so the plain mean) -> Normalize(p=2, eps 1e-12).
+    sentence-transformers==2.2.2 is pinned in requirements.txt:126 and absent here: restated from its Pooling /
+    Normalize modules; the encoder under it is pinned by tiny_minilm_ref.npz (HF BertModel, 32-wide heads)."""
+    h = bert_last_hidden_state(W, ids, n_heads, eps)
+    v = h.sum(0) / max(float(h.shape[0]), 1e-9)
+    return v / max(float(np.linalg.norm(v)), 1e-12) if normalize else v

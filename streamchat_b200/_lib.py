@@ -192,6 +192,7 @@ SYMBOLS = {
     "scb_resample_v_normalize": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp,
                                            _i32, _vp]),
     "scb_text_embed_layernorm": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _f, _i32, _vp, _i64, _vp]),
+    "scb_mean_pool_normalize": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "scb_avgpool2x2_tokens": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "scb_silu_mul": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i64, _vp]),
     "scb_rope_append": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i32, _f, _vp, _vp, _vp, _i64, _vp]),

@@ -228,6 +228,47 @@ norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Sentence embedding tail (sentence-transformers Pooling(mean) + Normalize): text t owns token rows
+// [offsets[t], offsets[t+1]) of the packed hidden states; out[t] = mean over its rows, divided by max(|mean|_2, 1e-12).
+// One CTA per text, thread = 8 consecutive dims (D <= 8 * blockDim), fp32 sums in token order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mean_pool_normalize_kernel(const __half* __restrict__ x, long long ld_x,
+                                                                  const int* __restrict__ offsets, int D,
+                                                                  float* __restrict__ out, long long ld_out,
+                                                                  int normalize) {
+  const int t = blockIdx.x;
+  const int r0 = offsets[t], r1 = offsets[t + 1];
+  const int i = threadIdx.x;
+  const bool live = i < (D >> 3);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (live)
+    for (int r = r0; r < r1; ++r) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + (long long)r * ld_x + i * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  const float inv = 1.f / fmaxf((float)(r1 - r0), 1e-9f);          // Pooling: sum / clamp(sum(mask), 1e-9)
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] *= inv;
+    ss += acc[e] * acc[e];
+  }
+  __shared__ float red[8];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+  const float scale = normalize ? 1.f / fmaxf(sqrtf(tot), 1e-12f) : 1.f;   // F.normalize(p=2, eps=1e-12)
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[(long long)t * ld_out + i * 8 + e] = acc[e] * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 2x2 average pool over a g x g token grid (SpatialPool avg, stride 2): in rows are
 // [n][tok_offset + y*g + x], out rows [n][(y/2)*(g/2) + x/2].
 // ------------------------------------------------------------------------------------------
@@ -800,6 +841,17 @@ int scb_avgpool2x2_tokens(const void* in, int64_t ld_in, int64_t img_stride_rows
       reinterpret_cast<const __half*>(in), ld_in, img_stride_rows, tok_offset, grid, dim,
       reinterpret_cast<__half*>(out), ld_out);
   SCB_LAUNCH_OK("pool2x2_kernel");
+  return SCB_OK;
+}
+
+int scb_mean_pool_normalize(const void* hidden, int64_t ld_hidden, const int32_t* offsets, int32_t n_texts,
+                            int32_t dim, float* out, int64_t ld_out, int32_t normalize, void* stream) {
+  SCB_REQUIRE(hidden && offsets && out && n_texts >= 1, SCB_ERR_INVALID_ARG, "scb_mean_pool_normalize: bad arguments");
+  SCB_REQUIRE(dim >= 8 && dim % 8 == 0 && dim <= 2048 && ld_hidden % 8 == 0 && aligned16(hidden), SCB_ERR_INVALID_ARG,
+              "scb_mean_pool_normalize: dim=%d must be a multiple of 8 up to 2048 with 16-byte aligned rows", dim);
+  mean_pool_normalize_kernel<<<(unsigned)n_texts, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(hidden), ld_hidden, offsets, dim, out, ld_out, normalize);
+  SCB_LAUNCH_OK("mean_pool_normalize_kernel");
   return SCB_OK;
 }
 

@@ -68,13 +68,50 @@ def load_memory_file(filepath: str, user_name: str, language: str = "cn") -> Lis
 
 
 class MemoryIndex:
-    """Device-resident flat index: embeddings [n, d] fp32 (unit rows) + the documents."""
+    """Device-resident flat index, APPEND-ONLY: rows live in a preallocated [capacity, d] fp32 buffer
+    in HBM and new dialogue turns are written behind the live rows in place — the reference rebuilds the FAISS index
+    from the whole history (and rewrites it on disk) on every question (memory_utils.py:76-83).  `embeddings` is the
+    view of the live rows `cosine_topk` reads; the buffer doubles when it is full."""
+
+    MIN_CAPACITY = 256
 
     def __init__(self, docs: List[Document], embeddings: torch.Tensor, embed_fn, chunk_size: int = CHUNK_SIZE):
-        self.docs = docs
-        self.embeddings = embeddings
+        self.docs = list(docs)
         self.embed_fn = embed_fn
         self.chunk_size = chunk_size
+        n, d = embeddings.shape
+        cap = self.MIN_CAPACITY
+        while cap < n:
+            cap *= 2
+        self._buf = torch.empty((cap, d), dtype=torch.float32, device=embeddings.device)
+        self._buf[:n].copy_(embeddings)
+        self.n = n
+        self.reallocations = 0
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        return self._buf[: self.n]
+
+    @property
+    def capacity(self) -> int:
+        return self._buf.shape[0]
+
+    def append(self, docs: Sequence[Document], rows: torch.Tensor) -> None:
+        """Add documents with their unit-norm embedding rows [m, d] behind the live rows (no restack of the history)."""
+        m = len(docs)
+        if rows.shape[0] != m or rows.shape[1] != self._buf.shape[1]:
+            raise ValueError(f"append: {m} documents but rows of shape {tuple(rows.shape)}")
+        if self.n + m > self.capacity:
+            cap = self.capacity
+            while cap < self.n + m:
+                cap *= 2
+            buf = torch.empty((cap, self._buf.shape[1]), dtype=torch.float32, device=self._buf.device)
+            buf[: self.n].copy_(self._buf[: self.n])
+            self._buf = buf
+            self.reallocations += 1
+        self._buf[self.n: self.n + m].copy_(rows.to(self._buf.device, torch.float32))
+        self.docs.extend(docs)
+        self.n += m
 
     def similarity_search_with_score(self, query: str, k: int = 4) -> List[Tuple[Document, float]]:
         q = self.embed_fn([query])[0]
@@ -128,14 +165,14 @@ class LocalMemoryRetrieval:
 
     def init_cfg(self, embedding_model: str = "minilm-l6", embedding_device="cuda", top_k=VECTOR_SEARCH_TOP_K,
                  language="cn", embed_fn: Optional[Callable[[Sequence[str]], torch.Tensor]] = None):
-        """`embed_fn(list[str]) -> [n, d]` unit-norm embeddings on the device.  Without it the HF
-        sentence encoder named by `embedding_model` is loaded (mean-pool + normalise, what
-        langchain's HuggingFaceEmbeddings does) — the text encoder itself is the 'next' row §8f-1."""
+        """`embed_fn(list[str]) -> [n, d]` unit-norm embeddings on the device.  Without it the sentence encoder named
+        by `embedding_model` (a key of `embedding_model_dict` or a local checkpoint directory) is loaded onto the
+        sm_100a kernels: BERT encoder -> mean pool -> L2 normalise, what langchain's HuggingFaceEmbeddings computes."""
         self.language = language
         self.top_k = top_k
         self.device = torch.device(embedding_device if str(embedding_device).startswith("cuda") else "cuda:0")
         if embed_fn is None:
-            embed_fn = _hf_sentence_embedder(embedding_model_dict[embedding_model], self.device)
+            embed_fn = _hf_sentence_embedder(embedding_model_dict.get(embedding_model, embedding_model), self.device)
         self.embeddings = embed_fn
 
     def init_memory_vector_store(self, filepath, vs_path=None, user_name=None, cur_date=None):
@@ -155,12 +192,21 @@ class LocalMemoryRetrieval:
             return None, loaded
         if not vs_path:
             vs_path = f"memory_index_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}"
-        emb = self._embed_cached([d.page_content for d in docs])
-        prev = self._stores.get(vs_path) if os.path.isdir(vs_path) else None
-        if prev is not None:                                                # FAISS.load_local + add_documents (:238-241)
-            docs = prev.docs + docs
-            emb = torch.cat([prev.embeddings, emb], 0)
-        self._stores[vs_path] = MemoryIndex(docs, emb, self.embeddings, self.chunk_size)
+        prev = self._stores.get(vs_path)
+        texts = [d.page_content for d in docs]
+        if prev is not None and os.path.isdir(vs_path):                     # FAISS.load_local + add_documents (:238-241)
+            prev.append(docs, self._embed_cached(texts))
+        elif prev is not None and len(prev.docs) <= len(docs) and \
+                all(a.page_content == b for a, b in zip(prev.docs, texts)) and \
+                all(a.metadata == b.metadata for a, b in zip(prev.docs, docs)):
+            # the driver deletes the index directory and rebuilds it from the whole history before every question
+            # (memory_utils.py:76-83): the history only ever GROWS, so the resident index is kept and the new turns
+            # are appended in place — same content as the rebuild, O(new turns) work
+            tail = docs[len(prev.docs):]
+            if tail:
+                prev.append(tail, self._embed_cached(texts[len(prev.docs):]))
+        else:
+            self._stores[vs_path] = MemoryIndex(docs, self._embed_cached(texts), self.embeddings, self.chunk_size)
         os.makedirs(vs_path, exist_ok=True)                                 # keeps the driver's exists()/rmtree logic valid
         return vs_path, loaded
 
@@ -225,18 +271,17 @@ class LocalMemoryRetrieval:
 
 
 def _hf_sentence_embedder(model_name: str, device: torch.device):
-    from transformers import AutoModel, AutoTokenizer
-    tok = AutoTokenizer.from_pretrained(model_name)
-    model = AutoModel.from_pretrained(model_name).to(device).eval()
+    """The dialogue-memory encoder (all-MiniLM-L6-v2, local_doc_qa.py:185-194) on the sm_100a kernels
+    (text_encoder.SentenceEncoder).  `model_name` is a local checkpoint directory, or a hub id that
+    `huggingface_hub.snapshot_download` can resolve from the local cache (there is no network at run time)."""
+    import os
 
-    @torch.no_grad()
-    def embed(texts: Sequence[str]) -> torch.Tensor:
-        enc = tok(list(texts), padding=True, truncation=True, return_tensors="pt").to(device)
-        h = model(**enc).last_hidden_state
-        m = enc["attention_mask"].unsqueeze(-1).float()
-        pooled = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)
-        return torch.nn.functional.normalize(pooled, p=2, dim=1)
-    return embed
+    from .text_encoder import SentenceEncoder
+    path = model_name
+    if not os.path.isdir(path):
+        from huggingface_hub import snapshot_download
+        path = snapshot_download(model_name, local_files_only=True)
+    return SentenceEncoder.from_pretrained(path, device)
 
 
 # ---- memory_bank/memory_utils.py ----------------------------------------------------------------

@@ -302,6 +302,20 @@ def text_embed_layernorm(ids: torch.Tensor, position_ids: torch.Tensor, word: to
     return out
 
 
+def mean_pool_normalize(hidden: torch.Tensor, offsets: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """Packed token rows [T, D] fp16 + int32 offsets [n + 1] -> [n, D] fp32 mean-pooled (and L2-normalised) rows
+    (sentence-transformers Pooling(mean) + Normalize, the dialogue-memory embedding)."""
+    dev = _require_cuda(hidden, offsets)
+    if offsets.dtype != torch.int32 or offsets.dim() != 1 or offsets.numel() < 2:
+        raise TypeError("offsets must be int32 [n + 1]")
+    _f16(hidden, "hidden")
+    n, dim = offsets.numel() - 1, hidden.shape[1]
+    out = torch.empty((n, dim), dtype=torch.float32, device=dev)
+    _call("scb_mean_pool_normalize", dev, _ptr(hidden), hidden.stride(0), _ptr(offsets), n, dim, _ptr(out), out.stride(0),
+          int(normalize))
+    return out
+
+
 def avgpool2x2_tokens(x: torch.Tensor, n_img: int, tokens_per_img: int, tok_offset: int, grid: int) -> torch.Tensor:
     """x [n_img*tokens_per_img, D] -> [n_img*(grid/2)^2, D]."""
     dev = _require_cuda(x)

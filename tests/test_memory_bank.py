@@ -49,6 +49,41 @@ def test_oracle_flat_l2_and_expansion(tmp_path):
     assert dates == "2024-05-02" and len(out) == 1 and "pasta" in out[0]
 
 
+def test_oracle_flat_l2_matches_fixture(golden_dir):
+    """oracle.index_flat_l2_search against the committed brute-force fixture of the published IndexFlatL2 definition."""
+    g = np.load(os.path.join(golden_dir, "flat_l2_ref.npz"))
+    s, i = omb.index_flat_l2_search(g["xb"], g["xq"], int(g["k"]))
+    np.testing.assert_array_equal(i, g["labels"])
+    np.testing.assert_allclose(s, g["distances"], rtol=1e-4, atol=2e-6)
+    s, i = omb.index_flat_l2_search(g["xb"][:2], g["xq"][1:2], 4)
+    assert i[0, 2:].tolist() == [-1, -1] and sorted(i[0, :2].tolist()) == [0, 1]
+
+
+@pytest.mark.gpu
+def test_gpu_flat_l2_matches_fixture_and_index_is_append_only(cuda, golden_dir):
+    """The device index against the same fixture (labels exact, squared-L2 scores 2 - 2 cos within 2e-6), then the
+    append-only behaviour (§8f-4): rows appended in place give the index a fresh build gives, the buffer is not
+    reallocated until it is full, and only the new rows are written."""
+    from streamchat_b200 import ops
+    from streamchat_b200.memory_bank import Document, MemoryIndex
+    g = np.load(os.path.join(golden_dir, "flat_l2_ref.npz"))
+    xb, xq, k = torch.from_numpy(g["xb"]).to(cuda), torch.from_numpy(g["xq"]).to(cuda), int(g["k"])
+    docs = [Document(f"turn {i}", {"source": "2024-05-01"}) for i in range(xb.shape[0])]
+    index = MemoryIndex(docs[:200], xb[:200], None)
+    assert index.capacity == 256 and index.n == 200
+    ptr = index._buf.data_ptr()
+    index.append(docs[200:250], xb[200:250])                       # fits: written behind the live rows, same buffer
+    assert index._buf.data_ptr() == ptr and index.reallocations == 0 and index.n == 250
+    index.append(docs[250:], xb[250:])                             # 257 > 256: one doubling
+    assert index.capacity == 512 and index.reallocations == 1 and len(index.docs) == 257
+    assert torch.equal(index.embeddings, xb)
+    scores, idx = ops.cosine_topk(index.embeddings, xq, k=k)
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["labels"])
+    np.testing.assert_allclose((2.0 - 2.0 * scores).cpu().numpy(), g["distances"], atol=2e-6)
+    with pytest.raises(ValueError):
+        index.append(docs[:2], xb[:3])
+
+
 @pytest.mark.gpu
 def test_local_memory_retrieval_matches_oracle(cuda, tmp_path):
     from streamchat_b200.memory_bank import (LocalMemoryRetrieval, build_prompt_with_search_memory_only_related,
@@ -80,7 +115,12 @@ def test_local_memory_retrieval_matches_oracle(cuda, tmp_path):
     assert "most relevant historical contextual conversation records" in prompt
     memory = save_local_memory(memory, [["new question", "new answer"]], "User", args)
     _, _, _, _, index2 = enter_name("User", memory, qa, args)
-    assert len(index2.docs) == len(index.docs) + 1
+    assert len(index2.docs) == 7                               # 6 documents + the new turn
+    assert index2 is index and index2.reallocations == 0        # the resident index was appended to, not rebuilt
+    docs2 = load_memory_file(path, "User", "en")
+    xb2 = _embed_np([d.page_content for d in docs2])
+    assert len(docs2) == 7 and torch.allclose(index2.embeddings.cpu(), torch.from_numpy(xb2), atol=1e-6)
+    assert qa.search_memory("new question", index2) == omb.search_memory(docs2, xb2, _embed_np(["new question"])[0], 1, 200)
     # unknown user -> fresh entry, no index
     _, um, _, _, idx = enter_name("Nobody", memory, qa, args)
     assert idx is None and um == {"name": "Nobody"}
@@ -143,6 +183,7 @@ def test_embedding_cache_and_snapshot_cpu(tmp_path):
     n_second = sum(len(t) for t in seen) - n_first
     store = qa.load_memory_index(vs)
     assert n_second == len(store.docs) - n_first > 0    # only the new turns went through the encoder
+    assert store.n == 5 and store.capacity == 256 and store.reallocations == 0    # appended in place, not restacked
     path = qa.save_snapshot(vs)
     qb = LocalMemoryRetrieval()
     qb._stores = {}

@@ -103,44 +103,28 @@ class KMeans(torch.nn.Module):
     batch.  Not supported (raise): k-means++ init, per-instance k, other distances.
     """
 
-    INIT_METHODS = ["rnd", "k-means++"]
-    NORM_METHODS = ["mean", "minmax", "unit"]
-
     def __init__(self, init_method: str = "rnd", num_init: int = 8, max_iter: int = 100,
                  distance=LpDistance, p_norm: int = 2, tol: float = 1e-4,
                  normalize: Optional[Union[str, bool]] = None, n_clusters: Optional[int] = 8,
                  verbose: bool = True, seed: Optional[int] = 123, **kwargs):
         super().__init__()
         self.init_method = init_method.lower()
-        self.num_init = num_init
-        self.max_iter = max_iter
-        self.p_norm = p_norm
-        self.tol = tol
-        self.normalize = normalize
-        self.n_clusters = n_clusters
-        self.verbose = verbose
-        self.seed = seed
+        self.num_init, self.max_iter, self.p_norm, self.tol = num_init, max_iter, p_norm, tol
+        self.normalize = ("mean" if normalize else None) if isinstance(normalize, bool) else normalize
+        self.n_clusters, self.verbose, self.seed = n_clusters, verbose, seed
         self.distance = distance(**kwargs) if isinstance(distance, type) else distance
         self._result = None
         self.eps = None
         self._k_max = None
-        # kmeans.py:108-134
-        if self.init_method not in self.INIT_METHODS:
-            raise ValueError(f"unknown <init_method>: {self.init_method}. Please choose one of {self.INIT_METHODS}")
-        if self.num_init <= 0:
-            raise ValueError(f"num_init should be > 0, but got {self.num_init}.")
-        if self.max_iter <= 0:
-            raise ValueError(f"max_iter should be > 0, but got {self.max_iter}.")
-        if self.p_norm <= 0:
-            raise ValueError(f"p_norm should be > 0, but got {self.p_norm}.")
-        if self.tol is not None and (self.tol < 0 or self.tol > 1):
-            raise ValueError(f"tol should be > 0 and < 1, but got {self.tol}.")
-        if isinstance(self.normalize, bool):
-            self.normalize = "mean" if self.normalize else None
-        if self.normalize is not None and self.normalize not in self.NORM_METHODS:
-            raise ValueError(f"unknown <normalize> method: {self.normalize}. Please choose one of {self.NORM_METHODS}")
-        if self.n_clusters is not None and self.n_clusters < 2:
-            raise ValueError(f"n_clusters should be > 1, but got {self.n_clusters}.")
+        # argument contract of the upstream constructor (kmeans.py:108-134), one check per argument
+        bad = [("init_method", self.init_method not in ("rnd", "k-means++")),
+               ("num_init", num_init <= 0), ("max_iter", max_iter <= 0), ("p_norm", p_norm <= 0),
+               ("tol", tol is not None and not 0 <= tol <= 1),
+               ("normalize", self.normalize not in (None, "mean", "minmax", "unit")),
+               ("n_clusters", n_clusters is not None and n_clusters < 2)]
+        for name, wrong in bad:
+            if wrong:
+                raise ValueError(f"KMeans: invalid value for {name}: {getattr(self, name)!r}")
         if not isinstance(self.distance, LpDistance) or self.p_norm != 2:
             raise NotImplementedError("only LpDistance with p_norm=2 is implemented on sm_100a")
 
@@ -150,92 +134,69 @@ class KMeans(torch.nn.Module):
 
     @property
     def num_clusters(self) -> Union[int, Tensor, Any]:
-        if not self.is_fitted:
-            return None
-        return self._result.k
+        return self._result.k if self.is_fitted else None
 
-    # kmeans.py:136-151
     def _check_x(self, x) -> Tensor:
+        """x must be a [BS, N, D] tensor (extra singleton dims are squeezed away, kmeans.py:136-151)."""
         if not isinstance(x, Tensor):
-            raise TypeError(f"x has to be a torch.Tensor but got {type(x)}.")
-        shp = x.shape
-        if len(shp) < 3:
-            raise ValueError(f"input <x> should be at least of shape (BS, N, D) with batch size BS, "
-                             f"number of points N and number of dimensions D but got {shp}.")
-        elif len(shp) > 3:
-            x = self._check_x(x.squeeze())
+            raise TypeError(f"x must be a torch.Tensor, got {type(x)}")
+        if x.dim() > 3:
+            x = x.squeeze()
+        if x.dim() != 3:
+            raise ValueError(f"x must have shape (BS, N, D), got {tuple(x.shape)}")
         self.eps = torch.finfo(x.dtype).eps
         return x
 
-    # kmeans.py:153-185
     def _check_k(self, k, dims, device=torch.device("cpu")) -> LongTensor:
-        bs, n, d = dims
-        if not isinstance(k, Tensor):
+        """Number of clusters per instance as a [BS] long tensor (kmeans.py:153-185); the kernel takes one common k."""
+        bs, n, _ = dims
+        if k is None:
+            k = self.n_clusters
             if k is None:
-                if self.n_clusters is None:
-                    raise ValueError("Did not provide number of clusters k on call and "
-                                     "did not specify default 'n_clusters' at initialization.")
-                k = self.n_clusters
-            if isinstance(k, int):
-                k = torch.empty(bs, dtype=torch.long).fill_(k)
-            else:
-                raise TypeError(f"k has to be int, torch.Tensor or None but got {type(k)}.")
-        if len(k.shape) > 1:
-            k = k.squeeze()
-            assert len(k.shape) == 1
-        if k.shape[0] == 1:
+                raise ValueError("no k given and no default n_clusters set")
+        if isinstance(k, int):
+            k = torch.full((bs,), k, dtype=torch.long)
+        elif not isinstance(k, Tensor):
+            raise TypeError(f"k must be an int, a tensor or None, got {type(k)}")
+        k = k.reshape(-1)
+        if k.numel() == 1:
             k = k.repeat(bs)
-        if (k >= n).any():
-            raise ValueError(f"Specified 'k' must be smaller than number of samples n={n}, but got: {k}.")
-        if (k <= 1).any():
-            raise ValueError("Clustering for k=1 is ambiguous.")
+        if bool((k >= n).any()) or bool((k <= 1).any()):
+            raise ValueError(f"k must satisfy 1 < k < n={n}, got {k.tolist()}")
         if int(k.min()) != int(k.max()):
             raise NotImplementedError("per-instance k is not implemented on sm_100a (one common k per batch)")
         self._k_max = int(k.max())
         return k.to(dtype=torch.long, device=device)
 
-    # kmeans.py:187-241
     def _check_centers(self, centers, dims, dtype=torch.float32, device=torch.device("cpu")) -> Tensor:
+        """Initial centers as [BS, num_init, K, D]; a [BS, K, D] tensor is shared by all restarts (kmeans.py:187-241)."""
         if not isinstance(centers, Tensor):
-            raise TypeError(f"centers has to be a torch.Tensor but got {type(centers)}.")
-        bs, n, d = dims
-        if len(centers.shape) == 3:
-            if centers.size(0) != bs or centers.size(1) != self._k_max or centers.size(2) != d:
-                raise ValueError(f"centers needs to be of shape ({bs}, {self._k_max}, {d}),"
-                                 f"but got {tuple(centers.shape)}.")
+            raise TypeError(f"centers must be a torch.Tensor, got {type(centers)}")
+        bs, _, d = dims
+        if centers.dim() == 3:
             if self.num_init > 1:
-                warn(f"Specified num_init={self.num_init} > 1 but provided only 1 center configuration "
-                     f"per instance. Using same center configuration for all {self.num_init} runs.")
-                centers = centers[:, None, :, :].expand(centers.size(0), self.num_init,
-                                                        centers.size(1), centers.size(2))
-            else:
-                centers = centers.unsqueeze(1)
-        elif len(centers.shape) == 4:
-            if (centers.size(0) != bs or centers.size(1) != self.num_init
-                    or centers.size(2) != self._k_max or centers.size(3) != d):
-                raise ValueError(f"centers needs to be of shape ({bs}, {self.num_init}, {self._k_max}, {d}),"
-                                 f"but got {tuple(centers.shape)}.")
-        else:
-            raise ValueError(f"centers have unsupported shape of {tuple(centers.shape)} instead of "
-                             f"({bs}, {self.num_init}, {self._k_max}, {d}).")
+                warn(f"one center configuration per instance given: all {self.num_init} restarts start from it")
+            centers = centers.unsqueeze(1).expand(-1, self.num_init, -1, -1)
+        want = (bs, self.num_init, self._k_max, d)
+        if tuple(centers.shape) != want:
+            raise ValueError(f"centers must have shape {want} (or without the restart dim), got {tuple(centers.shape)}")
         return centers.contiguous().to(dtype=dtype, device=device)
 
     @staticmethod
     def _normalize(x: Tensor, normalize: str, eps: float = 1e-8):
-        # kmeans.py:363-384 (input conditioning, element-wise; in place for mean/minmax as upstream)
+        """Input conditioning of kmeans.py:363-384 (torch element-wise ops on the caller's tensor, off the hot loop;
+        'mean' / 'minmax' modify x in place as upstream does)."""
         if normalize == "mean":
-            x -= x.mean(dim=1)[:, None, :]
-        elif normalize == "minmax":
-            x -= x.min(-1, keepdims=True).values
-            x /= x.max(-1, keepdims=True).values
-        elif normalize == "unit":
-            z_msk = x == 0
-            x = x.clone()
-            x[z_msk] = eps
-            x = torch.diag_embed(1.0 / (torch.norm(x, p=2, dim=-1))) @ x
-        else:
-            raise ValueError(f"unknown normalization type {normalize}.")
-        return x
+            x -= x.mean(dim=1, keepdim=True)
+            return x
+        if normalize == "minmax":
+            x -= x.min(-1, keepdim=True).values
+            x /= x.max(-1, keepdim=True).values
+            return x
+        if normalize == "unit":
+            x = torch.where(x == 0, torch.full_like(x, eps), x)
+            return x / torch.norm(x, p=2, dim=-1, keepdim=True)
+        raise ValueError(f"unknown normalization {normalize!r}")
 
     def _init_rnd(self, x: Tensor, k: LongTensor) -> Tensor:
         # kmeans.py:386-419 — identical draw (same generator seed, same multinomial call)

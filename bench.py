@@ -158,19 +158,20 @@ def workload_config(args, n_frames: int, tiny: bool, world: int) -> dict:
 
 def run_stream(session_factory, frames_dev, host_frames, segment, device, e2e: bool):
     """One step on one rank: the whole stream through a StreamingSession.  Returns (answer ids, h2d bytes, d2h bytes)."""
+    from streamchat_b200.pipeline import FramePrefetcher
     sess = session_factory()
     n = frames_dev.shape[0] if frames_dev is not None else host_frames.shape[0]
     h2d = d2h = 0
-    for s0 in range(0, n, segment):
-        if e2e:
-            seg = host_frames[s0:s0 + segment].to(device, non_blocking=True)   # pinned -> HBM inside the timed region
-            h2d += seg.numel() * seg.element_size()
-        else:
-            seg = frames_dev[s0:s0 + segment]
+    slices = [(s0, min(s0 + segment, n)) for s0 in range(0, n, segment)]
+    # e2e: pinned host frames -> HBM inside the timed region, segment i+1 staged on a copy stream while i is encoded
+    pre = FramePrefetcher(host_frames, slices, device) if e2e else None
+    for i, seg in (pre if e2e else ((i, frames_dev[a:b]) for i, (a, b) in enumerate(slices))):
         with _stage("encode"):
             feats = sess.ingest(seg)
         with _stage("memory_update"):
             sess.update_memory(feats, kmeans_init_indices=list(range(sess.cfg.num_clusters)))
+    if pre is not None:
+        h2d = pre.bytes_copied
     with _stage("answer"):
         text, ids = sess.answer(QUESTION)
     if e2e:
@@ -187,16 +188,16 @@ def run_stream_sharded(session_factory, gather_buffer, my_frames_dev, my_frames_
     sess = session_factory()
     sh = ShardedStreamingSession(sess, rank, world, n_frames, kmeans_init_indices=list(range(sess.cfg.num_clusters)),
                                  gather_buffer=gather_buffer)
+    from streamchat_b200.pipeline import FramePrefetcher
     h2d = d2h = 0
-    for i, first in enumerate(range(0, n_frames, segment)):
-        a, b = seg_slices[i]
-        if b > a and e2e:
-            seg = my_frames_host[a:b].to(device, non_blocking=True)
-            h2d += seg.numel() * seg.element_size()
-        else:
-            seg = my_frames_dev[a:b] if b > a else None
+    pre = FramePrefetcher(my_frames_host, seg_slices, device) if e2e else None
+    it = pre if e2e else ((i, (my_frames_dev[a:b] if b > a else None)) for i, (a, b) in enumerate(seg_slices))
+    for i, seg in it:
+        first = i * segment
         with _stage("encode"):
             sh.ingest_segment(first, min(segment, n_frames - first), seg)
+    if pre is not None:
+        h2d = pre.bytes_copied
     with _stage("captions"):
         sh.caption_my_chunks()
     with _stage("exchange"):

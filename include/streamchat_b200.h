@@ -76,8 +76,8 @@ typedef struct scb_cosine_topk_args {
   int32_t _pad;
   int64_t* out_indices;  /* [n_queries, k]; -1 where fewer than k rows exist */
   float* out_scores;     /* [n_queries, k]; -inf where fewer than k rows     */
-  void* workspace;
-  size_t workspace_bytes;
+  void* workspace;       /* the first 4*n_queries bytes (block tickets) must be ZERO before the first call; */
+  size_t workspace_bytes;/* every call leaves them zero, so one zero-initialised allocation serves all calls */
 } scb_cosine_topk_args;
 
 size_t scb_cosine_topk_workspace_bytes(int64_t n_rows, int32_t n_queries, int32_t k);

@@ -40,10 +40,11 @@ def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
 
 
 def _workspace(dev: torch.device, name: str, nbytes: int) -> torch.Tensor:
+    """Per-device scratch buffer, allocated ZEROED (kernels with self-resetting tickets rely on it) and grown on demand."""
     key = (dev.index, name)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
     return ws
 

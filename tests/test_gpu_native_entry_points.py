@@ -64,3 +64,29 @@ def test_vit_encode_is_graph_capturable_and_validates(cuda):
     assert b"workspace" in lib.scb_last_error()
     assert lib.scb_vit_encode(h, images.data_ptr(), 0, out.data_ptr(), None, ws.data_ptr(), ws.numel(), None) == -1
     assert lib.scb_vit_encode_workspace_bytes(h, 8) > lib.scb_vit_encode_workspace_bytes(h, 4) > 0
+
+
+def test_frame_prefetcher_overlaps_copies_without_changing_results(cuda):
+    """§8f-3: segments staged on a copy stream (two buffers, ready / free events) are the frames a plain copy delivers,
+    including ragged and empty segments, and a buffer is never overwritten before its consumer finished."""
+    from streamchat_b200.pipeline import FramePrefetcher
+    torch.manual_seed(0)
+    host = torch.randn(23, 3, 8, 8).half().pin_memory()
+    slices = [(0, 6), (6, 6), (6, 14), (14, 23)]
+    outs = []
+    pre = FramePrefetcher(host, slices, cuda)
+    for i, seg in pre:
+        if seg is None:
+            outs.append(None)
+            continue
+        y = seg.float() * 2                           # consumer work enqueued on the current stream
+        for _ in range(20):
+            y = y + seg.float()                       # keeps reading the buffer while the next copy is queued
+        outs.append(y)
+    torch.cuda.synchronize()
+    assert outs[1] is None and pre.bytes_copied == 23 * 3 * 8 * 8 * 2
+    for (a, b), y in zip(slices, outs):
+        if y is not None:
+            assert torch.equal(y.cpu(), host[a:b].float() * 22)
+    with pytest.raises(ValueError):
+        FramePrefetcher(torch.zeros(4, 3, 8, 8), [(0, 4)], cuda)

@@ -83,7 +83,7 @@ def main():
             formula=f"measured with {Ll} of 28 layers; full depth = time outside layers + 28 x per-layer time; 128 new tokens = "
                     f"prefill + 127 x per-token time", prefill_seconds=pre, seconds_per_token=tok, raw=gen)
     os.makedirs(os.path.join(ROOT, "baseline"), exist_ok=True)
-    path = os.path.join(ROOT, "baseline", "results.json")
+    path = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(ROOT, "baseline", "results.json")
     json.dump(out, open(path, "w"), indent=1)
     for r in out["results"]:
         print(f"{r['cpu_seconds']:10.4f} s  {'(extrapolated) ' if r['extrapolated'] else ''}{r['config']}")

@@ -206,6 +206,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global memory and may overlap the tail of the previous kernel on the stream; nothing below runs before that
+  // kernel has completed.  In the decode step's launch chain (8 launches per layer for wide batches) this hides the
+  // launch latency of every GEMM behind its predecessor.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -560,17 +566,19 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = scb_pdl_enabled() ? 1 : 0;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mw, ep));
   } else {
     const int grid = (int)(tiles < sms ? tiles : sms);
-    kern<<<grid, kGemmThreads, C::kSmemBytes, st>>>(ma, mw, ep);
+    SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(kGemmThreads), C::kSmemBytes, st, ma, mw, ep));
   }
   SCB_LAUNCH_OK("linear_tcgen05_kernel");
   return SCB_OK;

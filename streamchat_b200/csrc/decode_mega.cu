@@ -312,16 +312,72 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
 // ------------------------------------------------------------------------------------------
 // Prologues: build the stage's input rows in shared memory (act [R][act_ld] fp16).
 // ------------------------------------------------------------------------------------------
-// Pull this CTA's split of every live sequence's K and V rows of one layer into L2 ahead of the
-// attention stage (the addresses depend only on the context lengths).
+// ------------------------------------------------------------------------------------------
+// Attention work plan: the S = n_splits CTAs of a kv head share the live sequences' KV positions.
+//   R == 1: split j of the one sequence covers [j*L, (j+1)*L), L = ceil(len / S).
+//   R  > 1: every CTA works on ONE (sequence, split) — the sequences are attended CONCURRENTLY, not one after the
+//           other in every CTA (a short sequence's 37 tiny splits cost a full dependent-latency chain each:
+//           5.4 us per sequence per layer).  With L = ceil(sum(len) / (S - R)) and n_s = ceil(len_s / L) splits for
+//           sequence s, sum(n_s) < sum(len)/L + R <= S, so every split fits a CTA and no split is longer than L
+//           (the host sizes the score buffer for L <= ceil(R * ctx_cap / (S - R))).
+// Every CTA derives the same plan from kv_len[] (clamped as in attention_partial).
+// ------------------------------------------------------------------------------------------
+SCB_DEVICE int clamped_len(const MegaParams& p, int n) { return max(1, min(p.kv_len[n], (int)p.max_ctx)); }
+
+SCB_DEVICE int plan_split_len(const MegaParams& p) {
+  const int S = p.n_splits;
+  if (p.R == 1 || S <= p.R) return (clamped_len(p, 0) + S - 1) / S;   // S <= R: legacy mapping (see attn_plan)
+  int tot = 0;
+  for (int n = 0; n < p.R; ++n) tot += clamped_len(p, n);
+  return (tot + (S - p.R) - 1) / (S - p.R);
+}
+
+// number of splits of sequence n under the plan
+SCB_DEVICE int plan_splits_of(const MegaParams& p, int n, int L) {
+  if (p.R == 1 || p.n_splits <= p.R) return p.n_splits;
+  return (clamped_len(p, n) + L - 1) / L;
+}
+
+// CTA `j` (0..S) of a kv head -> (sequence, local split, [begin, end)); seq = -1: idle.  Legacy mapping (R == 1, or
+// fewer CTAs per head than sequences + 1): the caller loops over the sequences itself.
+SCB_DEVICE void attn_plan(const MegaParams& p, int j, int L, int& seq, int& jl, int& begin, int& end) {
+  seq = -1;
+  jl = begin = end = 0;
+  int first = 0;
+  for (int n = 0; n < p.R; ++n) {
+    const int len = clamped_len(p, n);
+    const int ns = (len + L - 1) / L;
+    if (j < first + ns) {
+      seq = n;
+      jl = j - first;
+      begin = jl * L;
+      end = min(len, begin + L);
+      return;
+    }
+    first += ns;
+  }
+}
+
+// Pull this CTA's part of the live K and V rows of one layer into L2 ahead of the attention stage (the addresses
+// depend only on the context lengths).
 SCB_DEVICE void prefetch_kv_l2(const MegaParams& p, const MegaLayer* ly, int hk, int split, int head_dim) {
   if (split >= p.n_splits) return;
+  const int L = plan_split_len(p);
+  const bool legacy = p.R == 1 || p.n_splits <= p.R;
   for (int n = 0; n < p.R; ++n) {
-    const int kv_len = max(1, min(p.kv_len[n], (int)p.max_ctx));   // same clamp as attention_partial
-    const int per = (kv_len + p.n_splits - 1) / p.n_splits;
-    const int begin = split * per, end = min(kv_len, begin + per);
+    int seq = n, begin, end, jl;
+    if (legacy) {
+      const int kv_len = clamped_len(p, n);
+      const int per = (kv_len + p.n_splits - 1) / p.n_splits;
+      begin = split * per;
+      end = min(kv_len, begin + per);
+    } else {
+      if (n > 0) break;
+      attn_plan(p, split, L, seq, jl, begin, end);
+      if (seq < 0) break;
+    }
     if (end <= begin) continue;
-    const size_t off = (size_t)n * p.cache_seq_stride + ((size_t)hk * p.max_ctx + begin) * head_dim;
+    const size_t off = (size_t)seq * p.cache_seq_stride + ((size_t)hk * p.max_ctx + begin) * head_dim;
     const long long bytes = (long long)(end - begin) * head_dim * 2;
     const char* kp = reinterpret_cast<const char*>(ly->k_cache + off);
     const char* vp = reinterpret_cast<const char*>(ly->v_cache + off);
@@ -447,7 +503,7 @@ SCB_DEVICE void prologue_copy(const MegaParams& p, __half* act, const __half* sr
 // ------------------------------------------------------------------------------------------
 template <int HD, int G>
 SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint8_t* scratch, int hk, int split,
-                                  int seq) {
+                                  int seq, int begin, int end) {
   constexpr int HALF = HD / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per_max = p.per_max, n_splits = p.n_splits;
@@ -468,9 +524,8 @@ SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint
   const bool kv_ok = kv_raw >= 1 && kv_raw <= max_pos;
   const int kv_len = max(1, min(kv_raw, (int)max_pos));
   const int pos = kv_len - 1;
-  const int per = (kv_len + n_splits - 1) / n_splits;
-  const int begin = split * per, end = min(kv_len, begin + per);
-  const int n_local = min(per_max, max(0, end - begin));
+  end = min(end, kv_len);
+  const int n_local = min(per_max, max(0, end - begin));   // the plan bounds every range by per_max (see attn_plan)
 
   if (tid < HALF) {
     const float f = p.inv_freq ? p.inv_freq[tid] : powf(p.theta, -(float)(2 * tid) / (float)HD);
@@ -659,15 +714,15 @@ SCB_DEVICE void attention_partial(const MegaParams& p, const MegaLayer* ly, uint
 // 256 threads = 32 dims x 8 split groups; a thread's <= 8 partial loads are issued before the split
 // weights exist (they do not depend on them), so a task costs one L2 round trip.
 template <int HD>
-SCB_DEVICE void attention_combine(const MegaParams& p, uint8_t* scratch, int task) {
+SCB_DEVICE void attention_combine(const MegaParams& p, uint8_t* scratch, int task, int L) {
   constexpr int QS = HD / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_splits = p.n_splits;
   float* w_s = reinterpret_cast<float*>(scratch);    // [kMaxSplits]
   float* inv_l = w_s + kMaxSplits;                   // [1]
   float* acc_s = inv_l + 8;                          // [8][32]
   const int head_task = task / QS, d = (task - head_task * QS) * 32 + lane;   // head_task = seq * n_q + head
-  const size_t base = (size_t)head_task * n_splits;
+  const size_t base = (size_t)head_task * p.n_splits;                         // slot stride stays n_splits
+  const int n_splits = plan_splits_of(p, head_task / p.n_q, L);               // live partials of this sequence
   const float* po = p.att_o + base * HD + d;
   float ov[kMaxSplits / kCWarps];
 #pragma unroll
@@ -796,12 +851,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     grid_sync(p, gen);
     SCB_STAMP(3);
     // ---- attention partials
-    if (split < p.n_splits)
-      for (int n = 0; n < p.R; ++n) attention_partial<HD, G>(p, ly, scratch, hk, split, n);
+    const int plan_L = plan_split_len(p);
+    if (split < p.n_splits) {
+      if (p.R == 1 || p.n_splits <= p.R) {
+        for (int n = 0; n < p.R; ++n) {
+          const int len = clamped_len(p, n), per = (len + p.n_splits - 1) / p.n_splits;
+          attention_partial<HD, G>(p, ly, scratch, hk, split, n, split * per, min(len, split * per + per));
+        }
+      } else {
+        int seq, jl, begin, end;
+        attn_plan(p, split, plan_L, seq, jl, begin, end);
+        if (seq >= 0) attention_partial<HD, G>(p, ly, scratch, hk, jl, seq, begin, end);
+      }
+    }
     SCB_STAMP(4);
     grid_sync(p, gen);
     SCB_STAMP(5);
-    for (int task = cta; task < p.R * p.n_q * (HD / 32); task += gridDim.x) attention_combine<HD>(p, scratch, task);
+    for (int task = cta; task < p.R * p.n_q * (HD / 32); task += gridDim.x)
+      attention_combine<HD>(p, scratch, task, plan_L);
     SCB_STAMP(6);
     grid_sync(p, gen);
     SCB_STAMP(7);
@@ -1178,7 +1245,11 @@ int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream) {
   p.logits = reinterpret_cast<__half*>(a->logits);
   p.ld_logits = a->ld_logits;
   const long long cap = (a->ctx_cap > 0 && a->ctx_cap < p.max_ctx) ? a->ctx_cap : p.max_ctx;
-  const int per_need = (int)((cap + p.n_splits - 1) / p.n_splits);
+  // longest KV range one CTA attends (see attn_plan): ceil(cap / S) for one sequence, ceil(R * cap / (S - R)) when the
+  // R sequences share the S CTAs of a kv head
+  const int per_need = (a->rows == 1 || p.n_splits <= a->rows)
+                           ? (int)((cap + p.n_splits - 1) / p.n_splits)
+                           : (int)(((long long)a->rows * cap + (p.n_splits - a->rows) - 1) / (p.n_splits - a->rows));
   p.per_max = ((per_need + 11) / 16) * 16 + 4;   // row stride = 4 mod 16 floats: conflict-free score stores
   // shared-memory budget: ring stages + max(activation rows, attention scratch)
   int kmax = p.H;

@@ -80,6 +80,25 @@ def bench_topk():
                       "index_gbs_hbm": 10000 * 1024 * 4 / med / 1e9, "l2_gbs": 64 * 10000 * 1024 * 4 / med / 1e9}))
 
 
+def bench_topk_small():
+    """Config #3 at its own size (10 000 x 1024) as a retrieval loop would see it: 48 back-to-back searches in ONE graph,
+    cycling over 6 index copies (246 MB fp32 > L2, so every search streams its index from HBM) — per-call latency at
+    sustained clocks, without the idle-GPU clock drop and event overhead of timing a single 10 us launch."""
+    for dt in (torch.float32, torch.float16):
+        idxs = [torch.randn(10000, 1024, device=dev, dtype=dt) for _ in range(6 if dt == torch.float32 else 12)]
+        q = torch.randn(1024, device=dev, dtype=dt)
+        n_calls = 48
+
+        def loop():
+            for i in range(n_calls):
+                ops.cosine_topk(idxs[i % len(idxs)], q, 8)
+        med, best = timeit(loop, iters=10, flush=False)
+        by = 10000 * 1024 * idxs[0].element_size()
+        print(json.dumps({"kernel": "cosine_topk", "n": 10000, "d": 1024, "dtype": str(dt), "k": 8, "calls_per_graph": n_calls,
+                          "us_per_call": med * 1e6 / n_calls, "best_us_per_call": best * 1e6 / n_calls,
+                          "gbs": by / (med / n_calls) / 1e9}))
+
+
 def bench_kmeans():
     T, F, K = 400, 144 * 3584, 5
     x = torch.randn(T, F, device=dev).half()

@@ -50,6 +50,68 @@ SCB_DEVICE void topk_insert(TopkList& l, float s, long long idx, int k, int lane
   }
 }
 
+// Compare-exchange step of a bitonic network over the 32 lanes: after it, in an ascending-rank ("best first")
+// block the lower lane of each pair holds the entry that ranks first.  Entries with i < 0 are empty (-inf, -1).
+SCB_DEVICE void bitonic_step(float& s, long long& i, int stride, bool best_first, int lane) {
+  const float os = __shfl_xor_sync(0xffffffffu, s, stride);
+  const long long oi = __shfl_xor_sync(0xffffffffu, i, stride);
+  const bool lower = (lane & stride) == 0;
+  const bool other_first = ranks_before(os, oi, s, i);
+  const bool take = (lower == best_first) ? other_first : !other_first;
+  if (take) {
+    s = os;
+    i = oi;
+  }
+}
+// Full sort of 32 lane-distributed entries, best first (lane 0 = best).
+SCB_DEVICE void bitonic_sort32(float& s, long long& i, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+    const bool best_first = (size == 32) || ((lane & size) == 0);
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) bitonic_step(s, i, stride, best_first, lane);
+  }
+}
+// (ls, li): sorted best-first list of 32; (s, i): 32 new entries in any order.  Leaves the best 32 of the 64 in
+// (ls, li), sorted: sort the new ones, pair list[l] with new[31 - l] (the better of each pair forms a bitonic
+// sequence holding the top 32), then one bitonic merge.  Constant cost, no data-dependent loop.
+SCB_DEVICE void merge_top32(float& ls, long long& li, float s, long long i, int lane) {
+  bitonic_sort32(s, i, lane);
+  const float rs = __shfl_sync(0xffffffffu, s, 31 - lane);
+  const long long ri = __shfl_sync(0xffffffffu, i, 31 - lane);
+  if (ranks_before(rs, ri, ls, li)) {
+    ls = rs;
+    li = ri;
+  }
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) bitonic_step(ls, li, stride, true, lane);
+}
+
+// Select the best k of the kWarps sorted lists in shared memory (list w at [w * kMaxK, w * kMaxK + k)) by COUNTING:
+// thread (w, j) counts the entries that rank before its own — rows are distinct, so the ranks are a permutation —
+// and the entries of rank < k land in out[rank].  All 256 threads work in parallel on <= 256 entries (the serial
+// insertion this replaces cost ~100 cycles per entry on one warp).  out_* must hold (-inf, -1) beforehand.
+SCB_DEVICE void select_topk_counting(const float* m_s, const long long* m_i, int k, float* out_s, long long* out_i,
+                                     int tid) {
+  if (tid < kWarps * k) {
+    const int w = tid / k, j = tid - w * k;
+    const float s = m_s[w * kMaxK + j];
+    const long long i = m_i[w * kMaxK + j];
+    if (i >= 0) {
+      int rank = 0;
+      for (int w2 = 0; w2 < kWarps; ++w2)
+        for (int j2 = 0; j2 < k; ++j2) {
+          const long long i2 = m_i[w2 * kMaxK + j2];
+          rank += (i2 >= 0 && ranks_before(m_s[w2 * kMaxK + j2], i2, s, i)) ? 1 : 0;
+        }
+      if (rank < k) {
+        out_s[rank] = s;
+        out_i[rank] = i;
+      }
+    }
+  }
+}
+
 template <typename T>
 struct Vec;
 template <>
@@ -96,11 +158,27 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
   __shared__ float red_s[kWarps];
   __shared__ float m_s[kWarps * kMaxK];
   __shared__ long long m_i[kWarps * kMaxK];
+  __shared__ float sel_s[kMaxK];
+  __shared__ long long sel_i[kMaxK];
   __shared__ unsigned is_last_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qi = blockIdx.y;
   const int gx = gridDim.x;
+
+  // ---- the first row's loads do not depend on the query: they are in flight while it is staged
+  constexpr int E = Vec<T>::kElems;
+  constexpr int KC = kChunks > 0 ? kChunks : 1;
+  const long long warp_stride = (long long)gx * kWarps;
+  long long r0 = (long long)blockIdx.x * kWarps + warp;
+  uint4 va[KC];
+  if constexpr (kVec && kChunks > 0) {
+    if (r0 < n_rows) {
+      const T* x0 = index + r0 * ld_index;
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) va[c] = ld_stream_u4(x0 + (c * 32 + lane) * E);
+    }
+  }
 
   // ---- stage the query in shared memory as fp32 and compute |q|
   float qq = 0.f;
@@ -123,8 +201,6 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
   list.s = -INFINITY;
   list.i = -1;
 
-  constexpr int E = Vec<T>::kElems;
-  const long long warp_stride = (long long)gx * kWarps;
   if constexpr (kVec && kChunks > 0) {
     // Software pipeline over this warp's rows: the 16-byte loads of row r+1 are in flight while row r is reduced
     // and inserted, so a warp's rows cost one memory latency in total instead of one each (small indices are
@@ -145,9 +221,7 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
       const float sim = dot / (fmaxf(sqrtf(xx), 1e-12f) * qn);
       topk_insert(list, sim, r, k, lane);
     };
-    long long r0 = (long long)blockIdx.x * kWarps + warp;
-    uint4 va[kChunks], vb[kChunks];
-    if (r0 < n_rows) load_row(va, r0);
+    uint4 vb[kChunks];
     while (r0 < n_rows) {
       const long long r1 = r0 + warp_stride;
       if (r1 < n_rows) load_row(vb, r1);
@@ -186,24 +260,22 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
     topk_insert(list, sim, row, k, lane);
   }
 
-  // ---- block merge: every warp publishes its list, warp 0 merges
+  // ---- block merge: every warp publishes its list; the block's best k are selected by counting ranks
   if (lane < k) {
     m_s[warp * kMaxK + lane] = list.s;
     m_i[warp * kMaxK + lane] = list.i;
   }
+  if (tid < kMaxK) {
+    sel_s[tid] = -INFINITY;
+    sel_i[tid] = -1;
+  }
+  __syncthreads();
+  select_topk_counting(m_s, m_i, k, sel_s, sel_i, tid);
   __syncthreads();
   if (warp == 0) {
-    for (int w = 1; w < kWarps; ++w) {
-      for (int j = 0; j < k; ++j) {
-        float s = m_s[w * kMaxK + j];
-        long long i = m_i[w * kMaxK + j];
-        if (i < 0) break;  // lists are sorted, the rest is empty
-        topk_insert(list, s, i, k, lane);
-      }
-    }
     if (lane < k) {
-      cand_s[((long long)qi * gx + blockIdx.x) * k + lane] = list.s;
-      cand_i[((long long)qi * gx + blockIdx.x) * k + lane] = list.i;
+      cand_s[((long long)qi * gx + blockIdx.x) * k + lane] = sel_s[lane];
+      cand_i[((long long)qi * gx + blockIdx.x) * k + lane] = sel_i[lane];
     }
     __threadfence();
     __syncwarp();
@@ -216,16 +288,18 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
   if (!is_last_s) return;
   __threadfence();
 
-  // ---- final merge by the last block of this query.  The gx*k candidates are read in rounds of kWarps*32*4: every
-  // lane requests its 4 candidates of a round up front (one L2 round trip per round, and one round covers 1024
-  // candidates — all of them at config #3's size); only candidates that beat the warp's current k-th entry are inserted.
-  list.s = -INFINITY;
-  list.i = -1;
+  // ---- final merge by the last block of this query.  Every warp keeps a sorted best-32 list and folds its share
+  // of the gx*k candidates into it 32 at a time with bitonic networks (constant cost per 32 candidates, no
+  // data-dependent insertion loop); a round of kWarps*32*4 candidates is requested up front (one L2 round trip,
+  // and one round covers all candidates at config #3's size).  The 8 lists then meet by counting ranks.
+  float ls = -INFINITY;
+  long long li = -1;
   {
     constexpr int kPer = 4;
     const int n_cand = gx * k;
     const float* cs = cand_s + (long long)qi * n_cand;
     const long long* ci = cand_i + (long long)qi * n_cand;
+    bool first = true;
     for (int base = 0; base < n_cand; base += kWarps * 32 * kPer) {
       float s_l[kPer];
       long long i_l[kPer];
@@ -241,38 +315,34 @@ cosine_topk_kernel(const T* __restrict__ index, const void* __restrict__ queries
       }
 #pragma unroll
       for (int j = 0; j < kPer; ++j) {
-        // threshold = current k-th entry (lane k-1); candidates not ranking before it cannot enter
-        const float th_s = __shfl_sync(0xffffffffu, list.s, k - 1);
-        const long long th_i = __shfl_sync(0xffffffffu, list.i, k - 1);
-        unsigned live = __ballot_sync(0xffffffffu, i_l[j] >= 0 && (th_i < 0 || ranks_before(s_l[j], i_l[j], th_s, th_i)));
-        while (live) {
-          const int src = __ffs(live) - 1;
-          live &= live - 1;
-          const float s = __shfl_sync(0xffffffffu, s_l[j], src);
-          const long long i = __shfl_sync(0xffffffffu, i_l[j], src);
-          topk_insert(list, s, i, k, lane);
+        if (base + (j * kWarps + warp) * 32 >= n_cand) break;      // warp-uniform: nothing left for this warp
+        if (first) {
+          ls = s_l[j];
+          li = i_l[j];
+          bitonic_sort32(ls, li, lane);
+          first = false;
+        } else {
+          merge_top32(ls, li, s_l[j], i_l[j], lane);
         }
       }
     }
   }
   __syncthreads();  // m_s/m_i reuse
   if (lane < k) {
-    m_s[warp * kMaxK + lane] = list.s;
-    m_i[warp * kMaxK + lane] = list.i;
+    m_s[warp * kMaxK + lane] = ls;
+    m_i[warp * kMaxK + lane] = li;
+  }
+  if (tid < kMaxK) {
+    sel_s[tid] = -INFINITY;
+    sel_i[tid] = -1;
   }
   __syncthreads();
+  select_topk_counting(m_s, m_i, k, sel_s, sel_i, tid);
+  __syncthreads();
   if (warp == 0) {
-    for (int w = 1; w < kWarps; ++w) {
-      for (int j = 0; j < k; ++j) {
-        float s = m_s[w * kMaxK + j];
-        long long i = m_i[w * kMaxK + j];
-        if (i < 0) break;
-        topk_insert(list, s, i, k, lane);
-      }
-    }
     if (lane < k) {
-      out_s[(long long)qi * k + lane] = list.s;
-      out_i[(long long)qi * k + lane] = list.i;
+      out_s[(long long)qi * k + lane] = sel_s[lane];
+      out_i[(long long)qi * k + lane] = sel_i[lane];
     }
     if (lane == 0) tickets[qi] = 0;  // leave the workspace reusable
   }

@@ -14,6 +14,7 @@
 // Algorithmic bytes per launch: n_rows*dim*sizeof(T) + n_queries*dim*sizeof(Tq) + n_queries*k*12.
 #include "scb_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -375,7 +376,10 @@ int launch(const scb_cosine_topk_args* a, cudaStream_t st) {
   // no memset launch on the path (a third of the time of a 10 000-row search)
 
   const int sms = scb_num_sms();
-  long long want = (a->n_rows + kWarps * 8 - 1) / (kWarps * 8);  // >= 8 rows per warp (software-pipelined): fewer candidates to merge
+  // rows per warp: fewer rows = shorter dependent chain per warp, more blocks = more candidates for the last block to
+  // merge (SCB_TOPK_RPW: tuning aid)
+  static const int rpw = [] { const char* e = getenv("SCB_TOPK_RPW"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+  long long want = (a->n_rows + kWarps * rpw - 1) / (kWarps * rpw);
   int gx = (int)(want < 1 ? 1 : (want > (long long)sms * 4 ? (long long)sms * 4 : want));
   if (gx > kMaxGx) gx = kMaxGx;
   dim3 grid(gx, a->n_queries);

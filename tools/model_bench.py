@@ -12,11 +12,13 @@ from streamchat_b200.vision import VisionEncoder  # noqa: E402
 
 dev = torch.device("cuda:0")
 cfg = SYNTHETIC["longva7b"]
-frames = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 5824
-once = "--once" in sys.argv
+ncu_mode = len(sys.argv) > 1 and sys.argv[1] == "ncu"          # one encode pass + one prefill, no warm-up (for ncu launch lists)
+argv = [a for a in sys.argv[1:] if a != "ncu"]
+frames = int(argv[0]) if len(argv) > 0 and argv[0].isdigit() else 100
+tokens = int(argv[1]) if len(argv) > 1 and argv[1].isdigit() else 5824
+once = "--once" in sys.argv or ncu_mode
 W = random_weights(cfg, dev, seed=0)
-vis = VisionEncoder(W, cfg.vision, dev, max_frames_per_pass=64)
+vis = VisionEncoder(W, cfg.vision, dev)
 eng = Qwen2Engine({k: v for k, v in W.items() if not k.startswith("model.vision_tower")}, cfg.llm, dev, max_ctx=32768)
 del W
 

@@ -372,13 +372,15 @@ def ours(args):
                 else "NCCL all_gather_into_tensor (in place)"
     roofline = None
     traffic = None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_decode_mega_traffic.json")
-    if os.path.exists(tpath):      # DRAM bytes of one decode step (1 sequence, ctx 5800) from the ncu capture named there
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = {"bytes_per_decode_step": tj["dram_read_bytes"] + tj["dram_write_bytes"],
-                   "algorithmic_bytes_same_step": tj["algorithmic_bytes"], "rows": tj["rows"], "ctx": tj["ctx"],
-                   "source": "profiles/r01_decode_mega_traffic.json"}
+    for tname in ("r02_decode_mega_traffic.json", "r01_decode_mega_traffic.json"):
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tname)
+        if os.path.exists(tpath):  # DRAM bytes of ONE decode_mega_kernel launch (rows / ctx as recorded) from the ncu capture named there
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = {"bytes_per_decode_step": tj["dram_read_bytes"] + tj["dram_write_bytes"],
+                       "algorithmic_bytes_same_step": tj["algorithmic_bytes"], "rows": tj["rows"], "ctx": tj["ctx"],
+                       "source": "profiles/" + tname}
+            break
     if dec_steps:
         achieved = dec_bytes / (dec_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "decode step: decode_mega_kernel (ONE persistent launch per step, <= 4 rows: TMA weight ring + "

@@ -13,7 +13,7 @@ SCB_NO_GRAPH=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control 
 timeout 300 python bench.py $RED > $O/bench_reduced.json 2> $O/bench_reduced.err
 python tools/ncu_summary.py $O/bench_reduced_launches.csv > $O/bench_reduced_summary.txt 2>&1
 # 2. encode pass (100 frames: the bench's pass size) + one prefill: per-kernel times, tensor-pipe activity, DRAM bytes
-timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum,dram__bytes_read.sum,dram__bytes_write.sum -k regex:linear_tcgen05\|attention_tcgen05\|norm_\|im2col\|pool2x2\|rope_append\|gemv_mma \
   --clock-control none -c 1200 --csv --log-file $O/encode_prefill_kernels.csv python tools/model_bench.py ncu > $O/model_bench_under_ncu.log 2>&1
 # 3. k-means merge shape and retrieval: per-kernel times + DRAM bytes
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kmeans\|cosine_topk \

@@ -377,11 +377,12 @@ int launch(const scb_cosine_topk_args* a, cudaStream_t st) {
 
   const int sms = scb_num_sms();
   // Grid: ONE wave whenever the index is small enough for it.  Two 256-thread blocks are resident per SM (95
-  // registers), so 2 x SMs blocks start together; a few blocks more would run as a second wave behind the first
-  // (measured: 313 blocks on 148 SMs cost 27 us, 157 blocks 20 us for the same 10 000 rows).  Within one wave, more
-  // blocks = fewer rows per warp = a shorter dependent chain; large indices take 4 x SMs blocks of many rows each.
-  // (SCB_TOPK_RPW: tuning aid, minimum rows per warp.)
-  static const int rpw = [] { const char* e = getenv("SCB_TOPK_RPW"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+  // registers), so 2 x SMs blocks start together; a few blocks more would run as a second wave behind the first.
+  // Measured on the 10 000-row index (48 back-to-back searches, us per search): 626 blocks 34.1, 313 blocks 27.4
+  // (two waves), 296 blocks 22.1, 157 blocks 19.8 — the per-block merge / ticket / candidate traffic outweighs the
+  // shorter per-warp row chain, so the minimum is 8 software-pipelined rows per warp.  Large indices take 4 x SMs
+  // blocks of many rows each.  (SCB_TOPK_RPW: tuning aid, minimum rows per warp.)
+  static const int rpw = [] { const char* e = getenv("SCB_TOPK_RPW"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
   const long long one_wave = 2ll * sms;
   long long want = (a->n_rows + kWarps * rpw - 1) / (kWarps * rpw);
   if (want > one_wave) want = (a->n_rows <= one_wave * kWarps * 16) ? one_wave : (want > 4ll * sms ? 4ll * sms : want);

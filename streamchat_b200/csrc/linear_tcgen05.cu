@@ -25,7 +25,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quadrant)
 
 template <int BN, bool CG2 = false>
 struct Cfg {
@@ -188,7 +188,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty[s], PAIR ? 16 : 8);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
@@ -285,8 +285,13 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quadrant, each draining one half of the tile's columns: with one warp per quadrant the
+    // epilogue of a K = 1024 tile (CLIP qkv / out / fc1: bias, quick-GELU or residual over 128 x 256 outputs per
+    // CTA) took as long as its main loop and the tensor pipe idled 40-60 % of the time (ncu: 37-58 % active against
+    // 94 % for K = 4096).
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;  // column half of the tile this warp drains
     int as = 0;
     uint32_t aphase = 0;
     for (long long t = t_first; t < n_tiles; t += t_step) {
@@ -301,7 +306,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const bool row_ok = row < ep.m;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         const long long col0 = (long long)tn * BN + c0;
         if (col0 >= ep.n) break;  // warp-uniform
         uint32_t v[32];

@@ -115,6 +115,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense 16-bit tensor throughput a kernel timed INSIDE a long step is held against: the sustained figure."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if d.get("bf16_tflops_sustained"):
+            return float(d["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    return 1380.0, "fallback (B200_PROFILING.md)"
+
+
 # ------------------------------------------------------------------------------------------------
 STAGE_EVENTS = []   # (stage name, start event, end event) of the last timed region
 
@@ -393,6 +403,14 @@ def ours(args):
                     "ms_per_decode_step": dec_ms / dec_steps, "decode_steps": dec_steps,
                     "share_of_step_time": dec_ms / (ms if ms else 1)}
 
+    roofline_tensor = None
+    if pre_ms > 0:
+        tpeak, tsrc = load_tensor_peak()
+        ach = breakdown["llm_prefill_tflops"]
+        roofline_tensor = {"bound": "tensor", "kernel": "LLM prefill stage: linear_tcgen05_kernel<256, pair> (84 % of the stage in the ncu "
+                           "launch list) + attention_tcgen05_kernel (13 %) + norms / rope; FLOPs = dense 2*6.525e9*T + causal attention",
+                           "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tsrc,
+                           "traffic": None, "share_of_step_time": pre_ms / (ms if ms else 1)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -404,6 +422,8 @@ def ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "impl": "ours",
         "breakdown_ms_per_step": breakdown,
     }
+    if roofline_tensor is not None:
+        line["roofline_tensor"] = roofline_tensor      # the tensor-bound half of the step, beside the HBM-bound `roofline`
     if weak is not None:
         line["weak"] = weak
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

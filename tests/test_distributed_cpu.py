@@ -90,18 +90,20 @@ def _describe(sess, ids):
 SEGMENTS = [(0, 12), (12, 12), (24, 12), (36, 6)]          # 42 frames: 11 chunks, the last one short (2 frames)
 
 
-def _single():
+def _single(segments=None, total=42):
+    segments = segments or SEGMENTS
     _patch_kmeans()
     np.random.seed(11)
-    frames = _frames(42)
+    frames = _frames(total)
     sess = _session(_FakeModel())
-    for first, n in SEGMENTS:
+    for first, n in segments:
         sess.update_memory(sess.ingest(frames[first:first + n]), kmeans_init_indices=[0, 1])
     text, ids = sess.answer("where are my keys")
     return _describe(sess, ids)
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, segments=None, total=42):
+    segments = segments or SEGMENTS
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -110,14 +112,15 @@ def _worker(rank, world, port, ret):
     from streamchat_b200.distributed import ShardedStreamingSession, make_gather_buffer, owned_chunks
     _patch_kmeans()
     np.random.seed(11)
-    frames = _frames(42)
+    frames = _frames(total)
     model = _FakeModel()
     sess = _session(model)
-    buf = make_gather_buffer(model, CHUNK, 42, rank, world)
-    assert isinstance(buf, torch.Tensor) and tuple(buf.shape) == (world, -(-11 // world), CHUNK * P, H)
-    sh = ShardedStreamingSession(sess, rank, world, 42, kmeans_init_indices=[0, 1], gather_buffer=buf)
+    buf = make_gather_buffer(model, CHUNK, total, rank, world)
+    n_chunks = -(-total // CHUNK)
+    assert isinstance(buf, torch.Tensor) and tuple(buf.shape) == (world, -(-n_chunks // world), CHUNK * P, H)
+    sh = ShardedStreamingSession(sess, rank, world, total, kmeans_init_indices=[0, 1], gather_buffer=buf)
     n_mine = 0
-    for first, n in SEGMENTS:
+    for first, n in segments:
         mine = owned_chunks(first // CHUNK, -(-n // CHUNK), rank, world)
         idx = [f for c in mine for f in range(c * CHUNK, min((c + 1) * CHUNK, first + n))]
         n_mine += len(idx)
@@ -129,10 +132,10 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def _run(world):
+def _run(world, segments=None, total=42):
     port = _free_port()
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, segments, total), nprocs=world, join=True)
     return [ret[r] for r in range(world)]
 
 
@@ -160,6 +163,16 @@ def test_sharded_stream_equals_single_process_world3():
     assert all(r[0] == want for r in res)
     assert [r[1] for r in res] == [16, 14, 12]                  # chunks {0,3,6,9} {1,4,7,10 (2 frames)} {2,5,8}
     assert sum(r[1] for r in res) == 42
+
+
+def test_more_ranks_than_chunks():
+    """A short stream (2 chunks) on 3 ranks: the rank that owns nothing still takes part in the gather and the replay and
+    ends with the same memory and answer (no merge happens: the tree is two captioned depth-0 nodes)."""
+    segs = [(0, 8)]
+    want = _single(segs, 8)
+    res = _run(3, segs, 8)
+    assert all(r[0] == want for r in res) and [r[1] for r in res] == [4, 4, 0]
+    assert res[2][2] == [] or all("caption" not in b for b in res[2][2])      # rank 2 generated no caption
 
 
 def test_chunk_ownership_and_shapes():

@@ -448,6 +448,8 @@ typedef struct scb_qwen2_decode_step_args {
   void* logits;              /* device [rows, ld_logits] fp16, written */
   int64_t ld_logits;
   int64_t ctx_cap;           /* upper bound of every kv_len (0 = max_ctx): sizes the score buffer */
+  int64_t ctx_sum;           /* optional upper bound of the SUM of the rows' kv_len (0 = rows * ctx_cap): a tighter
+                              * score buffer when a long context decodes next to short ones */
 } scb_qwen2_decode_step_args;
 
 int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle);

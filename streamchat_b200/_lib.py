@@ -123,7 +123,7 @@ class Qwen2DecodeStepArgs(C.Structure):
     _fields_ = [
         ("decoder", C.c_void_p), ("rows", C.c_int32), ("n_counters", C.c_int32),
         ("next_id", C.c_void_p), ("kv_len", C.c_void_p), ("counters", C.c_void_p),
-        ("logits", C.c_void_p), ("ld_logits", C.c_int64), ("ctx_cap", C.c_int64),
+        ("logits", C.c_void_p), ("ld_logits", C.c_int64), ("ctx_cap", C.c_int64), ("ctx_sum", C.c_int64),
     ]
 
 

@@ -57,6 +57,8 @@ struct StageShape {         // one weight matrix
   int chunks;               // ceil(k / 512)
   int split;                // 1: units are (tile, chunk) pairs cut anywhere; 0: whole tiles per CTA
   int n, k;
+  int g0;                   // > 0 (down_proj): CTAs [0, g0) stream k-chunks [0, nch0), CTAs [g0, G) the rest — a CTA then
+                            // needs only ITS K-half of the activation rows in shared memory (see unit_plan)
 };
 
 struct MegaParams {
@@ -143,17 +145,45 @@ struct Ring {
   int flat;        // units of this CTA's flattened sequence consumed by earlier stages (slot = index % n_stage)
 };
 
-// this CTA's unit range of a stage
-SCB_DEVICE void unit_range(const StageShape& s, long long& u0, long long& u1) {
+// This CTA's units of a stage.  A unit = (16-row tile, 512-k chunk); units are numbered tile-major over the
+// CTA's chunk range [ch0, ch0 + nch).  Three layouts:
+//   whole tiles        (split 0): CTA c owns tiles [c*T/G, (c+1)*T/G) with all their chunks;
+//   cut anywhere       (split 1): the T*chunks units are dealt out evenly; a tile spans at most two CTAs, whose
+//                                 partial sums land in partial slots 0 (has the tile's first chunk) and 1;
+//   K-halves           (g0 > 0):  CTAs [0, g0) work on chunks [0, nch0), the others on [nch0, chunks), each half cut
+//                                 anywhere as above (partial slots 2*half + {0, 1}).  The wide down_proj input
+//                                 (18 944 values per sequence) then occupies HALF the shared memory per sequence, which
+//                                 gives the weight ring back the stages 3- and 4-row steps were losing (6 -> 10, 4 -> 8).
+struct UnitPlan {
+  int u0, u1;      // unit range in the CTA's local numbering (tile = u / nch, local chunk = u % nch)
+  int nch, ch0;    // chunk range of this CTA
+  int pslot;       // first partial slot
+};
+SCB_DEVICE UnitPlan unit_plan(const StageShape& s) {
   const long long G = gridDim.x, c = blockIdx.x;
-  if (s.split) {
+  UnitPlan pl;
+  pl.nch = s.chunks;
+  pl.ch0 = 0;
+  pl.pslot = 0;
+  if (s.g0 > 0) {
+    const int nch0 = (s.chunks + 1) / 2;
+    const bool hi = c >= s.g0;
+    const long long cc = hi ? c - s.g0 : c, Gh = hi ? G - s.g0 : s.g0;
+    pl.nch = hi ? s.chunks - nch0 : nch0;
+    pl.ch0 = hi ? nch0 : 0;
+    pl.pslot = hi ? 2 : 0;
+    const long long U = (long long)s.n_tiles * pl.nch;
+    pl.u0 = (int)(cc * U / Gh);
+    pl.u1 = (int)((cc + 1) * U / Gh);
+  } else if (s.split) {
     const long long U = (long long)s.n_tiles * s.chunks;
-    u0 = c * U / G;
-    u1 = (c + 1) * U / G;
+    pl.u0 = (int)(c * U / G);
+    pl.u1 = (int)((c + 1) * U / G);
   } else {
-    u0 = (c * s.n_tiles / G) * s.chunks;
-    u1 = ((c + 1) * s.n_tiles / G) * s.chunks;
+    pl.u0 = (int)((c * s.n_tiles / G) * s.chunks);
+    pl.u1 = (int)(((c + 1) * s.n_tiles / G) * s.chunks);
   }
+  return pl;
 }
 
 SCB_DEVICE float block_sum_256(float v, float* red8) {   // consumers only; red8: 8 floats of scratch
@@ -197,9 +227,8 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
   const int g = lane >> 2, t = lane & 3;
   const int rho = (g >> 1) | ((g & 1) << 2);   // weight row (mod 8) fed to mma row g: keeps the 16-byte
                                                // reads of a quarter-warp on 8 distinct swizzled chunks
-  long long u0l, u1l;
-  unit_range(s, u0l, u1l);
-  const int u0 = (int)u0l, u1 = (int)u1l;
+  const UnitPlan pl = unit_plan(s);
+  const int u0 = pl.u0, u1 = pl.u1;
   const int R = p.R;
   const uint32_t ring_s = smem_u32(ring.buf);
   const uint32_t offa0 = (uint32_t)(rho * 128 + ((t ^ rho) << 4));          // k-step parity 0
@@ -207,7 +236,8 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
   const uint32_t act_s = smem_u32(act) + (uint32_t)((g * p.act_ld + t * 8) * 2);
   const bool b_live = g < R;
   const int f0 = ring.flat;   // flattened index of unit u0
-  const int chunks = s.chunks;
+  const int chunks = pl.nch;            // chunks per tile in THIS CTA's numbering
+  const int kglob0 = pl.ch0 * kUnitK;   // first k of the CTA's chunk range: act holds columns [kglob0, ...) of the input
   int tile = u0 / chunks;
   for (int ua = u0; ua < u1; ++tile) {
     const int ub = min(u1, (tile + 1) * chunks);
@@ -233,7 +263,7 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
         const uint4 a1 = lds128(base + off + 1024);
         uint4 b = make_uint4(0u, 0u, 0u, 0u);
         const int k = kbase + 32 * j;
-        if (b_live && k + t * 8 < s.k) b = lds128(act_s + (uint32_t)(k * 2));
+        if (b_live && kglob0 + k + t * 8 < s.k) b = lds128(act_s + (uint32_t)(k * 2));
         mma16816(d0, a0.x, a1.x, a0.y, a1.y, b.x, b.y);
         mma16816(d1, a0.z, a1.z, a0.w, a1.w, b.z, b.w);
       }
@@ -283,7 +313,7 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
             if (ly->qkv_b) v += __half2float(ly->qkv_b[o]);
             p.qkv_buf[(size_t)n * p.qkv_dim + o] = __float2half_rn(v);
           } else if (KIND == ST_O || KIND == ST_DOWN) {
-            float* part = (KIND == ST_O) ? p.part_o : p.part_d;
+            float* part = ((KIND == ST_O) ? p.part_o : p.part_d) + (size_t)pl.pslot * kRMax * p.H;
             const size_t slot_stride = (size_t)kRMax * p.H;
             const size_t idx = (size_t)n * p.H + o;
             if (has_first) {
@@ -393,7 +423,7 @@ SCB_DEVICE void prefetch_kv_l2(const MegaParams& p, const MegaLayer* ly, int hk,
 // A thread owns 8-element chunks; every global load of a pass is issued before the first use
 // (one L2 round trip per pass instead of one per element group).
 SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, const __half* res,
-                              const float* part, const __half* embed_rows, __half* x_out,
+                              const float* part, int n_slots, const __half* embed_rows, __half* x_out,
                               const __half* gamma, const MegaLayer* kv_layer = nullptr, int hk = 0, int split = 0,
                               int head_dim = 0) {
   constexpr int CH = 2;                         // chunks per thread per pass
@@ -406,10 +436,11 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
     const __half* er = embed_rows ? embed_rows + (size_t)p.next_id[n] * H : nullptr;
     for (int c0 = 0; c0 < n_chunks; c0 += kCThreads * CH) {
       uint4 rr[CH];
-      float4 q0[CH][2], q1[CH][2];
+      float4 q0[CH][2], q1[CH][2], q2[CH][2], q3[CH][2];
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const int c = min(c0 + j * kCThreads + tid, n_chunks - 1);   // clamped: loads stay unconditional (registers)
+        q2[j][0] = q2[j][1] = q3[j][0] = q3[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (er) {
           rr[j] = *reinterpret_cast<const uint4*>(er + c * 8);
           q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -419,6 +450,12 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
           const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
           q0[j][0] = __ldcg(s0); q0[j][1] = __ldcg(s0 + 1);
           q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
+          if (n_slots == 4) {      // K-halves (down_proj): slots 2, 3 hold the upper half's partial sums
+            const float4* s2 = reinterpret_cast<const float4*>(part + 2 * slot_stride + (size_t)n * H + c * 8);
+            const float4* s3 = reinterpret_cast<const float4*>(part + 3 * slot_stride + (size_t)n * H + c * 8);
+            q2[j][0] = __ldcg(s2); q2[j][1] = __ldcg(s2 + 1);
+            q3[j][0] = __ldcg(s3); q3[j][1] = __ldcg(s3 + 1);
+          }
         }
       }
       // the attention stage's K / V rows start their trip to L2 behind this batch's loads
@@ -433,8 +470,12 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
           if (!er) {
             const float a0[8] = {q0[j][0].x, q0[j][0].y, q0[j][0].z, q0[j][0].w, q0[j][1].x, q0[j][1].y, q0[j][1].z, q0[j][1].w};
             const float a1[8] = {q1[j][0].x, q1[j][0].y, q1[j][0].z, q1[j][0].w, q1[j][1].x, q1[j][1].y, q1[j][1].z, q1[j][1].w};
+            const float a2[8] = {q2[j][0].x, q2[j][0].y, q2[j][0].z, q2[j][0].w, q2[j][1].x, q2[j][1].y, q2[j][1].z, q2[j][1].w};
+            const float a3[8] = {q3[j][0].x, q3[j][0].y, q3[j][0].z, q3[j][0].w, q3[j][1].x, q3[j][1].y, q3[j][1].z, q3[j][1].w};
+            // fixed order: (lower K-half: slot 0 + slot 1) + (upper K-half: slot 2 + slot 3, zero without K-halves) + residual
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __half2float(__float2half_rn((a0[e] + a1[e]) + x[e]));
+            for (int e = 0; e < 8; ++e)
+              x[e] = __half2float(__float2half_rn(n_slots == 4 ? ((a0[e] + a1[e]) + (a2[e] + a3[e])) + x[e] : (a0[e] + a1[e]) + x[e]));
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
@@ -476,11 +517,12 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
 
 // act <- src rows ([R][len] fp16 in global, written by other CTAs before the last grid barrier);
 // five independent 16-byte L2 loads in flight per thread.
-SCB_DEVICE void prologue_copy(const MegaParams& p, __half* act, const __half* src, int len) {
+SCB_DEVICE void prologue_copy(const MegaParams& p, __half* act, const __half* src, int row_len, int col0, int len) {
+  // act[n][0 .. len) <- src[n][col0 .. col0 + len): the whole row (col0 = 0) or this CTA's K-half of it
   constexpr int U = 5;
   const int tid = threadIdx.x, n16 = len >> 3;
   for (int n = 0; n < p.R; ++n) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)n * len);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)n * row_len + col0);
     uint4* d4 = reinterpret_cast<uint4*>(act + (size_t)n * p.act_ld);
     for (int i0 = 0; i0 < n16; i0 += kCThreads * U) {
       uint4 v[U];
@@ -807,17 +849,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
       for (int m = 0; m < n_mats; ++m) {
         const StageShape& s = p.shp[m == n_mats - 1 ? ST_LM : (m & 3)];
         const CUtensorMap* map = p.maps + m;
-        long long u0, u1;
-        unit_range(s, u0, u1);
-        int tile = (int)(u0 / s.chunks), kc = (int)(u0 - (long long)tile * s.chunks);
-        for (long long u = u0; u < u1; ++u, ++kc) {
-          if (kc == s.chunks) {
+        const UnitPlan pl = unit_plan(s);
+        int tile = pl.u0 / pl.nch, kc = pl.u0 - tile * pl.nch;
+        for (int u = pl.u0; u < pl.u1; ++u, ++kc) {
+          if (kc == pl.nch) {
             kc = 0;
             ++tile;
           }
           mbar_wait(&empty[slot], phase ^ 1u);
           mbar_arrive_expect_tx(&full[slot], kUnitBytes);
-          tma_load_3d(ring_buf + (size_t)slot * kUnitBytes, map, &full[slot], 0, tile * kUnitRows, kc * 8);
+          tma_load_3d(ring_buf + (size_t)slot * kUnitBytes, map, &full[slot], 0, tile * kUnitRows, (pl.ch0 + kc) * 8);
           if (++slot == p.n_stage) {
             slot = 0;
             phase ^= 1u;
@@ -840,11 +881,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
 
   long long* prof = (p.prof && tid == 0) ? p.prof + (size_t)cta * p.n_layers * kProfStamps : nullptr;
 #define SCB_STAMP(i) do { if (prof) prof[l * kProfStamps + (i)] = clock64(); } while (0)
+  const int down_slots = p.shp[ST_DOWN].g0 > 0 ? 4 : 2;   // partial slots the down_proj stage fills
   for (int l = 0; l < p.n_layers; ++l) {
     const MegaLayer* ly = p.layers + l;
     SCB_STAMP(0);
     // ---- qkv: x = embedding rows (layer 0) or x2 + down partials; act = RMSNorm(x) * ln1
-    prologue_norm(p, act, red8, p.x2_buf, p.part_d, l == 0 ? p.embed : nullptr, p.x_buf, ly->ln1, ly, hk, split, HD);
+    prologue_norm(p, act, red8, p.x2_buf, p.part_d, down_slots, l == 0 ? p.embed : nullptr, p.x_buf, ly->ln1, ly, hk, split, HD);
     SCB_STAMP(1);
     run_stage<ST_QKV>(p, p.shp[ST_QKV], ly, ring, act, red, red_buf, best);
     SCB_STAMP(2);
@@ -873,21 +915,26 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     grid_sync(p, gen);
     SCB_STAMP(7);
     // ---- o_proj
-    prologue_copy(p, act, p.attn_buf, p.n_q * HD);
+    prologue_copy(p, act, p.attn_buf, p.n_q * HD, 0, p.n_q * HD);
     SCB_STAMP(8);
     run_stage<ST_O>(p, p.shp[ST_O], ly, ring, act, red, red_buf, best);
     SCB_STAMP(9);
     grid_sync(p, gen);
     SCB_STAMP(10);
     // ---- gate|up: x2 = x + o partials; act = RMSNorm(x2) * ln2
-    prologue_norm(p, act, red8, p.x_buf, p.part_o, nullptr, p.x2_buf, ly->ln2);
+    prologue_norm(p, act, red8, p.x_buf, p.part_o, 2, nullptr, p.x2_buf, ly->ln2);
     SCB_STAMP(11);
     run_stage<ST_GU>(p, p.shp[ST_GU], ly, ring, act, red, red_buf, best);
     SCB_STAMP(12);
     grid_sync(p, gen);
     SCB_STAMP(13);
     // ---- down
-    prologue_copy(p, act, p.gu_buf, p.I);
+    {
+      // down_proj input: the whole gated row, or (K-halves) only the columns of this CTA's chunk range
+      const UnitPlan dp = unit_plan(p.shp[ST_DOWN]);
+      const int col0 = dp.ch0 * kUnitK;
+      prologue_copy(p, act, p.gu_buf, p.I, col0, min(p.I - col0, dp.nch * kUnitK));
+    }
     SCB_STAMP(14);
     run_stage<ST_DOWN>(p, p.shp[ST_DOWN], ly, ring, act, red, red_buf, best);
     SCB_STAMP(15);
@@ -895,7 +942,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
   }
 #undef SCB_STAMP
   // ---- final norm + lm_head + arg-max
-  prologue_norm(p, act, red8, p.x2_buf, p.part_d, nullptr, nullptr, p.final_norm);
+  prologue_norm(p, act, red8, p.x2_buf, p.part_d, down_slots, nullptr, nullptr, p.final_norm);
   run_stage<ST_LM>(p, p.shp[ST_LM], nullptr, ring, act, red, red_buf, best);
   if (tid < kUnitRows * kRMax) {
     lm_v[tid] = best.v;
@@ -1015,6 +1062,7 @@ StageShape make_shape(long long n, long long k, int grid, bool may_split) {
   const long long U = (long long)s.n_tiles * s.chunks;
   // cutting tiles along K is only sound while a tile spans at most two CTAs (two partial slots)
   s.split = (may_split && U / grid >= s.chunks) ? 1 : 0;
+  s.g0 = 0;
   return s;
 }
 
@@ -1084,6 +1132,17 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
   p.shp[ST_O] = make_shape(d->hidden, attn_dim, grid, true);
   p.shp[ST_GU] = make_shape(2ll * d->inter, d->hidden, grid, false);
   p.shp[ST_DOWN] = make_shape(d->hidden, d->inter, grid, true);
+  {
+    // K-halves for down_proj (see unit_plan): CTAs split in proportion to the halves' chunk counts; sound while every
+    // half has at least as many tiles as CTAs (a tile then spans at most two CTAs of a half)
+    StageShape& sd = p.shp[ST_DOWN];
+    const int nch0 = (sd.chunks + 1) / 2, nch1 = sd.chunks - nch0;
+    int g0 = (int)(((long long)grid * nch0 + sd.chunks / 2) / sd.chunks);
+    if (g0 < 1) g0 = 1;
+    if (g0 > grid - 1) g0 = grid - 1;
+    static const int use_khalf = [] { const char* e = getenv("SCB_MEGA_KHALF"); return e ? atoi(e) : 1; }();
+    if (use_khalf && sd.split && nch1 >= 2 && grid >= 2 && sd.n_tiles >= g0 && sd.n_tiles >= grid - g0) sd.g0 = g0;
+  }
   p.shp[ST_LM] = make_shape(d->vocab, d->hidden, grid, false);
   int ns = grid / d->n_kv_heads;
   if (ns > kMaxSplits) ns = kMaxSplits;
@@ -1134,7 +1193,7 @@ int scb_qwen2_decoder_create(const scb_qwen2_decoder_desc* d, void** out_handle)
   const size_t o_x = take(kRMax * H * 2), o_x2 = take(kRMax * H * 2);
   const size_t o_qkv = take(kRMax * (size_t)qkv_dim * 2), o_attn = take(kRMax * (size_t)attn_dim * 2);
   const size_t o_gu = take(kRMax * I * 2);
-  const size_t o_po = take(2 * kRMax * H * 4), o_pd = take(2 * kRMax * H * 4);
+  const size_t o_po = take(2 * kRMax * H * 4), o_pd = take(4 * kRMax * H * 4);   // down_proj: up to 4 partial slots (K-halves)
   const size_t n_part = (size_t)kRMax * d->n_q_heads * ns;
   const size_t o_am = take(n_part * 4), o_al = take(n_part * 4), o_ao = take(n_part * d->head_dim * 4);
   const size_t o_cv = take((size_t)grid * kRMax * 4), o_ci = take((size_t)grid * kRMax * 4);
@@ -1247,13 +1306,19 @@ int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream) {
   const long long cap = (a->ctx_cap > 0 && a->ctx_cap < p.max_ctx) ? a->ctx_cap : p.max_ctx;
   // longest KV range one CTA attends (see attn_plan): ceil(cap / S) for one sequence, ceil(R * cap / (S - R)) when the
   // R sequences share the S CTAs of a kv head
+  // ctx_sum (optional): an upper bound of the SUM of the rows' lengths, tighter than rows * cap when the batch mixes
+  // a long context with short ones (the answer next to two summaries)
+  long long sum_cap = (long long)a->rows * cap;
+  if (a->ctx_sum > 0 && a->ctx_sum < sum_cap) sum_cap = a->ctx_sum;
   const int per_need = (a->rows == 1 || p.n_splits <= a->rows)
                            ? (int)((cap + p.n_splits - 1) / p.n_splits)
-                           : (int)(((long long)a->rows * cap + (p.n_splits - a->rows) - 1) / (p.n_splits - a->rows));
+                           : (int)((sum_cap + (p.n_splits - a->rows) - 1) / (p.n_splits - a->rows));
   p.per_max = ((per_need + 11) / 16) * 16 + 4;   // row stride = 4 mod 16 floats: conflict-free score stores
   // shared-memory budget: ring stages + max(activation rows, attention scratch)
   int kmax = p.H;
-  if (p.I > kmax) kmax = p.I;
+  // widest activation row a CTA keeps in shared memory: down_proj's input — all of it, or one K-half (unit_plan)
+  const int down_cols = p.shp[ST_DOWN].g0 > 0 ? ((p.shp[ST_DOWN].chunks + 1) / 2) * kUnitK : p.I;
+  if (down_cols > kmax) kmax = down_cols < p.I ? down_cols : p.I;
   if (p.n_q * h->head_dim > kmax) kmax = p.n_q * h->head_dim;
   p.act_ld = kmax + 8;
   size_t scratch = (size_t)p.R * p.act_ld * 2;

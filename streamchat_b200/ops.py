@@ -550,7 +550,7 @@ class Qwen2Decoder:
         self._h = h
 
     def step(self, rows: int, next_id: torch.Tensor, kv_len: torch.Tensor, logits: torch.Tensor,
-             counters: Optional[torch.Tensor] = None, ctx_cap: int = 0) -> None:
+             counters: Optional[torch.Tensor] = None, ctx_cap: int = 0, ctx_sum: int = 0) -> None:
         """One decode step for cache slots 0..rows-1: consumes next_id[:rows] (int64), writes the greedy
         next tokens back into it, fp16 logits into logits[:rows], and adds 1 to every int32 of `counters`."""
         _require_cuda(next_id, kv_len, logits, counters)
@@ -561,6 +561,7 @@ class Qwen2Decoder:
         a.next_id, a.kv_len, a.logits, a.ld_logits = next_id.data_ptr(), kv_len.data_ptr(), logits.data_ptr(), logits.stride(0)
         a.counters, a.n_counters = _ptr(counters), (counters.numel() if counters is not None else 0)
         a.ctx_cap = ctx_cap
+        a.ctx_sum = ctx_sum          # upper bound of sum(kv_len) over the rows (0: rows * ctx_cap)
         with torch.cuda.device(self.device):
             L.check(L.load().scb_qwen2_decode_step(C.byref(a), _stream(self.device)), "scb_qwen2_decode_step")
 

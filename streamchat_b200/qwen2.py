@@ -194,7 +194,7 @@ class Qwen2Engine:
         return ops.gemv(last, self.lm_head, out=self._logits[slot:slot + 1])
 
     # ---------------------------------------------------------------- decode
-    def _decode_step_launches(self, R: int = 1, ctx_cap: int = 0) -> None:
+    def _decode_step_launches(self, R: int = 1, ctx_cap: int = 0, ctx_sum: int = 0) -> None:
         """One cached decode step for the first R cache slots (5*layers + 2 launches): embedding
         gather (+ first RMSNorm), then per layer qkv GEMV -> fused RoPE/append/attention/combine ->
         o_proj GEMV (+residual, + post-attention RMSNorm by its last block) -> gate|up GEMV (SiLU-gate
@@ -207,7 +207,8 @@ class Qwen2Engine:
         if self._use_mega(R):
             cap = ctx_cap if 0 < ctx_cap < self.max_ctx else self.max_ctx
             try:
-                self._mega.step(R, self.next_id, self.state[1], self._logits, counters=self.state.view(-1), ctx_cap=cap)
+                self._mega.step(R, self.next_id, self.state[1], self._logits, counters=self.state.view(-1), ctx_cap=cap,
+                                ctx_sum=ctx_sum)
                 return
             except L.ScbError as e:
                 # e.g. a cooperative launch refused because the device is partitioned / shared, or a (rows, context)
@@ -285,9 +286,11 @@ class Qwen2Engine:
             b *= 2
         return min(b, self.max_ctx)
 
-    def _ensure_graph(self, R: int, ctx_cap: int = 0) -> "torch.cuda.CUDAGraph":
+    def _ensure_graph(self, R: int, ctx_cap: int = 0, ctx_sum: int = 0) -> "torch.cuda.CUDAGraph":
+        """One graph per (rows, context-capacity class, bound of the rows' total length — the persistent kernel sizes
+        its attention score buffer with it when a long context decodes next to short ones)."""
         ctx_cap = ctx_cap or self.max_ctx
-        g = self._graphs.get((R, ctx_cap))
+        g = self._graphs.get((R, ctx_cap, ctx_sum))
         if g is not None:
             return g
         # warm-up on a side stream (loads modules, sets func attributes), then capture.  Both scribble on
@@ -298,15 +301,15 @@ class Qwen2Engine:
         with torch.cuda.stream(s):
             self.state[0].fill_(0)
             self.state[1].fill_(1)
-            self._decode_step_launches(R, ctx_cap)
+            self._decode_step_launches(R, ctx_cap, ctx_sum)
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.state[0].fill_(0)
         self.state[1].fill_(1)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._decode_step_launches(R, ctx_cap)
-        self._graphs[(R, ctx_cap)] = g
+            self._decode_step_launches(R, ctx_cap, ctx_sum)
+        self._graphs[(R, ctx_cap, ctx_sum)] = g
         self.state.copy_(saved_state)
         self.next_id.copy_(saved_id)
         torch.cuda.synchronize(self.device)
@@ -330,12 +333,18 @@ class Qwen2Engine:
         self._check_context([int(x.shape[0]) for x in inputs_embeds_list], budgets)
         order = sorted(range(n), key=lambda i: -budgets[i])           # slot s holds caller's sequence order[s]
         cap = self._ctx_bucket(max(int(x.shape[0]) + b for x, b in zip(inputs_embeds_list, budgets)))
+        # bound of the total context of the first R slots (prompt + budget each), rounded up to 1 K: graph key and the
+        # persistent kernel's score-buffer size
+        need = [min(cap, int(inputs_embeds_list[i].shape[0]) + budgets[i]) for i in order]
+
+        def sum_bound(r: int) -> int:
+            return -(-sum(need[:r]) // 1024) * 1024
         if os.environ.get("SCB_NO_GRAPH") == "1":      # profiling aid: every kernel as its own launch (ncu launch lists)
             use_graph = False
         with torch.cuda.device(self.device):
             if use_graph:
                 for r in sorted({sum(1 for b in budgets if b > t) for t in [0] + budgets} - {0}):
-                    self._ensure_graph(r, cap)                          # before prefill (see _ensure_graph)
+                    self._ensure_graph(r, cap, sum_bound(r))            # before prefill (see _ensure_graph)
             self.reset()
             lens = []
             pf0 = pf1 = None
@@ -377,11 +386,11 @@ class Qwen2Engine:
                     break
                 Rn = sum(1 for b in slot_budget if b > step + 1)         # rows that need another token
                 if use_graph:
-                    self._graphs[(Rn, cap)].replay()
+                    self._graphs[(Rn, cap, sum_bound(Rn))].replay()
                     self.graph_replays += 1
                     self.graph_launches += self.launches_per_decode_step(Rn)
                 else:
-                    self._decode_step_launches(Rn, cap)
+                    self._decode_step_launches(Rn, cap, sum_bound(Rn))
                 prof_steps += 1
                 prof_bytes += self.weight_bytes() + sum(self.kv_bytes_per_token(lens[s_] + step) for s_ in range(Rn))
             if ev0 is not None:

@@ -1297,6 +1297,11 @@ int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream) {
   SCB_REQUIRE(a->n_counters == 0 || a->counters, SCB_ERR_INVALID_ARG, "scb_qwen2_decode_step: counters is NULL");
   MegaParams p = h->base;
   p.R = a->rows;
+  // K-halves for down_proj pay when the activation rows crowd the weight ring out of shared memory (3 and 4 rows:
+  // 6 -> 10 and 4 -> 8 stages; measured 3.82 -> 3.74 and 4.39 -> 3.96 ms per step); one- and two-row steps keep the
+  // whole-row layout (fewer tile flushes and partial slots per layer).  SCB_MEGA_KHALF=2 forces it for every width.
+  static const int khalf_mode = [] { const char* e = getenv("SCB_MEGA_KHALF"); return e ? atoi(e) : 1; }();
+  if (a->rows < 3 && khalf_mode != 2) p.shp[ST_DOWN].g0 = 0;
   p.next_id = reinterpret_cast<long long*>(a->next_id);
   p.kv_len = a->kv_len;
   p.counters = a->counters;

@@ -466,6 +466,15 @@ int scb_qwen2_decode_step(const scb_qwen2_decode_step_args* a, void* stream);
 size_t scb_qwen2_prefill_workspace_bytes(void* decoder, int64_t n_tokens);
 int scb_qwen2_prefill(void* decoder, const void* inputs_embeds, int64_t n_tokens, int32_t slot, int64_t pos0,
                       void* logits_row, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for several sequences in ONE pass: inputs_embeds stacks the prompts' rows (sequence after sequence,
+ * [sum(n_tokens), hidden]); n_tokens / slots / pos0 are HOST arrays of n_seqs entries (distinct cache slots); sequence
+ * q's last-position logits go to logits_rows + q * ld_logits.  Linear layers and norms run once over the stack (a lone
+ * 5.8 k-token prompt leaves the last tile wave of the o_proj / down_proj GEMMs two-thirds empty), RoPE + KV append +
+ * causal attention per sequence.  Bit-identical to n_seqs one-sequence calls; workspace =
+ * scb_qwen2_prefill_workspace_bytes(decoder, sum(n_tokens)). */
+int scb_qwen2_prefill_batch(void* decoder, const void* inputs_embeds, int32_t n_seqs, const int64_t* n_tokens_host,
+                            const int32_t* slots_host, const int64_t* pos0_host, void* logits_rows, int64_t ld_logits,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* Debug aid: per-CTA clock64 stamps of the last step, 16 per layer (layer start, then after every
  * prologue / stage / grid barrier).  The first call arms the recording and returns 0; later calls
  * copy [n_sm][n_layers][16] int64 into host_out (capacity in elements) and return the count; -1 on error. */

@@ -183,6 +183,8 @@ SYMBOLS = {
     "scb_qwen2_prefill_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "scb_qwen2_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
+    "scb_qwen2_prefill_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scb_qwen2_decoder_profile": (C.c_longlong, [C.c_void_p, C.POINTER(C.c_longlong), C.c_longlong]),
     "scb_im2col_patch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _vp]),
     "scb_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _f, _i64, _i32, _vp, _i64, _vp]),

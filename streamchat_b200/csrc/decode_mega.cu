@@ -1376,19 +1376,36 @@ size_t scb_qwen2_prefill_workspace_bytes(void* handle, int64_t n_tokens) {
   return off;
 }
 
-int scb_qwen2_prefill(void* handle, const void* inputs_embeds, int64_t n_tokens, int32_t slot, int64_t pos0,
-                      void* logits_row, void* workspace, size_t workspace_bytes, void* stream) {
+// Several sequences in ONE pass: the rows of all prompts are stacked ([sum(n_tokens), hidden], sequence after
+// sequence), every linear layer and norm runs once over the stack (a 5 816-token prompt alone leaves the last wave of
+// the o_proj / down_proj GEMMs two-thirds empty: 322 CTA-pair tiles on 74 pairs; five prompts stacked fill it), RoPE +
+// KV append and the causal attention run per sequence on its own rows, cache slot and start position.  Per row the
+// arithmetic is that of the one-sequence call (rows of a GEMM are independent): results are bit-identical.
+int scb_qwen2_prefill_batch(void* handle, const void* inputs_embeds, int32_t n_seqs, const int64_t* n_tokens_host,
+                            const int32_t* slots_host, const int64_t* pos0_host, void* logits_rows, int64_t ld_logits,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   MegaHandle* h = reinterpret_cast<MegaHandle*>(handle);
   SCB_REQUIRE(h != nullptr && h->magic == kMagic, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: bad decoder handle");
-  SCB_REQUIRE(inputs_embeds && logits_row && workspace, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: NULL buffer");
-  SCB_REQUIRE(n_tokens >= 1 && slot >= 0 && slot < h->max_seqs && pos0 >= 0 && pos0 + n_tokens <= h->base.max_ctx,
-              SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: tokens=%lld slot=%d pos0=%lld out of range (max_ctx %lld)",
-              (long long)n_tokens, slot, (long long)pos0, h->base.max_ctx);
-  const size_t need = scb_qwen2_prefill_workspace_bytes(handle, n_tokens);
+  SCB_REQUIRE(inputs_embeds && logits_rows && workspace && n_tokens_host && slots_host && pos0_host, SCB_ERR_INVALID_ARG,
+              "scb_qwen2_prefill: NULL buffer");
+  SCB_REQUIRE(n_seqs >= 1 && n_seqs <= 64, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: n_seqs=%d not in 1..64", n_seqs);
+  SCB_REQUIRE(n_seqs == 1 || ld_logits >= h->vocab, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: ld_logits < vocab");
+  int64_t total = 0;
+  for (int q = 0; q < n_seqs; ++q) {
+    const int64_t n = n_tokens_host[q], p0 = pos0_host[q];
+    const int slot = slots_host[q];
+    SCB_REQUIRE(n >= 1 && slot >= 0 && slot < h->max_seqs && p0 >= 0 && p0 + n <= h->base.max_ctx, SCB_ERR_INVALID_ARG,
+                "scb_qwen2_prefill: tokens=%lld slot=%d pos0=%lld out of range (max_ctx %lld)", (long long)n, slot,
+                (long long)p0, h->base.max_ctx);
+    for (int r = 0; r < q; ++r)
+      SCB_REQUIRE(slots_host[r] != slot, SCB_ERR_INVALID_ARG, "scb_qwen2_prefill: cache slot %d used twice in one batch", slot);
+    total += n;
+  }
+  const size_t need = scb_qwen2_prefill_workspace_bytes(handle, total);
   SCB_REQUIRE(workspace_bytes >= need, SCB_ERR_WORKSPACE, "scb_qwen2_prefill: workspace %zu B < required %zu B",
               workspace_bytes, need);
   const MegaParams& p = h->base;
-  const size_t T = (size_t)n_tokens;
+  const size_t T = (size_t)total;
   const int H = h->hidden, I = h->inter, hd = h->head_dim, QKV = h->qkv_dim, A = h->n_q * hd;
   char* ws = reinterpret_cast<char*>(workspace);
   size_t off = 0;
@@ -1409,7 +1426,7 @@ int scb_qwen2_prefill(void* handle, const void* inputs_embeds, int64_t n_tokens,
     scb_linear_args la;
     memset(&la, 0, sizeof(la));
     la.a = a; la.w = w; la.bias = bias; la.residual = res; la.out = out;
-    la.m = n_tokens; la.n = n; la.k = k;
+    la.m = total; la.n = n; la.k = k;
     la.lda = k; la.ldw = k; la.ldr = n; la.ldo = act == SCB_ACT_SILU_PAIR ? n / 2 : n;
     la.act = act; la.out_dtype = SCB_F16; la.batch = 1; la.alpha = 1.f;
     return scb_linear(&la, stream);
@@ -1420,45 +1437,62 @@ int scb_qwen2_prefill(void* handle, const void* inputs_embeds, int64_t n_tokens,
   int rc = SCB_OK;
   for (int l = 0; l < p.n_layers && rc == SCB_OK; ++l) {
     const MegaLayer& ly = h->host_layers[l];
-    __half* kc = ly.k_cache + (size_t)slot * p.cache_seq_stride;
-    __half* vc = ly.v_cache + (size_t)slot * p.cache_seq_stride;
-    rc = scb_rmsnorm(x, H, ly.ln1, p.eps, n_tokens, H, y, H, stream);
+    rc = scb_rmsnorm(x, H, ly.ln1, p.eps, total, H, y, H, stream);
     if (rc == SCB_OK) rc = linear(y, H, ly.w[0], QKV, ly.qkv_b, nullptr, qkv, SCB_ACT_NONE);
-    if (rc == SCB_OK)
-      rc = scb_rope_append(qkv, QKV, n_tokens, h->n_q, h->n_kv, hd, nullptr, (int32_t)pos0, p.theta, p.inv_freq, kc, vc,
+    int64_t row0 = 0;
+    for (int q = 0; q < n_seqs && rc == SCB_OK; ++q) {
+      const int64_t n = n_tokens_host[q], p0 = pos0_host[q];
+      __half* kc = ly.k_cache + (size_t)slots_host[q] * p.cache_seq_stride;
+      __half* vc = ly.v_cache + (size_t)slots_host[q] * p.cache_seq_stride;
+      __half* qrows = qkv + (size_t)row0 * QKV;
+      rc = scb_rope_append(qrows, QKV, n, h->n_q, h->n_kv, hd, nullptr, (int32_t)p0, p.theta, p.inv_freq, kc, vc,
                            p.max_ctx, stream);
-    if (rc == SCB_OK) {
-      scb_attention_args aa;
-      memset(&aa, 0, sizeof(aa));
-      aa.q = qkv; aa.k = kc; aa.v = vc; aa.out = ctx;
-      aa.batch = 1; aa.n_q_heads = h->n_q; aa.n_kv_heads = h->n_kv; aa.head_dim = hd;
-      aa.q_len = n_tokens; aa.kv_len = pos0 + n_tokens;
-      aa.q_stride_t = QKV; aa.q_stride_h = hd;
-      aa.k_stride_t = hd; aa.k_stride_h = p.max_ctx * hd;
-      aa.v_stride_t = hd; aa.v_stride_h = p.max_ctx * hd;
-      aa.o_stride_t = A; aa.o_stride_h = hd;
-      aa.scale = scale; aa.causal = 1;
-      rc = scb_attention(&aa, stream);
+      if (rc == SCB_OK) {
+        scb_attention_args aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.q = qrows; aa.k = kc; aa.v = vc; aa.out = ctx + (size_t)row0 * A;
+        aa.batch = 1; aa.n_q_heads = h->n_q; aa.n_kv_heads = h->n_kv; aa.head_dim = hd;
+        aa.q_len = n; aa.kv_len = p0 + n;
+        aa.q_stride_t = QKV; aa.q_stride_h = hd;
+        aa.k_stride_t = hd; aa.k_stride_h = p.max_ctx * hd;
+        aa.v_stride_t = hd; aa.v_stride_h = p.max_ctx * hd;
+        aa.o_stride_t = A; aa.o_stride_h = hd;
+        aa.scale = scale; aa.causal = 1;
+        rc = scb_attention(&aa, stream);
+      }
+      row0 += n;
     }
     __half* x2 = (x == xa) ? xb : xa;                       // never the buffer x lives in
     if (rc == SCB_OK) rc = linear(ctx, A, ly.w[1], H, nullptr, x, x2, SCB_ACT_NONE);
-    if (rc == SCB_OK) rc = scb_rmsnorm(x2, H, ly.ln2, p.eps, n_tokens, H, y, H, stream);
+    if (rc == SCB_OK) rc = scb_rmsnorm(x2, H, ly.ln2, p.eps, total, H, y, H, stream);
     if (rc == SCB_OK) rc = linear(y, H, ly.w[2], 2ll * I, nullptr, nullptr, gu, SCB_ACT_SILU_PAIR);
     xn = (x2 == xa) ? xb : xa;
     if (rc == SCB_OK) rc = linear(gu, I, ly.w[3], H, nullptr, x2, xn, SCB_ACT_NONE);
     x = xn;
   }
   if (rc != SCB_OK) return rc;
-  // final norm + lm_head on the last position only
-  rc = scb_rmsnorm(x + (T - 1) * H, H, p.final_norm, p.eps, 1, H, y, H, stream);
-  if (rc != SCB_OK) return rc;
-  scb_gemv_args ga;
-  memset(&ga, 0, sizeof(ga));
-  ga.a = y; ga.w = p.lm_head; ga.out = logits_row;
-  ga.n = h->vocab; ga.k = H; ga.lda = H; ga.ldw = H; ga.ldo = h->vocab;
-  ga.rows = 1; ga.prologue = SCB_PRO_NONE; ga.out_dtype = SCB_F16;
-  ga.workspace = gemv_ws; ga.workspace_bytes = scb_gemv_workspace_bytes(1);
-  return scb_gemv(&ga, stream);
+  // final norm + lm_head on the last position of every sequence
+  int64_t row0 = 0;
+  for (int q = 0; q < n_seqs; ++q) {
+    row0 += n_tokens_host[q];
+    rc = scb_rmsnorm(x + (size_t)(row0 - 1) * H, H, p.final_norm, p.eps, 1, H, y, H, stream);
+    if (rc != SCB_OK) return rc;
+    scb_gemv_args ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.a = y; ga.w = p.lm_head; ga.out = reinterpret_cast<__half*>(logits_rows) + (size_t)q * ld_logits;
+    ga.n = h->vocab; ga.k = H; ga.lda = H; ga.ldw = H; ga.ldo = h->vocab;
+    ga.rows = 1; ga.prologue = SCB_PRO_NONE; ga.out_dtype = SCB_F16;
+    ga.workspace = gemv_ws; ga.workspace_bytes = scb_gemv_workspace_bytes(1);
+    rc = scb_gemv(&ga, stream);
+    if (rc != SCB_OK) return rc;
+  }
+  return SCB_OK;
+}
+
+int scb_qwen2_prefill(void* handle, const void* inputs_embeds, int64_t n_tokens, int32_t slot, int64_t pos0,
+                      void* logits_row, void* workspace, size_t workspace_bytes, void* stream) {
+  return scb_qwen2_prefill_batch(handle, inputs_embeds, 1, &n_tokens, &slot, &pos0, logits_row, 0, workspace,
+                                 workspace_bytes, stream);
 }
 
 }  // extern "C"

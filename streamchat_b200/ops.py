@@ -581,6 +581,29 @@ class Qwen2Decoder:
             L.check(lib.scb_qwen2_prefill(self._h, inputs_embeds.data_ptr(), T, slot, pos0, logits_row.data_ptr(),
                                           ws.data_ptr(), ws.numel(), _stream(self.device)), "scb_qwen2_prefill")
 
+    def prefill_batch(self, stacked: torch.Tensor, n_tokens: list, slots: list, pos0: list, logits: torch.Tensor) -> None:
+        """scb_qwen2_prefill_batch: several prompts (rows stacked in `stacked` [sum(n_tokens), H]) in ONE pass; sequence q's
+        last-position logits land in logits[q]."""
+        _require_cuda(stacked, logits)
+        if stacked.dtype != torch.float16 or not stacked.is_contiguous() or logits.dtype != torch.float16:
+            raise TypeError("Qwen2Decoder.prefill_batch: contiguous fp16 rows, fp16 logits")
+        lib = L.load()
+        n = len(n_tokens)
+        if stacked.shape[0] != sum(n_tokens) or len(slots) != n or len(pos0) != n or logits.shape[0] < n:
+            raise ValueError("prefill_batch: inconsistent sequence lists")
+        need = int(lib.scb_qwen2_prefill_workspace_bytes(self._h, int(stacked.shape[0])))
+        ws = getattr(self, "_prefill_ws", None)
+        if ws is None or ws.numel() < need:
+            self._prefill_ws = None
+            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)     # zero: the lm_head GEMV's ticket
+            self._prefill_ws = ws
+        nt = (C.c_int64 * n)(*[int(t) for t in n_tokens])
+        sl = (C.c_int32 * n)(*[int(t) for t in slots])
+        p0 = (C.c_int64 * n)(*[int(t) for t in pos0])
+        with torch.cuda.device(self.device):
+            L.check(lib.scb_qwen2_prefill_batch(self._h, stacked.data_ptr(), n, nt, sl, p0, logits.data_ptr(), logits.stride(0),
+                                                ws.data_ptr(), ws.numel(), _stream(self.device)), "scb_qwen2_prefill_batch")
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             L.load().scb_qwen2_decoder_destroy(self._h)

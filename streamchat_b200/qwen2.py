@@ -49,6 +49,7 @@ class Qwen2Engine:
         self.decode_splits = decode_splits
         self.max_batch = max_batch
         self.mega_rows = int(os.environ.get("SCB_DECODE_MEGA_ROWS", "4"))   # widest batch the persistent kernel takes
+        self.prefill_group_tokens = int(os.environ.get("SCB_PREFILL_GROUP_TOKENS", "30000"))   # rows stacked per prefill pass
         if max_batch < 1 or max_batch > 32:
             raise ValueError('max_batch must be in 1..32 (sequences decoded in lock-step)')
         c = cfg
@@ -351,10 +352,33 @@ class Qwen2Engine:
             if self.profile is not None:
                 pf0, pf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 pf0.record()
-            for s_, i in enumerate(order):
-                logits = self.prefill(inputs_embeds_list[i], slot=s_)
-                ops.argmax_rows(logits, out=self.next_id[s_:s_ + 1])
-                lens.append(self.ctx_lens[s_])
+            if n > 1 and self._mega is not None and os.environ.get("SCB_NATIVE_PREFILL", "1") != "0" \
+                    and os.environ.get("SCB_PREFILL_GROUP", "1") != "0":
+                # prompts are prefilled in GROUPS: their rows stacked, every linear layer once over the stack
+                # (scb_qwen2_prefill_batch) — same arithmetic per row, fuller GEMM waves than one prompt at a time
+                xs = [inputs_embeds_list[i].to(device=self.device, dtype=torch.float16) for i in order]
+                s0 = 0
+                while s0 < n:
+                    s1, tok = s0, 0
+                    while s1 < n and (s1 == s0 or tok + xs[s1].shape[0] <= self.prefill_group_tokens):
+                        tok += xs[s1].shape[0]
+                        s1 += 1
+                    for x_ in xs[s0:s1]:
+                        if x_.shape[0] > self.max_ctx:
+                            raise ValueError(f"context {x_.shape[0]} exceeds max_ctx {self.max_ctx}")
+                    stacked = xs[s0] if s1 == s0 + 1 else torch.cat(xs[s0:s1], 0)
+                    self._mega.prefill_batch(stacked.contiguous(), [int(x_.shape[0]) for x_ in xs[s0:s1]], list(range(s0, s1)),
+                                             [0] * (s1 - s0), self._logits[s0:])
+                    for s_ in range(s0, s1):
+                        self.ctx_lens[s_] = int(xs[s_].shape[0])
+                        lens.append(self.ctx_lens[s_])
+                    s0 = s1
+                ops.argmax_rows(self._logits[:n], out=self.next_id[:n])
+            else:
+                for s_, i in enumerate(order):
+                    logits = self.prefill(inputs_embeds_list[i], slot=s_)
+                    ops.argmax_rows(logits, out=self.next_id[s_:s_ + 1])
+                    lens.append(self.ctx_lens[s_])
             if pf0 is not None:
                 pf1.record()
                 self.profile.append({"kind": "prefill", "events": (pf0, pf1), "tokens": sum(lens), "rows": n,

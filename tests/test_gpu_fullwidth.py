@@ -167,3 +167,32 @@ def test_native_prefill_equals_per_launch_prefill_at_7b_width(cuda, qwen7b_2laye
     assert torch.equal(res["1"][0], res["0"][0]) and torch.equal(res["1"][1], res["0"][1])
     for ka, kb in zip(res["1"][2] + res["1"][3], res["0"][2] + res["0"][3]):
         assert torch.equal(ka, kb)
+
+
+def test_stacked_prefill_equals_one_prompt_at_a_time_at_7b_width(cuda, qwen7b_2layers, monkeypatch):
+    """scb_qwen2_prefill_batch (several prompts stacked, every GEMM once over the stack) leaves the logits and KV rows
+    of the one-prompt-at-a-time prefill, bit for bit, and generate_batch gives the same ids either way."""
+    lcfg, W, Wc, eng = qwen7b_2layers
+    xs = [_prompt(Wc, 12, n, 40 + n).to(cuda) for n in (300, 37, 140)]
+    eng.reset()
+    want = []
+    for q, x in enumerate(xs):
+        lg = eng.prefill(x, slot=q + 2).clone()
+        want.append((lg, [k[q + 2, :, : x.shape[0]].clone() for k in eng.k_cache], [v[q + 2, :, : x.shape[0]].clone() for v in eng.v_cache]))
+    eng.reset()
+    logits = torch.zeros((3, lcfg.vocab_size), dtype=torch.float16, device=cuda)
+    eng._mega.prefill_batch(torch.cat(xs, 0), [int(x.shape[0]) for x in xs], [5, 6, 7], [0, 0, 0], logits)
+    for q, x in enumerate(xs):
+        assert torch.equal(logits[q:q + 1], want[q][0])
+        for l in range(len(eng.k_cache)):
+            assert torch.equal(eng.k_cache[l][5 + q, :, : x.shape[0]], want[q][1][l])
+            assert torch.equal(eng.v_cache[l][5 + q, :, : x.shape[0]], want[q][2][l])
+    monkeypatch.setenv("SCB_PREFILL_GROUP", "1")
+    a = eng.generate_batch(xs, 5)
+    monkeypatch.setenv("SCB_PREFILL_GROUP", "0")
+    b = eng.generate_batch(xs, 5)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # argument validation: a cache slot twice in one batch
+    from streamchat_b200 import _lib as L
+    with pytest.raises(L.ScbError, match="twice"):
+        eng._mega.prefill_batch(torch.cat(xs[:2], 0), [300, 37], [1, 1], [0, 0], logits)

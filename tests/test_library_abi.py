@@ -45,6 +45,7 @@ def test_version_and_error_string():
     assert lib.scb_qwen2_prefill(None, None, 16, 0, 0, None, None, 0, None) == -1
     assert b"handle" in lib.scb_last_error()
     assert lib.scb_qwen2_decoder_destroy(None) == -1
+    assert lib.scb_qwen2_prefill_batch(None, None, 2, None, None, None, None, 0, None, 0, None) == -1
     assert lib.scb_qwen2_decoder_max_rows() >= 1
     assert lib.scb_vit_encode_workspace_bytes(None, 4) == 0
     assert lib.scb_vit_encode(None, None, 4, None, None, None, 0, None) == -1

@@ -195,4 +195,4 @@ def test_stacked_prefill_equals_one_prompt_at_a_time_at_7b_width(cuda, qwen7b_2l
     # argument validation: a cache slot twice in one batch
     from streamchat_b200 import _lib as L
     with pytest.raises(L.ScbError, match="twice"):
-        eng._mega.prefill_batch(torch.cat(xs[:2], 0), [300, 37], [1, 1], [0, 0], logits)
+        eng._mega.prefill_batch(torch.cat(xs[:2], 0), [int(xs[0].shape[0]), int(xs[1].shape[0])], [1, 1], [0, 0], logits)

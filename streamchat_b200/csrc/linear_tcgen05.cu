@@ -552,15 +552,6 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
     const long long tiles_m = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
     const long long a_bytes = (long long)a->m * a->k * 2;
     int gm = (a_bytes <= (48ll << 20)) ? (int)tiles_m : (PAIR ? 4 : 8);
-    // A does not fit L2 and W is large (the Qwen2 layers: 25-271 MB): every group of M tiles streams W from HBM again,
-    // so the group is made as tall as L2 allows (~48 MB of A rows) instead of 4 tiles — a stack of five 5.8 k-token
-    // prompts then reads W five times, like five separate prefills, not 29 times
-    const long long w_bytes = (long long)a->n * a->k * 2;
-    if (a_bytes > (48ll << 20) && w_bytes > (32ll << 20)) {
-      const long long rows = PAIR ? 2 * BM : BM;
-      const long long tall = (48ll << 20) / (rows * a->k * 2);
-      if (tall > gm) gm = (int)tall;
-    }
     if (force_gm > 0) gm = force_gm;
     if (gm > tiles_m) gm = (int)tiles_m;
     ep.gm = gm < 1 ? 1 : gm;

@@ -353,9 +353,11 @@ class Qwen2Engine:
                 pf0, pf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 pf0.record()
             if n > 1 and self._mega is not None and os.environ.get("SCB_NATIVE_PREFILL", "1") != "0" \
-                    and os.environ.get("SCB_PREFILL_GROUP", "1") != "0":
-                # prompts are prefilled in GROUPS: their rows stacked, every linear layer once over the stack
-                # (scb_qwen2_prefill_batch) — same arithmetic per row, fuller GEMM waves than one prompt at a time
+                    and os.environ.get("SCB_PREFILL_GROUP", "0") == "1":
+                # opt-in (SCB_PREFILL_GROUP=1): prompts prefilled in GROUPS, their rows stacked, every linear layer once
+                # over the stack (scb_qwen2_prefill_batch) — same arithmetic per row, fuller GEMM waves.  Measured on the
+                # bench (same box, A/B/A): 2 189 / 2 205 ms of prefill per stream against 2 137 ms one prompt at a time —
+                # the taller GEMMs push A out of L2 and the power-capped clock down, so the default stays one at a time
                 xs = [inputs_embeds_list[i].to(device=self.device, dtype=torch.float16) for i in order]
                 s0 = 0
                 while s0 < n:

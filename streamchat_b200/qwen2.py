@@ -49,6 +49,7 @@ class Qwen2Engine:
         self.decode_splits = decode_splits
         self.max_batch = max_batch
         self.mega_rows = int(os.environ.get("SCB_DECODE_MEGA_ROWS", "4"))   # widest batch the persistent kernel takes
+        self.wide_min_rows = int(os.environ.get("SCB_WIDE_MIN_ROWS", "9"))   # batches this wide run the tcgen05 split-K chain
         self.prefill_group_tokens = int(os.environ.get("SCB_PREFILL_GROUP_TOKENS", "30000"))   # rows stacked per prefill pass
         if max_batch < 1 or max_batch > 32:
             raise ValueError('max_batch must be in 1..32 (sequences decoded in lock-step)')
@@ -230,7 +231,7 @@ class Qwen2Engine:
         L0 = self.layers[0]
         ops.gather_rows_rmsnorm(self.embed, self.next_id[:R], L0["ln1"], eps, out=x, norm_out=nrm)
         n_layers = len(self.layers)
-        wide = R > 8
+        wide = R >= self.wide_min_rows
         for i, ly in enumerate(self.layers):
             nxt_gamma = self.layers[i + 1]["ln1"] if i + 1 < n_layers else self.final_norm
             nxt_w = self.layers[i + 1]["qkv_w"] if i + 1 < n_layers else self.lm_head
@@ -254,7 +255,7 @@ class Qwen2Engine:
                 ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])
                 ops.gemv(self._gu[:R], ly["down_w"], residual=x2, out=x, post_norm=(nxt_gamma, nrm, eps),
                          prefetch=nxt_w)
-        if R > 8:
+        if wide:
             ops.linear(nrm, self.lm_head, out=self._logits[:R])
             ops.argmax_rows(self._logits[:R], out=self.next_id[:R], counter=self.state.view(-1))
         else:
@@ -267,8 +268,9 @@ class Qwen2Engine:
     def launches_per_decode_step(self, R: int = 1) -> int:
         if self._use_mega(R):
             return 1
-        # <= 8 rows: gather+norm, 5 per layer, lm_head with fused arg-max; wider: split-K GEMM + reduce pairs
-        return 1 + self.cfg.num_hidden_layers * (8 if R > 8 else 5) + (2 if R > 8 else 1)
+        # narrow chain: gather+norm, 5 per layer, lm_head with fused arg-max; wide: split-K GEMM + reduce pairs
+        wide = R >= self.wide_min_rows
+        return 1 + self.cfg.num_hidden_layers * (8 if wide else 5) + (2 if wide else 1)
 
     def _check_context(self, prompt_lens, budgets) -> None:
         """A generation of `b` new tokens after a prompt of T tokens appends KV rows up to position T + b - 2 and

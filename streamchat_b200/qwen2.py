@@ -49,7 +49,10 @@ class Qwen2Engine:
         self.decode_splits = decode_splits
         self.max_batch = max_batch
         self.mega_rows = int(os.environ.get("SCB_DECODE_MEGA_ROWS", "4"))   # widest batch the persistent kernel takes
-        self.wide_min_rows = int(os.environ.get("SCB_WIDE_MIN_ROWS", "9"))   # batches this wide run the tcgen05 split-K chain
+        # batches this wide run the tcgen05 split-K chain; narrower ones the persistent kernel (<= mega_rows) or, where it
+        # is unavailable, the GEMV chain.  Measured per step at LongVA-7B shapes (ctx 5 800): 5 / 7 / 8 rows 4.60 / 4.81 /
+        # 4.64 ms on the split-K chain against 5.18 / 5.57 / 5.61 ms on the GEMV chain
+        self.wide_min_rows = int(os.environ.get("SCB_WIDE_MIN_ROWS", "5"))
         self.prefill_group_tokens = int(os.environ.get("SCB_PREFILL_GROUP_TOKENS", "30000"))   # rows stacked per prefill pass
         if max_batch < 1 or max_batch > 32:
             raise ValueError('max_batch must be in 1..32 (sequences decoded in lock-step)')

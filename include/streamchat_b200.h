@@ -552,7 +552,9 @@ typedef struct scb_allgather_embed_args {
   void* const* peer_bufs;    /* HOST array [world]: every rank's buffer as mapped in THIS process (own at [rank]) */
   int32_t rank, world;       /* world <= 16 */
   int64_t slice_bytes;       /* bytes per rank, multiple of 16 */
-  uint32_t epoch;            /* >= 1, strictly increasing over the calls on one set of buffers */
+  uint32_t epoch;            /* >= 1, strictly increasing over the calls on one set of buffers; 0: the call number is kept
+                              * on the device (in the flag block), so the launch can be replayed from a CUDA graph — do
+                              * not mix both modes on one set of buffers */
   int32_t _pad;
 } scb_allgather_embed_args;
 

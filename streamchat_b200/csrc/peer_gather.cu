@@ -37,6 +37,12 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 
 __global__ void __launch_bounds__(kThreads) peer_allgather_kernel(PeerTable t, int rank, int world, long long slice_bytes,
                                                                   unsigned epoch) {
+  // epoch == 0: the call number lives on the DEVICE (own flag block, word kMaxWorld + 1) — every CTA reads it before
+  // it takes its ticket, the last CTA stores the incremented value at the very end — so the launch can be replayed from
+  // a CUDA graph (the per-layer exchanges of a tensor-parallel decode step)
+  unsigned* epoch_dev = t.flags[rank] + kMaxWorld + 1;
+  const bool dev_epoch = epoch == 0;
+  if (dev_epoch) epoch = *reinterpret_cast<volatile unsigned*>(epoch_dev) + 1u;
   const char* src = t.buf[rank] + (long long)rank * slice_bytes;
   const long long n16 = slice_bytes / 16;
   const long long total = n16 * (world - 1);
@@ -63,10 +69,20 @@ __global__ void __launch_bounds__(kThreads) peer_allgather_kernel(PeerTable t, i
   // ---- wait for every peer's slice to have landed in MY buffer
   if (threadIdx.x < world && threadIdx.x != rank) {
     const unsigned* f = t.flags[rank] + threadIdx.x;
-    while ((int)(ld_acquire_sys(f) - epoch) < 0) __nanosleep(200);
+    // bounded: a peer that died or never launched must not hang this GPU — after ~20 s the wait gives up and records
+    // the fact in the flag block (word kMaxWorld + 2), which the host can read back (the data is then incomplete)
+    long long spins = 0;
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+      __nanosleep(200);
+      if (++spins > 50000000ll) {
+        t.flags[rank][kMaxWorld + 2] = 1u + (unsigned)threadIdx.x;
+        break;
+      }
+    }
   }
   __syncthreads();
   __threadfence_system();
+  if (dev_epoch && threadIdx.x == 0) *epoch_dev = epoch;
 }
 
 }  // namespace
@@ -125,8 +141,7 @@ int scb_allgather_embed(const scb_allgather_embed_args* a, void* stream) {
               "scb_allgather_embed: rank=%d world=%d (world <= %d)", a->rank, a->world, kMaxWorld);
   SCB_REQUIRE(a->slice_bytes > 0 && a->slice_bytes % 16 == 0, SCB_ERR_INVALID_ARG,
               "scb_allgather_embed: slice_bytes=%lld must be a positive multiple of 16", (long long)a->slice_bytes);
-  SCB_REQUIRE(a->epoch != 0 && a->peer_bufs != nullptr, SCB_ERR_INVALID_ARG,
-              "scb_allgather_embed: epoch must be >= 1 and peer_bufs non-NULL");
+  SCB_REQUIRE(a->peer_bufs != nullptr, SCB_ERR_INVALID_ARG, "scb_allgather_embed: peer_bufs is NULL");
   if (a->world == 1) return SCB_OK;
   PeerTable t;
   memset(&t, 0, sizeof(t));

@@ -397,6 +397,27 @@ def linear_splitk(a: torch.Tensor, w: torch.Tensor, n_splits: int, partial: torc
     return out
 
 
+def splitk_reduce(partial: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  residual: Optional[torch.Tensor] = None,
+                  post_norm: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> torch.Tensor:
+    """out[r, :] = fp16(sum_s partial[s, r, :] (+ bias) (+ residual[r, :])) summed in slice order, optionally followed by
+    post_norm_out[r, :] = RMSNorm(out[r, :]) * gamma (scb_splitk_reduce).  partial [S, rows, N] fp32 — K-slices of a
+    split-K GEMM or the ranks' partial sums of a row-parallel layer."""
+    dev = _require_cuda(partial, out, bias, residual)
+    if partial.dtype != torch.float32 or partial.dim() != 3 or partial.stride(2) != 1:
+        raise TypeError("splitk_reduce: partial must be fp32 [S, rows, N] with contiguous rows")
+    S, rows, n = partial.shape
+    pg = po = None
+    pld, pe = 0, 0.0
+    if post_norm is not None:
+        pg, po, pe = post_norm
+        pld = po.stride(0)
+    _call("scb_splitk_reduce", dev, _ptr(partial), partial.stride(0), partial.stride(1), S, rows, n, _ptr(bias),
+          _ptr(residual), residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), _ptr(pg), _ptr(po),
+          pld, pe)
+    return out
+
+
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None,
                 counter: Optional[torch.Tensor] = None) -> torch.Tensor:
     dev = _require_cuda(logits, out, counter)
@@ -706,8 +727,11 @@ class PeerGather:
     rank of `group` must call it; it raises on every rank if ANY rank cannot map its peers (the caller then lets NCCL
     move the bytes)."""
 
-    def __init__(self, shape, dtype: torch.dtype, rank: int, world: int, device, group=None):
+    def __init__(self, shape, dtype: torch.dtype, rank: int, world: int, device, group=None, device_epoch: bool = False):
+        """`device_epoch`: the call number of `allgather()` lives on the device, so the launch can be captured in a CUDA
+        graph and replayed (the per-layer exchanges of tp_decode.TensorParallelDecoder)."""
         import torch.distributed as dist
+        self.device_epoch = device_epoch
         if shape[0] != world:
             raise ValueError("PeerGather: shape[0] must be the world size")
         self.rank, self.world, self.device = rank, world, torch.device(device)
@@ -759,7 +783,7 @@ class PeerGather:
     def allgather(self) -> None:
         self.epoch += 1
         a = L.AllgatherEmbedArgs(peer_bufs=C.cast(self._table, C.POINTER(C.c_void_p)), rank=self.rank, world=self.world,
-                                 slice_bytes=self.slice_bytes, epoch=self.epoch)
+                                 slice_bytes=self.slice_bytes, epoch=0 if self.device_epoch else self.epoch)
         with torch.cuda.device(self.device):
             L.check(L.load().scb_allgather_embed(C.byref(a), _stream(self.device)), "scb_allgather_embed")
 

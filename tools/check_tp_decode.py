@@ -69,6 +69,17 @@ def main():
         cfg = SYNTHETIC["longva7b"].llm
         eng = Qwen2Engine(llm_weights(cfg, 0, 0.02), cfg, device, max_ctx=32768, max_batch=1)
         tp = TensorParallelDecoder(eng, rank, world)
+        # numeric check at full shapes: ONE decode step from the same prefilled state, TP logits vs the persistent kernel's
+        x = (torch.randn(700, cfg.hidden_size, device=device) * 0.02).half()
+        eng.generate(x, 2)                                   # persistent kernel: prefill + one step
+        ref = eng._logits[0].float().clone()
+        tp.generate(x, 2)                                    # same prefill, one TP step
+        got = tp.px_l.buffer.view(-1).float()
+        rel = float((got - ref).norm() / ref.norm())
+        top2 = torch.topk(ref, 2).values
+        out["one_step_logits"] = {"rel_l2_vs_persistent_kernel": rel, "argmax_equal": bool(int(got.argmax()) == int(ref.argmax())),
+                                  "ref_top2_margin_rel": float((top2[0] - top2[1]) / ref.abs().max())}
+        ok = ok and rel < 5e-3
         timing = {}
         for ctx in (5800, 18000):
             x = (torch.randn(ctx, cfg.hidden_size, device=device) * 0.02).half()

@@ -16,5 +16,16 @@ Pinning status:
                                 beyond the reference's own call sites (utiles.py:17,732,764)
   * vit / qwen2                 pinned against the reference's longva classes + HF transformers
                                 5.5.0 (pinned upstream: 4.37.2) run here on tiny configs
+  * memory_bank.*               restates langchain 0.0.142 FAISS + faiss-cpu IndexFlatL2 + the patched
+                                neighbour expansion (local_doc_qa.py:135-178); packages absent: pinned only
+                                against an independent brute force of the published IndexFlatL2 definition
+                                (tests/golden/flat_l2_ref.npz) — PARITY UNPINNED against the faiss binary
+  * text_encoder.*              pinned against HF BertModel run here (BERT and MiniLM-shaped tiny configs)
+  * preprocess.*                pinned bit-exactly against Pillow + HF CLIPImageProcessor run here
 The reference ships no tests, golden vectors or fixtures of its own.
+
+oracle/_ref/ (git-ignored; staged by oracle/stage_ref.py from /root/reference during build()) is an UNMODIFIED copy
+of the reference's hot-path sources.  oracle/ref_runner.py runs it: the reference's own LlavaQwenForCausalLM /
+weighted_kmeans_feature / torch_kmeans on the host cores for bench.py's cpu_baseline and --impl reference legs
+(kind "reference"), and tests/test_gpu_dropin_driver.py AST-extracts the driver's own functions from it.
 """

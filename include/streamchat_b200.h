@@ -250,6 +250,34 @@ int scb_gather_rows_rmsnorm(const void* table, const int64_t* ids, int64_t n_ids
                             int64_t ld_out, const void* gamma, float eps, void* norm_out,
                             int64_t ld_norm, void* stream);
 
+/* Split-K linear with the reduction fused into the GEMM launch (decode steps of wide batches: o_proj / down_proj / qkv of
+ * nn.Linear, modeling_qwen2.py:74-88,229-243, run for a handful of rows, where N alone gives too few tiles to pull the
+ * weights at HBM speed): out[r,n] = fp16(sum_s a[r, s*ks:(s+1)*ks] . w[n, s*ks:(s+1)*ks] + bias[n] + residual[r,n]),
+ * slices summed in index order, then optionally post_norm_out[r,:] = RMSNorm(out[r,:]) * gamma (modeling_qwen2.py:249-263).
+ * One CTA per (n tile of 128, K slice): ceil(m/128) * ceil(n/128) * n_splits must not exceed the SM count
+ * (SCB_ERR_UNSUPPORTED otherwise: run scb_linear with fp32 partials + scb_splitk_reduce).  `partial` holds
+ * n_splits*m*n floats of scratch; `workspace` (scb_linear_splitk_workspace_bytes) must be zero before the FIRST call and
+ * is left zero by every call, so one buffer serves a whole stream-ordered launch chain. */
+typedef struct scb_linear_splitk_args {
+  const void* a;         /* [m, k] fp16, leading dim lda (multiple of 8) */
+  const void* w;         /* [n, k] fp16, leading dim ldw (multiple of 8) */
+  const void* bias;      /* [n] fp16 or NULL */
+  const void* residual;  /* [m, n] fp16, leading dim ldr, or NULL */
+  void* partial;         /* fp32 scratch, n_splits*m*n elements */
+  void* out;             /* [m, n] fp16, leading dim ldo */
+  const void* post_norm_gamma; /* [n] fp16 or NULL */
+  void* post_norm_out;   /* [m, n] fp16, leading dim post_norm_ld, or NULL */
+  void* workspace;
+  int64_t workspace_bytes;
+  int64_t m, n, k;
+  int64_t lda, ldw, ldr, ldo, post_norm_ld;
+  int32_t n_splits;
+  float post_norm_eps;
+} scb_linear_splitk_args;
+
+int64_t scb_linear_splitk_workspace_bytes(int64_t m, int64_t n);
+int scb_linear_splitk(const scb_linear_splitk_args* a, void* stream);
+
 /* Tail of a split-K decode layer (wide batches run o_proj / down_proj / qkv as S independent K-slices
  * through scb_linear with fp32 partial outputs): out[r,n] = fp16(sum_s partial[s,r,n] + bias[n] +
  * residual[r,n]) summed in split order, then optionally post_norm_out[r,:] = RMSNorm(out[r,:]) * gamma. */

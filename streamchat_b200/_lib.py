@@ -57,6 +57,17 @@ class LinearArgs(C.Structure):
     ]
 
 
+class LinearSplitKArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("partial", C.c_void_p), ("out", C.c_void_p), ("post_norm_gamma", C.c_void_p), ("post_norm_out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
+        ("lda", C.c_int64), ("ldw", C.c_int64), ("ldr", C.c_int64), ("ldo", C.c_int64), ("post_norm_ld", C.c_int64),
+        ("n_splits", C.c_int32), ("post_norm_eps", C.c_float),
+    ]
+
+
 class AttentionArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
@@ -169,6 +180,8 @@ SYMBOLS = {
     "scb_peer_close": (C.c_int, [C.c_void_p]),
     "scb_allgather_embed": (C.c_int, [C.POINTER(AllgatherEmbedArgs), C.c_void_p]),
     "scb_linear": (C.c_int, [C.POINTER(LinearArgs), C.c_void_p]),
+    "scb_linear_splitk": (C.c_int, [C.POINTER(LinearSplitKArgs), C.c_void_p]),
+    "scb_linear_splitk_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "scb_attention": (C.c_int, [C.POINTER(AttentionArgs), C.c_void_p]),
     "scb_gemv": (C.c_int, [C.POINTER(GemvArgs), C.c_void_p]),
     "scb_gemv_workspace_bytes": (C.c_size_t, [_i32]),

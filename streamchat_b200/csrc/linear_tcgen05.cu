@@ -38,7 +38,28 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Split-K with the reduction fused into the GEMM (TAIL instantiation; decode steps of wide batches).  Every CTA owns
+// ONE (n tile, K slice) and stores its fp32 partial; the CTA that arrives LAST at the tile's ticket sums the slices in
+// index order (deterministic), applies bias / residual, stores the fp16 rows and the tile's per-row sums of squares.
+// With a post-norm, the finishing CTAs of a row block then meet at a second counter (they are all resident: the host
+// launches at most one CTA per SM and one tile per CTA) and each normalises ITS columns of the finished rows
+// (Qwen2RMSNorm, modeling_qwen2.py:249-263) — what took a GEMM launch + a one-block-per-row reduce launch is one launch.
+struct SplitKTail {
+  __half* out;
+  const __half* bias;
+  const __half* residual;
+  const __half* gamma;     // post-norm weight or nullptr
+  __half* pn_out;
+  long long ldo, ldr, pn_ld;
+  unsigned* tile_tickets;  // [tiles_m * tiles_n] zero before the first launch; left zero
+  unsigned* row_arrive;    // [tiles_m]            "
+  unsigned* row_depart;    // [tiles_m]            "
+  float* ssq;              // [tiles_m * BM, tiles_n] sums of squares of the stored fp16 values
+  float eps;
+};
+
 struct EpiParams {
+  SplitKTail tail;
   const __half* bias;
   const __half* residual;
   void* out;
@@ -148,7 +169,14 @@ SCB_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN, bool PAIR>
+SCB_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+SCB_DEVICE unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BN, bool PAIR, bool TAIL = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_w, const EpiParams ep) {
@@ -437,6 +465,126 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         as = 0;
         aphase ^= 1;
       }
+      if constexpr (TAIL) {
+        static_assert(!TAIL || (BN == 128 && !PAIR), "the fused split-K tail maps one warp onto the 128 columns of a tile");
+        __shared__ unsigned tail_ticket;
+        const SplitKTail& tk = ep.tail;
+        const int e = (int)threadIdx.x - 64, ew = e >> 5;   // epilogue thread / warp index
+        __threadfence();                                    // this warp's partial stores, device-wide
+        epi_bar_sync();
+        if (e == 0) tail_ticket = atomicAdd(&tk.tile_tickets[tm * tiles_n + tn], 1u);
+        epi_bar_sync();
+        if (tail_ticket == (unsigned)(ep.batch - 1)) {      // CTA-uniform: every slice of this tile is stored
+          __threadfence();
+          if (e == 0) tk.tile_tickets[tm * tiles_n + tn] = 0u;
+          const int rows_here = (int)min((long long)BM, ep.m - (long long)tm * BM);
+          const long long col = (long long)tn * BN + lane * 4;
+          const bool col_ok = col < ep.n;                   // n is a multiple of 4
+          const float* part = reinterpret_cast<const float*>(ep.out);
+          uint2 keep[BM / 8];
+#pragma unroll
+          for (int i = 0; i < BM / 8; ++i) keep[i] = make_uint2(0u, 0u);
+          // warp ew: rows ew, ew + 8, ...; lane: 4 columns.  Four rows x four slices of loads are in flight at a time
+          // (one L2 round trip per 16 partial vectors; issued one by one they cost 16 round trips for a 25-row batch)
+#pragma unroll
+          for (int i0 = 0; i0 < BM / 8; i0 += 4) {
+            if (ew + 8 * i0 < rows_here) {                  // warp-uniform
+              float4 acc[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int sp0 = 0; sp0 < ep.batch; sp0 += 4) {
+                float4 v[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int rl = min(ew + 8 * (i0 + q), rows_here - 1);          // clamped: loads stay unconditional
+                  const long long rr = (long long)tm * BM + rl;
+#pragma unroll
+                  for (int d = 0; d < 4; ++d) {
+                    const int sp = min(sp0 + d, ep.batch - 1);
+                    v[q][d] = __ldcg(reinterpret_cast<const float4*>(part + (long long)sp * ep.stride_o + rr * ep.ldo +
+                                                                     (col_ok ? col : 0)));
+                  }
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d)                 // slices in index order
+                  if (sp0 + d < ep.batch) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      acc[q].x += v[q][d].x; acc[q].y += v[q][d].y; acc[q].z += v[q][d].z; acc[q].w += v[q][d].w;
+                    }
+                  }
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int rl = ew + 8 * (i0 + q);
+                if (rl < rows_here) {                       // warp-uniform
+                  const long long rr = (long long)tm * BM + rl;
+                  float ss = 0.f;
+                  if (col_ok) {
+                    float4 a4 = acc[q];
+                    if (tk.bias) {
+                      const uint2 bq = *reinterpret_cast<const uint2*>(tk.bias + col);
+                      const float2 b0 = h2_to_f2(bq.x), b1 = h2_to_f2(bq.y);
+                      a4.x += b0.x; a4.y += b0.y; a4.z += b1.x; a4.w += b1.y;
+                    }
+                    if (tk.residual) {
+                      const uint2 rq = *reinterpret_cast<const uint2*>(tk.residual + rr * tk.ldr + col);
+                      const float2 r0 = h2_to_f2(rq.x), r1 = h2_to_f2(rq.y);
+                      a4.x += r0.x; a4.y += r0.y; a4.z += r1.x; a4.w += r1.y;
+                    }
+                    uint2 o;
+                    o.x = f2_to_h2(a4.x, a4.y);
+                    o.y = f2_to_h2(a4.z, a4.w);
+                    *reinterpret_cast<uint2*>(tk.out + rr * tk.ldo + col) = o;
+                    keep[i0 + q] = o;
+                    const float2 h0 = h2_to_f2(o.x), h1 = h2_to_f2(o.y);   // the norm sees the stored fp16 values
+                    ss = h0.x * h0.x + h0.y * h0.y + h1.x * h1.x + h1.y * h1.y;
+                  }
+                  if (tk.pn_out) {
+                    ss = warp_sum(ss);
+                    if (lane == 0) tk.ssq[rr * tiles_n + tn] = ss;
+                  }
+                }
+              }
+            }
+          }
+          if (tk.pn_out) {
+            __threadfence();
+            epi_bar_sync();
+            if (e == 0) {
+              atomicAdd(&tk.row_arrive[tm], 1u);
+              unsigned spins = 0;
+              while (ld_acquire_gpu(&tk.row_arrive[tm]) < (unsigned)tiles_n)
+                if (++spins > (1u << 27)) __trap();         // a finishing CTA never arrived: fail loudly, do not hang
+            }
+            epi_bar_sync();
+#pragma unroll
+            for (int i = 0; i < BM / 8; ++i) {
+              const int rl = ew + 8 * i;
+              if (rl < rows_here) {
+                const long long rr = (long long)tm * BM + rl;
+                float ss = 0.f;
+                for (int j = lane; j < tiles_n; j += 32) ss += __ldcg(&tk.ssq[rr * tiles_n + j]);
+                ss = warp_sum(ss);
+                const float rstd = rsqrtf(ss / (float)ep.n + tk.eps);
+                if (col_ok) {
+                  const uint2 g = *reinterpret_cast<const uint2*>(tk.gamma + col);
+                  const float2 x0 = h2_to_f2(keep[i].x), x1 = h2_to_f2(keep[i].y), g0 = h2_to_f2(g.x), g1 = h2_to_f2(g.y);
+                  uint2 o;
+                  o.x = f2_to_h2(__half2float(__float2half_rn(x0.x * rstd)) * g0.x, __half2float(__float2half_rn(x0.y * rstd)) * g0.y);
+                  o.y = f2_to_h2(__half2float(__float2half_rn(x1.x * rstd)) * g1.x, __half2float(__float2half_rn(x1.y * rstd)) * g1.y);
+                  *reinterpret_cast<uint2*>(tk.pn_out + rr * tk.pn_ld + col) = o;
+                }
+              }
+            }
+            epi_bar_sync();
+            if (e == 0 && atomicAdd(&tk.row_depart[tm], 1u) == (unsigned)(tiles_n - 1)) {
+              tk.row_arrive[tm] = 0u;                       // every finishing CTA of the row block is past its wait
+              tk.row_depart[tm] = 0u;
+            }
+          }
+        }
+      }
     }
   }
 
@@ -527,8 +675,8 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long k, lon
   return SCB_OK;
 }
 
-template <int BN, bool PAIR>
-int launch(const scb_linear_args* a, cudaStream_t st) {
+template <int BN, bool PAIR, bool TAIL = false>
+int launch(const scb_linear_args* a, cudaStream_t st, const SplitKTail* tail = nullptr) {
   using C = Cfg<BN, PAIR>;
   CUtensorMap ma, mw;
   int rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->stride_a, a->batch, BM);
@@ -536,6 +684,7 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, PAIR ? BN / 2 : BN);
   if (rc != SCB_OK) return rc;
   EpiParams ep;
+  ep.tail = tail ? *tail : SplitKTail{};
   ep.bias = reinterpret_cast<const __half*>(a->bias);
   ep.residual = reinterpret_cast<const __half*>(a->residual);
   ep.out = a->out;
@@ -559,11 +708,14 @@ int launch(const scb_linear_args* a, cudaStream_t st) {
   const int ov = ep.out_f32 ? 4 : 8;
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
-  auto kern = linear_tcgen05_kernel<BN, PAIR>;
+  auto kern = linear_tcgen05_kernel<BN, PAIR, TAIL>;
   SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);  // per instantiation
   const long long tm_sched = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
   const long long tiles = tm_sched * ((a->n + BN - 1) / BN) * a->batch;
   const int sms = scb_num_sms();
+  if (TAIL) SCB_REQUIRE(tiles <= sms, SCB_ERR_UNSUPPORTED,
+                        "scb_linear_splitk: %lld tiles need one resident CTA each, %d SMs (use scb_linear + scb_splitk_reduce)",
+                        tiles, sms);
   if (PAIR) {
     const int clusters = (int)(tiles < sms / 2 ? tiles : sms / 2);
     cudaLaunchConfig_t cfg = {};
@@ -629,4 +781,63 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
   // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two M tiles to pair up
   if (use_pair && a->m > BM) return launch<256, true>(a, st);
   return launch<256, false>(a, st);
+}
+
+// workspace of the fused tail in 4-byte words: tile tickets, row arrive / depart counters, per-(row, n tile) sums of squares
+// Fixed offsets, whatever (m, n) a call has: the counters must never share words with the sums of squares an earlier
+// call of another shape left behind (only the counters are guaranteed zero between calls).
+constexpr long long kTailCounters = 256;   // >= SM count: one tile per CTA, one CTA per SM
+static long long splitk_ws_words(long long m, long long n) {
+  const long long tm = (m + BM - 1) / BM, tn = (n + 127) / 128;
+  return 3 * kTailCounters + tm * BM * tn;
+}
+
+extern "C" int64_t scb_linear_splitk_workspace_bytes(int64_t m, int64_t n) {
+  return m >= 1 && n >= 1 ? 4 * splitk_ws_words(m, n) : 0;
+}
+
+extern "C" int scb_linear_splitk(const scb_linear_splitk_args* a, void* stream) {
+  SCB_REQUIRE(a != nullptr, SCB_ERR_INVALID_ARG, "scb_linear_splitk: args is NULL");
+  SCB_REQUIRE(a->m >= 1 && a->n >= 1 && a->k >= 1 && a->n_splits >= 1, SCB_ERR_INVALID_ARG,
+              "scb_linear_splitk: m=%lld n=%lld k=%lld n_splits=%d must be >= 1", (long long)a->m, (long long)a->n,
+              (long long)a->k, a->n_splits);
+  SCB_REQUIRE(a->a && a->w && a->partial && a->out && a->workspace, SCB_ERR_INVALID_ARG, "scb_linear_splitk: NULL buffer");
+  const long long ks = a->k / a->n_splits;
+  SCB_REQUIRE(ks * a->n_splits == a->k && ks % 8 == 0, SCB_ERR_INVALID_ARG,
+              "scb_linear_splitk: k=%lld cannot be cut into %d slices of a multiple of 8", (long long)a->k, a->n_splits);
+  SCB_REQUIRE(a->n % 4 == 0 && a->lda >= a->k && a->ldw >= a->k && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldo >= a->n &&
+                  a->ldo % 4 == 0 && (!a->residual || (a->ldr >= a->n && a->ldr % 4 == 0)) &&
+                  (!a->post_norm_out || (a->post_norm_gamma && a->post_norm_ld >= a->n && a->post_norm_ld % 4 == 0)),
+              SCB_ERR_INVALID_ARG, "scb_linear_splitk: n and the leading dimensions must keep rows 8-byte aligned");
+  SCB_REQUIRE((uintptr_t)a->a % 16 == 0 && (uintptr_t)a->w % 16 == 0 && (uintptr_t)a->partial % 16 == 0 &&
+                  (uintptr_t)a->out % 8 == 0 && (uintptr_t)a->workspace % 4 == 0,
+              SCB_ERR_INVALID_ARG, "scb_linear_splitk: misaligned buffer");
+  SCB_REQUIRE(a->workspace_bytes >= scb_linear_splitk_workspace_bytes(a->m, a->n), SCB_ERR_INVALID_ARG,
+              "scb_linear_splitk: workspace of %lld bytes, %lld needed", (long long)a->workspace_bytes,
+              (long long)scb_linear_splitk_workspace_bytes(a->m, a->n));
+  const long long tm = (a->m + BM - 1) / BM, tn = (a->n + 127) / 128;
+  scb_linear_args la = {};
+  la.a = a->a; la.w = a->w; la.out = a->partial;
+  la.m = a->m; la.n = a->n; la.k = ks;
+  la.lda = a->lda; la.ldw = a->ldw; la.ldo = a->n;
+  la.act = SCB_ACT_NONE; la.out_dtype = SCB_F32; la.batch = a->n_splits;
+  la.stride_a = ks; la.stride_w = ks; la.stride_o = a->m * a->n;
+  la.alpha = 1.f;
+  SplitKTail tk = {};
+  tk.out = reinterpret_cast<__half*>(a->out);
+  tk.bias = reinterpret_cast<const __half*>(a->bias);
+  tk.residual = reinterpret_cast<const __half*>(a->residual);
+  tk.gamma = reinterpret_cast<const __half*>(a->post_norm_gamma);
+  tk.pn_out = reinterpret_cast<__half*>(a->post_norm_out);
+  tk.ldo = a->ldo; tk.ldr = a->ldr; tk.pn_ld = a->post_norm_ld;
+  unsigned* ws = reinterpret_cast<unsigned*>(a->workspace);
+  SCB_REQUIRE(tm * tn * a->n_splits <= kTailCounters, SCB_ERR_UNSUPPORTED,
+              "scb_linear_splitk: %lld tiles, at most %lld (use scb_linear + scb_splitk_reduce)", tm * tn * a->n_splits,
+              kTailCounters);
+  tk.tile_tickets = ws;
+  tk.row_arrive = ws + kTailCounters;
+  tk.row_depart = ws + 2 * kTailCounters;
+  tk.ssq = reinterpret_cast<float*>(ws + 3 * kTailCounters);
+  tk.eps = a->post_norm_eps;
+  return launch<128, false, true>(&la, reinterpret_cast<cudaStream_t>(stream), &tk);
 }

@@ -367,19 +367,48 @@ def gather_rows_rmsnorm(table: torch.Tensor, ids: torch.Tensor, gamma: torch.Ten
           out.stride(0), _ptr(gamma), eps, _ptr(norm_out), norm_out.stride(0))
 
 
+def splitk_tail_workspace(rows: int, n: int, device: torch.device) -> torch.Tensor:
+    """Zeroed ticket / row-statistics buffer of the fused split-K linear (scb_linear_splitk leaves it zero, so one buffer
+    serves every launch of a stream-ordered chain with at most `rows` rows and `n` columns)."""
+    return torch.zeros(L.load().scb_linear_splitk_workspace_bytes(rows, n) // 4, dtype=torch.int32, device=device)
+
+
+def linear_splitk_fits_one_launch(rows: int, n: int, n_splits: int, device: torch.device) -> bool:
+    """One resident CTA per (n tile, K slice): the fused reduction needs every CTA of the launch on the GPU at once."""
+    return -(-rows // 128) * -(-n // 128) * n_splits <= torch.cuda.get_device_properties(device).multi_processor_count
+
+
 def linear_splitk(a: torch.Tensor, w: torch.Tensor, n_splits: int, partial: torch.Tensor, out: torch.Tensor,
                   bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                  post_norm: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> torch.Tensor:
+                  post_norm: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+                  tail_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = a @ w.T (+bias) (+residual) for few rows and a long K: the K range is cut into `n_splits`
     slices that run as a batched tcgen05 GEMM (one CTA wave streams every weight byte once, fp32 partials
-    in `partial` [n_splits, rows, N]), then one reduce launch sums them in order and applies the epilogue
-    (and optionally the RMSNorm of the finished rows)."""
+    in `partial` [n_splits, rows, N]).  With `tail_ws` (splitk_tail_workspace) and one CTA per tile the last CTA of each
+    n tile sums the slices in order and applies the epilogue — and the RMSNorm of the finished rows — inside the same
+    launch (scb_linear_splitk); otherwise a second launch does (scb_splitk_reduce)."""
     dev = _require_cuda(a, w, partial, out, bias, residual)
     rows, k = a.shape
     n = w.shape[0]
     ks = k // n_splits
     if ks * n_splits != k or ks % 8:
         raise ValueError(f"k={k} cannot be cut into {n_splits} slices of a multiple of 8")
+    if tail_ws is not None and linear_splitk_fits_one_launch(rows, n, n_splits, dev):
+        if partial.numel() < n_splits * rows * n or partial.dtype != torch.float32 or not partial.is_contiguous():
+            raise ValueError("linear_splitk: partial must be a contiguous fp32 buffer of n_splits*rows*n elements")
+        pg = po = None
+        pld, pe = 0, 0.0
+        if post_norm is not None:
+            pg, po, pe = post_norm
+            pld = po.stride(0)
+        args = L.LinearSplitKArgs(a=_ptr(a), w=_ptr(w), bias=_ptr(bias), residual=_ptr(residual), partial=_ptr(partial),
+                                  out=_ptr(out), post_norm_gamma=_ptr(pg), post_norm_out=_ptr(po), workspace=_ptr(tail_ws),
+                                  workspace_bytes=tail_ws.numel() * tail_ws.element_size(), m=rows, n=n, k=k,
+                                  lda=a.stride(0), ldw=w.stride(0), ldr=residual.stride(0) if residual is not None else 0,
+                                  ldo=out.stride(0), post_norm_ld=pld, n_splits=n_splits, post_norm_eps=pe)
+        with torch.cuda.device(dev):
+            L.check(L.load().scb_linear_splitk(C.byref(args), _stream(dev)), "scb_linear_splitk")
+        return out
     args = L.LinearArgs(a=_ptr(a), w=_ptr(w), bias=None, residual=None, out=_ptr(partial), m=rows, n=n, k=ks,
                         lda=a.stride(0), ldw=w.stride(0), ldr=0, ldo=partial.stride(1), act=L.ACT_NONE,
                         out_dtype=L.SCB_F32, batch=n_splits, stride_a=ks, stride_w=ks, stride_r=0,

@@ -102,6 +102,12 @@ class Qwen2Engine:
         # split-K partials of the wide-batch path: [splits <= 8, rows, widest N]
         n_max = max(qkv_dim, c.hidden_size)
         self._part = torch.zeros((8, B, n_max), dtype=torch.float32, device=self.device)
+        # SCB_SPLITK_FUSED=1: reduction + epilogue + RMSNorm inside the split-K GEMM launch (scb_linear_splitk) instead of
+        # a reduce launch behind it — measured SLOWER (25 rows 5.40 -> 5.96 ms, 7 rows 4.69 -> 4.78 ms per step: the tail's
+        # ticket / partial / row-counter round trips run while the weight stream keeps L2 busy, the separate reduce
+        # kernel runs with programmatic dependent launch in a quiet memory system), so it stays opt-in
+        self._tail_ws = (ops.splitk_tail_workspace(B, n_max, self.device)
+                         if os.environ.get("SCB_SPLITK_FUSED", "0") == "1" else None)
         self._down_splits = next((s_ for s_ in (4, 8, 2, 1) if c.intermediate_size % (8 * s_) == 0), 1)
         self._qkv = torch.zeros((B, qkv_dim), dtype=torch.float16, device=self.device)
         self._attn = torch.zeros((B, c.num_attention_heads, hd), dtype=torch.float16, device=self.device)
@@ -241,7 +247,7 @@ class Qwen2Engine:
             if wide:
                 # wide batches: the A-fragment reads of the streaming GEMV (R x K per 8 weight rows) outgrow
                 # L1, so every layer runs on the tcgen05 GEMM — split over K where N alone gives too few tiles
-                ops.linear_splitk(nrm, ly["qkv_w"], 4, self._part, self._qkv[:R], bias=ly["qkv_b"])
+                ops.linear_splitk(nrm, ly["qkv_w"], 4, self._part, self._qkv[:R], bias=ly["qkv_b"], tail_ws=self._tail_ws)
             else:
                 ops.gemv(nrm, ly["qkv_w"], bias=ly["qkv_b"], out=self._qkv[:R])
             ops.decode_attention_fused(self._qkv[:R], self.inv_freq, c.rope_theta, self.k_cache[i], self.v_cache[i],
@@ -249,10 +255,11 @@ class Qwen2Engine:
                                        out=self._attn[:R], prefetch=None if wide else ly["o_w"], ctx_cap=cap)
             attn2d = self._attn[:R].view(R, Hq * hd)
             if wide:
-                ops.linear_splitk(attn2d, ly["o_w"], 4, self._part, x2, residual=x, post_norm=(ly["ln2"], nrm, eps))
+                ops.linear_splitk(attn2d, ly["o_w"], 4, self._part, x2, residual=x, post_norm=(ly["ln2"], nrm, eps),
+                                  tail_ws=self._tail_ws)
                 ops.linear(nrm, ly["gu_w"], act=L.ACT_SILU_PAIR, out=self._gu[:R])
                 ops.linear_splitk(self._gu[:R], ly["down_w"], self._down_splits, self._part, x, residual=x2,
-                                  post_norm=(nxt_gamma, nrm, eps))
+                                  post_norm=(nxt_gamma, nrm, eps), tail_ws=self._tail_ws)
             else:
                 ops.gemv(attn2d, ly["o_w"], residual=x, out=x2, post_norm=(ly["ln2"], nrm, eps), prefetch=ly["gu_w"])
                 ops.gemv(nrm, ly["gu_w"], epilogue=L.EPI_SILU_PAIR, out=self._gu[:R], prefetch=ly["down_w"])

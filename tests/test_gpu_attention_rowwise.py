@@ -391,3 +391,82 @@ def test_linear_splitk_matches_gemv(cuda, rows, n, k, splits):
     assert ((nrm.float() - ref_n).abs() <= 2e-3 * (ref_n.abs() + 1e-3)).all()
     ref_v = ops.gemv(a, w, bias=bias, residual=res)
     assert (out.float() - ref_v.float()).abs().max().item() <= 2e-3 * (ref.abs().max().item() + 1)
+
+
+@pytest.mark.parametrize("rows,n,k,splits,with_norm", [(25, 3584, 18944, 4, True), (25, 4608, 3584, 4, False),
+                                                       (7, 3584, 3584, 4, True), (3, 256, 512, 2, True),
+                                                       (128, 3584, 3584, 4, True), (25, 200, 512, 2, True)])
+def test_linear_splitk_fused_tail(cuda, rows, n, k, splits, with_norm):
+    """scb_linear_splitk (reduction + epilogue + RMSNorm inside the GEMM launch) against the two-launch path: the
+    finished rows are BIT-identical (same slices summed in the same order), the normalised rows agree to the ordering
+    of the sum of squares (1 fp16 ulp); the ticket workspace comes back zero, so repeated calls on one buffer — the
+    qkv / o / down chain of a decode step, different N each — keep working."""
+    from streamchat_b200 import ops
+    torch.manual_seed(rows + n + 1)
+    a = torch.randn(rows, k, device=cuda).half()
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()
+    res = torch.randn(rows, n, device=cuda).half()
+    bias = torch.randn(n, device=cuda).half()
+    gamma = (1 + 0.1 * torch.randn(n, device=cuda)).half()
+    part = torch.zeros(8, 128, max(n, 4608), device=cuda, dtype=torch.float32)
+    ws = ops.splitk_tail_workspace(128, 4608, cuda)
+    assert ops.linear_splitk_fits_one_launch(rows, n, splits, cuda)
+    pn = lambda t: (gamma, t, 1e-6) if with_norm else None
+    out0, nrm0 = torch.zeros(rows, n, device=cuda, dtype=torch.float16), torch.zeros(rows, n, device=cuda, dtype=torch.float16)
+    ops.linear_splitk(a, w, splits, part, out0, bias=bias, residual=res, post_norm=pn(nrm0))
+    for rep in range(3):
+        out1, nrm1 = torch.full_like(out0, 7.0), torch.full_like(out0, 7.0)
+        part.fill_(float("nan"))
+        ops.linear_splitk(a, w, splits, part, out1, bias=bias, residual=res, post_norm=pn(nrm1), tail_ws=ws)
+        assert torch.equal(out1, out0), f"rep {rep}"
+        if with_norm:
+            assert torch.equal(nrm1, ops.rmsnorm(out1, gamma, 1e-6)) or \
+                ((nrm1.float() - nrm0.float()).abs() <= 2e-3 * (nrm0.float().abs() + 1e-3)).all()
+        assert int(ws[:768].abs().sum().item()) == 0, "tickets must be left zero"
+    # no residual / no bias
+    out2 = torch.zeros_like(out0)
+    ops.linear_splitk(a, w, splits, part, out2, tail_ws=ws)
+    ref = (a.double() @ w.double().t()).cpu()
+    assert ((out2.double().cpu() - ref).abs() <= 2e-3 * (ref.abs() + 1)).all()
+
+
+def test_linear_splitk_too_many_tiles_takes_two_launches(cuda):
+    """More (n tile, K slice) pairs than SMs: the wrapper runs GEMM + reduce (the fused tail needs every CTA resident)."""
+    from streamchat_b200 import ops
+    torch.manual_seed(5)
+    rows, n, k, splits = 4, 4608, 1024, 8
+    assert not ops.linear_splitk_fits_one_launch(rows, n, splits, cuda)
+    a = torch.randn(rows, k, device=cuda).half()
+    w = (torch.randn(n, k, device=cuda) * 0.02).half()
+    part = torch.zeros(8, 16, n, device=cuda, dtype=torch.float32)
+    ws = ops.splitk_tail_workspace(16, n, cuda)
+    out = torch.zeros(rows, n, device=cuda, dtype=torch.float16)
+    ops.linear_splitk(a, w, splits, part, out, tail_ws=ws)
+    ref = (a.double() @ w.double().t()).cpu()
+    assert ((out.double().cpu() - ref).abs() <= 2e-3 * (ref.abs() + 1)).all()
+
+
+def test_linear_splitk_fused_shapes_share_one_workspace(cuda):
+    """qkv (N = 4608) -> o (N = 3584, post-norm) -> down (K = 18944, post-norm) on ONE ticket buffer, twice over, as
+    in a decode step: the sums of squares one shape leaves behind must not be read as another shape's tickets."""
+    from streamchat_b200 import ops
+    torch.manual_seed(11)
+    rows = 25
+    shapes = [(4608, 3584, False), (3584, 3584, True), (3584, 18944, True)]
+    ws = ops.splitk_tail_workspace(32, 4608, cuda)
+    part = torch.zeros(8, 32, 4608, device=cuda, dtype=torch.float32)
+    data = []
+    for n, k, norm in shapes:
+        a = torch.randn(rows, k, device=cuda).half()
+        w = (torch.randn(n, k, device=cuda) * 0.02).half()
+        gamma = (1 + 0.1 * torch.randn(n, device=cuda)).half()
+        ref, ref_n = torch.zeros(rows, n, device=cuda, dtype=torch.float16), torch.zeros(rows, n, device=cuda, dtype=torch.float16)
+        ops.linear_splitk(a, w, 4, part, ref, post_norm=(gamma, ref_n, 1e-6) if norm else None)
+        data.append((a, w, gamma, norm, ref, ref_n))
+    for rep in range(2):
+        for a, w, gamma, norm, ref, ref_n in data:
+            out, nrm = torch.zeros_like(ref), torch.zeros_like(ref)
+            ops.linear_splitk(a, w, 4, part, out, post_norm=(gamma, nrm, 1e-6) if norm else None, tail_ws=ws)
+            assert torch.equal(out, ref), (rep, tuple(w.shape))
+            if norm:
+                assert ((nrm.float() - ref_n.float()).abs() <= 2e-3 * (ref_n.float().abs() + 1e-3)).all()

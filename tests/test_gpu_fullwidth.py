@@ -150,6 +150,26 @@ def test_qwen2_7b_width_25_row_splitk_chain_vs_oracle(cuda, qwen7b_2layers):
     assert n_div <= 5, n_div        # ties below fp16 resolution are rare events, not the norm
 
 
+def test_fused_splitk_chain_gives_the_same_ids_at_7b_width(cuda, qwen7b_2layers):
+    """Opt-in scb_linear_splitk (reduction inside the GEMM launch) under the 25-row chain: the finished rows are
+    bit-identical to the two-launch path, the normalised rows differ at most in the order of the sum of squares —
+    same greedy ids on every row."""
+    from streamchat_b200 import ops
+    lcfg, W, Wc, eng = qwen7b_2layers
+    xs = [_prompt(Wc, 16, 24 + 2 * i, 100 + i).to(cuda) for i in range(25)]
+    base = eng.generate_batch(xs, 6)
+    assert eng._tail_ws is None
+    eng._tail_ws = ops.splitk_tail_workspace(eng.max_batch, eng._part.shape[2], cuda)
+    eng._graphs.clear()
+    try:
+        fused = eng.generate_batch(xs, 6)
+    finally:
+        eng._tail_ws = None
+        eng._graphs.clear()
+    same = sum(a[0].tolist() == b[0].tolist() for a, b in zip(base, fused))
+    assert same >= 24, same      # a 1-ulp difference of a normalised value may flip a sub-resolution tie
+
+
 def test_native_prefill_equals_per_launch_prefill_at_7b_width(cuda, qwen7b_2layers, monkeypatch):
     """scb_qwen2_prefill (one native call) and the per-launch Python prefill issue the same kernels: bit-identical
     logits and KV rows at full width, including a continuation (pos0 > 0)."""

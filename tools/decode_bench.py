@@ -20,7 +20,7 @@ eng = Qwen2Engine(W, cfg.llm, dev, max_ctx=8192, max_batch=max(Rs))
 del W
 x = (torch.randn(ctx, cfg.llm.hidden_size, device=dev) * 0.02).half()
 for R in Rs:
-    for use_graph in (True, False):
+    for use_graph in ((True,) if os.environ.get("DECODE_BENCH_GRAPH_ONLY") else (True, False)):
         steps = 64
         eng.generate_batch([x] * R, 4, use_graph=use_graph)     # warm-up / capture
         torch.cuda.synchronize()

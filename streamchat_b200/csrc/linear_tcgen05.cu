@@ -27,15 +27,22 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quadrant)
 
-template <int BN, bool CG2 = false>
+constexpr int kStoreBoxBytes = 32 * 64 * 2;
+
+// STAGED: fp16 rows leave through shared-memory boxes + TMA stores (one ring stage is traded for the staging buffers);
+// otherwise (fp32 split-K partials, SiLU-pair outputs) every thread stores its own row pieces and the ring keeps 6 stages.
+template <int BN, bool CG2 = false, bool STAGED = false>
 struct Cfg {
   // CG2 (CTA pair, cta_group::2 MMA): a CTA stages only ITS half of the W tile -> 32 KB per stage, 6 stages
-  static constexpr int kStages = CG2 ? 6 : ((BN == 256) ? 4 : 6);
+  static constexpr int kStages = (BN == 256 && !CG2) ? 4 : (STAGED ? 5 : 6);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (CG2 ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // output staging: every epilogue warp owns kStoreBufs boxes of 32 rows x 64 columns fp16 (4 KB, 128-byte swizzle)
+  static constexpr int kStoreBufs = (BN == 256 && !CG2) ? 1 : 2;
+  static constexpr int kStoreBytes = STAGED ? 8 * kStoreBufs * kStoreBoxBytes : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // Split-K with the reduction fused into the GEMM (TAIL instantiation; decode steps of wide batches).  Every CTA owns
@@ -169,6 +176,18 @@ SCB_DEVICE void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+SCB_DEVICE void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+SCB_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+SCB_DEVICE void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+SCB_DEVICE void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 SCB_DEVICE void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
 SCB_DEVICE unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -176,18 +195,20 @@ SCB_DEVICE unsigned ld_acquire_gpu(const unsigned* p) {
   return v;
 }
 
-template <int BN, bool PAIR, bool TAIL = false>
+template <int BN, bool PAIR, bool TAIL = false, bool STAGED = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
-                      const __grid_constant__ CUtensorMap map_w, const EpiParams ep) {
-  using C = Cfg<BN, PAIR>;
+                      const __grid_constant__ CUtensorMap map_w,
+                      const __grid_constant__ CUtensorMap map_o, const EpiParams ep) {
+  using C = Cfg<BN, PAIR, STAGED>;
   extern __shared__ uint8_t smem_raw[];
   // 128-byte swizzle atoms need 1024-byte aligned tile bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_o = smem + C::kStages * C::kStageBytes;      // [8 warps][kStoreBufs][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + C::kStoreBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + C::kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]
@@ -210,6 +231,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
+    if (STAGED) tma_prefetch_desc(&map_o);
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -320,6 +342,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     // 94 % for K = 4096).
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int chalf = (warp - 2) >> 2;  // column half of the tile this warp drains
+    int n_box = 0;                      // staging boxes this warp has handed to TMA stores
     int as = 0;
     uint32_t aphase = 0;
     for (long long t = t_first; t < n_tiles; t += t_step) {
@@ -328,10 +351,22 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       int tm, tn;
       tile_coords(r, tiles_m, tiles_n, ep.gm, tm, tn);
       if (PAIR) tm = 2 * tm + crank;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
       const long long row = (long long)tm * BM + quad * 32 + lane;
       const bool row_ok = row < ep.m;
+      // Residual rows are fetched one 32-column chunk AHEAD (the first one before the accumulator is even complete):
+      // loaded where they are used, each chunk exposed a full L2 round trip inside the tile's epilogue chain and the
+      // residual GEMMs of the CLIP tower (out_proj, fc2) were epilogue-bound by it.
+      const bool res_ahead = ep.residual != nullptr && ep.res_vec && row_ok;
+      const __half* res_row = ep.residual ? ep.residual + (long long)b * ep.stride_r + row * ep.ldr + (long long)tn * BN : nullptr;
+      uint4 rcur[4], rnxt[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rcur[q] = rnxt[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (res_ahead && (long long)tn * BN + chalf * (BN / 2) + 32 <= ep.n) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rcur[q] = *reinterpret_cast<const uint4*>(res_row + chalf * (BN / 2) + q * 8);
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
@@ -339,8 +374,17 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         if (col0 >= ep.n) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        if (res_ahead && c0 + 32 < (chalf + 1) * (BN / 2) && col0 + 64 <= ep.n) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rnxt[q] = *reinterpret_cast<const uint4*>(res_row + c0 + 32 + q * 8);
+        }
+        if (STAGED && (c0 & 32) == 0) {
+          // first half of a 64-column box: its staging buffer must have been read by the store issued kStoreBufs boxes ago
+          if (n_box >= C::kStoreBufs && lane == 0) bulk_wait_group_read<C::kStoreBufs - 1>();
+          __syncwarp();
+        }
         tmem_ld_wait();
-        if (row_ok) {
+        if (row_ok || STAGED) {
           const bool full_chunk = col0 + 32 <= ep.n;
           float f[32];
 #pragma unroll
@@ -375,12 +419,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
           }
-          if (ep.residual) {
+          if (ep.residual && row_ok) {
             const __half* rp = ep.residual + (long long)b * ep.stride_r + row * ep.ldr + col0;
             if (full_chunk && ep.res_vec) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
+                const uint4 rv = rcur[q];
                 float2 r0 = h2_to_f2(rv.x), r1 = h2_to_f2(rv.y), r2 = h2_to_f2(rv.z),
                        r3 = h2_to_f2(rv.w);
                 f[q * 8 + 0] += r0.x; f[q * 8 + 1] += r0.y; f[q * 8 + 2] += r1.x;
@@ -433,6 +477,22 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < ep.n) op[j] = f[j];
             }
+          } else if (STAGED) {
+            // fp16 row piece (64 B) into the warp's staging box [32 rows][128 B], 16-byte chunks XOR-swizzled by the
+            // row (the layout SWIZZLE_128B tensor maps expect; conflict-free for a warp storing one chunk per row).
+            // Per-thread global stores of 16 B at a row stride of 2-8 KB made the stores the bottleneck of every
+            // K = 1024 GEMM of the CLIP tower (qkv 302 us with, 234 us without them).
+            uint8_t* box = smem_o + ((warp - 2) * C::kStoreBufs + (n_box % C::kStoreBufs)) * kStoreBoxBytes + lane * 128;
+            const int ch0 = (c0 & 32) >> 3;      // first 16-byte chunk of this half inside the 128-byte row
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = f2_to_h2(f[q * 8 + 0], f[q * 8 + 1]);
+              o.y = f2_to_h2(f[q * 8 + 2], f[q * 8 + 3]);
+              o.z = f2_to_h2(f[q * 8 + 4], f[q * 8 + 5]);
+              o.w = f2_to_h2(f[q * 8 + 6], f[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(box + (((ch0 + q) ^ (lane & 7)) << 4)) = o;
+            }
           } else {
             __half* op = reinterpret_cast<__half*>(ep.out) + (long long)b * ep.stride_o +
                          row * ep.ldo + col0;
@@ -452,6 +512,20 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                 if (col0 + j < ep.n) op[j] = __float2half_rn(f[j]);
             }
           }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rcur[q] = rnxt[q];
+        if (STAGED && ((c0 & 32) != 0 || col0 + 32 >= ep.n)) {
+          // box complete (or the row ends inside it): one TMA store of 32 rows x 64 columns; rows >= m and columns
+          // >= n are clipped by the tensor map
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o, smem_o + ((warp - 2) * C::kStoreBufs + (n_box % C::kStoreBufs)) * kStoreBoxBytes,
+                         (int)((long long)tn * BN + (c0 & ~63)), (int)((long long)tm * BM + quad * 32), b);
+            bulk_commit_group();
+          }
+          ++n_box;
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above): release the stage
@@ -588,6 +662,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   }
 
+  if (STAGED && warp >= 2 && lane == 0) bulk_wait_group<0>();   // staged rows are written before the CTA retires
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / read it
@@ -675,14 +750,28 @@ int make_map(CUtensorMap* out, const void* ptr, long long rows, long long k, lon
   return SCB_OK;
 }
 
-template <int BN, bool PAIR, bool TAIL = false>
+// fp16 outputs with 16-byte aligned rows leave through shared memory and TMA box stores (SCB_LINEAR_TMA_STORE=0: every
+// thread stores its own row pieces)
+bool staged_store(const scb_linear_args* a) {
+  static const int use_tma_store = [] { const char* e = getenv("SCB_LINEAR_TMA_STORE"); return e ? atoi(e) : 1; }();
+  return use_tma_store && a->out_dtype == SCB_F16 && a->act != SCB_ACT_SILU_PAIR && a->ldo % 8 == 0 &&
+         (a->batch == 1 || a->stride_o % 8 == 0);
+}
+
+template <int BN, bool PAIR, bool TAIL = false, bool STAGED = false>
 int launch(const scb_linear_args* a, cudaStream_t st, const SplitKTail* tail = nullptr) {
-  using C = Cfg<BN, PAIR>;
+  using C = Cfg<BN, PAIR, STAGED>;
   CUtensorMap ma, mw;
   int rc = make_map(&ma, a->a, a->m, a->k, a->lda, a->stride_a, a->batch, BM);
   if (rc != SCB_OK) return rc;
   rc = make_map(&mw, a->w, a->n, a->k, a->ldw, a->stride_w, a->batch, PAIR ? BN / 2 : BN);
   if (rc != SCB_OK) return rc;
+  constexpr bool tma_store = STAGED;
+  CUtensorMap mo = ma;
+  if (tma_store) {
+    rc = make_map(&mo, a->out, a->m, a->n, a->ldo, a->stride_o, a->batch, 32);
+    if (rc != SCB_OK) return rc;
+  }
   EpiParams ep;
   ep.tail = tail ? *tail : SplitKTail{};
   ep.bias = reinterpret_cast<const __half*>(a->bias);
@@ -708,7 +797,7 @@ int launch(const scb_linear_args* a, cudaStream_t st, const SplitKTail* tail = n
   const int ov = ep.out_f32 ? 4 : 8;
   ep.out_vec = (a->ldo % ov == 0) && (a->batch == 1 || a->stride_o % ov == 0);
   ep.res_vec = (a->ldr % 8 == 0) && (a->batch == 1 || a->stride_r % 8 == 0);
-  auto kern = linear_tcgen05_kernel<BN, PAIR, TAIL>;
+  auto kern = linear_tcgen05_kernel<BN, PAIR, TAIL, STAGED>;
   SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);  // per instantiation
   const long long tm_sched = PAIR ? (((a->m + BM - 1) / BM) + 1) / 2 : (a->m + BM - 1) / BM;
   const long long tiles = tm_sched * ((a->n + BN - 1) / BN) * a->batch;
@@ -732,10 +821,10 @@ int launch(const scb_linear_args* a, cudaStream_t st, const SplitKTail* tail = n
     at[1].val.programmaticStreamSerializationAllowed = scb_pdl_enabled() ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mw, ep));
+    SCB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, ep));
   } else {
     const int grid = (int)(tiles < sms ? tiles : sms);
-    SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(kGemmThreads), C::kSmemBytes, st, ma, mw, ep));
+    SCB_CUDA_OK(scb_launch_pdl(kern, dim3(grid), dim3(kGemmThreads), C::kSmemBytes, st, ma, mw, mo, ep));
   }
   SCB_LAUNCH_OK("linear_tcgen05_kernel");
   return SCB_OK;
@@ -776,11 +865,12 @@ extern "C" int scb_linear(const scb_linear_args* a, void* stream) {
   const long long tiles256 = ((a->m + BM - 1) / BM) * ((a->n + 255) / 256) * a->batch;
   static const int force_bn = [] { const char* e = getenv("SCB_LINEAR_BN"); return e ? atoi(e) : 0; }();   // tuning aid
   static const int use_pair = [] { const char* e = getenv("SCB_LINEAR_PAIR"); return e ? atoi(e) : 1; }();   // 0: single-CTA tiles only
-  if (force_bn == 128) return launch<128, false>(a, st);
-  if (a->n <= 128 || (tiles256 < scb_num_sms() && force_bn != 256)) return launch<128, false>(a, st);
+  const bool staged = staged_store(a);
+  if (force_bn == 128 || a->n <= 128 || (tiles256 < scb_num_sms() && force_bn != 256))
+    return staged ? launch<128, false, false, true>(a, st) : launch<128, false>(a, st);
   // CTA pairs (cta_group::2, UMMA M = 256) whenever there are at least two M tiles to pair up
-  if (use_pair && a->m > BM) return launch<256, true>(a, st);
-  return launch<256, false>(a, st);
+  if (use_pair && a->m > BM) return staged ? launch<256, true, false, true>(a, st) : launch<256, true>(a, st);
+  return staged ? launch<256, false, false, true>(a, st) : launch<256, false>(a, st);
 }
 
 // workspace of the fused tail in 4-byte words: tile tickets, row arrive / depart counters, per-(row, n tile) sums of squares

@@ -150,8 +150,10 @@ norm_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restri
 // registers (<= 8 x 16 B each), statistics by shuffles only — no block barriers, 4x fewer blocks.
 constexpr int kWarpNormMaxChunks = 8;
 
-template <int KIND>
-__global__ void __launch_bounds__(256)
+// CHUNKS = 16-byte pieces of the row per lane: 4 for D <= 1024 (the CLIP width: half the registers, twice the resident
+// warps — the kernel is bound by bytes in flight per SM), 8 up to 2048.
+template <int KIND, int CHUNKS = kWarpNormMaxChunks>
+__global__ void __launch_bounds__(256, CHUNKS <= 4 ? 4 : 2)
 norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __restrict__ gamma,
                  const __half* __restrict__ beta, float eps, int D, long long rows,
                  __half* __restrict__ out, long long ld_out, const __half* __restrict__ cls,
@@ -160,7 +162,7 @@ norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __r
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = D >> 3;
-  float v[kWarpNormMaxChunks][8];
+  float v[CHUNKS][8];
   const __half* src;
   const __half* posrow = nullptr;
   if constexpr (KIND == 2) {
@@ -172,7 +174,7 @@ norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __r
   }
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < kWarpNormMaxChunks; ++c) {
+  for (int c = 0; c < CHUNKS; ++c) {
     const int i = c * 32 + lane;
     if (i < nvec) {
       unpack8(*reinterpret_cast<const uint4*>(src + i * 8), v[c]);
@@ -194,7 +196,7 @@ norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __r
     mean = s / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < kWarpNormMaxChunks; ++c) {
+    for (int c = 0; c < CHUNKS; ++c) {
       const int i = c * 32 + lane;
       if (i < nvec) {
 #pragma unroll
@@ -208,7 +210,7 @@ norm_warp_kernel(const __half* __restrict__ x, long long ld_x, const __half* __r
     rstd = rsqrtf(q / (float)D + eps);
   }
 #pragma unroll
-  for (int c = 0; c < kWarpNormMaxChunks; ++c) {
+  for (int c = 0; c < CHUNKS; ++c) {
     const int i = c * 32 + lane;
     if (i < nvec) {
       float g[8], o[8];
@@ -759,13 +761,17 @@ static int norm_common(int kind, const void* x, int64_t ld_x, const void* gamma,
     const unsigned blocks = (unsigned)((rows + 7) / 8);
     const __half* c16 = reinterpret_cast<const __half*>(cls);
     const __half* p16 = reinterpret_cast<const __half*>(pos);
-    if (kind == 0)
-      norm_warp_kernel<0><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
-    else if (kind == 1)
-      norm_warp_kernel<1><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
-    else
-      norm_warp_kernel<2><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, c16, p16,
-                                                  tokens_per_img);
+    const bool narrow = dim <= 32 * 8 * 4;
+    if (kind == 0) {
+      if (narrow) norm_warp_kernel<0, 4><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
+      else norm_warp_kernel<0><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
+    } else if (kind == 1) {
+      if (narrow) norm_warp_kernel<1, 4><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
+      else norm_warp_kernel<1><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, nullptr, nullptr, 0);
+    } else {
+      if (narrow) norm_warp_kernel<2, 4><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, c16, p16, tokens_per_img);
+      else norm_warp_kernel<2><<<blocks, 256, 0, st>>>(xh, ld_x, g, b, eps, dim, rows, o, ld_out, c16, p16, tokens_per_img);
+    }
     SCB_LAUNCH_OK("norm_warp_kernel");
     return SCB_OK;
   }

@@ -106,3 +106,37 @@ def test_linear_linearity_full_size(cuda):
     y2 = ops.linear(a2, w, out_dtype=torch.float32)
     y12 = ops.linear((a1.float() + a2.float()).half(), w, out_dtype=torch.float32)
     assert (y12 - (y1 + y2)).abs().max().item() < 2e-2
+
+
+def test_linear_fp16_rows_through_staged_box_stores(cuda):
+    """fp16 outputs leave through shared memory + TMA box stores (32 rows x 64 columns) when their rows are 16-byte
+    aligned: ragged m / n (clipped boxes), a row pitch wider than n (column slice of a bigger buffer: the neighbours
+    must stay untouched), batched outputs, and the per-thread store path for an unaligned pitch."""
+    from streamchat_b200 import ops
+    torch.manual_seed(21)
+    for m, n, k in [(33, 40, 64), (257, 72, 128), (600, 1000, 320), (95, 264, 64)]:
+        a = torch.randn(m, k).half().to(cuda)
+        w = (torch.randn(n, k) * 0.1).half().to(cuda)
+        bias = torch.randn(n).half().to(cuda)
+        res = torch.randn(m, n).half().to(cuda)
+        big = torch.full((m + 3, n + 24), 7.0, dtype=torch.float16, device=cuda)
+        view = big[1:m + 1, 8:8 + n]                       # pitch n + 24 (multiple of 8), 16-byte aligned start
+        ops.linear(a, w, bias=bias, residual=res, act=1, out=view)
+        _check(view, _ref(a.cpu(), w.cpu(), bias.cpu(), res.cpu(), 1), tol=3e-3)
+        untouched = big.clone()
+        untouched[1:m + 1, 8:8 + n] = 7.0
+        assert bool((untouched == 7.0).all()), "a box store wrote outside the output view"
+    # batched fp16 output
+    b, m, n, k = 3, 100, 160, 64
+    q = torch.randn(b, m, k).half().to(cuda)
+    kk = torch.randn(b, n, k).half().to(cuda)
+    out = ops.linear(q, kk, alpha=0.125)
+    assert out.dtype == torch.float16
+    _check(out, _ref(q.cpu(), kk.cpu(), alpha=0.125))
+    # pitch not a multiple of 8 elements: rows are not 16-byte aligned, every thread stores its own row pieces
+    m, n, k = 70, 100, 64
+    a = torch.randn(m, k).half().to(cuda)
+    w = (torch.randn(n, k) * 0.1).half().to(cuda)
+    out = ops.linear(a, w)
+    assert out.stride(0) == 100
+    _check(out, _ref(a.cpu(), w.cpu()))

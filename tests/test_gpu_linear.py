@@ -140,3 +140,24 @@ def test_linear_fp16_rows_through_staged_box_stores(cuda):
     out = ops.linear(a, w)
     assert out.stride(0) == 100
     _check(out, _ref(a.cpu(), w.cpu()))
+
+
+def test_linear_prefill_shapes_against_fp32_matmul(cuda):
+    """o_proj / down_proj of a 5 816-token caption prefill (CTA-pair tiles, staged box stores, ragged m = 45.4 x 128,
+    a partial last wave) against an fp32 matmul of the same fp16 operands, bias and residual included."""
+    from streamchat_b200 import ops
+    torch.manual_seed(31)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for m, n, k in [(5816, 3584, 3584), (5816, 3584, 18944)]:
+            a = (torch.randn(m, k, device=cuda) * 0.5).half()
+            w = (torch.randn(n, k, device=cuda) * 0.02).half()
+            bias = torch.randn(n, device=cuda).half()
+            res = torch.randn(m, n, device=cuda).half()
+            out = ops.linear(a, w, bias=bias, residual=res)
+            ref = a.float() @ w.float().t() + bias.float() + res.float()
+            err = (out.float() - ref).abs()
+            assert bool((err <= 2e-3 * (ref.abs() + 1.0)).all()), float(err.max())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev

@@ -57,6 +57,17 @@ SCB_DEVICE float ex2_approx(float x) {
   return y;
 }
 
+// A operand from tensor memory (rows = lanes, two fp16 along K per 32-bit column), B from shared memory
+SCB_DEVICE void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 struct AttnParams {
   __half* out;
   long long o_stride_b, o_stride_t, o_stride_h;
@@ -72,27 +83,33 @@ constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ?
 // D = 128).  1: S + O fit 256 columns and the tiles 112 KB, so TWO CTAs share an SM and fill each other's
 // softmax / MMA gaps with 8 softmax warps per SM instead of 4 (D = 64: the CLIP tower, where the 4-warp
 // softmax of a lone CTA left the tensor pipe idle 85 % of the time).
-template <int D, int kBKV, int NSB, int KS>
+// PT: P stays in tensor memory — the softmax thread of a row writes fp16 P over the first half of the S columns it
+// has just read (tcgen05.st) and P·V takes its A operand from there.  The S buffers alternate by block, so P_{j+1} is
+// written while P·V_j still reads P_j: the shared-memory P tile was single-buffered, which put every P·V into the
+// per-block dependency chain (switching the whole softmax arithmetic off shortened the kernel by only 8 %).
+template <int D, int kBKV, int NSB, int KS, bool PT = false>
 struct ACfg {
   static constexpr int kSub = D / 64;                  // 64-column sub-tiles per row
   static constexpr int kQBytes = kBQ * D * 2;
   static constexpr int kKBytes = kBKV * D * 2;
-  static constexpr int kPBytes = kBQ * kBKV * 2;
+  static constexpr int kPBytes = PT ? 0 : kBQ * kBKV * 2;
+  static_assert(!PT || KS == 1, "P in tensor memory: one thread per row");
   static constexpr int kThreads = (2 + 4 * KS) * 32;   // TMA warp, MMA warp, 4*KS softmax warps
   static constexpr int kXBytes = KS == 2 ? 3 * 2 * kBQ * 4 : 0;   // max (x2 parities) / sum exchange between the halves of a row
   static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kKBytes + kPBytes + 192 + kXBytes;
   //   S buffers: [sb*kBKV, (sb+1)*kBKV)   O_j: [NSB*kBKV, NSB*kBKV + D)
   static constexpr int kOCol = NSB * kBKV;
   static constexpr int kTmemCols = pow2_cols(NSB * kBKV + D);
-  static constexpr int kMinBlocks = (kTmemCols <= 256 && 2 * (kSmemBytes + 1024) <= 228 * 1024) ? 2 : 1;
+  static constexpr int kBySmem = (228 * 1024) / (kSmemBytes + 1024), kByTmem = 512 / kTmemCols;
+  static constexpr int kMinBlocks = kBySmem < kByTmem ? (kBySmem < 3 ? kBySmem : 3) : (kByTmem < 3 ? kByTmem : 3);
 };
 
-template <int D, int kBKV, int NSB, int KS>
-__global__ void __launch_bounds__((ACfg<D, kBKV, NSB, KS>::kThreads), (ACfg<D, kBKV, NSB, KS>::kMinBlocks))
+template <int D, int kBKV, int NSB, int KS, bool PT>
+__global__ void __launch_bounds__((ACfg<D, kBKV, NSB, KS, PT>::kThreads), (ACfg<D, kBKV, NSB, KS, PT>::kMinBlocks))
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
                          const __grid_constant__ CUtensorMap map_k,
                          const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
-  using C = ACfg<D, kBKV, NSB, KS>;
+  using C = ACfg<D, kBKV, NSB, KS, PT>;
   // 128-byte swizzle atoms need 1024-byte aligned tiles; there is no static shared memory in this
   // kernel, so the dynamic window starts aligned (checked below — two CTAs per SM leave no slack).
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -210,11 +227,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kBKV / 16; ++kk) {
-          const uint64_t da =
-              umma_desc_k_sw128(smem_u32(sp + (kk / 4) * (kBQ * 128))) + (uint64_t)((kk % 4) * 2);
           const uint64_t db = umma_desc_mn_sw128(smem_u32(sv + st * C::kKBytes + kk * 2048),
                                                  (uint32_t)(kBKV * 128));
-          umma_f16_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);   // O accumulates over the blocks
+          if (PT) {
+            // P_j lives in the columns of S_j: 16 keys = 8 columns per MMA
+            umma_f16_ts(tmem_o, tmem_s + (uint32_t)((j % NSB) * kBKV + kk * 8), db, idesc_o, (j | kk) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da =
+                umma_desc_k_sw128(smem_u32(sp + (kk / 4) * (kBQ * 128))) + (uint64_t)((kk % 4) * 2);
+            umma_f16_ss(tmem_o, da, db, idesc_o, (j | kk) != 0 ? 1u : 0u);   // O accumulates over the blocks
+          }
         }
         umma_commit(&v_empty[st]);
         umma_commit(o_full);
@@ -293,12 +315,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       }
       // P·V_{j-1} must have finished READING the P tile before block j overwrites it (this also observes every
       // phase of o_full in order — an mbarrier parity wait is only sound one phase behind)
-      if (j > 0 && !o_seen) mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+      // (PT: nothing to wait for — P_j goes to the other S buffer; o_full can be at most one phase ahead of a thread
+      // that has not yet delivered P_j, so the rescale and the final wait above / below stay sound without it)
+      if (!PT && j > 0 && !o_seen) mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
       // ---- P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
       unsigned long long sc2, mb2, l2 = 0ull;
       asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(p.scale_log2));
       asm("mov.b64 %0, {%1, %1};" : "=l"(mb2) : "f"(-mb));
+      uint32_t pt[PT ? CW / 2 : 1];      // PT: the row's fp16 P values, two per register
 #pragma unroll
       for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t packed[16];
@@ -314,14 +339,24 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
           asm("add.f32x2 %0, %0, %1;" : "+l"(l2) : "l"(e2));
           packed[i >> 1] = f2_to_h2(p0, p1);
         }
-        const int cc = half * CW + c0;     // column inside the kBKV-wide P tile
-        uint8_t* tile = sp + (cc / 64) * (kBQ * 128) + r * 128;
+        if constexpr (PT) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((cc % 64) / 8 + q) ^ (r & 7);
-          *reinterpret_cast<uint4*>(tile + chunk * 16) =
-              make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+          for (int i = 0; i < 16; ++i) pt[c0 / 2 + i] = packed[i];
+        } else {
+          const int cc = half * CW + c0;     // column inside the kBKV-wide P tile
+          uint8_t* tile = sp + (cc / 64) * (kBQ * 128) + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((cc % 64) / 8 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(tile + chunk * 16) =
+                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+          }
         }
+      }
+      if constexpr (PT) {
+        static_assert(!PT || CW == 64, "P in tensor memory: 64-key blocks (one 32-column store per row)");
+        tmem_st_32x32b_x32(tmem_s + (uint32_t)(sb * kBKV) + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&pt[0]));
+        tmem_st_wait();
       }
       {
         float la, lb;
@@ -330,7 +365,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       }
       // S_j fully consumed -> the issuer may overwrite this buffer with S_{j+NSB}; P_j (and a rescaled O) ready
       tc_fence_before();
-      fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor core
+      if (!PT) fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor core
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&s_empty[sb]);
@@ -425,9 +460,9 @@ int make_map4(CUtensorMap* out, const void* ptr, int d, long long len, int heads
   return SCB_OK;
 }
 
-template <int D, int kBKV, int NSB, int KS>
+template <int D, int kBKV, int NSB, int KS, bool PT = false>
 int launch_attn(const scb_attention_args* a, cudaStream_t st) {
-  using C = ACfg<D, kBKV, NSB, KS>;
+  using C = ACfg<D, kBKV, NSB, KS, PT>;
   CUtensorMap mq, mk, mv;
   int rc = make_map4(&mq, a->q, D, a->q_len, a->n_q_heads, a->batch, a->q_stride_t, a->q_stride_h,
                      a->q_stride_b, kBQ);
@@ -445,7 +480,7 @@ int launch_attn(const scb_attention_args* a, cudaStream_t st) {
   p.n_q_heads = a->n_q_heads; p.n_kv_heads = a->n_kv_heads;
   p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  auto kern = attention_tcgen05_kernel<D, kBKV, NSB, KS>;
+  auto kern = attention_tcgen05_kernel<D, kBKV, NSB, KS, PT>;
   SCB_SET_FUNC_ATTR_ONCE_PER_DEVICE(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   dim3 grid((unsigned)((a->q_len + kBQ - 1) / kBQ), (unsigned)a->n_q_heads, (unsigned)a->batch);
   kern<<<grid, C::kThreads, C::kSmemBytes, st>>>(mq, mk, mv, p);
@@ -478,13 +513,17 @@ extern "C" int scb_attention(const scb_attention_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // variants: 0 = 128-key blocks, one thread per row; 1 = 128-key blocks, two threads per row (8 softmax
   // warps); 2 = 64-key blocks, one thread per row, TWO CTAs per SM (256 TMEM columns, 112 KB each): the two
-  // CTAs drift apart, so one reads S from TMEM (64 B/clk/SM) while the other one is in its exp2 phase.
-  static const int v64 = [] { const char* e = getenv("SCB_ATTN64"); return e ? atoi(e) : 2; }();
-  static const int v128 = [] { const char* e = getenv("SCB_ATTN128"); return e ? atoi(e) : 2; }();
+  // CTAs drift apart, so one reads S from TMEM (64 B/clk/SM) while the other one is in its exp2 phase;
+  // 3 (default) = 2 with P kept in tensor memory (see ACfg): 285 -> 265 us for a 5 824-token causal prefill head
+  // set, 217 -> 200 us for 64 CLIP frames.  (One S buffer and three CTAs per SM for D = 64 spills: 911 us.)
+  static const int v64 = [] { const char* e = getenv("SCB_ATTN64"); return e ? atoi(e) : 3; }();
+  static const int v128 = [] { const char* e = getenv("SCB_ATTN128"); return e ? atoi(e) : 3; }();
   if (a->head_dim == 64) {
+    if (v64 == 3) return launch_attn<64, 64, 2, 1, true>(a, st);     // P in tensor memory
     if (v64 == 2) return launch_attn<64, 64, 2, 1>(a, st);
     return v64 == 1 ? launch_attn<64, 128, 2, 2>(a, st) : launch_attn<64, 128, 2, 1>(a, st);
   }
+  if (v128 == 3) return launch_attn<128, 64, 2, 1, true>(a, st);     // P in tensor memory
   if (v128 == 2) return launch_attn<128, 64, 2, 1>(a, st);
   return v128 == 1 ? launch_attn<128, 128, 2, 2>(a, st) : launch_attn<128, 128, 2, 1>(a, st);
 }

@@ -411,6 +411,20 @@ def ours(args):
                            "launch list) + attention_tcgen05_kernel (13 %) + norms / rope; FLOPs = dense 2*6.525e9*T + causal attention",
                            "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tsrc,
                            "traffic": None, "share_of_step_time": pre_ms / (ms if ms else 1)}
+    roofline_encode = None
+    if breakdown.get("encode"):
+        # the other tensor-bound stage: CLIP tower + projector + pool over this rank's frames (rank 0's stage time)
+        tpeak, tsrc = load_tensor_peak()
+        enc_frames = int(frames_dev.shape[0])
+        enc_flops = model.vision.flops_per_frame() * enc_frames
+        ach = enc_flops / (breakdown["encode"] * 1e-3) / 1e12
+        breakdown["encode_tflops"] = ach
+        roofline_encode = {"bound": "tensor", "kernel": "encode stage: linear_tcgen05_kernel<256, pair> (75 % of a pass in the ncu launch "
+                           "list) + attention_tcgen05_kernel<64> (17 %) + LayerNorm / im2col / pool; FLOPs = "
+                           f"{model.vision.flops_per_frame() / 1e9:.2f} GF per frame (the tower layers feature_select needs, projector "
+                           "Linear-2 after the pool)",
+                           "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tsrc,
+                           "traffic": None, "frames": enc_frames, "share_of_step_time": breakdown["encode"] * args.steps / (ms if ms else 1)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -424,6 +438,8 @@ def ours(args):
     }
     if roofline_tensor is not None:
         line["roofline_tensor"] = roofline_tensor      # the tensor-bound half of the step, beside the HBM-bound `roofline`
+    if roofline_encode is not None:
+        line["roofline_encode"] = roofline_encode
     if weak is not None:
         line["weak"] = weak
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -315,8 +315,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
       }
       // P·V_{j-1} must have finished READING the P tile before block j overwrites it (this also observes every
       // phase of o_full in order — an mbarrier parity wait is only sound one phase behind)
-      // (PT: nothing to wait for — P_j goes to the other S buffer; o_full can be at most one phase ahead of a thread
-      // that has not yet delivered P_j, so the rescale and the final wait above / below stay sound without it)
+      // (PT: P_j goes to the other S buffer, so the wait moves behind the P store — see there)
       if (!PT && j > 0 && !o_seen) mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * p.scale_log2;
       // ---- P = exp2(S*scale - m), row sum, fp16 P into the swizzled A-operand tile
@@ -357,6 +356,13 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q,
         static_assert(!PT || CW == 64, "P in tensor memory: 64-key blocks (one 32-column store per row)");
         tmem_st_32x32b_x32(tmem_s + (uint32_t)(sb * kBKV) + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&pt[0]));
         tmem_st_wait();
+        // P_j is PUBLISHED only after P·V_{j-1} has completed, i.e. after the issuer has consumed p_full phase j-1.
+        // Without this the softmax warps — S_{j+1} is usually waiting for them — can finish block j+1 as well and
+        // complete p_full TWICE before a delayed issuer (a late V tile) has polled it once; its parity wait then sees
+        // the barrier two phases on, takes it for "not yet", and the CTA deadlocks.  P·V_{j-1} is long done by the
+        // time a block's exponentials are, so the wait costs nothing; it also keeps every thread's view of o_full
+        // one phase behind at most (rescale above, final read below).
+        if (j > 0 && !o_seen) mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
       }
       {
         float la, lb;

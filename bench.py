@@ -415,7 +415,7 @@ def ours(args):
     if breakdown.get("encode"):
         # the other tensor-bound stage: CLIP tower + projector + pool over this rank's frames (rank 0's stage time)
         tpeak, tsrc = load_tensor_peak()
-        enc_frames = int(frames_dev.shape[0])
+        enc_frames = int(host_frames.shape[0])          # this rank's frames of the stream (frames_dev may be released by now)
         enc_flops = model.vision.flops_per_frame() * enc_frames
         ach = enc_flops / (breakdown["encode"] * 1e-3) / 1e12
         breakdown["encode_tflops"] = ach

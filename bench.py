@@ -232,10 +232,23 @@ def ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    device = torch.device(f"cuda:{local}")
+        # NCCL writes its version banner to STDOUT when the communicator is created (NCCL_DEBUG=VERSION/INFO in the
+        # environment): create it here, with file descriptor 1 pointed at stderr, so that stdout carries the JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(device)
+            dist.init_process_group("nccl", device_id=device)
+            dist.all_reduce(torch.zeros(1, device=device))
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     torch.cuda.set_device(device)
     _lib.load()
 

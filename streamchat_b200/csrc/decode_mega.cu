@@ -149,15 +149,18 @@ struct Ring {
 // CTA's chunk range [ch0, ch0 + nch).  Three layouts:
 //   whole tiles        (split 0): CTA c owns tiles [c*T/G, (c+1)*T/G) with all their chunks;
 //   cut anywhere       (split 1): the T*chunks units are dealt out evenly; a tile spans at most two CTAs, whose
-//                                 partial sums land in partial slots 0 (has the tile's first chunk) and 1;
+//                                 partial sums meet in ONE zero-initialised fp32 slot through red.add — 0 + a + b is
+//                                 the same value in either order, so the result stays deterministic, and the next
+//                                 prologue reads one slot per K-half instead of two (it is bound by those bytes:
+//                                 every CTA re-reads every row);
 //   K-halves           (g0 > 0):  CTAs [0, g0) work on chunks [0, nch0), the others on [nch0, chunks), each half cut
-//                                 anywhere as above (partial slots 2*half + {0, 1}).  The wide down_proj input
+//                                 anywhere as above (partial slot = half).  The wide down_proj input
 //                                 (18 944 values per sequence) then occupies HALF the shared memory per sequence, which
 //                                 gives the weight ring back the stages 3- and 4-row steps were losing (6 -> 10, 4 -> 8).
 struct UnitPlan {
   int u0, u1;      // unit range in the CTA's local numbering (tile = u / nch, local chunk = u % nch)
   int nch, ch0;    // chunk range of this CTA
-  int pslot;       // first partial slot
+  int pslot;       // partial slot of this CTA's K-half
 };
 SCB_DEVICE UnitPlan unit_plan(const StageShape& s) {
   const long long G = gridDim.x, c = blockIdx.x;
@@ -171,7 +174,7 @@ SCB_DEVICE UnitPlan unit_plan(const StageShape& s) {
     const long long cc = hi ? c - s.g0 : c, Gh = hi ? G - s.g0 : s.g0;
     pl.nch = hi ? s.chunks - nch0 : nch0;
     pl.ch0 = hi ? nch0 : 0;
-    pl.pslot = hi ? 2 : 0;
+    pl.pslot = hi ? 1 : 0;
     const long long U = (long long)s.n_tiles * pl.nch;
     pl.u0 = (int)(cc * U / Gh);
     pl.u1 = (int)((cc + 1) * U / Gh);
@@ -282,8 +285,6 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
       }
       cbar();
       red_buf ^= 1;
-      const bool has_first = tile * chunks >= u0;
-      const bool has_last = (tile + 1) * chunks <= u1;
       if (KIND == ST_GU) {
         // rows (2i, 2i+1) = (gate_i, up_i): out = fp16(silu(fp16 gate)) * fp16 up  (modeling_qwen2.py:41-48)
         if (tid < 8 * kRMax) {
@@ -314,14 +315,7 @@ SCB_DEVICE void run_stage(const MegaParams& p, const StageShape& s, const MegaLa
             p.qkv_buf[(size_t)n * p.qkv_dim + o] = __float2half_rn(v);
           } else if (KIND == ST_O || KIND == ST_DOWN) {
             float* part = ((KIND == ST_O) ? p.part_o : p.part_d) + (size_t)pl.pslot * kRMax * p.H;
-            const size_t slot_stride = (size_t)kRMax * p.H;
-            const size_t idx = (size_t)n * p.H + o;
-            if (has_first) {
-              part[idx] = v;
-              if (has_last) part[slot_stride + idx] = 0.f;
-            } else {
-              part[slot_stride + idx] = v;
-            }
+            atomicAdd(part + (size_t)n * p.H + o, v);   // at most two contributions per element onto a zeroed slot
           } else {  // ST_LM
             const __half hv = __float2half_rn(v);
             p.logits[(size_t)n * p.ld_logits + o] = hv;
@@ -436,25 +430,20 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
     const __half* er = embed_rows ? embed_rows + (size_t)p.next_id[n] * H : nullptr;
     for (int c0 = 0; c0 < n_chunks; c0 += kCThreads * CH) {
       uint4 rr[CH];
-      float4 q0[CH][2], q1[CH][2], q2[CH][2], q3[CH][2];
+      float4 q0[CH][2], q1[CH][2];
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const int c = min(c0 + j * kCThreads + tid, n_chunks - 1);   // clamped: loads stay unconditional (registers)
-        q2[j][0] = q2[j][1] = q3[j][0] = q3[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (er) {
           rr[j] = *reinterpret_cast<const uint4*>(er + c * 8);
-          q0[j][0] = q0[j][1] = q1[j][0] = q1[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
           rr[j] = __ldcg(reinterpret_cast<const uint4*>(res + (size_t)n * H + c * 8));
           const float4* s0 = reinterpret_cast<const float4*>(part + (size_t)n * H + c * 8);
-          const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
           q0[j][0] = __ldcg(s0); q0[j][1] = __ldcg(s0 + 1);
-          q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
-          if (n_slots == 4) {      // K-halves (down_proj): slots 2, 3 hold the upper half's partial sums
-            const float4* s2 = reinterpret_cast<const float4*>(part + 2 * slot_stride + (size_t)n * H + c * 8);
-            const float4* s3 = reinterpret_cast<const float4*>(part + 3 * slot_stride + (size_t)n * H + c * 8);
-            q2[j][0] = __ldcg(s2); q2[j][1] = __ldcg(s2 + 1);
-            q3[j][0] = __ldcg(s3); q3[j][1] = __ldcg(s3 + 1);
+          if (n_slots == 2) {      // K-halves (down_proj): slot 1 holds the upper half's partial sums
+            const float4* s1 = reinterpret_cast<const float4*>(part + slot_stride + (size_t)n * H + c * 8);
+            q1[j][0] = __ldcg(s1); q1[j][1] = __ldcg(s1 + 1);
           }
         }
       }
@@ -470,12 +459,11 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
           if (!er) {
             const float a0[8] = {q0[j][0].x, q0[j][0].y, q0[j][0].z, q0[j][0].w, q0[j][1].x, q0[j][1].y, q0[j][1].z, q0[j][1].w};
             const float a1[8] = {q1[j][0].x, q1[j][0].y, q1[j][0].z, q1[j][0].w, q1[j][1].x, q1[j][1].y, q1[j][1].z, q1[j][1].w};
-            const float a2[8] = {q2[j][0].x, q2[j][0].y, q2[j][0].z, q2[j][0].w, q2[j][1].x, q2[j][1].y, q2[j][1].z, q2[j][1].w};
-            const float a3[8] = {q3[j][0].x, q3[j][0].y, q3[j][0].z, q3[j][0].w, q3[j][1].x, q3[j][1].y, q3[j][1].z, q3[j][1].w};
-            // fixed order: (lower K-half: slot 0 + slot 1) + (upper K-half: slot 2 + slot 3, zero without K-halves) + residual
+            // fixed order: (lower K-half) + (upper K-half, absent without K-halves) + residual; each half is the
+            // commutative sum of its (at most two) CTA contributions
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              x[e] = __half2float(__float2half_rn(n_slots == 4 ? ((a0[e] + a1[e]) + (a2[e] + a3[e])) + x[e] : (a0[e] + a1[e]) + x[e]));
+              x[e] = __half2float(__float2half_rn(n_slots == 2 ? (a0[e] + a1[e]) + x[e] : a0[e] + x[e]));
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
@@ -513,6 +501,16 @@ SCB_DEVICE void prologue_norm(const MegaParams& p, __half* act, float* red8, con
     }
   }
   cbar();
+}
+
+// The partial slots go back to zero once EVERY CTA has read them (the caller sits behind the grid barrier that follows
+// the reading prologue); each CTA clears its share of the R live rows.  The next red.add into them is several grid
+// barriers away.
+SCB_DEVICE void zero_partials(const MegaParams& p, float* part, int n_slots) {
+  const size_t slot_stride = (size_t)kRMax * p.H;
+  const int n = p.R * p.H;
+  for (int sl = 0; sl < n_slots; ++sl)
+    for (int i = blockIdx.x * kCThreads + threadIdx.x; i < n; i += gridDim.x * kCThreads) part[sl * slot_stride + i] = 0.f;
 }
 
 // act <- src rows ([R][len] fp16 in global, written by other CTAs before the last grid barrier);
@@ -881,7 +879,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
 
   long long* prof = (p.prof && tid == 0) ? p.prof + (size_t)cta * p.n_layers * kProfStamps : nullptr;
 #define SCB_STAMP(i) do { if (prof) prof[l * kProfStamps + (i)] = clock64(); } while (0)
-  const int down_slots = p.shp[ST_DOWN].g0 > 0 ? 4 : 2;   // partial slots the down_proj stage fills
+  const int down_slots = p.shp[ST_DOWN].g0 > 0 ? 2 : 1;   // partial slots the down_proj stage fills (one per K-half)
   for (int l = 0; l < p.n_layers; ++l) {
     const MegaLayer* ly = p.layers + l;
     SCB_STAMP(0);
@@ -892,6 +890,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     SCB_STAMP(2);
     grid_sync(p, gen);
     SCB_STAMP(3);
+    zero_partials(p, p.part_d, down_slots);   // every CTA has read the previous layer's down_proj sums
     // ---- attention partials
     const int plan_L = plan_split_len(p);
     if (split < p.n_splits) {
@@ -922,12 +921,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     grid_sync(p, gen);
     SCB_STAMP(10);
     // ---- gate|up: x2 = x + o partials; act = RMSNorm(x2) * ln2
-    prologue_norm(p, act, red8, p.x_buf, p.part_o, 2, nullptr, p.x2_buf, ly->ln2);
+    prologue_norm(p, act, red8, p.x_buf, p.part_o, 1, nullptr, p.x2_buf, ly->ln2);
     SCB_STAMP(11);
     run_stage<ST_GU>(p, p.shp[ST_GU], ly, ring, act, red, red_buf, best);
     SCB_STAMP(12);
     grid_sync(p, gen);
     SCB_STAMP(13);
+    zero_partials(p, p.part_o, 1);            // every CTA has read the o_proj sums
     // ---- down
     {
       // down_proj input: the whole gated row, or (K-halves) only the columns of this CTA's chunk range
@@ -964,6 +964,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(const __gr
     p.cand_idx[(size_t)cta * kRMax + tid] = bi;
   }
   grid_sync(p, gen);
+  zero_partials(p, p.part_d, down_slots);     // read by the final norm above: the next step starts from zeroed slots
   if (cta == 0) {
     if (warp < p.R) {
       float bv = -INFINITY;

@@ -82,7 +82,7 @@ struct MegaParams {
   long long ld_logits;
   // workspace (handle-owned)
   __half *x_buf, *x2_buf, *qkv_buf, *attn_buf, *gu_buf;
-  float *part_o, *part_d;               // [2][kRMax][H]
+  float *part_o, *part_d;               // [slot][kRMax][H] fp32, zero between uses: o_proj 1 slot, down_proj 1 per K-half
   float *att_m, *att_l, *att_o;         // [kRMax][n_q][n_splits] (+ [HD])
   float* cand_val;                      // [grid][kRMax]
   int* cand_idx;

@@ -24,4 +24,4 @@ for name, n, k, act, res in [("qkv", 3072, 1024, L.ACT_NONE, False), ("out", 102
     tm, tb = timeit(lambda: torch.matmul(a, w.t(), out=out), flush=False)
     fl = 2.0 * m * n * k
     print(json.dumps({"gemm": name, "m": m, "n": n, "k": k, "us": round(med * 1e6, 1), "tflops": round(fl / med / 1e12, 1),
-                      "cublas_no_epilogue_tflops": round(fl / tm / 1e12, 1), "dbg": os.environ.get("SCB_LINEAR_DBG", "0")}))
+                      "cublas_no_epilogue_tflops": round(fl / tm / 1e12, 1), "tma_store": os.environ.get("SCB_LINEAR_TMA_STORE", "1")}))

@@ -87,7 +87,8 @@ def test_ctypes_structs_match_header_layout(tmp_path):
         "scb_decode_attention_args": _lib.DecodeAttentionArgs,
         "scb_decode_attention_fused_args": _lib.DecodeAttentionFusedArgs,
         "scb_qwen2_decoder_desc": _lib.Qwen2DecoderDesc, "scb_qwen2_decode_step_args": _lib.Qwen2DecodeStepArgs,
-        "scb_vit_encoder_desc": _lib.VitEncoderDesc,
+        "scb_vit_encoder_desc": _lib.VitEncoderDesc, "scb_linear_splitk_args": _lib.LinearSplitKArgs,
+        "scb_allgather_embed_args": _lib.AllgatherEmbedArgs,
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "streamchat_b200.h")}"',
              'int main(void) {']
